@@ -1,0 +1,228 @@
+// oracle/ref_shim.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Thin extern "C" shim over the UNMODIFIED reference library (compiled from /root/reference by
+// oracle/Makefile `ref`).  It only calls the reference's own public API:
+//   VectorIndex::CreateInstance / SetParameter / BuildIndex / SaveIndex / LoadIndex
+//                                   (AnnService/inc/Core/VectorIndex.h:28-214)
+//   VectorIndex::SearchIndex(const void*,int,int,bool,BasicResult*)   (VectorIndex.cpp:454-463)
+//   VectorIndex::SearchIndex(QueryResult&)                            (BKTIndex.cpp:595-620)
+//   COMMON::DistanceCalcSelector<T> / DistanceUtils::Compute*_{SSE,AVX,AVX512}
+//                                   (inc/Core/Common/DistanceUtils.h:118-163)
+// so that python (ctypes) tests and bench.py's cpu_baseline / --impl reference leg can run the
+// reference itself.  Nothing in the product library links against this file.
+#include "inc/Core/VectorIndex.h"
+#include "inc/Core/SearchQuery.h"
+#include "inc/Core/Common/DistanceUtils.h"
+#include "inc/Core/Common/InstructionUtils.h"
+#include "inc/Core/Common/WorkSpace.h"
+#include "inc/Helper/Logging.h"
+
+#include <omp.h>
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace SPTAG;
+
+namespace {
+
+struct RefHandle {
+    std::shared_ptr<VectorIndex> index;
+};
+
+// silence the reference's Info-level chatter (build progress, "Delete workspace happens!")
+class QuietLogger : public Helper::Logger {
+public:
+    explicit QuietLogger(Helper::LogLevel lvl) : m_level(lvl) {}
+    void Logging(const char* title, Helper::LogLevel level, const char* file, int line,
+                 const char* func, const char* format, ...) override {
+        if (level < m_level) return;
+        va_list args;
+        va_start(args, format);
+        std::fprintf(stderr, "[ref:%d] ", (int)level);
+        std::vfprintf(stderr, format, args);
+        va_end(args);
+    }
+private:
+    Helper::LogLevel m_level;
+};
+
+// Work-space factory that lets us read the reference's per-query counters
+// (WorkSpace.h:303-308) without patching it.  SetWorkSpaceFactory (BKT/Index.h:199-216)
+// dynamic_casts from IWorkSpaceFactory<IWorkSpace> to IWorkSpaceFactory<WorkSpace>, so the
+// object must inherit both (SURVEY.md 8a').
+struct SideA : COMMON::IWorkSpaceFactory<COMMON::IWorkSpace> {
+    std::unique_ptr<COMMON::IWorkSpace> GetWorkSpace() override { return nullptr; }
+    void ReturnWorkSpace(std::unique_ptr<COMMON::IWorkSpace>) override {}
+    virtual ~SideA() {}
+};
+struct SideB : COMMON::IWorkSpaceFactory<COMMON::WorkSpace> {
+    static thread_local std::unique_ptr<COMMON::WorkSpace> tl_ws;
+    static thread_local COMMON::WorkSpace* tl_last;
+    std::unique_ptr<COMMON::WorkSpace> GetWorkSpace() override { return std::move(tl_ws); }
+    void ReturnWorkSpace(std::unique_ptr<COMMON::WorkSpace> ws) override {
+        tl_last = ws.get();
+        tl_ws = std::move(ws);
+    }
+    virtual ~SideB() {}
+};
+thread_local std::unique_ptr<COMMON::WorkSpace> SideB::tl_ws;
+thread_local COMMON::WorkSpace* SideB::tl_last = nullptr;
+struct PinnedFactory : SideA, SideB {};
+
+void apply_params(VectorIndex* idx, const char* params) {
+    // "Name=Value;Name=Value"
+    if (!params) return;
+    std::string s(params);
+    size_t pos = 0;
+    while (pos < s.size()) {
+        size_t end = s.find(';', pos);
+        if (end == std::string::npos) end = s.size();
+        std::string kv = s.substr(pos, end - pos);
+        size_t eq = kv.find('=');
+        if (eq != std::string::npos)
+            idx->SetParameter(kv.substr(0, eq).c_str(), kv.substr(eq + 1).c_str());
+        pos = end + 1;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// 512 / 256 / 128 / 0: which DistanceUtils variant the reference's cpuid dispatch selects here
+int ref_isa(void) {
+    if (COMMON::InstructionSet::AVX512()) return 512;
+    if (COMMON::InstructionSet::AVX2() || COMMON::InstructionSet::AVX()) return 256;
+    if (COMMON::InstructionSet::SSE2() || COMMON::InstructionSet::SSE()) return 128;
+    return 0;
+}
+
+void ref_quiet(int min_level) {
+    SetLogger(std::make_shared<QuietLogger>((Helper::LogLevel)min_level));
+}
+
+// algo: 0 BKT, 1 KDT.  value_type: 0 int8, 1 uint8, 2 int16, 3 float.  metric: 0 L2, 1 Cosine.
+void* ref_build(int algo, int value_type, int metric, const void* data, int n, int dim,
+                int threads, const char* params) {
+    auto idx = VectorIndex::CreateInstance((IndexAlgoType)algo, (VectorValueType)value_type);
+    if (!idx) return nullptr;
+    idx->SetParameter("DistCalcMethod", metric == 0 ? "L2" : (metric == 1 ? "Cosine" : "InnerProduct"));
+    idx->SetParameter("NumberOfThreads", std::to_string(threads).c_str());
+    apply_params(idx.get(), params);
+    if (idx->BuildIndex(data, n, dim) != ErrorCode::Success) return nullptr;
+    auto* h = new RefHandle();
+    h->index = idx;
+    return h;
+}
+
+int ref_save(void* h, const char* folder) {
+    return (int)((RefHandle*)h)->index->SaveIndex(std::string(folder));
+}
+
+void* ref_load(const char* folder) {
+    std::shared_ptr<VectorIndex> idx;
+    if (VectorIndex::LoadIndex(std::string(folder), idx) != ErrorCode::Success || !idx) return nullptr;
+    auto* h = new RefHandle();
+    h->index = idx;
+    return h;
+}
+
+void ref_free(void* h) { delete (RefHandle*)h; }
+
+int ref_set_param(void* h, const char* name, const char* value) {
+    return (int)((RefHandle*)h)->index->SetParameter(name, value);
+}
+
+int ref_get_param(void* h, const char* name, char* out, int cap) {
+    std::string v = ((RefHandle*)h)->index->GetParameter(name);
+    std::snprintf(out, cap, "%s", v.c_str());
+    return (int)v.size();
+}
+
+int ref_num_samples(void* h) { return ((RefHandle*)h)->index->GetNumSamples(); }
+int ref_dim(void* h) { return ((RefHandle*)h)->index->GetFeatureDim(); }
+const void* ref_sample(void* h, int i) { return ((RefHandle*)h)->index->GetSample(i); }
+
+// THE reference call the product replaces: VectorIndex::SearchIndex(batch) (VectorIndex.cpp:454-463).
+// Results are pre-initialised the way a default-constructed BasicResult is (SearchResult.h:72).
+// Wall-clock seconds of the SearchIndex call only are written to *seconds.
+int ref_search_batch(void* h, const void* queries, int nq, int k, int threads,
+                     int* ids, float* dists, double* seconds) {
+    auto& idx = ((RefHandle*)h)->index;
+    std::vector<BasicResult> res((size_t)nq * k);
+    if (threads > 0) omp_set_num_threads(threads);
+    auto t0 = std::chrono::steady_clock::now();
+    ErrorCode ec = idx->SearchIndex(queries, nq, k, false, res.data());
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    for (size_t i = 0; i < res.size(); ++i) {
+        ids[i] = res[i].VID;
+        dists[i] = res[i].Dist;
+    }
+    return (int)ec;
+}
+
+// Install the counter-reading factory (single-query stats below need it). Irreversible for h.
+int ref_enable_stats(void* h) {
+    auto& idx = ((RefHandle*)h)->index;
+    std::unique_ptr<COMMON::IWorkSpaceFactory<COMMON::IWorkSpace>> f(static_cast<SideA*>(new PinnedFactory()));
+    return (int)idx->SetWorkSpaceFactory(std::move(f));
+}
+
+// Single-query VectorIndex::SearchIndex(QueryResult&) + the reference's own counters:
+// stats[0]=m_iNumberOfCheckedLeaves, [1]=m_iNumberOfTreeCheckedLeaves, [2]=NGQueue.size(), [3]=SPTQueue.size()
+int ref_search_one_stats(void* h, const void* query, int k, int* ids, float* dists, int* stats) {
+    auto& idx = ((RefHandle*)h)->index;
+    QueryResult res(query, k, false);
+    ErrorCode ec = idx->SearchIndex(res);
+    for (int i = 0; i < k; ++i) {
+        ids[i] = res.GetResult(i)->VID;
+        dists[i] = res.GetResult(i)->Dist;
+    }
+    COMMON::WorkSpace* ws = SideB::tl_last;
+    if (stats && ws) {
+        stats[0] = ws->m_iNumberOfCheckedLeaves;
+        stats[1] = ws->m_iNumberOfTreeCheckedLeaves;
+        stats[2] = ws->m_NGQueue.size();
+        stats[3] = ws->m_SPTQueue.size();
+    }
+    return (int)ec;
+}
+
+// Distance through the reference's own run-time dispatch (DistanceUtils.h:118-163).
+float ref_distance(int metric, int value_type, const void* a, const void* b, int dim) {
+    DistCalcMethod m = (DistCalcMethod)metric;
+    switch (value_type) {
+    case 0: return COMMON::DistanceCalcSelector<std::int8_t>(m)((const std::int8_t*)a, (const std::int8_t*)b, dim);
+    case 1: return COMMON::DistanceCalcSelector<std::uint8_t>(m)((const std::uint8_t*)a, (const std::uint8_t*)b, dim);
+    case 2: return COMMON::DistanceCalcSelector<std::int16_t>(m)((const std::int16_t*)a, (const std::int16_t*)b, dim);
+    default: return COMMON::DistanceCalcSelector<float>(m)((const float*)a, (const float*)b, dim);
+    }
+}
+
+// Explicit ISA variant for float (isa = 512/256/128/0=scalar template), so the restatement can
+// be pinned against every summation tree, not only the one this host dispatches to.
+float ref_distance_f32_isa(int isa, int metric, const float* a, const float* b, int dim) {
+    using DU = COMMON::DistanceUtils;
+    if (metric == 0) {
+        if (isa == 512) return DU::ComputeL2Distance_AVX512(a, b, dim);
+        if (isa == 256) return DU::ComputeL2Distance_AVX(a, b, dim);
+        if (isa == 128) return DU::ComputeL2Distance_SSE(a, b, dim);
+        return DU::ComputeL2Distance<float>(a, b, dim);
+    }
+    if (isa == 512) return DU::ComputeCosineDistance_AVX512(a, b, dim);
+    if (isa == 256) return DU::ComputeCosineDistance_AVX(a, b, dim);
+    if (isa == 128) return DU::ComputeCosineDistance_SSE(a, b, dim);
+    return DU::ComputeCosineDistance<float>(a, b, dim);
+}
+
+// many pairs at once: a[i*dim..], b[i*dim..] -> out[i]
+void ref_distance_f32_many(int isa, int metric, const float* a, const float* b, int dim, int n, float* out) {
+    for (int i = 0; i < n; ++i)
+        out[i] = ref_distance_f32_isa(isa, metric, a + (size_t)i * dim, b + (size_t)i * dim, dim);
+}
+
+}  // extern "C"

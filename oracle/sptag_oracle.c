@@ -1,0 +1,657 @@
+/* oracle/sptag_oracle.c
+ *
+ * TEST INFRASTRUCTURE ONLY.  A plain-C CPU restatement of the reference's batched search path
+ * (microsoft/SPTAG @ /root/reference, paths below relative to AnnService/).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load this
+ * library, and there only as the checker / CPU baseline -- never as the product path.
+ *
+ * Parity pin: this restatement is checked (tests/test_oracle_pin.py) against
+ *   (1) the reference's own known-answer tests (Test/src/AlgoTest.cpp:163-201,
+ *       Test/cuda/distance_tests.cu:15-17, Test/src/DistanceTest.cpp:36-50) and
+ *   (2) outputs of the UNMODIFIED reference compiled here as oracle/_ref/libsptag_ref.so
+ *       (ids, distances and the WorkSpace counters, bit for bit, on the same index files).
+ *
+ * What is restated, with the reference lines each function follows:
+ *   distance          src/Core/Common/DistanceUtils.cpp:297-303 (REPEAT), :650-682 (L2 AVX512),
+ *                     :1016-1046 (cosine AVX512), :616-648/:982-1014 (AVX), :590-614/:958-980 (SSE),
+ *                     inc/Core/Common/DistanceUtils.h:25-79 (scalar templates)
+ *   heap              inc/Core/Common/Heap.h:13-106
+ *   m_Results         inc/Core/Common/WorkSpace.h:167-225 (DistPriorityQueue)
+ *   visited set       inc/Core/Common/WorkSpace.h:43-165 (OptHashPosVector) -- semantically an
+ *                     exact set (two tables, then DoubleSize()); restated as a byte map over N
+ *   work space        inc/Core/Common/WorkSpace.h:230-320
+ *   top-K             inc/Core/Common/QueryResultSet.h:17-120
+ *   BKT seed lookup   inc/Core/Common/BKTree.h:696-769 (InitSearchTrees, m_bfs == 0), :771-799 (SearchTrees)
+ *   BKT graph search  src/Core/BKT/BKTIndex.cpp:268-352 (Search), :463-508 (dispatch), :595-620
+ *   KDT seed lookup   inc/Core/Common/KDTree.h:213-271
+ *   KDT graph search  src/Core/KDT/KDTIndex.cpp:182-241, :268-318
+ *   batch loop        src/Core/VectorIndex.cpp:454-463
+ */
+#include "sptag_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* Common.h:122  MaxDist = numeric_limits<float>::max() / 10 */
+static float kMaxDist(void) { return FLT_MAX / 10; }
+float ora_max_dist(void) { return kMaxDist(); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* distance                                                                                   */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Compiled with -ffp-contract=off: every mul/add/sub below rounds separately, which is what the
+ * reference's intrinsics do in its g++ -O3 build (vsubps/vmulps/vaddps, no FMA); the reference's
+ * plain-C scalar tails ARE contracted by g++ on an FMA target, hence the explicit fmaf() there
+ * (re-verified by tests/test_oracle_pin.py). */
+
+static inline float term_f32(int cosine, float x, float y)
+{
+    if (cosine) return x * y;
+    float d = x - y;
+    return d * d;
+}
+
+static inline float tail_f32(int cosine, float x, float y, float acc)
+{
+    if (cosine) return fmaf(x, y, acc);
+    float d = x - y;
+    return fmaf(d, d, acc);
+}
+
+static float dist_f32(int cosine, int width, const float* x, const float* y, int len)
+{
+    int i = 0, j;
+    float diff;
+    if (width == 16) {
+        /* ComputeL2Distance_AVX512 / ComputeCosineDistance_AVX512 (float) */
+        float a16[16], a8[8], a4[4];
+        for (j = 0; j < 16; j++) a16[j] = 0.0f;
+        for (; i + 16 <= len; i += 16)
+            for (j = 0; j < 16; j++) a16[j] = a16[j] + term_f32(cosine, x[i + j], y[i + j]);
+        for (j = 0; j < 8; j++) a8[j] = a16[j] + a16[j + 8];
+        for (; i + 8 <= len; i += 8)
+            for (j = 0; j < 8; j++) a8[j] = a8[j] + term_f32(cosine, x[i + j], y[i + j]);
+        for (j = 0; j < 4; j++) a4[j] = a8[j] + a8[j + 4];
+        for (; i + 4 <= len; i += 4)
+            for (j = 0; j < 4; j++) a4[j] = a4[j] + term_f32(cosine, x[i + j], y[i + j]);
+        diff = a4[0] + a4[1] + a4[2] + a4[3];
+    } else if (width == 8) {
+        /* ComputeL2Distance_AVX / ComputeCosineDistance_AVX (float): 16 per trip = two 8-wide adds */
+        float a8[8], a4[4];
+        for (j = 0; j < 8; j++) a8[j] = 0.0f;
+        for (; i + 16 <= len; i += 16) {
+            for (j = 0; j < 8; j++) a8[j] = a8[j] + term_f32(cosine, x[i + j], y[i + j]);
+            for (j = 0; j < 8; j++) a8[j] = a8[j] + term_f32(cosine, x[i + 8 + j], y[i + 8 + j]);
+        }
+        for (j = 0; j < 4; j++) a4[j] = a8[j] + a8[j + 4];
+        for (; i + 4 <= len; i += 4)
+            for (j = 0; j < 4; j++) a4[j] = a4[j] + term_f32(cosine, x[i + j], y[i + j]);
+        diff = a4[0] + a4[1] + a4[2] + a4[3];
+    } else if (width == 4) {
+        /* ComputeL2Distance_SSE / ComputeCosineDistance_SSE (float) */
+        float a4[4];
+        for (j = 0; j < 4; j++) a4[j] = 0.0f;
+        for (; i + 4 <= len; i += 4)
+            for (j = 0; j < 4; j++) a4[j] = a4[j] + term_f32(cosine, x[i + j], y[i + j]);
+        diff = a4[0] + a4[1] + a4[2] + a4[3];
+    } else {
+        /* DistanceUtils.h:25-44 / :60-79 scalar templates: one accumulator, contracted by g++ */
+        diff = 0.0f;
+        for (; i + 4 <= len; i += 4)
+            for (j = 0; j < 4; j++) diff = tail_f32(cosine, x[i + j], y[i + j], diff);
+    }
+    for (; i < len; i++) diff = tail_f32(cosine, x[i], y[i], diff);
+    /* float base is 1 (CommonUtils.h GetBase<float>) */
+    return cosine ? 1 - diff : diff;
+}
+
+float ora_distance(int32_t metric, int32_t value_type, int32_t simd_width,
+                   const void* x, const void* y, int32_t dim)
+{
+    int cosine = (metric != ORA_L2);
+    if (value_type == ORA_FLOAT)
+        return dist_f32(cosine, simd_width, (const float*)x, (const float*)y, dim);
+    return NAN; /* integer element types: not on the float configs; added with the int8 row */
+}
+
+void ora_distance_f32_many(int32_t metric, int32_t simd_width, const float* a, const float* b,
+                           int32_t dim, int32_t n, float* out)
+{
+    int cosine = (metric != ORA_L2);
+    for (int32_t i = 0; i < n; i++)
+        out[i] = dist_f32(cosine, simd_width, a + (size_t)i * dim, b + (size_t)i * dim, dim);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Heap<NodeDistPair>  (Heap.h:13-106, SearchResult.h:11-27)                                   */
+/* ------------------------------------------------------------------------------------------ */
+
+typedef struct {
+    int32_t node;
+    float distance;
+} pair_t;
+
+typedef struct {
+    pair_t* heap; /* 1-based; heap[0] stays the default (-1, MaxDist) */
+    int length, count, lastlevel;
+} heap_t;
+
+static void heap_resize(heap_t* h, int size)
+{
+    free(h->heap);
+    h->length = size;
+    h->heap = (pair_t*)malloc(sizeof(pair_t) * ((size_t)size + 1));
+    for (int i = 0; i <= size; i++) {
+        h->heap[i].node = -1;
+        h->heap[i].distance = kMaxDist();
+    }
+    h->count = 0;
+    h->lastlevel = (int)pow(2.0, floor(log2((float)size)));
+}
+
+static void heap_clear(heap_t* h, int size)
+{
+    if (size > h->length) heap_resize(h, size);
+    h->count = 0;
+}
+
+static inline pair_t* heap_top(heap_t* h) { return h->count == 0 ? &h->heap[0] : &h->heap[1]; }
+
+static void heap_insert(heap_t* h, pair_t value)
+{
+    int loc;
+    pair_t* a = h->heap;
+    if (h->count == h->length) {
+        int maxi = h->lastlevel;
+        for (int i = h->lastlevel + 1; i <= h->length; i++)
+            if (a[maxi].distance < a[i].distance) maxi = i;
+        if (value.distance > a[maxi].distance) return;
+        loc = maxi;
+    } else {
+        loc = ++(h->count);
+    }
+    int par = (loc >> 1);
+    while (par > 0 && value.distance < a[par].distance) {
+        a[loc] = a[par];
+        loc = par;
+        par >>= 1;
+    }
+    a[loc] = value;
+}
+
+static inline void pair_swap(pair_t* x, pair_t* y)
+{
+    pair_t t = *x;
+    *x = *y;
+    *y = t;
+}
+
+static void heap_heapify(heap_t* h)
+{
+    pair_t* a = h->heap;
+    int parent = 1, next = 2;
+    while (next < h->count) {
+        if (a[next].distance > a[next + 1].distance) next++;
+        if (a[next].distance < a[parent].distance) {
+            pair_swap(&a[parent], &a[next]);
+            parent = next;
+            next <<= 1;
+        } else
+            break;
+    }
+    if (next == h->count && a[next].distance < a[parent].distance) pair_swap(&a[parent], &a[next]);
+}
+
+/* T& pop(): returns the slot the old root was swapped into */
+static pair_t heap_pop(heap_t* h)
+{
+    if (h->count == 0) return h->heap[0];
+    pair_swap(&h->heap[1], &h->heap[h->count]);
+    h->count--;
+    heap_heapify(h);
+    return h->heap[h->count + 1];
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* DistPriorityQueue  (WorkSpace.h:167-225)                                                    */
+/* ------------------------------------------------------------------------------------------ */
+
+typedef struct {
+    int size, length, count;
+    float* data;
+} dpq_t;
+
+static void dpq_clear(dpq_t* q, int count_)
+{
+    if (count_ > q->size) {
+        q->size = count_;
+        free(q->data);
+        q->data = (float*)malloc(sizeof(float) * ((size_t)count_ + 1));
+    }
+    q->data[1] = kMaxDist();
+    q->length = 1;
+    q->count = count_;
+}
+
+static int dpq_insert(dpq_t* q, float dist)
+{
+    float* d = q->data;
+    if (dist > d[1]) return 0;
+    if (q->length == q->count) {
+        d[1] = dist;
+        int parent = 1, next = 2;
+        while (next < q->length) {
+            if (d[next] < d[next + 1]) next++;
+            if (d[next] > d[parent]) {
+                float t = d[parent];
+                d[parent] = d[next];
+                d[next] = t;
+                parent = next;
+                next <<= 1;
+            } else
+                break;
+        }
+        if (next == q->length && d[next] > d[parent]) {
+            float t = d[parent];
+            d[parent] = d[next];
+            d[next] = t;
+        }
+    } else {
+        int next = ++(q->length), parent = (next >> 1);
+        while (parent > 0 && dist > d[parent]) {
+            d[next] = d[parent];
+            next = parent;
+            parent >>= 1;
+        }
+        d[next] = dist;
+    }
+    return 1;
+}
+
+static inline float dpq_worst(const dpq_t* q) { return q->data[1]; }
+
+/* ------------------------------------------------------------------------------------------ */
+/* QueryResultSet  (QueryResultSet.h:17-120)                                                   */
+/* ------------------------------------------------------------------------------------------ */
+
+typedef struct {
+    int32_t vid;
+    float dist;
+} res_t;
+
+static inline int res_less(res_t a, res_t b)
+{
+    return (a.dist < b.dist) || ((a.dist == b.dist) && (a.vid < b.vid));
+}
+
+static void res_heapify(res_t* r, int count)
+{
+    int parent = 0, next = 1, maxidx = count - 1;
+    while (next < maxidx) {
+        if (res_less(r[next], r[next + 1])) next++;
+        if (res_less(r[parent], r[next])) {
+            res_t t = r[next];
+            r[next] = r[parent];
+            r[parent] = t;
+            parent = next;
+            next = (parent << 1) + 1;
+        } else
+            break;
+    }
+    if (next == maxidx && res_less(r[parent], r[next])) {
+        res_t t = r[parent];
+        r[parent] = r[next];
+        r[next] = t;
+    }
+}
+
+static int res_add_point(res_t* r, int k, int32_t index, float dist)
+{
+    if (dist < r[0].dist || (dist == r[0].dist && index < r[0].vid)) {
+        r[0].vid = index;
+        r[0].dist = dist;
+        res_heapify(r, k);
+        return 1;
+    }
+    return 0;
+}
+
+static void res_sort(res_t* r, int k)
+{
+    for (int i = k - 1; i >= 0; i--) {
+        res_t t = r[0];
+        r[0] = r[i];
+        r[i] = t;
+        res_heapify(r, i);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* WorkSpace  (WorkSpace.h:230-320)                                                            */
+/* ------------------------------------------------------------------------------------------ */
+
+typedef struct {
+    uint8_t* visited; /* exact set over [0, n) standing in for OptHashPosVector */
+    int32_t n;
+    heap_t ng, spt;
+    dpq_t results;
+    int no_better, tree_checked, checked, max_check;
+    /* our own accounting (algorithmic bytes) */
+    int ndist, nexpand, ntree;
+} ws_t;
+
+static void ws_init(ws_t* ws, int32_t n, int max_check_alloc)
+{
+    memset(ws, 0, sizeof(*ws));
+    ws->n = n;
+    ws->visited = (uint8_t*)calloc((size_t)n + 1, 1);
+    heap_resize(&ws->spt, max_check_alloc * 10);
+    heap_resize(&ws->ng, max_check_alloc * 30);
+    dpq_clear(&ws->results, max_check_alloc / 16 > 1 ? max_check_alloc / 16 : 1);
+}
+
+static void ws_reset(ws_t* ws, int max_check, int result_num)
+{
+    memset(ws->visited, 0, (size_t)ws->n + 1);
+    heap_clear(&ws->spt, max_check * 10);
+    heap_clear(&ws->ng, max_check * 30);
+    dpq_clear(&ws->results, max_check / 16 > result_num ? max_check / 16 : result_num);
+    ws->no_better = 0;
+    ws->tree_checked = 0;
+    ws->checked = 0;
+    ws->max_check = max_check;
+    ws->ndist = ws->nexpand = ws->ntree = 0;
+}
+
+static void ws_free(ws_t* ws)
+{
+    free(ws->visited);
+    free(ws->ng.heap);
+    free(ws->spt.heap);
+    free(ws->results.data);
+}
+
+/* returns nonzero if idx was already present (OptHashPosVector::CheckAndSet, WorkSpace.h:113-117) */
+static inline int ws_check_and_set(ws_t* ws, int32_t idx)
+{
+    if (ws->visited[idx]) return 1;
+    ws->visited[idx] = 1;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* search                                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+
+typedef struct {
+    const ora_index* idx;
+    const void* query;
+    size_t row_bytes;
+    int cosine;
+} qctx_t;
+
+static inline float qdist(const qctx_t* c, ws_t* ws, int32_t id)
+{
+    ws->ndist++;
+    const char* row = (const char*)c->idx->vectors + (size_t)id * c->row_bytes;
+    return ora_distance(c->idx->metric, c->idx->value_type, c->idx->simd_width, c->query, row, c->idx->dim);
+}
+
+static inline int not_deleted(const ora_index* idx, int32_t id)
+{
+    /* StaticDispatch::CheckIfNotDeleted / AlwaysTrue (BKTIndex.cpp:437-440, :471-507) */
+    if (idx->deleted == NULL || idx->num_deleted == 0) return 1;
+    return idx->deleted[id] != 1;
+}
+
+/* BKTree::InitSearchTrees (BKTree.h:696-769), default m_bfs == 0 path */
+static void bkt_init_search_trees(const qctx_t* c, ws_t* ws)
+{
+    const ora_index* idx = c->idx;
+    const ora_bkt_node* nodes = (const ora_bkt_node*)idx->nodes;
+    for (int i = 0; i < idx->tree_num; i++) {
+        int32_t start = idx->tree_starts[i];
+        const ora_bkt_node* node = &nodes[start];
+        ws->ntree++;
+        if (node->childStart < 0) {
+            pair_t p = {start, qdist(c, ws, node->centerid)};
+            heap_insert(&ws->spt, p);
+        } else {
+            for (int32_t begin = node->childStart; begin < node->childEnd; begin++) {
+                ws->ntree++;
+                pair_t p = {begin, qdist(c, ws, nodes[begin].centerid)};
+                heap_insert(&ws->spt, p);
+            }
+        }
+    }
+}
+
+/* BKTree::SearchTrees (BKTree.h:771-799) */
+static void bkt_search_trees(const qctx_t* c, ws_t* ws, int limits)
+{
+    const ora_bkt_node* nodes = (const ora_bkt_node*)c->idx->nodes;
+    while (ws->spt.count != 0) {
+        pair_t bcell = heap_pop(&ws->spt);
+        const ora_bkt_node* tnode = &nodes[bcell.node];
+        ws->ntree++;
+        if (tnode->childStart < 0) {
+            if (!ws_check_and_set(ws, tnode->centerid)) {
+                ws->checked++;
+                pair_t p = {tnode->centerid, bcell.distance};
+                heap_insert(&ws->ng, p);
+            }
+            if (ws->checked >= limits) break;
+        } else {
+            if (!ws_check_and_set(ws, tnode->centerid)) {
+                pair_t p = {tnode->centerid, bcell.distance};
+                heap_insert(&ws->ng, p);
+            }
+            for (int32_t begin = tnode->childStart; begin < tnode->childEnd; begin++) {
+                ws->ntree++;
+                pair_t p = {begin, qdist(c, ws, nodes[begin].centerid)};
+                heap_insert(&ws->spt, p);
+            }
+        }
+    }
+}
+
+/* BKT::Index<T>::Search<notDeleted, CheckDup, AlwaysTrue> (BKTIndex.cpp:268-352) as dispatched by the
+ * public SearchIndex (searchDuplicated = true, no filter; :463-508, :595-620) */
+static void bkt_search(const qctx_t* c, ws_t* ws, res_t* res, int k)
+{
+    const ora_index* idx = c->idx;
+    const ora_bkt_node* nodes = (const ora_bkt_node*)idx->nodes;
+    bkt_init_search_trees(c, ws);
+    bkt_search_trees(c, ws, idx->initial_pivots);
+    const int checkPos = idx->degree - 1;
+
+    while (ws->ng.count != 0) {
+        pair_t gnode = heap_pop(&ws->ng);
+        int32_t tmpNode = gnode.node;
+        const int32_t* node = idx->graph + (size_t)tmpNode * idx->degree;
+        ws->nexpand++;
+
+        if (gnode.distance <= res[0].dist) {
+            int32_t checkNode = node[checkPos];
+            if (checkNode < -1) {
+                const ora_bkt_node* tnode = &nodes[-2 - checkNode];
+                int32_t i = -tnode->childStart;
+                do {
+                    if (not_deleted(idx, tmpNode)) {
+                        if (!res_add_point(res, k, tmpNode, gnode.distance)) break; /* CheckDup */
+                    }
+                    if (i <= 0) break;
+                    tmpNode = nodes[i].centerid;
+                } while (i++ < tnode->childEnd);
+            } else {
+                if (not_deleted(idx, tmpNode)) res_add_point(res, k, tmpNode, gnode.distance);
+            }
+        } else {
+            if (not_deleted(idx, tmpNode)) {
+                if (gnode.distance > dpq_worst(&ws->results) || ws->checked > ws->max_check) {
+                    res_sort(res, k);
+                    return;
+                }
+            }
+        }
+        for (int i = 0; i <= checkPos; i++) {
+            int32_t nn_index = node[i];
+            if (nn_index < 0) break;
+            if (ws_check_and_set(ws, nn_index)) continue;
+            float distance2leaf = qdist(c, ws, nn_index);
+            ws->checked++;
+            if (dpq_insert(&ws->results, distance2leaf)) {
+                pair_t p = {nn_index, distance2leaf};
+                heap_insert(&ws->ng, p);
+            }
+        }
+        if (heap_top(&ws->ng)->distance > heap_top(&ws->spt)->distance) {
+            bkt_search_trees(c, ws, idx->other_pivots + ws->checked);
+        }
+    }
+    res_sort(res, k);
+}
+
+/* KDTree::KDTSearch (KDTree.h:233-271); the recursion is a tail call, restated as a loop */
+static void kdt_search_node(const qctx_t* c, ws_t* ws, int32_t node, float distBound)
+{
+    const ora_index* idx = c->idx;
+    const ora_kdt_node* nodes = (const ora_kdt_node*)idx->nodes;
+    for (;;) {
+        if (node < 0) {
+            int32_t index = -node - 1;
+            if (index >= idx->n) return;
+            if (ws_check_and_set(ws, index)) return;
+            ++ws->tree_checked;
+            ++ws->checked;
+            pair_t p = {index, qdist(c, ws, index)};
+            heap_insert(&ws->ng, p);
+            return;
+        }
+        const ora_kdt_node* tnode = &nodes[node];
+        ws->ntree++;
+        /* split test reads the raw (un-quantized) query, KDTree.h:255 */
+        float diff = ((const float*)c->query)[tnode->split_dim] - tnode->split_value;
+        float distanceBound = distBound + diff * diff;
+        int32_t otherChild, bestChild;
+        if (diff < 0) {
+            bestChild = tnode->left;
+            otherChild = tnode->right;
+        } else {
+            otherChild = tnode->left;
+            bestChild = tnode->right;
+        }
+        pair_t p = {otherChild, distanceBound};
+        heap_insert(&ws->spt, p);
+        node = bestChild;
+    }
+}
+
+static void kdt_search_trees(const qctx_t* c, ws_t* ws, int limits)
+{
+    while (ws->spt.count != 0 && ws->checked < limits) {
+        pair_t tcell = heap_pop(&ws->spt);
+        kdt_search_node(c, ws, tcell.node, tcell.distance);
+    }
+}
+
+/* KDT::Index<T>::Search<Q, notDeleted> (KDTIndex.cpp:182-241) */
+static void kdt_search(const qctx_t* c, ws_t* ws, res_t* res, int k)
+{
+    const ora_index* idx = c->idx;
+    for (int i = 0; i < idx->tree_num; i++) kdt_search_node(c, ws, idx->tree_starts[i], 0);
+    kdt_search_trees(c, ws, idx->initial_pivots);
+    while (ws->ng.count != 0) {
+        pair_t gnode = heap_pop(&ws->ng);
+        const int32_t* node = idx->graph + (size_t)gnode.node * idx->degree;
+        ws->nexpand++;
+        if (not_deleted(idx, gnode.node)) {
+            if (!res_add_point(res, k, gnode.node, gnode.distance) && ws->checked > ws->max_check) {
+                res_sort(res, k);
+                return;
+            }
+        }
+        float upperBound = res[0].dist > gnode.distance ? res[0].dist : gnode.distance;
+        int bLocalOpt = 1;
+        for (int i = 0; i < idx->degree; i++) {
+            int32_t nn_index = node[i];
+            if (nn_index < 0) break;
+            if (ws_check_and_set(ws, nn_index)) continue;
+            float distance2leaf = qdist(c, ws, nn_index);
+            if (distance2leaf <= upperBound) bLocalOpt = 0;
+            ws->checked++;
+            pair_t p = {nn_index, distance2leaf};
+            heap_insert(&ws->ng, p);
+        }
+        if (bLocalOpt)
+            ws->no_better++;
+        else
+            ws->no_better = 0;
+        if (ws->no_better > idx->no_better_threshold) {
+            if (ws->tree_checked <= ws->checked / 10) {
+                kdt_search_trees(c, ws, idx->other_pivots + ws->checked);
+            } else if (gnode.distance > res[0].dist) {
+                break;
+            }
+        }
+    }
+    res_sort(res, k);
+}
+
+int ora_search_batch(const ora_index* idx, const void* queries, int32_t nq, int32_t k,
+                     int32_t* ids, float* dists, int32_t* stats, int32_t threads)
+{
+    static const size_t elem[4] = {1, 1, 2, 4};
+    const size_t row_bytes = elem[idx->value_type] * (size_t)idx->dim;
+    /* a fresh thread's work space: Initialize(max(MaxCheck, MaxCheckForRefineGraph)) then
+     * Reset(MaxCheck, K) (BKTIndex.cpp:600-605) */
+    const int alloc_check = idx->max_check > idx->max_check_refine ? idx->max_check : idx->max_check_refine;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#else
+    (void)threads;
+#endif
+#pragma omp parallel
+    {
+        ws_t ws;
+        ws_init(&ws, idx->n, alloc_check);
+        res_t* res = (res_t*)malloc(sizeof(res_t) * (size_t)(k > 0 ? k : 1));
+#pragma omp for schedule(dynamic, 10)
+        for (int32_t q = 0; q < nq; q++) {
+            qctx_t c = {idx, (const char*)queries + (size_t)q * row_bytes, row_bytes, idx->metric != ORA_L2};
+            for (int i = 0; i < k; i++) {
+                res[i].vid = -1;
+                res[i].dist = kMaxDist();
+            }
+            ws_reset(&ws, idx->max_check, k);
+            if (idx->tree_kind == ORA_BKT)
+                bkt_search(&c, &ws, res, k);
+            else
+                kdt_search(&c, &ws, res, k);
+            for (int i = 0; i < k; i++) {
+                ids[(size_t)q * k + i] = res[i].vid;
+                dists[(size_t)q * k + i] = res[i].dist;
+            }
+            if (stats) {
+                int32_t* s = stats + (size_t)q * ORA_ST_COUNT;
+                s[ORA_ST_CHECKED] = ws.checked;
+                s[ORA_ST_TREE_CHECKED] = ws.tree_checked;
+                s[ORA_ST_NG_LEFT] = ws.ng.count;
+                s[ORA_ST_SPT_LEFT] = ws.spt.count;
+                s[ORA_ST_NDIST] = ws.ndist;
+                s[ORA_ST_NEXPAND] = ws.nexpand;
+                s[ORA_ST_NTREE] = ws.ntree;
+                s[7] = 0;
+            }
+        }
+        free(res);
+        ws_free(&ws);
+    }
+    return 0;
+}

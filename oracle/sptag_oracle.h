@@ -1,0 +1,79 @@
+/* oracle/sptag_oracle.h -- TEST INFRASTRUCTURE ONLY (see sptag_oracle.c header). */
+#ifndef SPTAG_ORACLE_H_
+#define SPTAG_ORACLE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* value types / metrics use the reference's enum order (DefinitionList.h:6-9, :36-38) */
+enum { ORA_INT8 = 0, ORA_UINT8 = 1, ORA_INT16 = 2, ORA_FLOAT = 3 };
+enum { ORA_L2 = 0, ORA_COSINE = 1, ORA_INNERPRODUCT = 2 };
+enum { ORA_BKT = 0, ORA_KDT = 1 };
+
+typedef struct {
+    int32_t centerid, childStart, childEnd; /* BKTree.h:25-32 */
+} ora_bkt_node;
+
+typedef struct {
+    int32_t left, right, split_dim;
+    float split_value; /* KDTree.h:22-28 */
+} ora_kdt_node;
+
+typedef struct {
+    /* vectors.bin (Dataset.h:146-180): row-major n x dim, no padding */
+    int32_t n, dim;
+    int32_t value_type, metric;
+    const void* vectors;
+    /* graph.bin (NeighborhoodGraph.h:606-615): n x degree int32, -1 padded */
+    int32_t degree;
+    const int32_t* graph;
+    /* tree.bin (BKTree.h:635-645 / KDTree.h:123-133) */
+    int32_t tree_kind, tree_num, node_count;
+    const int32_t* tree_starts;
+    const void* nodes;
+    /* deletes.bin (Labelset.h:78-83): one byte per vector, 1 = deleted; NULL or num_deleted==0 -> none */
+    const int8_t* deleted;
+    int32_t num_deleted;
+    /* search parameters (BKT/ParameterDefinitionList.h:44-49; KDT/ParameterDefinitionList.h) */
+    int32_t max_check;               /* MaxCheck */
+    int32_t max_check_refine;        /* MaxCheckForRefineGraph (sizes the work space) */
+    int32_t initial_pivots;          /* NumberOfInitialDynamicPivots */
+    int32_t other_pivots;            /* NumberOfOtherDynamicPivots */
+    int32_t no_better_threshold;     /* ThresholdOfNumberOfContinuousNoBetterPropagation (KDT) */
+    /* which DistanceUtils variant to restate: 16 = AVX512, 8 = AVX/AVX2, 4 = SSE, 1 = scalar template */
+    int32_t simd_width;
+} ora_index;
+
+/* per-query counters, all int32 */
+enum {
+    ORA_ST_CHECKED = 0,   /* WorkSpace::m_iNumberOfCheckedLeaves at exit */
+    ORA_ST_TREE_CHECKED,  /* WorkSpace::m_iNumberOfTreeCheckedLeaves (KDT only) */
+    ORA_ST_NG_LEFT,       /* NGQueue.size() at exit */
+    ORA_ST_SPT_LEFT,      /* SPTQueue.size() at exit */
+    ORA_ST_NDIST,         /* distance evaluations (graph neighbours + tree centres/leaves) */
+    ORA_ST_NEXPAND,       /* NGQueue pops that read a graph row */
+    ORA_ST_NTREE,         /* tree nodes read (popped SPT cells + children scanned) */
+    ORA_ST_COUNT = 8
+};
+
+float ora_max_dist(void);
+
+float ora_distance(int32_t metric, int32_t value_type, int32_t simd_width,
+                   const void* x, const void* y, int32_t dim);
+
+void ora_distance_f32_many(int32_t metric, int32_t simd_width, const float* a, const float* b,
+                           int32_t dim, int32_t n, float* out);
+
+/* Restatement of VectorIndex::SearchIndex(batch) (VectorIndex.cpp:454-463): nq queries of `dim`
+ * elements of the index value type, k results each; ids/dists are [nq*k]; stats is [nq*ORA_ST_COUNT]
+ * or NULL.  threads <= 0 -> OpenMP default.  Returns 0 (ErrorCode::Success). */
+int ora_search_batch(const ora_index* idx, const void* queries, int32_t nq, int32_t k,
+                     int32_t* ids, float* dists, int32_t* stats, int32_t threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,284 @@
+"""Test-side helpers (TEST INFRASTRUCTURE): ctypes bindings for
+
+* ``oracle/_ref/libsptag_ref.so``   -- the UNMODIFIED reference compiled by ``oracle/Makefile ref``
+* ``oracle/_build/libsptag_oracle.so`` -- our plain-C restatement (``oracle/sptag_oracle.c``)
+
+plus a numpy reader for the reference's on-disk index folder (formats: SURVEY.md section 8 f1;
+``Dataset.h:146-180``, ``NeighborhoodGraph.h:606-615``, ``BKTree.h:635-645``, ``KDTree.h:123-133``,
+``Labelset.h:78-83``, ``VectorIndex.cpp:197-222``).  Nothing here is imported by the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libsptag_ref.so")
+ORA_SO = os.path.join(ROOT, "oracle", "_build", "libsptag_oracle.so")
+DATA_DIR = os.path.join(ROOT, "tests", "_data")
+
+VT_INT8, VT_UINT8, VT_INT16, VT_FLOAT = 0, 1, 2, 3
+NP_OF_VT = {VT_INT8: np.int8, VT_UINT8: np.uint8, VT_INT16: np.int16, VT_FLOAT: np.float32}
+VT_OF_NAME = {"Int8": VT_INT8, "UInt8": VT_UINT8, "Int16": VT_INT16, "Float": VT_FLOAT}
+METRIC_OF_NAME = {"L2": 0, "Cosine": 1, "InnerProduct": 2}
+ALGO_OF_NAME = {"BKT": 0, "KDT": 1}
+ORA_ST_COUNT = 8
+ST_CHECKED, ST_TREE_CHECKED, ST_NG_LEFT, ST_SPT_LEFT, ST_NDIST, ST_NEXPAND, ST_NTREE = range(7)
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def build_port():
+    """(Re)build the C restatement; cheap (gcc, <2 s)."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
+
+
+# ------------------------------------------------------------------------------------------------
+# reference shim
+# ------------------------------------------------------------------------------------------------
+_ref = None
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        L = C.CDLL(REF_SO)
+        L.ref_build.restype = C.c_void_p
+        L.ref_build.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p]
+        L.ref_save.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_load.restype = C.c_void_p
+        L.ref_load.argtypes = [C.c_char_p]
+        L.ref_free.argtypes = [C.c_void_p]
+        L.ref_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.ref_get_param.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
+        L.ref_num_samples.argtypes = [C.c_void_p]
+        L.ref_dim.argtypes = [C.c_void_p]
+        L.ref_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_enable_stats.argtypes = [C.c_void_p]
+        L.ref_search_one_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_distance.restype = C.c_float
+        L.ref_distance.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_distance_f32_isa.restype = C.c_float
+        L.ref_distance_f32_isa.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_distance_f32_many.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ref_quiet(3)  # warnings and errors only
+        _ref = L
+    return _ref
+
+
+class RefIndex:
+    """The reference's VectorIndex behind the shim."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise RuntimeError("reference index handle is null")
+        self.h = C.c_void_p(handle)
+
+    @classmethod
+    def build(cls, algo, data, metric, threads=8, params=""):
+        data = np.ascontiguousarray(data)
+        vt = {np.dtype(np.int8): VT_INT8, np.dtype(np.uint8): VT_UINT8,
+              np.dtype(np.int16): VT_INT16, np.dtype(np.float32): VT_FLOAT}[data.dtype]
+        h = ref().ref_build(ALGO_OF_NAME[algo], vt, METRIC_OF_NAME[metric], data.ctypes.data,
+                            data.shape[0], data.shape[1], threads, params.encode())
+        return cls(h)
+
+    @classmethod
+    def load(cls, folder):
+        return cls(ref().ref_load(folder.encode()))
+
+    def save(self, folder):
+        os.makedirs(folder, exist_ok=True)
+        rc = ref().ref_save(self.h, folder.encode())
+        if rc != 0:
+            raise RuntimeError("SaveIndex failed: %d" % rc)
+
+    def set_param(self, name, value):
+        return ref().ref_set_param(self.h, name.encode(), str(value).encode())
+
+    def search(self, queries, k, threads=0):
+        queries = np.ascontiguousarray(queries)
+        nq = queries.shape[0]
+        ids = np.empty((nq, k), np.int32)
+        dists = np.empty((nq, k), np.float32)
+        sec = C.c_double()
+        rc = ref().ref_search_batch(self.h, queries.ctypes.data, nq, k, threads, ids.ctypes.data,
+                                    dists.ctypes.data, C.byref(sec))
+        if rc != 0:
+            raise RuntimeError("reference SearchIndex failed: %d" % rc)
+        return ids, dists, sec.value
+
+    def enable_stats(self):
+        return ref().ref_enable_stats(self.h)
+
+    def search_one_stats(self, query, k):
+        query = np.ascontiguousarray(query)
+        ids = np.empty(k, np.int32)
+        dists = np.empty(k, np.float32)
+        stats = np.zeros(4, np.int32)
+        ref().ref_search_one_stats(self.h, query.ctypes.data, k, ids.ctypes.data, dists.ctypes.data,
+                                   stats.ctypes.data)
+        return ids, dists, stats
+
+
+# ------------------------------------------------------------------------------------------------
+# on-disk index folder -> numpy
+# ------------------------------------------------------------------------------------------------
+class IndexFiles:
+    """Flat numpy view of a reference index folder."""
+
+    def __init__(self, folder):
+        self.folder = folder
+        self.params = {}
+        with open(os.path.join(folder, "indexloader.ini")) as f:
+            for line in f:
+                line = line.strip()
+                if "=" in line and not line.startswith("["):
+                    k, v = line.split("=", 1)
+                    self.params[k] = v
+        p = self.params
+        self.algo = p["IndexAlgoType"]
+        self.value_type = VT_OF_NAME[p["ValueType"]]
+        self.metric = METRIC_OF_NAME[p.get("DistCalcMethod", "Cosine")]
+        dt = NP_OF_VT[self.value_type]
+
+        raw = np.fromfile(os.path.join(folder, p.get("VectorFilePath", "vectors.bin")), dtype=np.uint8)
+        self.n, self.dim = (int(v) for v in raw[:8].view(np.int32))
+        self.vectors = raw[8:8 + self.n * self.dim * np.dtype(dt).itemsize].view(dt).reshape(self.n, self.dim)
+
+        raw = np.fromfile(os.path.join(folder, p.get("GraphFilePath", "graph.bin")), dtype=np.int32)
+        gn, self.degree = int(raw[0]), int(raw[1])
+        assert gn == self.n
+        self.graph = raw[2:2 + gn * self.degree].reshape(gn, self.degree)
+
+        raw = np.fromfile(os.path.join(folder, p.get("TreeFilePath", "tree.bin")), dtype=np.int32)
+        self.tree_num = int(raw[0])
+        self.tree_starts = np.ascontiguousarray(raw[1:1 + self.tree_num])
+        self.node_count = int(raw[1 + self.tree_num])
+        body = raw[2 + self.tree_num:]
+        if self.algo == "BKT":
+            nodes = body[:self.node_count * 3].reshape(self.node_count, 3)
+            # LoadTrees appends a (-1,-1,-1) sentinel if the last node is not one (BKTree.h:662)
+            if self.node_count > 0 and nodes[-1, 0] != -1:
+                nodes = np.vstack([nodes, np.array([[-1, -1, -1]], np.int32)])
+            self.nodes = np.ascontiguousarray(nodes)
+        else:
+            self.nodes = np.ascontiguousarray(body[:self.node_count * 4].reshape(self.node_count, 4))
+
+        dpath = os.path.join(folder, p.get("DeleteVectorFilePath", "deletes.bin"))
+        self.num_deleted = 0
+        self.deleted = None
+        if os.path.exists(dpath):
+            raw = np.fromfile(dpath, dtype=np.uint8)
+            self.num_deleted = int(raw[:4].view(np.int32)[0])
+            rows = int(raw[4:8].view(np.int32)[0])
+            self.deleted = np.ascontiguousarray(raw[12:12 + rows].view(np.int8))
+
+    def int_param(self, name, default):
+        return int(self.params.get(name, default))
+
+
+# ------------------------------------------------------------------------------------------------
+# C restatement
+# ------------------------------------------------------------------------------------------------
+class _OraIndex(C.Structure):
+    _fields_ = [("n", C.c_int32), ("dim", C.c_int32), ("value_type", C.c_int32), ("metric", C.c_int32),
+                ("vectors", C.c_void_p), ("degree", C.c_int32), ("graph", C.c_void_p),
+                ("tree_kind", C.c_int32), ("tree_num", C.c_int32), ("node_count", C.c_int32),
+                ("tree_starts", C.c_void_p), ("nodes", C.c_void_p), ("deleted", C.c_void_p),
+                ("num_deleted", C.c_int32), ("max_check", C.c_int32), ("max_check_refine", C.c_int32),
+                ("initial_pivots", C.c_int32), ("other_pivots", C.c_int32),
+                ("no_better_threshold", C.c_int32), ("simd_width", C.c_int32)]
+
+
+_ora = None
+
+
+def ora():
+    global _ora
+    if _ora is None:
+        if not os.path.exists(ORA_SO):
+            build_port()
+        L = C.CDLL(ORA_SO)
+        L.ora_max_dist.restype = C.c_float
+        L.ora_distance.restype = C.c_float
+        L.ora_distance.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
+        L.ora_distance_f32_many.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                            C.c_int32, C.c_void_p]
+        L.ora_search_batch.argtypes = [C.POINTER(_OraIndex), C.c_void_p, C.c_int32, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        _ora = L
+    return _ora
+
+
+class OracleIndex:
+    """oracle/sptag_oracle.c over an IndexFiles."""
+
+    def __init__(self, files, simd_width=16):
+        self.files = files
+        self.simd_width = simd_width
+        self.max_check = files.int_param("MaxCheck", 8192)
+        self.max_check_refine = files.int_param("MaxCheckForRefineGraph", 8192)
+        self.initial_pivots = files.int_param("NumberOfInitialDynamicPivots", 50)
+        self.other_pivots = files.int_param("NumberOfOtherDynamicPivots", 4)
+        self.no_better_threshold = files.int_param("ThresholdOfNumberOfContinuousNoBetterPropagation", 3)
+
+    def _struct(self):
+        f = self.files
+        s = _OraIndex()
+        s.n, s.dim, s.value_type, s.metric = f.n, f.dim, f.value_type, f.metric
+        s.vectors = f.vectors.ctypes.data
+        s.degree = f.degree
+        s.graph = f.graph.ctypes.data
+        s.tree_kind = ALGO_OF_NAME[f.algo]
+        s.tree_num = f.tree_num
+        s.node_count = f.nodes.shape[0]
+        s.tree_starts = f.tree_starts.ctypes.data
+        s.nodes = f.nodes.ctypes.data
+        s.deleted = f.deleted.ctypes.data if (f.deleted is not None and f.num_deleted > 0) else None
+        s.num_deleted = f.num_deleted
+        s.max_check = self.max_check
+        s.max_check_refine = self.max_check_refine
+        s.initial_pivots = self.initial_pivots
+        s.other_pivots = self.other_pivots
+        s.no_better_threshold = self.no_better_threshold
+        s.simd_width = self.simd_width
+        return s
+
+    def search(self, queries, k, threads=0, want_stats=True):
+        queries = np.ascontiguousarray(queries)
+        nq = queries.shape[0]
+        ids = np.empty((nq, k), np.int32)
+        dists = np.empty((nq, k), np.float32)
+        stats = np.zeros((nq, ORA_ST_COUNT), np.int32)
+        s = self._struct()
+        rc = ora().ora_search_batch(C.byref(s), queries.ctypes.data, nq, k, ids.ctypes.data,
+                                    dists.ctypes.data, stats.ctypes.data if want_stats else None, threads)
+        assert rc == 0
+        return ids, dists, stats
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data (BASELINE.md generators, numpy flavour -- parity is always checked on the SAME
+# saved index files, so the exact libstdc++ sequence is not needed)
+# ------------------------------------------------------------------------------------------------
+def gen_iid(n, dim, seed):
+    return np.random.default_rng(seed).standard_normal((n, dim), dtype=np.float32)
+
+
+def gen_lowrank(n, dim, rank, seed, noise=0.1):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((rank, dim), dtype=np.float32) / np.float32(np.sqrt(rank))
+    z = rng.standard_normal((n, rank), dtype=np.float32)
+    return (z @ A + np.float32(noise) * rng.standard_normal((n, dim), dtype=np.float32)).astype(np.float32)
+
+
+def normalize_rows(x):
+    x = x.astype(np.float32)
+    nrm = np.sqrt((x.astype(np.float64) ** 2).sum(1))
+    nrm[nrm == 0] = 1
+    return (x / nrm[:, None]).astype(np.float32)
