@@ -1,0 +1,156 @@
+/* sptag_b200.h -- C ABI of libsptag_b200: the B200-native drop-in for SPTAG's batched in-memory
+ * search path (BKT/KDT seed lookup -> RNG best-first expansion -> DistanceUtils inner loop).
+ *
+ * Every entry point names the reference interface it replaces (paths relative to
+ * /root/reference/AnnService).  Plain pointers and sizes only; no C++ or torch types cross this
+ * boundary.  Return values are the reference's ErrorCode numerics
+ * (inc/Core/DefinitionList.h:54-68): 0 Success, 1 Fail, 0x12 MemoryOverFlow, 0x13 LackOfInputs,
+ * 0x15 EmptyIndex, 0x17 DimensionSizeMismatch, 0x02 FailedOpenFile, 0x10 ParamNotFound,
+ * 0x11 FailedParseValue.
+ *
+ * There is NO CPU fallback: every search call runs the sm_100a kernels or fails.
+ */
+#ifndef SPTAG_B200_H_
+#define SPTAG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ErrorCode numerics (inc/Core/DefinitionList.h:54-68) */
+#define SPTAG_B200_SUCCESS 0x0000
+#define SPTAG_B200_FAIL 0x0001
+#define SPTAG_B200_FAILED_OPEN_FILE 0x0002
+#define SPTAG_B200_PARAM_NOT_FOUND 0x0010
+#define SPTAG_B200_FAILED_PARSE_VALUE 0x0011
+#define SPTAG_B200_MEMORY_OVERFLOW 0x0012
+#define SPTAG_B200_LACK_OF_INPUTS 0x0013
+#define SPTAG_B200_EMPTY_INDEX 0x0015
+#define SPTAG_B200_DIMENSION_MISMATCH 0x0017
+
+/* enum orders follow inc/Core/DefinitionList.h:6-9 (VectorValueType), :36-38 (DistCalcMethod),
+ * :92-93 (IndexAlgoType) */
+#define SPTAG_B200_VT_INT8 0
+#define SPTAG_B200_VT_UINT8 1
+#define SPTAG_B200_VT_INT16 2
+#define SPTAG_B200_VT_FLOAT 3
+#define SPTAG_B200_METRIC_L2 0
+#define SPTAG_B200_METRIC_COSINE 1
+#define SPTAG_B200_METRIC_INNERPRODUCT 2
+#define SPTAG_B200_ALGO_BKT 0
+#define SPTAG_B200_ALGO_KDT 1
+
+typedef struct sptag_b200_index* sptag_b200_handle;
+
+/* Host-side description of an already-built index: exactly the arrays the reference keeps in
+ * BKT::Index<T> / KDT::Index<T> (m_pSamples, m_pGraph, m_pTrees, m_deletedID) and persists as
+ * vectors.bin / graph.bin / tree.bin / deletes.bin (Dataset.h:146-180, NeighborhoodGraph.h:606-615,
+ * BKTree.h:635-645, KDTree.h:123-133, Labelset.h:78-83).  The library copies everything to HBM;
+ * the host arrays may be freed after sptag_b200_create returns. */
+typedef struct {
+    int32_t struct_size;   /* sizeof(sptag_b200_index_desc), for ABI growth */
+    int32_t device;        /* CUDA device ordinal; -1 = current device */
+    int32_t algo;          /* SPTAG_B200_ALGO_* */
+    int32_t value_type;    /* SPTAG_B200_VT_* (element type T of the index) */
+    int32_t metric;        /* SPTAG_B200_METRIC_* */
+    int32_t num_vectors;   /* N (Dataset::R()) */
+    int32_t dim;           /* Dataset::C() */
+    int32_t graph_degree;  /* NeighborhoodSize = graph.bin cols */
+    const void* vectors;   /* N x dim, row-major, unpadded (vectors.bin body) */
+    const int32_t* graph;  /* N x graph_degree, -1 padded; last slot < -1 = duplicate back-pointer */
+    int32_t tree_num;      /* BKTNumber / KDTNumber */
+    int32_t node_count;    /* tree node count */
+    const int32_t* tree_starts; /* tree_num root indices */
+    const void* tree_nodes;     /* BKT: node_count x {centerid, childStart, childEnd} int32 (BKTree.h:25-32);
+                                   KDT: node_count x {left, right, split_dim, split_value} (KDTree.h:22-28) */
+    const int8_t* deleted; /* N tombstone bytes (1 = deleted) or NULL (Labelset.h:43-57) */
+    int32_t num_deleted;   /* Labelset::Count(); 0 disables the tombstone test (BKTIndex.cpp:473) */
+    int32_t id_offset;     /* added to every returned id >= 0 (vector-partition shards; 0 otherwise) */
+} sptag_b200_index_desc;
+
+/* Per-query work counters; they equal the reference's WorkSpace counters (WorkSpace.h:303-308) and
+ * feed the algorithmic-bytes roofline figure.  8 x int32 per query. */
+#define SPTAG_B200_STATS_PER_QUERY 8
+#define SPTAG_B200_ST_CHECKED 0      /* m_iNumberOfCheckedLeaves at exit */
+#define SPTAG_B200_ST_TREE_CHECKED 1 /* m_iNumberOfTreeCheckedLeaves (KDT) */
+#define SPTAG_B200_ST_NG_LEFT 2      /* m_NGQueue.size() at exit */
+#define SPTAG_B200_ST_SPT_LEFT 3     /* m_SPTQueue.size() at exit */
+#define SPTAG_B200_ST_NDIST 4        /* distance evaluations D_q */
+#define SPTAG_B200_ST_NEXPAND 5      /* graph rows read E_q */
+#define SPTAG_B200_ST_NTREE 6        /* tree nodes read Tn_q */
+#define SPTAG_B200_ST_FLAGS 7        /* 0 = ok; nonzero = internal error for this query */
+
+/* Replaces: VectorIndex::CreateInstance + LoadIndexData for an index already in host memory
+ * (VectorIndex.cpp:566-614, BKTIndex.cpp:85-106). */
+int sptag_b200_create(const sptag_b200_index_desc* desc, sptag_b200_handle* out);
+
+/* Replaces: VectorIndex::LoadIndex(folder, index) (VectorIndex.cpp:617-681): parses
+ * indexloader.ini and the four binary files of a reference index folder and uploads them. */
+int sptag_b200_load(const char* folder, int32_t device, int32_t id_offset, sptag_b200_handle* out);
+
+/* Replaces: VectorIndex destructor. */
+void sptag_b200_destroy(sptag_b200_handle h);
+
+/* Replaces: VectorIndex::SetParameter / GetParameter (BKTIndex.cpp:980-1025) for the search-time
+ * parameters, same names as the ini file: MaxCheck, MaxCheckForRefineGraph,
+ * NumberOfInitialDynamicPivots, NumberOfOtherDynamicPivots,
+ * ThresholdOfNumberOfContinuousNoBetterPropagation.  Additional B200 tuning knobs (not in the
+ * reference) are prefixed "B200.": B200.QueriesPerSM, B200.StageRows, B200.Stages,
+ * B200.NGCacheEntries, B200.SPTCacheEntries, B200.SimdWidth (16/8/4: which DistanceUtils
+ * summation tree to reproduce bit-exactly; default 16 = AVX-512). */
+int sptag_b200_set_param(sptag_b200_handle h, const char* name, const char* value);
+int sptag_b200_get_param(sptag_b200_handle h, const char* name, char* value_out, int32_t capacity);
+
+/* Replaces: VectorIndex::SearchIndex(const void* p_vector, int p_vectorCount, int p_neighborCount,
+ * bool p_withMeta, BasicResult* p_results) (VectorIndex.h:103, VectorIndex.cpp:454-463).
+ * queries: HOST buffer, num_queries x dim elements of the index value type, row-major, borrowed.
+ * out_ids / out_dists: HOST buffers [num_queries x k]; ascending by (dist, id); unfilled slots are
+ * id -1 / dist MaxDist (FLT_MAX/10) exactly like a default BasicResult (SearchResult.h:72).
+ * out_stats: HOST buffer [num_queries x 8] int32 or NULL.  Blocking.  H2D/D2H copies included. */
+int sptag_b200_search(sptag_b200_handle h, const void* queries, int32_t num_queries, int32_t k,
+                      int32_t* out_ids, float* out_dists, int32_t* out_stats);
+
+/* Same call with every buffer already resident in HBM on the index's device (device pointers) and
+ * stream-ordered on `cuda_stream` (a cudaStream_t; NULL = default stream).  Does not synchronise. */
+int sptag_b200_search_device(sptag_b200_handle h, const void* d_queries, int32_t num_queries, int32_t k,
+                             int32_t* d_out_ids, float* d_out_dists, int32_t* d_out_stats,
+                             void* cuda_stream);
+
+/* Replaces: the reference's DistanceCalcSelector<T>(method)(query, m_pSamples[id], dim) call
+ * (DistanceUtils.h:118-163; call site BKTIndex.cpp:339) for a ragged list of ids per query:
+ * out[q*ids_per_query + j] = dist(query_q, vector[ids[q*ids_per_query + j]]) (ids < 0 -> MaxDist).
+ * Host buffers; blocking.  Exists so the inner loop can be parity-tested on its own. */
+int sptag_b200_distance_batch(sptag_b200_handle h, const void* queries, int32_t num_queries,
+                              const int32_t* ids, int32_t ids_per_query, float* out);
+
+/* Vector-partition sharding: merges `num_lists` per-shard result lists of a query
+ * batch, each [num_queries x k] ascending by (dist,id), into the global top-k with the comparator
+ * of QueryResultSet.h:17-26.  All pointers are DEVICE pointers on `device`; lists are laid out
+ * [num_lists][num_queries][k] (the layout an all-gather produces).  Stream-ordered. */
+int sptag_b200_merge_topk(int32_t device, const int32_t* d_ids, const float* d_dists, int32_t num_lists,
+                          int32_t num_queries, int32_t k, int32_t* d_out_ids, float* d_out_dists,
+                          void* cuda_stream);
+
+/* Device time in milliseconds of the search kernel(s) of the most recent sptag_b200_search*
+ * call on this handle, measured with CUDA events on the launching stream (synchronises). */
+int sptag_b200_last_kernel_ms(sptag_b200_handle h, float* ms_out);
+
+/* Number of kernels this library launched so far in this process (for bench.py's gpu_launches). */
+int64_t sptag_b200_launch_count(void);
+
+/* Index facts (VectorIndex::GetNumSamples / GetFeatureDim / ...). */
+int32_t sptag_b200_num_vectors(sptag_b200_handle h);
+int32_t sptag_b200_dim(sptag_b200_handle h);
+int32_t sptag_b200_value_type(sptag_b200_handle h);
+int32_t sptag_b200_metric(sptag_b200_handle h);
+int32_t sptag_b200_algo(sptag_b200_handle h);
+
+/* Human-readable text for the last failure on this thread. */
+const char* sptag_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPTAG_B200_H_ */

@@ -101,10 +101,12 @@ static float dist_f32(int cosine, int width, const float* x, const float* y, int
             for (j = 0; j < 4; j++) a4[j] = a4[j] + term_f32(cosine, x[i + j], y[i + j]);
         diff = a4[0] + a4[1] + a4[2] + a4[3];
     } else {
-        /* DistanceUtils.h:25-44 / :60-79 scalar templates: one accumulator, contracted by g++ */
+        /* DistanceUtils.h:25-44 / :60-79 scalar templates: one accumulator.  g++ -O3 SLP-vectorises the
+         * 4-unrolled body (vsubps/vmulps, then four separately rounded vaddss) and FMA-contracts only
+         * the scalar remainder loop (checked against the compiled reference in tests/test_oracle_pin.py) */
         diff = 0.0f;
         for (; i + 4 <= len; i += 4)
-            for (j = 0; j < 4; j++) diff = tail_f32(cosine, x[i + j], y[i + j], diff);
+            for (j = 0; j < 4; j++) diff = diff + term_f32(cosine, x[i + j], y[i + j]);
     }
     for (; i < len; i++) diff = tail_f32(cosine, x[i], y[i], diff);
     /* float base is 1 (CommonUtils.h GetBase<float>) */

@@ -1,0 +1,195 @@
+"""ctypes binding of libsptag_b200 (include/sptag_b200.h).
+
+This is plumbing for tests and bench.py: every call goes through the C ABI, exactly the entry
+points a C++/cgo/JNI host would bind.  There is no fallback -- if the CUDA library is missing or
+the device is not a B200 the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsptag_b200.so")
+
+STATS_PER_QUERY = 8
+ST_CHECKED, ST_TREE_CHECKED, ST_NG_LEFT, ST_SPT_LEFT, ST_NDIST, ST_NEXPAND, ST_NTREE, ST_FLAGS = range(8)
+
+VT_INT8, VT_UINT8, VT_INT16, VT_FLOAT = 0, 1, 2, 3
+METRIC_L2, METRIC_COSINE, METRIC_IP = 0, 1, 2
+ALGO_BKT, ALGO_KDT = 0, 1
+
+EXPORTS = [
+    "sptag_b200_create", "sptag_b200_load", "sptag_b200_destroy", "sptag_b200_set_param",
+    "sptag_b200_get_param", "sptag_b200_search", "sptag_b200_search_device", "sptag_b200_distance_batch",
+    "sptag_b200_merge_topk", "sptag_b200_last_kernel_ms", "sptag_b200_launch_count",
+    "sptag_b200_num_vectors", "sptag_b200_dim", "sptag_b200_value_type", "sptag_b200_metric",
+    "sptag_b200_algo", "sptag_b200_last_error",
+]
+
+
+class IndexDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("algo", C.c_int32),
+                ("value_type", C.c_int32), ("metric", C.c_int32), ("num_vectors", C.c_int32),
+                ("dim", C.c_int32), ("graph_degree", C.c_int32), ("vectors", C.c_void_p),
+                ("graph", C.c_void_p), ("tree_num", C.c_int32), ("node_count", C.c_int32),
+                ("tree_starts", C.c_void_p), ("tree_nodes", C.c_void_p), ("deleted", C.c_void_p),
+                ("num_deleted", C.c_int32), ("id_offset", C.c_int32)]
+
+
+class SptagB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("sptag_b200 error 0x%04x: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libsptag_b200.so; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SptagB200Error(1, "CUDA library %s is missing -- build it with __graft_entry__.build(); "
+                                    "there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.sptag_b200_create.argtypes = [C.POINTER(IndexDesc), C.POINTER(C.c_void_p)]
+        L.sptag_b200_load.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.sptag_b200_destroy.argtypes = [C.c_void_p]
+        L.sptag_b200_destroy.restype = None
+        L.sptag_b200_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.sptag_b200_get_param.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int32]
+        L.sptag_b200_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sptag_b200_search_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sptag_b200_distance_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        L.sptag_b200_merge_topk.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sptag_b200_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.sptag_b200_launch_count.restype = C.c_int64
+        for f in ("num_vectors", "dim", "value_type", "metric", "algo"):
+            getattr(L, "sptag_b200_" + f).argtypes = [C.c_void_p]
+        L.sptag_b200_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise SptagB200Error(rc, lib().sptag_b200_last_error().decode(errors="replace"))
+
+
+class B200Index:
+    """Handle to a device-resident index (the product side of VectorIndex for the search path)."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+
+    # -- construction ---------------------------------------------------------------------------
+    @classmethod
+    def load(cls, folder, device=-1, id_offset=0):
+        """VectorIndex::LoadIndex(folder) for the search path."""
+        h = C.c_void_p()
+        _check(lib().sptag_b200_load(os.fsencode(folder), device, id_offset, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def create(cls, *, algo, value_type, metric, vectors, graph, tree_starts, tree_nodes, deleted=None,
+               num_deleted=0, device=-1, id_offset=0):
+        vectors = np.ascontiguousarray(vectors)
+        graph = np.ascontiguousarray(graph, dtype=np.int32)
+        tree_starts = np.ascontiguousarray(tree_starts, dtype=np.int32)
+        tree_nodes = np.ascontiguousarray(tree_nodes)
+        d = IndexDesc()
+        d.struct_size = C.sizeof(IndexDesc)
+        d.device = device
+        d.algo, d.value_type, d.metric = algo, value_type, metric
+        d.num_vectors, d.dim = vectors.shape
+        d.graph_degree = graph.shape[1]
+        d.vectors = vectors.ctypes.data
+        d.graph = graph.ctypes.data
+        d.tree_num = tree_starts.shape[0]
+        d.node_count = tree_nodes.shape[0]
+        d.tree_starts = tree_starts.ctypes.data
+        d.tree_nodes = tree_nodes.ctypes.data
+        if deleted is not None and num_deleted > 0:
+            deleted = np.ascontiguousarray(deleted, dtype=np.int8)
+            d.deleted = deleted.ctypes.data
+            d.num_deleted = num_deleted
+        d.id_offset = id_offset
+        h = C.c_void_p()
+        _check(lib().sptag_b200_create(C.byref(d), C.byref(h)))
+        return cls(h.value)
+
+    def close(self):
+        if self._h:
+            lib().sptag_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- facts / parameters ---------------------------------------------------------------------
+    @property
+    def num_vectors(self):
+        return lib().sptag_b200_num_vectors(self._h)
+
+    @property
+    def dim(self):
+        return lib().sptag_b200_dim(self._h)
+
+    @property
+    def metric(self):
+        return lib().sptag_b200_metric(self._h)
+
+    def set_param(self, name, value):
+        """VectorIndex::SetParameter (same names as the reference's ini file)."""
+        _check(lib().sptag_b200_set_param(self._h, name.encode(), str(value).encode()))
+
+    def get_param(self, name):
+        buf = C.create_string_buffer(64)
+        _check(lib().sptag_b200_get_param(self._h, name.encode(), buf, 64))
+        return buf.value.decode()
+
+    # -- search ---------------------------------------------------------------------------------
+    def search(self, queries, k, want_stats=False, out_ids=None, out_dists=None):
+        """VectorIndex::SearchIndex(batch) with HOST buffers (numpy or pinned torch memory viewed as numpy)."""
+        queries = np.ascontiguousarray(queries)
+        nq = queries.shape[0]
+        ids = out_ids if out_ids is not None else np.empty((nq, k), np.int32)
+        dists = out_dists if out_dists is not None else np.empty((nq, k), np.float32)
+        stats = np.zeros((nq, STATS_PER_QUERY), np.int32) if want_stats else None
+        _check(lib().sptag_b200_search(self._h, queries.ctypes.data, nq, k, ids.ctypes.data, dists.ctypes.data,
+                                       stats.ctypes.data if want_stats else None))
+        return (ids, dists, stats) if want_stats else (ids, dists)
+
+    def search_device(self, d_queries_ptr, nq, k, d_ids_ptr, d_dists_ptr, d_stats_ptr=0, stream=0):
+        """Same call with device pointers (e.g. torch tensor .data_ptr()), stream-ordered, no sync."""
+        _check(lib().sptag_b200_search_device(self._h, d_queries_ptr, nq, k, d_ids_ptr, d_dists_ptr,
+                                              d_stats_ptr or None, stream or None))
+
+    def distance_batch(self, queries, ids):
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        out = np.empty(ids.shape, np.float32)
+        _check(lib().sptag_b200_distance_batch(self._h, queries.ctypes.data, queries.shape[0], ids.ctypes.data,
+                                               ids.shape[1], out.ctypes.data))
+        return out
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        _check(lib().sptag_b200_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+
+def merge_topk(device, d_ids_ptr, d_dists_ptr, num_lists, nq, k, d_out_ids_ptr, d_out_dists_ptr, stream=0):
+    _check(lib().sptag_b200_merge_topk(device, d_ids_ptr, d_dists_ptr, num_lists, nq, k, d_out_ids_ptr,
+                                       d_out_dists_ptr, stream or None))
+
+
+def launch_count():
+    return int(lib().sptag_b200_launch_count())

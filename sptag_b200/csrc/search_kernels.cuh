@@ -1,0 +1,720 @@
+// search_kernels.cuh -- sm_100a device code of the batched search hot path.
+//
+// One warp (one 32-thread CTA) owns one query at a time and runs the reference's whole
+// per-query algorithm on the device:
+//   BKT::Index<T>::Search            (AnnService/src/Core/BKT/BKTIndex.cpp:268-352)
+//   BKTree::InitSearchTrees/SearchTrees (inc/Core/Common/BKTree.h:696-799)
+//   Heap<NodeDistPair>               (inc/Core/Common/Heap.h:13-106)      -> exact binary-heap emulation
+//   DistPriorityQueue m_Results      (inc/Core/Common/WorkSpace.h:167-225) -> multiset in registers
+//   OptHashPosVector visited set     (inc/Core/Common/WorkSpace.h:43-165) -> exact bitmap in HBM/L2
+//   QueryResultSet top-K             (inc/Core/Common/QueryResultSet.h:17-120) -> sorted list, one entry per lane
+//   DistanceUtils float L2 / cosine  (src/Core/Common/DistanceUtils.cpp:650-682, :1016-1046)
+//                                     -> same 16-accumulator summation tree, no FMA, bit-exact
+//
+// Candidate vectors (graph neighbours / tree-centre rows) are gathered with 1-D TMA bulk copies
+// (cp.async.bulk global->shared, mbarrier complete_tx) into a per-warp shared-memory ring and
+// reduced from there; the two priority queues keep their first entries in shared memory and spill
+// the tail of the array to a per-slot arena in HBM so the emulation stays exact at any size.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sptag_b200 {
+
+// Common.h:122  MaxDist = numeric_limits<float>::max() / 10 (float arithmetic)
+#define SPTAG_B200_MAXDIST (3.402823466e+38F / 10)
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kStatsPerQuery = 8;
+
+struct SearchParams {
+    // index (device resident)
+    const unsigned char* vectors;          // rows padded to a 16-byte multiple
+    unsigned long long row_stride_bytes;   // bytes between rows (multiple of 16)
+    int row_bytes;                         // bytes copied per row (multiple of 16)
+    int n, dim;
+    const int* graph;
+    int degree;
+    const int* nodes;                      // BKT: 3 x int32 per node; KDT: 4 x 32 bit per node
+    const int* tree_starts;
+    int tree_num, node_count;
+    const signed char* deleted;            // nullptr when there are no tombstones
+    // queries / outputs (device)
+    const unsigned char* queries;
+    unsigned long long query_stride_bytes;
+    int nq, k;
+    int* out_ids;
+    float* out_dists;
+    int* out_stats;                        // nullable
+    int id_offset;
+    // search parameters
+    int max_check, initial_pivots, other_pivots, no_better_threshold;
+    int ng_length, ng_lastlevel, spt_length, spt_lastlevel;  // the reference's Heap::length/lastlevel
+    int mres_cap;                          // max(MaxCheck/16, K)
+    // per-slot scratch in HBM
+    unsigned int* visited;
+    unsigned long long visited_words;      // per slot, multiple of 4
+    int2* ng_spill;
+    unsigned long long ng_spill_entries;   // per slot
+    int2* spt_spill;
+    unsigned long long spt_spill_entries;  // per slot
+    unsigned int* work_counter;
+    // shared-memory layout (bytes from the dynamic smem base)
+    int stage_rows, stages, slot_stride;
+    int h_ng, h_spt;
+    int off_ng, off_spt, off_cand, off_bar, off_query;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared 1-D bulk copy executed by the TMA unit; completion is signalled on `bar`
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// distance: the reference's AVX-512 float summation tree, one half-warp per row
+// ------------------------------------------------------------------------------------------
+template <bool COSINE>
+__device__ __forceinline__ float dist_term(float x, float y) {
+    if (COSINE) return __fmul_rn(x, y);
+    float d = __fsub_rn(x, y);
+    return __fmul_rn(d, d);
+}
+template <bool COSINE>
+__device__ __forceinline__ float dist_tail(float x, float y, float acc) {
+    // the reference's plain-C scalar tail is FMA-contracted by g++
+    if (COSINE) return __fmaf_rn(x, y, acc);
+    float d = __fsub_rn(x, y);
+    return __fmaf_rn(d, d, acc);
+}
+
+// Registers holding this lane's slice of the query: element 16c + (lane & 15) for every full
+// 16-chunk c.  DIM == 0 is the generic variant (query read from shared memory every time).
+template <int DIM>
+struct QueryRegs {
+    float q[DIM / 16 > 0 ? DIM / 16 : 1];
+};
+
+// Distance of the query to one row staged in shared memory, computed by a half-warp.
+// Lane j (0..15) owns accumulator j of ComputeL2Distance_AVX512 / ComputeCosineDistance_AVX512;
+// the folds 16 -> 8 -> 4 -> 1 and the 8-/4-wide/scalar tails follow DistanceUtils.cpp:650-682.
+// The result is valid in lane j == 0 of the half-warp.  Must be called by all 32 lanes.
+template <int DIM, bool COSINE>
+__device__ __forceinline__ float half_warp_distance(const float* __restrict__ row, const QueryRegs<DIM>& qr,
+                                                    const float* __restrict__ qs, int dim, int j) {
+    float acc = 0.0f;
+    if (DIM > 0) {
+#pragma unroll
+        for (int c = 0; c < DIM / 16; ++c) acc = __fadd_rn(acc, dist_term<COSINE>(qr.q[c], row[16 * c + j]));
+    } else {
+        const int nch = dim >> 4;
+        for (int c = 0; c < nch; ++c) acc = __fadd_rn(acc, dist_term<COSINE>(qs[16 * c + j], row[16 * c + j]));
+    }
+    const int d = (DIM > 0) ? DIM : dim;
+    int off = (d >> 4) << 4;
+    // diff256 = lo(diff512) + hi(diff512)
+    float a8 = __fadd_rn(acc, __shfl_down_sync(kFull, acc, 8, 16));
+    if (d & 8) {
+        if (j < 8) a8 = __fadd_rn(a8, dist_term<COSINE>(qs[off + j], row[off + j]));
+        off += 8;
+    }
+    // diff128 = lo(diff256) + hi(diff256)
+    float a4 = __fadd_rn(a8, __shfl_down_sync(kFull, a8, 4, 16));
+    if (d & 4) {
+        if (j < 4) a4 = __fadd_rn(a4, dist_term<COSINE>(qs[off + j], row[off + j]));
+        off += 4;
+    }
+    // DIFF128[0] + DIFF128[1] + DIFF128[2] + DIFF128[3], left to right
+    const float a1 = __shfl_sync(kFull, a4, 1, 16);
+    const float a2 = __shfl_sync(kFull, a4, 2, 16);
+    const float a3 = __shfl_sync(kFull, a4, 3, 16);
+    float s = __fadd_rn(__fadd_rn(__fadd_rn(a4, a1), a2), a3);
+    for (int i = off; i < d; ++i) s = dist_tail<COSINE>(qs[i], row[i], s);
+    return COSINE ? __fsub_rn(1.0f, s) : s;
+}
+
+// ------------------------------------------------------------------------------------------
+// Heap<NodeDistPair>: exact emulation of Heap.h:13-106.  entry = (node, distance bits) as int2.
+// Index 0 holds the default pair (-1, MaxDist); indices 1..H live in shared memory, the rest of
+// the array in the per-slot HBM arena.
+// ------------------------------------------------------------------------------------------
+struct WarpHeap {
+    int2* s;  // shared memory, indices [0, H]
+    int2* g;  // global memory, indexed by the same index (entries <= H unused)
+    int H;
+    int count;
+    int length, lastlevel;
+};
+
+__device__ __forceinline__ int2 heap_ld(const WarpHeap& h, int i) { return i <= h.H ? h.s[i] : h.g[i]; }
+__device__ __forceinline__ void heap_st(const WarpHeap& h, int i, int2 v) {
+    if (i <= h.H)
+        h.s[i] = v;
+    else
+        h.g[i] = v;
+}
+__device__ __forceinline__ float pair_dist(int2 v) { return __int_as_float(v.y); }
+__device__ __forceinline__ int2 make_pair(int node, float d) { return make_int2(node, __float_as_int(d)); }
+
+// Heap::Top(): slot 0 (-1, MaxDist) when empty (Heap.h:36)
+__device__ __forceinline__ float heap_top_dist(const WarpHeap& h) {
+    return h.count == 0 ? SPTAG_B200_MAXDIST : pair_dist(h.s[1]);
+}
+
+// Heap::insert (Heap.h:39-62).  The sift-up path (the ancestors loc>>1, loc>>2, ...) is loaded by
+// one lane per level, the stop level is found with a ballot, and the shifted parents plus the new
+// value are stored in one step -- the resulting array is identical to the sequential loop's.
+__device__ __forceinline__ void heap_insert(WarpHeap& h, int node, float d, int lane) {
+    int loc;
+    if (h.count == h.length) {
+        // full heap: replace the first maximum of the last level [lastlevel, length] (Heap.h:43-49)
+        float best = -1.0f;
+        int besti = 0x7fffffff;
+        bool have = false;
+        for (int i = h.lastlevel + lane; i <= h.length; i += 32) {
+            float v = pair_dist(heap_ld(h, i));
+            if (!have || v > best) {  // strict '<' in the reference keeps the earliest maximum
+                best = v;
+                besti = i;
+                have = true;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ob = __shfl_xor_sync(kFull, best, o);
+            int oi = __shfl_xor_sync(kFull, besti, o);
+            bool oh = __shfl_xor_sync(kFull, (int)have, o) != 0;
+            if (oh && (!have || ob > best || (ob == best && oi < besti))) {
+                best = ob;
+                besti = oi;
+                have = true;
+            }
+        }
+        if (d > best) return;
+        loc = besti;
+    } else {
+        loc = ++h.count;
+    }
+    const int anc = loc >> (lane + 1);
+    int2 av = make_int2(0, 0);
+    if (anc > 0) av = heap_ld(h, anc);
+    const bool stop = (anc <= 0) || !(d < pair_dist(av));
+    const int s = __ffs(__ballot_sync(kFull, stop)) - 1;  // levels 0..s-1 move down
+    if (lane < s)
+        heap_st(h, loc >> lane, av);
+    else if (lane == s)
+        heap_st(h, loc >> s, make_pair(node, d));
+    __syncwarp();
+}
+
+// Heap::pop (Heap.h:73-82) + heapify (Heap.h:92-105).  Executed redundantly by every lane
+// (uniform loads broadcast); lane 0 stores.  Returns the old root.
+__device__ __forceinline__ int2 heap_pop(WarpHeap& h, int lane) {
+    if (h.count == 0) return make_pair(-1, SPTAG_B200_MAXDIST);
+    const int2 top = heap_ld(h, 1);
+    const int2 cur = heap_ld(h, h.count);
+    h.count--;
+    const float cd = pair_dist(cur);
+    int parent = 1, next = 2;
+    while (next < h.count) {
+        int2 a = heap_ld(h, next);
+        const int2 b = heap_ld(h, next + 1);
+        if (pair_dist(a) > pair_dist(b)) {
+            next++;
+            a = b;
+        }
+        if (pair_dist(a) < cd) {
+            if (lane == 0) heap_st(h, parent, a);
+            parent = next;
+            next <<= 1;
+        } else
+            break;
+    }
+    if (next == h.count) {
+        const int2 a = heap_ld(h, next);
+        if (pair_dist(a) < cd) {
+            if (lane == 0) heap_st(h, parent, a);
+            parent = next;
+        }
+    }
+    if (lane == 0 && h.count > 0) heap_st(h, parent, cur);
+    __syncwarp();
+    return top;
+}
+
+// ------------------------------------------------------------------------------------------
+// DistPriorityQueue m_Results (WorkSpace.h:167-225): a multiset of the `cap` smallest distances
+// seen so far, pre-filled with MaxDist (the reference's sentinel root plus its still-empty slots);
+// insert(d) rejects iff d > worst(), otherwise replaces one maximum.  Held in registers:
+// slot s = r*32 + lane.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned float_key(float f) {
+    unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+template <int RPL>
+struct MResults {
+    float m[RPL];
+    float lmax;   // this lane's maximum
+    float worst;  // warp-wide maximum (uniform)
+
+    __device__ __forceinline__ void reset(int cap, int lane) {
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) m[r] = (r * 32 + lane < cap) ? SPTAG_B200_MAXDIST : -INFINITY;
+        lmax = m[0];
+        worst = SPTAG_B200_MAXDIST;
+    }
+    __device__ __forceinline__ bool insert(float d, int lane) {
+        if (d > worst) return false;
+        const int owner = __ffs(__ballot_sync(kFull, lmax == worst)) - 1;
+        if (lane == owner) {
+            bool done = false;
+            float nm = -INFINITY;
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                if (!done && m[r] == lmax) {
+                    m[r] = d;
+                    done = true;
+                }
+                nm = fmaxf(nm, m[r]);
+            }
+            lmax = nm;
+        }
+        worst = key_float(__reduce_max_sync(kFull, float_key(lmax)));
+        return true;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// The per-query state of one warp
+// ------------------------------------------------------------------------------------------
+struct BktNodeDev {
+    int centerid, childStart, childEnd;
+};
+
+template <int DIM, bool COSINE, int RPL>
+struct WarpSearch {
+    const SearchParams& p;
+    const int lane, half, j;
+    // shared memory
+    unsigned char* ring;
+    int* cand_id;
+    float* cand_dist;
+    uint64_t* bars;
+    float* qs;
+    // HBM scratch of this slot
+    unsigned int* visited;
+    // queues
+    WarpHeap ng, spt;
+    MResults<RPL> mres;
+    // top-K: lane i holds the i-th best (dist, id)
+    float tk_d;
+    int tk_id;
+    float worst_d;
+    int worst_id;
+    // query slice
+    QueryRegs<DIM> qr;
+    // counters
+    int checked, ndist, nexpand, ntree;
+    unsigned phase_bits;
+
+    __device__ __forceinline__ WarpSearch(const SearchParams& p_, int lane_)
+        : p(p_), lane(lane_), half(lane_ >> 4), j(lane_ & 15) {}
+
+    __device__ __forceinline__ unsigned char* slot_ptr(int s) const {
+        return ring + (size_t)s * p.slot_stride + ((s & 1) << 6);
+    }
+
+    // OptHashPosVector::CheckAndSet for a warp-uniform id: true if already present
+    __device__ __forceinline__ bool check_and_set_uniform(int id) {
+        const unsigned w = __ldcg(&visited[id >> 5]);
+        const unsigned bit = 1u << (id & 31);
+        const bool was = (w & bit) != 0;
+        if (!was && lane == 0) visited[id >> 5] = w | bit;
+        __syncwarp();
+        return was;
+    }
+
+    // QueryResultSet::AddPoint (QueryResultSet.h:77-87) on the sorted register list
+    __device__ __forceinline__ bool add_point(int id, float d) {
+        if (!(d < worst_d || (d == worst_d && id < worst_id))) return false;
+        const bool less = (lane < p.k) && ((tk_d < d) || (tk_d == d && tk_id < id));
+        const int pos = __popc(__ballot_sync(kFull, less));
+        const float pd = __shfl_up_sync(kFull, tk_d, 1);
+        const int pi = __shfl_up_sync(kFull, tk_id, 1);
+        if (lane < p.k) {
+            if (lane > pos) {
+                tk_d = pd;
+                tk_id = pi;
+            } else if (lane == pos) {
+                tk_d = d;
+                tk_id = id;
+            }
+        }
+        worst_d = __shfl_sync(kFull, tk_d, p.k - 1);
+        worst_id = __shfl_sync(kFull, tk_id, p.k - 1);
+        return true;
+    }
+
+    __device__ __forceinline__ bool not_deleted(int id) const {
+        return p.deleted == nullptr || p.deleted[id] != 1;
+    }
+
+    __device__ __forceinline__ void issue_stage(int t, int cnt) {
+        const int base = t * p.stage_rows;
+        const int rows = min(p.stage_rows, cnt - base);
+        const int st = t % p.stages;
+        if (lane == 0) mbar_arrive_expect_tx(&bars[st], (uint32_t)rows * (uint32_t)p.row_bytes);
+        __syncwarp();
+        if (lane < rows) {
+            const int id = cand_id[base + lane];
+            tma_load_1d(slot_ptr(st * p.stage_rows + lane), p.vectors + (size_t)id * p.row_stride_bytes,
+                        (uint32_t)p.row_bytes, &bars[st]);
+        }
+    }
+
+    // distances of the query to cand_id[0..cnt) -> cand_dist[0..cnt).  cnt <= 32.
+    __device__ __forceinline__ void compute_dists(int cnt) {
+        if (cnt <= 0) return;
+        __syncwarp();
+        fence_proxy_async();  // earlier generic-proxy reads of the ring precede the async writes
+        const int nst = (cnt + p.stage_rows - 1) / p.stage_rows;
+        const int pre = min(nst, p.stages);
+        for (int t = 0; t < pre; ++t) issue_stage(t, cnt);
+        for (int t = 0; t < nst; ++t) {
+            const int st = t % p.stages;
+            mbar_wait(&bars[st], (phase_bits >> st) & 1u);
+            phase_bits ^= (1u << st);
+            const int base = t * p.stage_rows;
+            const int rows = min(p.stage_rows, cnt - base);
+            for (int pr = 0; 2 * pr < rows; ++pr) {
+                const int r = 2 * pr + half;
+                const float* row = reinterpret_cast<const float*>(slot_ptr(st * p.stage_rows + r));
+                const float d = half_warp_distance<DIM, COSINE>(row, qr, qs, p.dim, j);
+                if (j == 0 && r < rows) cand_dist[base + r] = d;
+            }
+            __syncwarp();
+            if (t + p.stages < nst) {
+                fence_proxy_async();
+                issue_stage(t + p.stages, cnt);
+            }
+        }
+        __syncwarp();
+        ndist += cnt;
+    }
+
+    // BKTree::InitSearchTrees (BKTree.h:696-769), m_bfs == 0
+    __device__ __forceinline__ void push_children(int cs, int ce) {
+        for (int base = cs; base < ce; base += 32) {
+            const int cnt = min(32, ce - base);
+            __syncwarp();
+            if (lane < cnt) cand_id[lane] = p.nodes[3 * (base + lane)];
+            ntree += cnt;
+            compute_dists(cnt);
+            for (int r = 0; r < cnt; ++r) heap_insert(spt, base + r, cand_dist[r], lane);
+        }
+    }
+
+    __device__ __forceinline__ void init_search_trees() {
+        for (int t = 0; t < p.tree_num; ++t) {
+            const int start = p.tree_starts[t];
+            const int centerid = p.nodes[3 * start], cs = p.nodes[3 * start + 1], ce = p.nodes[3 * start + 2];
+            ntree++;
+            if (cs < 0) {
+                __syncwarp();
+                if (lane == 0) cand_id[0] = centerid;
+                compute_dists(1);
+                heap_insert(spt, start, cand_dist[0], lane);
+            } else {
+                push_children(cs, ce);
+            }
+        }
+    }
+
+    // BKTree::SearchTrees (BKTree.h:771-799)
+    __device__ __forceinline__ void search_trees(int limit) {
+        while (spt.count != 0) {
+            const int2 bcell = heap_pop(spt, lane);
+            const int centerid = p.nodes[3 * bcell.x], cs = p.nodes[3 * bcell.x + 1], ce = p.nodes[3 * bcell.x + 2];
+            ntree++;
+            if (cs < 0) {
+                if (!check_and_set_uniform(centerid)) {
+                    checked++;
+                    heap_insert(ng, centerid, pair_dist(bcell), lane);
+                }
+                if (checked >= limit) break;
+            } else {
+                if (!check_and_set_uniform(centerid)) heap_insert(ng, centerid, pair_dist(bcell), lane);
+                push_children(cs, ce);
+            }
+        }
+    }
+
+    // BKT::Index<T>::Search<notDeleted, CheckDup, AlwaysTrue> (BKTIndex.cpp:268-352)
+    __device__ __forceinline__ void bkt_search() {
+        init_search_trees();
+        search_trees(p.initial_pivots);
+        const int checkPos = p.degree - 1;
+        while (ng.count != 0) {
+            const int2 gnode = heap_pop(ng, lane);
+            int tmpNode = gnode.x;
+            const float gdist = pair_dist(gnode);
+            const int* node = p.graph + (size_t)tmpNode * p.degree;
+            nexpand++;
+            // lane i reads neighbour i of the first 32-wide chunk while the accept logic runs
+            int nn = (lane <= checkPos) ? node[lane] : -1;
+
+            if (gdist <= worst_d) {
+                const int checkNode = node[checkPos];
+                if (checkNode < -1) {
+                    // duplicate group: the back-pointer names the BKT node listing exact duplicates
+                    const int tn = -2 - checkNode;
+                    const int tcs = p.nodes[3 * tn + 1], tce = p.nodes[3 * tn + 2];
+                    int i = -tcs;
+                    do {
+                        if (not_deleted(tmpNode)) {
+                            if (!add_point(tmpNode, gdist)) break;
+                        }
+                        if (i <= 0) break;
+                        tmpNode = p.nodes[3 * i];
+                    } while (i++ < tce);
+                } else {
+                    if (not_deleted(tmpNode)) add_point(tmpNode, gdist);
+                }
+            } else {
+                if (not_deleted(tmpNode)) {
+                    if (gdist > mres.worst || checked > p.max_check) return;
+                }
+            }
+
+            for (int cbase = 0; cbase <= checkPos; cbase += 32) {
+                if (cbase > 0) nn = (cbase + lane <= checkPos) ? node[cbase + lane] : -1;
+                const bool in_row = (cbase + lane <= checkPos);
+                // the scan stops at the first negative entry (BKTIndex.cpp:333-336)
+                const unsigned negmask = __ballot_sync(kFull, in_row && nn < 0) | ~__ballot_sync(kFull, in_row);
+                const int first_neg = negmask ? (__ffs(negmask) - 1) : 32;
+                const bool active = lane < first_neg;
+                // a repeated id inside the row is "visited" by the time its second copy is reached
+                const unsigned same = __match_any_sync(kFull, active ? nn : (-1 - lane));
+                const bool leader = active && ((__ffs(same) - 1) == lane);
+                bool fresh = false;
+                if (leader) {
+                    const unsigned bit = 1u << (nn & 31);
+                    const unsigned old = atomicOr(&visited[nn >> 5], bit);
+                    fresh = (old & bit) == 0;
+                }
+                const unsigned freshmask = __ballot_sync(kFull, fresh);
+                const int cnt = __popc(freshmask);
+                __syncwarp();
+                if (fresh) cand_id[__popc(freshmask & ((1u << lane) - 1u))] = nn;
+                compute_dists(cnt);
+                for (int r = 0; r < cnt; ++r) {
+                    const float d = cand_dist[r];
+                    checked++;
+                    if (mres.insert(d, lane)) heap_insert(ng, cand_id[r], d, lane);
+                }
+                if (first_neg < 32) break;
+            }
+            if (heap_top_dist(ng) > heap_top_dist(spt)) search_trees(p.other_pivots + checked);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// kernel: persistent warps pull queries from a global counter
+// ------------------------------------------------------------------------------------------
+template <int DIM, bool COSINE, int RPL>
+__global__ void __launch_bounds__(32) bkt_search_kernel(const SearchParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x;
+    WarpSearch<DIM, COSINE, RPL> w(p, lane);
+    w.ring = smem;
+    w.cand_id = reinterpret_cast<int*>(smem + p.off_cand);
+    w.cand_dist = reinterpret_cast<float*>(smem + p.off_cand + 128);
+    w.bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+    w.qs = reinterpret_cast<float*>(smem + p.off_query);
+    w.visited = p.visited + (size_t)blockIdx.x * p.visited_words;
+    w.ng.s = reinterpret_cast<int2*>(smem + p.off_ng);
+    w.ng.g = p.ng_spill + (size_t)blockIdx.x * p.ng_spill_entries;
+    w.ng.H = p.h_ng;
+    w.ng.length = p.ng_length;
+    w.ng.lastlevel = p.ng_lastlevel;
+    w.spt.s = reinterpret_cast<int2*>(smem + p.off_spt);
+    w.spt.g = p.spt_spill + (size_t)blockIdx.x * p.spt_spill_entries;
+    w.spt.H = p.h_spt;
+    w.spt.length = p.spt_length;
+    w.spt.lastlevel = p.spt_lastlevel;
+    w.phase_bits = 0;
+
+    if (lane == 0) {
+        for (int s = 0; s < p.stages; ++s) mbar_init(&w.bars[s], 1);
+        mbar_fence_init();
+        w.ng.s[0] = make_pair(-1, SPTAG_B200_MAXDIST);
+        w.spt.s[0] = make_pair(-1, SPTAG_B200_MAXDIST);
+    }
+    __syncwarp();
+
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = (int)atomicAdd(p.work_counter, 1u);
+        q = __shfl_sync(kFull, q, 0);
+        if (q >= p.nq) break;
+
+        // ---- WorkSpace::Reset (WorkSpace.h:265-278) ----
+        {
+            uint4* v4 = reinterpret_cast<uint4*>(w.visited);
+            const size_t n4 = p.visited_words >> 2;
+            for (size_t i = lane; i < n4; i += 32) v4[i] = make_uint4(0, 0, 0, 0);
+        }
+        w.ng.count = 0;
+        w.spt.count = 0;
+        w.mres.reset(p.mres_cap, lane);
+        w.tk_d = SPTAG_B200_MAXDIST;
+        w.tk_id = -1;
+        w.worst_d = SPTAG_B200_MAXDIST;
+        w.worst_id = -1;
+        w.checked = w.ndist = w.nexpand = w.ntree = 0;
+        // query -> shared memory (+ registers for the static-DIM variants)
+        {
+            const float* qg = reinterpret_cast<const float*>(p.queries + (size_t)q * p.query_stride_bytes);
+            for (int i = lane; i < p.dim; i += 32) w.qs[i] = qg[i];
+            __syncwarp();
+            if (DIM > 0) {
+#pragma unroll
+                for (int c = 0; c < DIM / 16; ++c) w.qr.q[c] = w.qs[16 * c + (lane & 15)];
+            }
+        }
+        __syncwarp();
+
+        w.bkt_search();
+
+        // ---- QueryResultSet::SortResult: the register list is already ascending by (dist, id) ----
+        if (lane < p.k) {
+            const int id = w.tk_id;
+            p.out_ids[(size_t)q * p.k + lane] = (id >= 0) ? id + p.id_offset : id;
+            p.out_dists[(size_t)q * p.k + lane] = w.tk_d;
+        }
+        if (p.out_stats != nullptr && lane == 0) {
+            int* s = p.out_stats + (size_t)q * kStatsPerQuery;
+            s[0] = w.checked;
+            s[1] = 0;
+            s[2] = w.ng.count;
+            s[3] = w.spt.count;
+            s[4] = w.ndist;
+            s[5] = w.nexpand;
+            s[6] = w.ntree;
+            s[7] = 0;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone batched distance kernel (inner-loop parity): one half-warp per (query, id)
+// ------------------------------------------------------------------------------------------
+template <bool COSINE>
+__global__ void distance_batch_kernel(const unsigned char* vectors, unsigned long long row_stride_bytes, int n,
+                                      int dim, const float* queries, int nq, const int* ids, int ids_per_query,
+                                      float* out) {
+    const int lane = threadIdx.x & 31;
+    const int j = lane & 15;
+    const long long hw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const long long total = (long long)nq * ids_per_query;
+    // all 32 lanes of a warp run the same number of iterations (shuffles inside)
+    const long long pair = hw >> 1;
+    const long long npairs = (total + 1) >> 1;
+    if (pair >= npairs) return;
+    const bool valid = hw < total;
+    const long long item = valid ? hw : total - 1;
+    const int q = (int)(item / ids_per_query);
+    const int id = ids[item];
+    const bool ok = (id >= 0 && id < n);
+    const float* row = reinterpret_cast<const float*>(vectors + (size_t)(ok ? id : 0) * row_stride_bytes);
+    const float* qv = queries + (size_t)q * dim;
+    QueryRegs<0> qr;
+    const float d = half_warp_distance<0, COSINE>(row, qr, qv, dim, j);
+    if (valid && j == 0) out[item] = ok ? d : SPTAG_B200_MAXDIST;
+}
+
+// ------------------------------------------------------------------------------------------
+// k-way merge of per-shard top-k lists (QueryResultSet.h:17-26 comparator): one thread per query
+// ------------------------------------------------------------------------------------------
+__global__ void merge_topk_kernel(const int* __restrict__ ids, const float* __restrict__ dists, int num_lists,
+                                  int nq, int k, int* __restrict__ out_ids, float* __restrict__ out_dists) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    // every list is ascending; keep one cursor per list (num_lists <= 16)
+    int cur[16];
+    for (int l = 0; l < num_lists; ++l) cur[l] = 0;
+    for (int o = 0; o < k; ++o) {
+        int bl = -1, bid = -1;
+        float bd = 0.0f;
+        for (int l = 0; l < num_lists; ++l) {
+            if (cur[l] >= k) continue;
+            const size_t at = ((size_t)l * nq + q) * k + cur[l];
+            const int id = ids[at];
+            const float d = dists[at];
+            if (id < 0) {  // unfilled tail of this list
+                cur[l] = k;
+                continue;
+            }
+            if (bl < 0 || d < bd || (d == bd && id < bid)) {
+                bl = l;
+                bd = d;
+                bid = id;
+            }
+        }
+        if (bl < 0) {
+            out_ids[(size_t)q * k + o] = -1;
+            out_dists[(size_t)q * k + o] = SPTAG_B200_MAXDIST;
+        } else {
+            out_ids[(size_t)q * k + o] = bid;
+            out_dists[(size_t)q * k + o] = bd;
+            cur[bl]++;
+        }
+    }
+}
+
+}  // namespace sptag_b200

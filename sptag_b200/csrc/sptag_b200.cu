@@ -1,0 +1,640 @@
+// sptag_b200.cu -- C-ABI implementation (include/sptag_b200.h) over the sm_100a search kernels.
+//
+// Host side of the drop-in boundary: index upload (the arrays BKT::Index<T> keeps in m_pSamples /
+// m_pGraph / m_pTrees / m_deletedID, AnnService/inc/Core/BKT/Index.h), the reference's on-disk
+// folder reader (VectorIndex.cpp:617-681), parameter handling with the reference's names
+// (BKT/ParameterDefinitionList.h:44-49), per-slot scratch management and the kernel launches.
+// No torch, no CPU fallback: a search either runs the CUDA kernels or returns an error code.
+#include "../../include/sptag_b200.h"
+#include "search_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+using namespace sptag_b200;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_OK(expr)                                                                            \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return fail(SPTAG_B200_FAIL, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                     \
+    } while (0)
+
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return 0;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&ptr, need);
+        if (e != cudaSuccess) return fail(SPTAG_B200_MEMORY_OVERFLOW, "cudaMalloc(%zu) failed: %s", need,
+                                          cudaGetErrorString(e));
+        bytes = need;
+        return 0;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+};
+
+size_t value_size(int vt) {
+    switch (vt) {
+    case SPTAG_B200_VT_INT8:
+    case SPTAG_B200_VT_UINT8: return 1;
+    case SPTAG_B200_VT_INT16: return 2;
+    case SPTAG_B200_VT_FLOAT: return 4;
+    }
+    return 0;
+}
+
+size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct sptag_b200_index {
+    int device = 0;
+    int algo = 0, value_type = SPTAG_B200_VT_FLOAT, metric = 0;
+    int n = 0, dim = 0, degree = 0, tree_num = 0, node_count = 0, num_deleted = 0, id_offset = 0;
+    size_t row_stride = 0;  // bytes, multiple of 16
+    // device-resident index
+    DeviceBuffer d_vectors, d_graph, d_nodes, d_tree_starts, d_deleted;
+    // search parameters (reference names)
+    int max_check = 8192, max_check_refine = 8192, initial_pivots = 50, other_pivots = 4, no_better_threshold = 3;
+    // B200 tuning knobs
+    int queries_per_sm = 0;  // 0 = auto
+    int stage_rows = 0;      // 0 = auto
+    int stages = 2;
+    int h_ng = 1024, h_spt = 512;
+    int simd_width = 16;
+    // scratch
+    DeviceBuffer d_visited, d_ng_spill, d_spt_spill, d_counter;
+    DeviceBuffer d_queries, d_ids, d_dists, d_stats;  // staging for the host-buffer entry point
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    bool timed = false;
+    int num_sms = 0;
+    size_t smem_optin = 0;
+    std::mutex mu;
+};
+
+namespace {
+
+int heap_lastlevel(int size) {
+    // Heap::Resize: lastlevel = int(pow(2.0, floor(log2((float)size))))  (Heap.h:24)
+    return (int)std::pow(2.0, std::floor(std::log2((float)size)));
+}
+
+template <int DIM, bool COSINE, int RPL>
+int launch_bkt(const SearchParams& p, int grid, size_t smem, cudaStream_t stream) {
+    auto kern = bkt_search_kernel<DIM, COSINE, RPL>;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 32, smem, stream>>>(p);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <int DIM, bool COSINE>
+int launch_bkt_rpl(const SearchParams& p, int grid, size_t smem, cudaStream_t stream) {
+    if (p.mres_cap <= 32 * 16) return launch_bkt<DIM, COSINE, 16>(p, grid, smem, stream);
+    if (p.mres_cap <= 32 * 32) return launch_bkt<DIM, COSINE, 32>(p, grid, smem, stream);
+    return fail(SPTAG_B200_LACK_OF_INPUTS, "max(MaxCheck/16, K) = %d exceeds the supported 1024", p.mres_cap);
+}
+
+template <bool COSINE>
+int launch_bkt_dim(const SearchParams& p, int grid, size_t smem, cudaStream_t stream) {
+    switch (p.dim) {
+    case 128: return launch_bkt_rpl<128, COSINE>(p, grid, smem, stream);
+    case 768: return launch_bkt_rpl<768, COSINE>(p, grid, smem, stream);
+    default: return launch_bkt_rpl<0, COSINE>(p, grid, smem, stream);
+    }
+}
+
+// Fill SearchParams + launch geometry for this handle.  Allocates per-slot scratch.
+int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& smem, int nq) {
+    if (h->algo != SPTAG_B200_ALGO_BKT)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "only BKT indexes are searchable in this build");
+    if (h->value_type != SPTAG_B200_VT_FLOAT)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "only float vectors are searchable in this build");
+    if (h->simd_width != 16)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "B200.SimdWidth %d not built (16 only)", h->simd_width);
+    if (k < 1 || k > 32) return fail(SPTAG_B200_LACK_OF_INPUTS, "k = %d outside the supported range [1, 32]", k);
+
+    memset(&p, 0, sizeof(p));
+    p.vectors = (const unsigned char*)h->d_vectors.ptr;
+    p.row_stride_bytes = h->row_stride;
+    p.row_bytes = (int)h->row_stride;
+    p.n = h->n;
+    p.dim = h->dim;
+    p.graph = (const int*)h->d_graph.ptr;
+    p.degree = h->degree;
+    p.nodes = (const int*)h->d_nodes.ptr;
+    p.tree_starts = (const int*)h->d_tree_starts.ptr;
+    p.tree_num = h->tree_num;
+    p.node_count = h->node_count;
+    p.deleted = (h->num_deleted > 0) ? (const signed char*)h->d_deleted.ptr : nullptr;
+    p.k = k;
+    p.id_offset = h->id_offset;
+    p.max_check = h->max_check;
+    p.initial_pivots = h->initial_pivots;
+    p.other_pivots = h->other_pivots;
+    p.no_better_threshold = h->no_better_threshold;
+    // a fresh thread's WorkSpace: Initialize(max(MaxCheck, MaxCheckForRefineGraph)) then
+    // Reset(MaxCheck, K) (BKTIndex.cpp:600-605, WorkSpace.h:243-278)
+    const int alloc_check = std::max(h->max_check, h->max_check_refine);
+    p.ng_length = alloc_check * 30;
+    p.ng_lastlevel = heap_lastlevel(p.ng_length);
+    p.spt_length = alloc_check * 10;
+    p.spt_lastlevel = heap_lastlevel(p.spt_length);
+    p.mres_cap = std::max(h->max_check / 16, k);
+
+    // ---- shared-memory layout ----
+    int stage_rows = h->stage_rows;
+    if (stage_rows <= 0) {
+        stage_rows = (int)(12288 / h->row_stride);
+        stage_rows = std::max(2, std::min(16, stage_rows));
+    }
+    stage_rows &= ~1;
+    if (stage_rows < 2) stage_rows = 2;
+    if (stage_rows > 32) stage_rows = 32;
+    const int stages = std::max(1, std::min(8, h->stages));
+    p.stage_rows = stage_rows;
+    p.stages = stages;
+    p.slot_stride = (int)round_up(h->row_stride + 64, 128);
+    p.h_ng = std::max(1, h->h_ng);
+    p.h_spt = std::max(1, h->h_spt);
+    size_t off = (size_t)stage_rows * stages * p.slot_stride;
+    p.off_ng = (int)off;
+    off += round_up((size_t)(p.h_ng + 1) * 8, 16);
+    p.off_spt = (int)off;
+    off += round_up((size_t)(p.h_spt + 1) * 8, 16);
+    p.off_cand = (int)off;
+    off += 256;
+    p.off_bar = (int)off;
+    off += round_up((size_t)stages * 8, 16);
+    p.off_query = (int)off;
+    off += round_up((size_t)h->dim * 4 + 16, 16);
+    smem = round_up(off, 128);
+    if (smem > h->smem_optin)
+        return fail(SPTAG_B200_MEMORY_OVERFLOW, "shared memory per query slot %zu exceeds %zu", smem, h->smem_optin);
+
+    int per_sm = h->queries_per_sm;
+    const int fit = (int)std::min<size_t>(32, (228 * 1024) / (smem + 1024));
+    if (per_sm <= 0) per_sm = std::min(fit, 16);
+    per_sm = std::max(1, std::min(per_sm, fit));
+    grid = std::max(1, std::min(nq, h->num_sms * per_sm));
+
+    // ---- per-slot scratch ----
+    p.visited_words = round_up(((size_t)h->n + 1 + 31) / 32, 4);
+    p.ng_spill_entries = (size_t)std::min<long long>((long long)p.ng_length, (long long)h->n + 2) + 2;
+    p.spt_spill_entries = (size_t)std::min<long long>((long long)p.spt_length, (long long)h->node_count + 2) + 2;
+    const size_t slots = (size_t)h->num_sms * 32;  // upper bound on grid so re-configuration never reallocates
+    const size_t use_slots = std::min(slots, (size_t)std::max(grid, 1));
+    (void)use_slots;
+    const size_t alloc_slots = (size_t)h->num_sms * per_sm;
+    if (int rc = h->d_visited.ensure(alloc_slots * p.visited_words * 4)) return rc;
+    if (int rc = h->d_ng_spill.ensure(alloc_slots * p.ng_spill_entries * 8)) return rc;
+    if (int rc = h->d_spt_spill.ensure(alloc_slots * p.spt_spill_entries * 8)) return rc;
+    if (int rc = h->d_counter.ensure(256)) return rc;
+    p.visited = (unsigned int*)h->d_visited.ptr;
+    p.ng_spill = (int2*)h->d_ng_spill.ptr;
+    p.spt_spill = (int2*)h->d_spt_spill.ptr;
+    p.work_counter = (unsigned int*)h->d_counter.ptr;
+    return 0;
+}
+
+int search_device_impl(sptag_b200_index* h, const void* d_queries, int nq, int k, int* d_ids, float* d_dists,
+                       int* d_stats, cudaStream_t stream) {
+    if (nq <= 0) return SPTAG_B200_SUCCESS;
+    SearchParams p;
+    int grid = 0;
+    size_t smem = 0;
+    if (int rc = configure(h, k, p, grid, smem, nq)) return rc;
+    p.queries = (const unsigned char*)d_queries;
+    p.query_stride_bytes = (size_t)h->dim * value_size(h->value_type);
+    p.nq = nq;
+    p.out_ids = d_ids;
+    p.out_dists = d_dists;
+    p.out_stats = d_stats;
+    CUDA_OK(cudaMemsetAsync(p.work_counter, 0, 4, stream));
+    CUDA_OK(cudaEventRecord(h->ev_start, stream));
+    int rc = (h->metric == SPTAG_B200_METRIC_L2) ? launch_bkt_dim<false>(p, grid, smem, stream)
+                                                 : launch_bkt_dim<true>(p, grid, smem, stream);
+    if (rc) return rc;
+    CUDA_OK(cudaEventRecord(h->ev_stop, stream));
+    h->timed = true;
+    return SPTAG_B200_SUCCESS;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+bool read_file(const std::string& path, std::vector<char>& out) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) return false;
+    std::streamsize sz = f.tellg();
+    f.seekg(0);
+    out.resize((size_t)sz);
+    return (bool)f.read(out.data(), sz);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sptag_b200_last_error(void) { return g_last_error.c_str(); }
+
+int64_t sptag_b200_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int sptag_b200_create(const sptag_b200_index_desc* desc, sptag_b200_handle* out) {
+    if (!desc || !out) return fail(SPTAG_B200_LACK_OF_INPUTS, "null descriptor");
+    *out = nullptr;
+    if (desc->struct_size != (int32_t)sizeof(sptag_b200_index_desc))
+        return fail(SPTAG_B200_FAIL, "descriptor size mismatch: %d vs %zu", desc->struct_size,
+                    sizeof(sptag_b200_index_desc));
+    if (desc->num_vectors <= 0 || !desc->vectors || !desc->graph || !desc->tree_nodes || !desc->tree_starts)
+        return fail(SPTAG_B200_EMPTY_INDEX, "empty index");
+    if (desc->dim <= 0 || desc->graph_degree <= 0 || desc->tree_num <= 0 || desc->node_count <= 0)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "bad index shape");
+    const size_t vs = value_size(desc->value_type);
+    if (vs == 0) return fail(SPTAG_B200_LACK_OF_INPUTS, "bad value type %d", desc->value_type);
+
+    int device = desc->device;
+    if (device < 0) CUDA_OK(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(SPTAG_B200_FAIL, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+
+    auto* h = new sptag_b200_index();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    h->algo = desc->algo;
+    h->value_type = desc->value_type;
+    h->metric = desc->metric;
+    h->n = desc->num_vectors;
+    h->dim = desc->dim;
+    h->degree = desc->graph_degree;
+    h->tree_num = desc->tree_num;
+    h->node_count = desc->node_count;
+    h->num_deleted = desc->deleted ? desc->num_deleted : 0;
+    h->id_offset = desc->id_offset;
+    const size_t row_bytes = (size_t)h->dim * vs;
+    h->row_stride = round_up(row_bytes, 16);  // TMA bulk copies need 16-byte aligned rows and sizes
+
+    auto destroy_on_fail = [&](int rc) {
+        sptag_b200_destroy(h);
+        return rc;
+    };
+    // one spare row so a 16-byte padded read of the last row stays in bounds
+    if (int rc = h->d_vectors.ensure(((size_t)h->n + 1) * h->row_stride)) return destroy_on_fail(rc);
+    if (h->row_stride == row_bytes) {
+        if (cudaMemcpy(h->d_vectors.ptr, desc->vectors, (size_t)h->n * row_bytes, cudaMemcpyHostToDevice) !=
+            cudaSuccess)
+            return destroy_on_fail(fail(SPTAG_B200_FAIL, "vector upload failed"));
+    } else {
+        cudaMemset(h->d_vectors.ptr, 0, ((size_t)h->n + 1) * h->row_stride);
+        if (cudaMemcpy2D(h->d_vectors.ptr, h->row_stride, desc->vectors, row_bytes, row_bytes, (size_t)h->n,
+                         cudaMemcpyHostToDevice) != cudaSuccess)
+            return destroy_on_fail(fail(SPTAG_B200_FAIL, "vector upload failed"));
+    }
+    const size_t graph_bytes = (size_t)h->n * h->degree * 4;
+    if (int rc = h->d_graph.ensure(graph_bytes)) return destroy_on_fail(rc);
+    cudaMemcpy(h->d_graph.ptr, desc->graph, graph_bytes, cudaMemcpyHostToDevice);
+    const size_t node_bytes = (size_t)h->node_count * (h->algo == SPTAG_B200_ALGO_BKT ? 12 : 16);
+    // BKT: one extra sentinel node (the reference's LoadTrees appends (-1,-1,-1), BKTree.h:662)
+    if (int rc = h->d_nodes.ensure(node_bytes + 16)) return destroy_on_fail(rc);
+    cudaMemset(h->d_nodes.ptr, 0xff, node_bytes + 16);
+    cudaMemcpy(h->d_nodes.ptr, desc->tree_nodes, node_bytes, cudaMemcpyHostToDevice);
+    if (int rc = h->d_tree_starts.ensure((size_t)h->tree_num * 4)) return destroy_on_fail(rc);
+    cudaMemcpy(h->d_tree_starts.ptr, desc->tree_starts, (size_t)h->tree_num * 4, cudaMemcpyHostToDevice);
+    if (h->num_deleted > 0) {
+        if (int rc = h->d_deleted.ensure((size_t)h->n)) return destroy_on_fail(rc);
+        cudaMemcpy(h->d_deleted.ptr, desc->deleted, (size_t)h->n, cudaMemcpyHostToDevice);
+    }
+    if (cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess)
+        return destroy_on_fail(fail(SPTAG_B200_FAIL, "cudaEventCreate failed"));
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess)
+        return destroy_on_fail(fail(SPTAG_B200_FAIL, "index upload failed"));
+    *out = h;
+    return SPTAG_B200_SUCCESS;
+}
+
+void sptag_b200_destroy(sptag_b200_handle h) {
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    cudaSetDevice(h->device);
+    h->d_vectors.release();
+    h->d_graph.release();
+    h->d_nodes.release();
+    h->d_tree_starts.release();
+    h->d_deleted.release();
+    h->d_visited.release();
+    h->d_ng_spill.release();
+    h->d_spt_spill.release();
+    h->d_counter.release();
+    h->d_queries.release();
+    h->d_ids.release();
+    h->d_dists.release();
+    h->d_stats.release();
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+    delete h;
+}
+
+int sptag_b200_load(const char* folder, int32_t device, int32_t id_offset, sptag_b200_handle* out) {
+    if (!folder || !out) return fail(SPTAG_B200_LACK_OF_INPUTS, "null argument");
+    *out = nullptr;
+    const std::string dir(folder);
+    // indexloader.ini: "[Index]" section of Name=Value lines (VectorIndex.cpp:197-222, :617-681)
+    std::ifstream ini(dir + "/indexloader.ini");
+    if (!ini) return fail(SPTAG_B200_FAILED_OPEN_FILE, "cannot open %s/indexloader.ini", folder);
+    std::map<std::string, std::string> kv;
+    std::string line;
+    while (std::getline(ini, line)) {
+        while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
+        if (line.empty() || line[0] == '[' || line[0] == ';' || line[0] == '#') continue;
+        size_t eq = line.find('=');
+        if (eq == std::string::npos) continue;
+        kv[line.substr(0, eq)] = line.substr(eq + 1);
+    }
+    auto get = [&](const char* name, const char* def) {
+        auto it = kv.find(name);
+        return it == kv.end() ? std::string(def) : it->second;
+    };
+    sptag_b200_index_desc d;
+    memset(&d, 0, sizeof(d));
+    d.struct_size = sizeof(d);
+    d.device = device;
+    d.id_offset = id_offset;
+    const std::string algo = get("IndexAlgoType", "BKT");
+    if (algo == "BKT")
+        d.algo = SPTAG_B200_ALGO_BKT;
+    else if (algo == "KDT")
+        d.algo = SPTAG_B200_ALGO_KDT;
+    else
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "unsupported IndexAlgoType %s", algo.c_str());
+    const std::string vt = get("ValueType", "Float");
+    if (vt == "Float")
+        d.value_type = SPTAG_B200_VT_FLOAT;
+    else if (vt == "Int8")
+        d.value_type = SPTAG_B200_VT_INT8;
+    else if (vt == "UInt8")
+        d.value_type = SPTAG_B200_VT_UINT8;
+    else if (vt == "Int16")
+        d.value_type = SPTAG_B200_VT_INT16;
+    else
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "unsupported ValueType %s", vt.c_str());
+    const std::string dm = get("DistCalcMethod", "Cosine");  // reference default is Cosine
+    d.metric = (dm == "L2") ? SPTAG_B200_METRIC_L2
+                            : (dm == "InnerProduct" ? SPTAG_B200_METRIC_INNERPRODUCT : SPTAG_B200_METRIC_COSINE);
+
+    std::vector<char> vec, graph, tree, del;
+    if (!read_file(dir + "/" + get("VectorFilePath", "vectors.bin"), vec) || vec.size() < 8)
+        return fail(SPTAG_B200_FAILED_OPEN_FILE, "cannot read vectors file in %s", folder);
+    if (!read_file(dir + "/" + get("GraphFilePath", "graph.bin"), graph) || graph.size() < 8)
+        return fail(SPTAG_B200_FAILED_OPEN_FILE, "cannot read graph file in %s", folder);
+    if (!read_file(dir + "/" + get("TreeFilePath", "tree.bin"), tree) || tree.size() < 8)
+        return fail(SPTAG_B200_FAILED_OPEN_FILE, "cannot read tree file in %s", folder);
+    const bool have_del = read_file(dir + "/" + get("DeleteVectorFilePath", "deletes.bin"), del) && del.size() >= 12;
+
+    // vectors.bin: int32 rows, int32 cols, rows*cols*T (Dataset.h:146-180)
+    const int32_t* vh = (const int32_t*)vec.data();
+    d.num_vectors = vh[0];
+    d.dim = vh[1];
+    if (vec.size() < 8 + (size_t)d.num_vectors * d.dim * value_size(d.value_type))
+        return fail(SPTAG_B200_FAIL, "vectors file truncated");
+    d.vectors = vec.data() + 8;
+    // graph.bin: int32 N, int32 degree, N*degree int32 (NeighborhoodGraph.h:606-615)
+    const int32_t* gh = (const int32_t*)graph.data();
+    if (gh[0] != d.num_vectors) return fail(SPTAG_B200_FAIL, "graph rows %d != vectors %d", gh[0], d.num_vectors);
+    d.graph_degree = gh[1];
+    if (graph.size() < 8 + (size_t)gh[0] * gh[1] * 4) return fail(SPTAG_B200_FAIL, "graph file truncated");
+    d.graph = gh + 2;
+    // tree.bin: int32 treeNumber, starts[], int32 nodeCount, nodes[] (BKTree.h:635-645, KDTree.h:123-133)
+    const int32_t* th = (const int32_t*)tree.data();
+    d.tree_num = th[0];
+    d.tree_starts = th + 1;
+    d.node_count = th[1 + d.tree_num];
+    d.tree_nodes = th + 2 + d.tree_num;
+    const size_t node_sz = d.algo == SPTAG_B200_ALGO_BKT ? 12 : 16;
+    if (tree.size() < (size_t)(2 + d.tree_num) * 4 + (size_t)d.node_count * node_sz)
+        return fail(SPTAG_B200_FAIL, "tree file truncated");
+    // deletes.bin: int32 count, then Dataset<int8> (int32 rows, int32 cols, bytes) (Labelset.h:78-83)
+    if (have_del) {
+        const int32_t* dh = (const int32_t*)del.data();
+        d.num_deleted = dh[0];
+        if (d.num_deleted > 0 && del.size() >= 12 + (size_t)d.num_vectors) d.deleted = (const int8_t*)(del.data() + 12);
+        else d.num_deleted = 0;
+    }
+    sptag_b200_handle h = nullptr;
+    if (int rc = sptag_b200_create(&d, &h)) return rc;
+    static const char* names[] = {"MaxCheck", "MaxCheckForRefineGraph", "NumberOfInitialDynamicPivots",
+                                  "NumberOfOtherDynamicPivots", "ThresholdOfNumberOfContinuousNoBetterPropagation"};
+    for (const char* nm : names) {
+        auto it = kv.find(nm);
+        if (it != kv.end()) sptag_b200_set_param(h, nm, it->second.c_str());
+    }
+    *out = h;
+    return SPTAG_B200_SUCCESS;
+}
+
+int sptag_b200_set_param(sptag_b200_handle h, const char* name, const char* value) {
+    if (!h || !name || !value) return fail(SPTAG_B200_LACK_OF_INPUTS, "null argument");
+    char* end = nullptr;
+    const long v = strtol(value, &end, 10);
+    if (end == value) return fail(SPTAG_B200_FAILED_PARSE_VALUE, "cannot parse '%s' for %s", value, name);
+    std::lock_guard<std::mutex> lock(h->mu);
+    const std::string n(name);
+    if (n == "MaxCheck") h->max_check = (int)v;
+    else if (n == "MaxCheckForRefineGraph") h->max_check_refine = (int)v;
+    else if (n == "NumberOfInitialDynamicPivots") h->initial_pivots = (int)v;
+    else if (n == "NumberOfOtherDynamicPivots") h->other_pivots = (int)v;
+    else if (n == "ThresholdOfNumberOfContinuousNoBetterPropagation") h->no_better_threshold = (int)v;
+    else if (n == "B200.QueriesPerSM") h->queries_per_sm = (int)v;
+    else if (n == "B200.StageRows") h->stage_rows = (int)v;
+    else if (n == "B200.Stages") h->stages = (int)v;
+    else if (n == "B200.NGCacheEntries") h->h_ng = (int)v;
+    else if (n == "B200.SPTCacheEntries") h->h_spt = (int)v;
+    else if (n == "B200.SimdWidth") h->simd_width = (int)v;
+    else return fail(SPTAG_B200_PARAM_NOT_FOUND, "unknown parameter %s", name);
+    return SPTAG_B200_SUCCESS;
+}
+
+int sptag_b200_get_param(sptag_b200_handle h, const char* name, char* value_out, int32_t capacity) {
+    if (!h || !name || !value_out || capacity <= 0) return fail(SPTAG_B200_LACK_OF_INPUTS, "null argument");
+    std::lock_guard<std::mutex> lock(h->mu);
+    const std::string n(name);
+    long v;
+    if (n == "MaxCheck") v = h->max_check;
+    else if (n == "MaxCheckForRefineGraph") v = h->max_check_refine;
+    else if (n == "NumberOfInitialDynamicPivots") v = h->initial_pivots;
+    else if (n == "NumberOfOtherDynamicPivots") v = h->other_pivots;
+    else if (n == "ThresholdOfNumberOfContinuousNoBetterPropagation") v = h->no_better_threshold;
+    else if (n == "B200.QueriesPerSM") v = h->queries_per_sm;
+    else if (n == "B200.StageRows") v = h->stage_rows;
+    else if (n == "B200.Stages") v = h->stages;
+    else if (n == "B200.NGCacheEntries") v = h->h_ng;
+    else if (n == "B200.SPTCacheEntries") v = h->h_spt;
+    else if (n == "B200.SimdWidth") v = h->simd_width;
+    else return fail(SPTAG_B200_PARAM_NOT_FOUND, "unknown parameter %s", name);
+    snprintf(value_out, (size_t)capacity, "%ld", v);
+    return SPTAG_B200_SUCCESS;
+}
+
+int sptag_b200_search_device(sptag_b200_handle h, const void* d_queries, int32_t num_queries, int32_t k,
+                             int32_t* d_out_ids, float* d_out_dists, int32_t* d_out_stats, void* cuda_stream) {
+    if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
+    if (num_queries < 0 || (num_queries > 0 && (!d_queries || !d_out_ids || !d_out_dists)))
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "null buffer");
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceGuard guard(h->device);
+    return search_device_impl(h, d_queries, num_queries, k, d_out_ids, d_out_dists, d_out_stats,
+                              (cudaStream_t)cuda_stream);
+}
+
+int sptag_b200_search(sptag_b200_handle h, const void* queries, int32_t num_queries, int32_t k, int32_t* out_ids,
+                      float* out_dists, int32_t* out_stats) {
+    if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
+    if (num_queries < 0 || (num_queries > 0 && (!queries || !out_ids || !out_dists)))
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "null buffer");
+    if (num_queries == 0) return SPTAG_B200_SUCCESS;
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceGuard guard(h->device);
+    const size_t qbytes = (size_t)num_queries * h->dim * value_size(h->value_type);
+    const size_t rn = (size_t)num_queries * k;
+    if (int rc = h->d_queries.ensure(qbytes)) return rc;
+    if (int rc = h->d_ids.ensure(rn * 4)) return rc;
+    if (int rc = h->d_dists.ensure(rn * 4)) return rc;
+    if (out_stats)
+        if (int rc = h->d_stats.ensure((size_t)num_queries * kStatsPerQuery * 4)) return rc;
+    cudaStream_t stream = nullptr;
+    CUDA_OK(cudaMemcpyAsync(h->d_queries.ptr, queries, qbytes, cudaMemcpyHostToDevice, stream));
+    if (int rc = search_device_impl(h, h->d_queries.ptr, num_queries, k, (int*)h->d_ids.ptr, (float*)h->d_dists.ptr,
+                                    out_stats ? (int*)h->d_stats.ptr : nullptr, stream))
+        return rc;
+    CUDA_OK(cudaMemcpyAsync(out_ids, h->d_ids.ptr, rn * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemcpyAsync(out_dists, h->d_dists.ptr, rn * 4, cudaMemcpyDeviceToHost, stream));
+    if (out_stats)
+        CUDA_OK(cudaMemcpyAsync(out_stats, h->d_stats.ptr, (size_t)num_queries * kStatsPerQuery * 4,
+                                cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    return SPTAG_B200_SUCCESS;
+}
+
+int sptag_b200_distance_batch(sptag_b200_handle h, const void* queries, int32_t num_queries, const int32_t* ids,
+                              int32_t ids_per_query, float* out) {
+    if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
+    if (!queries || !ids || !out || num_queries <= 0 || ids_per_query <= 0)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "null buffer");
+    if (h->value_type != SPTAG_B200_VT_FLOAT)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "only float vectors are supported in this build");
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceGuard guard(h->device);
+    const size_t qbytes = (size_t)num_queries * h->dim * 4;
+    const size_t total = (size_t)num_queries * ids_per_query;
+    DeviceBuffer dq, di, dout;
+    int rc = 0;
+    if ((rc = dq.ensure(qbytes)) || (rc = di.ensure(total * 4)) || (rc = dout.ensure(total * 4))) {
+        dq.release(); di.release(); dout.release();
+        return rc;
+    }
+    cudaMemcpy(dq.ptr, queries, qbytes, cudaMemcpyHostToDevice);
+    cudaMemcpy(di.ptr, ids, total * 4, cudaMemcpyHostToDevice);
+    const long long halfwarps = (long long)((total + 1) / 2) * 2;
+    const int threads = 256;
+    const long long blocks = (halfwarps * 16 + threads - 1) / threads;
+    if (h->metric == SPTAG_B200_METRIC_L2)
+        distance_batch_kernel<false><<<(unsigned)blocks, threads>>>((const unsigned char*)h->d_vectors.ptr,
+                                                                   h->row_stride, h->n, h->dim, (const float*)dq.ptr,
+                                                                   num_queries, (const int*)di.ptr, ids_per_query,
+                                                                   (float*)dout.ptr);
+    else
+        distance_batch_kernel<true><<<(unsigned)blocks, threads>>>((const unsigned char*)h->d_vectors.ptr,
+                                                                  h->row_stride, h->n, h->dim, (const float*)dq.ptr,
+                                                                  num_queries, (const int*)di.ptr, ids_per_query,
+                                                                  (float*)dout.ptr);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout.ptr, total * 4, cudaMemcpyDeviceToHost);
+    dq.release(); di.release(); dout.release();
+    if (e != cudaSuccess) return fail(SPTAG_B200_FAIL, "distance_batch failed: %s", cudaGetErrorString(e));
+    return SPTAG_B200_SUCCESS;
+}
+
+int sptag_b200_merge_topk(int32_t device, const int32_t* d_ids, const float* d_dists, int32_t num_lists,
+                          int32_t num_queries, int32_t k, int32_t* d_out_ids, float* d_out_dists, void* cuda_stream) {
+    if (!d_ids || !d_dists || !d_out_ids || !d_out_dists) return fail(SPTAG_B200_LACK_OF_INPUTS, "null buffer");
+    if (num_lists < 1 || num_lists > 16) return fail(SPTAG_B200_LACK_OF_INPUTS, "num_lists %d outside [1,16]", num_lists);
+    if (num_queries <= 0 || k <= 0) return SPTAG_B200_SUCCESS;
+    if (device < 0) CUDA_OK(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    const int threads = 128;
+    merge_topk_kernel<<<(num_queries + threads - 1) / threads, threads, 0, (cudaStream_t)cuda_stream>>>(
+        d_ids, d_dists, num_lists, num_queries, k, d_out_ids, d_out_dists);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return SPTAG_B200_SUCCESS;
+}
+
+int sptag_b200_last_kernel_ms(sptag_b200_handle h, float* ms_out) {
+    if (!h || !ms_out) return fail(SPTAG_B200_LACK_OF_INPUTS, "null argument");
+    if (!h->timed) return fail(SPTAG_B200_FAIL, "no search has run on this handle yet");
+    DeviceGuard guard(h->device);
+    CUDA_OK(cudaEventSynchronize(h->ev_stop));
+    CUDA_OK(cudaEventElapsedTime(ms_out, h->ev_start, h->ev_stop));
+    return SPTAG_B200_SUCCESS;
+}
+
+int32_t sptag_b200_num_vectors(sptag_b200_handle h) { return h ? h->n : 0; }
+int32_t sptag_b200_dim(sptag_b200_handle h) { return h ? h->dim : 0; }
+int32_t sptag_b200_value_type(sptag_b200_handle h) { return h ? h->value_type : -1; }
+int32_t sptag_b200_metric(sptag_b200_handle h) { return h ? h->metric : -1; }
+int32_t sptag_b200_algo(sptag_b200_handle h) { return h ? h->algo : -1; }
+
+}  // extern "C"

@@ -1,0 +1,68 @@
+"""Generate the small reference index folders used by the parity tests (TEST INFRASTRUCTURE).
+
+Every index is BUILT AND SAVED BY THE UNMODIFIED REFERENCE (oracle/_ref/libsptag_ref.so:
+VectorIndex::BuildIndex + SaveIndex), so the files are exactly what the reference's own
+LoadIndex consumes.  Output goes to tests/_data/<name>/ (git-ignored, travels to the GPU box
+with the gpurun snapshot).  Run:  python tests/make_test_data.py [name ...]
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import reflib  # noqa: E402
+
+
+def _line_data():
+    # Test/src/AlgoTest.cpp:163-201: n=2000, dim=10, vec[i] = (i, ..., i)
+    n, m = 2000, 10
+    return (np.arange(n, dtype=np.float32)[:, None] * np.ones((1, m), np.float32)).copy()
+
+
+def _dup_data():
+    # many exact duplicates -> BKT duplicate groups (BKTree.h:598-609) and graph back-pointers
+    base = reflib.gen_iid(1500, 24, 11)
+    reps = np.concatenate([base, base[:400], base[:400], base[100:160]])
+    rng = np.random.default_rng(12)
+    return reps[rng.permutation(reps.shape[0])].copy()
+
+
+# name -> (algo, metric, data generator, queries generator, build params)
+SPECS = {
+    "algo_line_bkt": ("BKT", "L2", _line_data, lambda: np.array([[0] * 10, [2] * 10, [4] * 10], np.float32), ""),
+    "bkt_l2_20k_32": ("BKT", "L2", lambda: reflib.gen_iid(20000, 32, 1), lambda: reflib.gen_iid(500, 32, 2), ""),
+    "bkt_cos_10k_128": ("BKT", "Cosine", lambda: reflib.gen_lowrank(10000, 128, 16, 3),
+                        lambda: reflib.normalize_rows(reflib.gen_lowrank(300, 128, 16, 4)), ""),
+    "bkt_l2_10k_128": ("BKT", "L2", lambda: reflib.gen_iid(10000, 128, 5), lambda: reflib.gen_iid(300, 128, 6), ""),
+    "bkt_l2_5k_100": ("BKT", "L2", lambda: reflib.gen_iid(5000, 100, 7), lambda: reflib.gen_iid(200, 100, 8), ""),
+    "bkt_l2_3k_30": ("BKT", "L2", lambda: reflib.gen_iid(3000, 30, 17), lambda: reflib.gen_iid(200, 30, 18), ""),
+    "bkt_cos_3k_768": ("BKT", "Cosine", lambda: reflib.gen_lowrank(3000, 768, 32, 9),
+                       lambda: reflib.normalize_rows(reflib.gen_lowrank(100, 768, 32, 10)), ""),
+    "bkt_l2_dups": ("BKT", "L2", _dup_data, lambda: reflib.gen_iid(200, 24, 13), ""),
+    "kdt_l2_10k_64": ("KDT", "L2", lambda: reflib.gen_iid(10000, 64, 14), lambda: reflib.gen_iid(300, 64, 15), ""),
+}
+
+
+def make(name, force=False):
+    folder = os.path.join(reflib.DATA_DIR, name)
+    if os.path.exists(os.path.join(folder, "indexloader.ini")) and os.path.exists(
+            os.path.join(folder, "queries.npy")) and not force:
+        return folder
+    if not reflib.have_ref():
+        raise RuntimeError("oracle/_ref/libsptag_ref.so missing: run `make -C oracle ref` where /root/reference exists")
+    algo, metric, gen_data, gen_q, params = SPECS[name]
+    data = np.ascontiguousarray(gen_data())
+    t = time.time()
+    idx = reflib.RefIndex.build(algo, data, metric, threads=os.cpu_count() or 8, params=params)
+    idx.save(folder)
+    np.save(os.path.join(folder, "queries.npy"), np.ascontiguousarray(gen_q()))
+    print("built %-18s n=%d dim=%d in %.1fs" % (name, data.shape[0], data.shape[1], time.time() - t), flush=True)
+    return folder
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(SPECS)
+    for nm in names:
+        make(nm)

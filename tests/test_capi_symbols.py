@@ -1,0 +1,45 @@
+"""CPU test: the C-ABI library loads without a GPU and exports every symbol include/sptag_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "sptag_b200.h")
+LIB = os.path.join(ROOT, "sptag_b200", "lib", "libsptag_b200.so")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sptag_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_boundary():
+    syms = declared_symbols()
+    for must in ("sptag_b200_create", "sptag_b200_load", "sptag_b200_search", "sptag_b200_search_device",
+                 "sptag_b200_set_param", "sptag_b200_destroy", "sptag_b200_merge_topk"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(LIB):
+        import __graft_entry__
+        __graft_entry__.build()
+    L = ctypes.CDLL(LIB)
+    for s in declared_symbols():
+        assert hasattr(L, s), "libsptag_b200.so does not export %s" % s
+
+
+def test_python_binding_lists_the_same_symbols():
+    from sptag_b200 import capi
+    assert sorted(capi.EXPORTS) == declared_symbols()
+
+
+def test_null_handle_is_rejected_without_a_gpu():
+    from sptag_b200 import capi
+    L = capi.lib()
+    assert L.sptag_b200_search(None, None, 1, 1, None, None, None) == 0x15  # EmptyIndex
+    assert b"null handle" in L.sptag_b200_last_error()
+    assert L.sptag_b200_num_vectors(None) == 0

@@ -1,0 +1,215 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA search path, called through the C ABI,
+against the oracle (oracle/sptag_oracle.c) on the same reference-built index files -- ids bit-exact,
+distances bit-exact (same summation tree, tolerance 0 ulp; the north star allows 1e-4 relative),
+and the per-query work counters equal to the reference's WorkSpace counters."""
+import os
+
+import numpy as np
+import pytest
+
+import reflib
+from conftest import data_folder
+
+pytestmark = pytest.mark.gpu
+
+BKT_SETS = ["algo_line_bkt", "bkt_l2_20k_32", "bkt_cos_10k_128", "bkt_l2_10k_128", "bkt_l2_5k_100",
+            "bkt_l2_3k_30", "bkt_cos_3k_768", "bkt_l2_dups"]
+
+
+def _compare(idx, files, q, k, mc, tag):
+    from sptag_b200 import capi
+    idx.set_param("MaxCheck", mc)
+    ids, dists, stats = idx.search(q, k, want_stats=True)
+    o = reflib.OracleIndex(files)
+    o.max_check = mc
+    ids_o, d_o, st_o = o.search(q, k)
+    bad = np.nonzero((ids != ids_o).any(axis=1))[0]
+    assert bad.size == 0, "%s MaxCheck=%d: %d/%d queries differ, first %d: gpu %s oracle %s" % (
+        tag, mc, bad.size, q.shape[0], bad[0], ids[bad[0]], ids_o[bad[0]])
+    assert np.array_equal(dists.view(np.int32), d_o.view(np.int32)), (tag, mc)
+    for a, b in [(capi.ST_CHECKED, reflib.ST_CHECKED), (capi.ST_NG_LEFT, reflib.ST_NG_LEFT),
+                 (capi.ST_SPT_LEFT, reflib.ST_SPT_LEFT), (capi.ST_NDIST, reflib.ST_NDIST),
+                 (capi.ST_NEXPAND, reflib.ST_NEXPAND), (capi.ST_NTREE, reflib.ST_NTREE)]:
+        assert np.array_equal(stats[:, a], st_o[:, b]), (tag, mc, "stat", a)
+    assert not stats[:, capi.ST_FLAGS].any()
+
+
+@pytest.mark.parametrize("name", BKT_SETS)
+def test_bkt_search_bit_exact(name):
+    from sptag_b200 import B200Index
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))
+    k = 3 if name == "algo_line_bkt" else 10
+    idx = B200Index.load(folder)
+    try:
+        for mc in [8192, 1024, 64]:
+            _compare(idx, files, q, k, mc, name)
+    finally:
+        idx.close()
+
+
+def test_algo_line_known_answer_on_gpu():
+    # Test/src/AlgoTest.cpp:163-201
+    from sptag_b200 import B200Index
+    folder = data_folder("algo_line_bkt")
+    idx = B200Index.load(folder)
+    q = np.array([[0] * 10, [2] * 10, [4] * 10], np.float32)
+    ids, dists = idx.search(q, 3)
+    assert [set(r) for r in ids.tolist()] == [{0, 1, 2}, {2, 1, 3}, {4, 3, 5}]
+    assert dists.tolist() == [[0, 10, 40], [0, 10, 10], [0, 10, 10]]
+    idx.close()
+
+
+@pytest.mark.parametrize("knobs", [
+    {"B200.StageRows": 2, "B200.Stages": 1},
+    {"B200.StageRows": 6, "B200.Stages": 3},
+    {"B200.NGCacheEntries": 7, "B200.SPTCacheEntries": 5},       # nearly everything spills to HBM
+    {"B200.NGCacheEntries": 64, "B200.SPTCacheEntries": 4096},
+    {"B200.QueriesPerSM": 1},
+    {"B200.QueriesPerSM": 16},
+])
+def test_tuning_knobs_do_not_change_results(knobs):
+    from sptag_b200 import B200Index
+    folder = data_folder("bkt_l2_20k_32")
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:200]
+    idx = B200Index.load(folder)
+    for name, v in knobs.items():
+        idx.set_param(name, v)
+    try:
+        for mc in [2048, 128]:
+            _compare(idx, files, q, 10, mc, str(knobs))
+    finally:
+        idx.close()
+
+
+@pytest.mark.parametrize("k", [1, 5, 32])
+def test_result_counts(k):
+    from sptag_b200 import B200Index
+    folder = data_folder("bkt_l2_10k_128")
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:100]
+    idx = B200Index.load(folder)
+    try:
+        _compare(idx, files, q, k, 1024, "k=%d" % k)
+    finally:
+        idx.close()
+
+
+def test_full_heap_replacement_path():
+    # tiny MaxCheck AND tiny MaxCheckForRefineGraph make Heap::insert hit its count == length branch (Heap.h:43-49)
+    from sptag_b200 import B200Index
+    folder = data_folder("bkt_l2_20k_32")
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:200]
+    idx = B200Index.load(folder)
+    try:
+        for mc in [16, 48]:
+            idx.set_param("MaxCheck", mc)
+            idx.set_param("MaxCheckForRefineGraph", mc)
+            ids, dists, stats = idx.search(q, 10, want_stats=True)
+            o = reflib.OracleIndex(files)
+            o.max_check = mc
+            o.max_check_refine = mc
+            ids_o, d_o, st_o = o.search(q, 10)
+            assert np.array_equal(ids, ids_o)
+            assert np.array_equal(dists.view(np.int32), d_o.view(np.int32))
+            assert np.array_equal(stats[:, 3], st_o[:, reflib.ST_SPT_LEFT])
+    finally:
+        idx.close()
+
+
+def test_deleted_vectors_are_skipped():
+    from sptag_b200 import B200Index, capi
+    folder = data_folder("bkt_l2_10k_128")
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:100]
+    rng = np.random.default_rng(3)
+    deleted = (rng.random(files.n) < 0.3).astype(np.int8)
+    files.deleted = deleted
+    files.num_deleted = int(deleted.sum())
+    idx = B200Index.create(algo=capi.ALGO_BKT, value_type=capi.VT_FLOAT, metric=files.metric, vectors=files.vectors,
+                           graph=files.graph, tree_starts=files.tree_starts, tree_nodes=files.nodes[:files.node_count],
+                           deleted=deleted, num_deleted=files.num_deleted)
+    try:
+        idx.set_param("MaxCheck", 2048)
+        ids, dists = idx.search(q, 10)
+        o = reflib.OracleIndex(files)
+        o.max_check = 2048
+        ids_o, d_o, _ = o.search(q, 10)
+        assert np.array_equal(ids, ids_o)
+        assert np.array_equal(dists.view(np.int32), d_o.view(np.int32))
+        assert not deleted[ids[ids >= 0]].any()
+    finally:
+        idx.close()
+
+
+def test_id_offset_for_shards():
+    from sptag_b200 import B200Index
+    folder = data_folder("bkt_l2_3k_30")
+    q = np.load(os.path.join(folder, "queries.npy"))[:50]
+    a = B200Index.load(folder)
+    b = B200Index.load(folder, id_offset=1000000)
+    ia, da = a.search(q, 10)
+    ib, db = b.search(q, 10)
+    assert np.array_equal(np.where(ia >= 0, ia + 1000000, ia), ib)
+    assert np.array_equal(da, db)
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_distance_kernel_bit_exact_all_dims(metric):
+    """The inner loop alone (sptag_b200_distance_batch) vs the oracle's AVX-512 tree for many dims incl. tails."""
+    from sptag_b200 import B200Index, capi
+    rng = np.random.default_rng(11)
+    L = reflib.ora()
+    for dim in [1, 3, 4, 7, 8, 12, 15, 16, 17, 24, 28, 31, 32, 33, 64, 100, 127, 128, 131, 200, 384, 768, 960, 1000]:
+        n, nq, per = 257, 9, 33
+        x = rng.standard_normal((n, dim), dtype=np.float32)
+        q = rng.standard_normal((nq, dim), dtype=np.float32)
+        graph = np.full((n, 4), -1, np.int32)
+        nodes = np.array([[n, 1, 2], [0, -1, -1], [-1, -1, -1]], np.int32)
+        idx = B200Index.create(algo=capi.ALGO_BKT, value_type=capi.VT_FLOAT, metric=metric, vectors=x, graph=graph,
+                               tree_starts=np.array([0], np.int32), tree_nodes=nodes)
+        ids = rng.integers(0, n, (nq, per)).astype(np.int32)
+        ids[0, 0] = -1
+        out = idx.distance_batch(q, ids)
+        exp = np.empty_like(out)
+        for i in range(nq):
+            a = np.ascontiguousarray(np.repeat(q[i:i + 1], per, 0))
+            b = np.ascontiguousarray(x[np.maximum(ids[i], 0)])
+            L.ora_distance_f32_many(metric, 16, a.ctypes.data, b.ctypes.data, dim, per, exp[i].ctypes.data)
+        exp[0, 0] = L.ora_max_dist()
+        assert np.array_equal(out.view(np.int32), exp.view(np.int32)), dim
+        idx.close()
+
+
+def test_merge_topk_matches_comparator():
+    import torch
+    from sptag_b200 import capi
+    rng = np.random.default_rng(5)
+    G, nq, k = 4, 300, 10
+    d = np.sort(rng.integers(0, 50, (G, nq, k)).astype(np.float32), axis=2)  # many ties
+    ids = rng.permutation(G * nq * k).astype(np.int32).reshape(G, nq, k)
+    # sort each list by (dist, id)
+    for g in range(G):
+        for i in range(nq):
+            order = np.lexsort((ids[g, i], d[g, i]))
+            ids[g, i], d[g, i] = ids[g, i][order], d[g, i][order]
+    ids[1, :, 7:] = -1
+    d[1, :, 7:] = reflib.ora().ora_max_dist()
+    t_ids = torch.from_numpy(ids).cuda()
+    t_d = torch.from_numpy(d).cuda()
+    o_ids = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    o_d = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    capi.merge_topk(0, t_ids.data_ptr(), t_d.data_ptr(), G, nq, k, o_ids.data_ptr(), o_d.data_ptr(),
+                    torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for i in range(nq):
+        cand = [(d[g, i, j], ids[g, i, j]) for g in range(G) for j in range(k) if ids[g, i, j] >= 0]
+        cand.sort()
+        exp = cand[:k]
+        assert o_ids[i].tolist() == [c[1] for c in exp]
+        assert o_d[i].tolist() == [c[0] for c in exp]

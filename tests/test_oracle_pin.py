@@ -1,0 +1,175 @@
+"""CPU tests: pin the C restatement (oracle/sptag_oracle.c) against
+
+1. the reference's own known-answer tests (Test/src/AlgoTest.cpp:163-201,
+   Test/cuda/distance_tests.cu:15-17, Test/src/DistanceTest.cpp:36-50),
+2. committed golden vectors produced by the UNMODIFIED reference (tests/golden/*.npz,
+   generator tests/golden/make_golden.py),
+3. the reference itself (oracle/_ref/libsptag_ref.so), bit for bit, where it is available.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import reflib
+from conftest import data_folder
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+needs_ref = pytest.mark.skipif(not reflib.have_ref(), reason="oracle/_ref not built on this box")
+
+
+def _ora_dist(metric, width, a, b):
+    L = reflib.ora()
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    return L.ora_distance(metric, reflib.VT_FLOAT, width, a.ctypes.data, b.ctypes.data, a.shape[0])
+
+
+# ---------------------------------------------------------------------------------------------
+# known answers from the reference's tests
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [4, 10, 16, 100, 128, 384, 768])
+@pytest.mark.parametrize("width", [16, 8, 4, 1])
+def test_static_distances_known_answer(oracle_lib, dim, width):
+    # Test/cuda/distance_tests.cu:15-17: vectors (0..), (1..), (2..): L2 = {D, 4D, D}, cosine = {BASE, BASE, BASE-2D}
+    v = [np.full(dim, i, np.float32) for i in range(3)]
+    assert _ora_dist(0, width, v[0], v[1]) == dim
+    assert _ora_dist(0, width, v[0], v[2]) == 4 * dim
+    assert _ora_dist(0, width, v[1], v[2]) == dim
+    assert _ora_dist(1, width, v[0], v[1]) == 1
+    assert _ora_dist(1, width, v[0], v[2]) == 1
+    assert _ora_dist(1, width, v[1], v[2]) == 1 - 2 * dim
+
+
+@pytest.mark.parametrize("width", [16, 8, 4, 1])
+def test_simd_tree_close_to_naive(oracle_lib, width):
+    # Test/src/DistanceTest.cpp:36-50: SIMD result within 1e-5 relative of the naive scalar loop,
+    # cosine convention base^2 - dot, random dimension in [2, 256), values in (-1, 1)
+    rng = np.random.default_rng(123)
+    for _ in range(200):
+        dim = int(rng.integers(2, 256))
+        x = rng.uniform(-1, 1, dim).astype(np.float32)
+        y = rng.uniform(-1, 1, dim).astype(np.float32)
+        l2 = float(((x.astype(np.float64) - y.astype(np.float64)) ** 2).sum())
+        cos = 1.0 - float((x.astype(np.float64) * y.astype(np.float64)).sum())
+        assert _ora_dist(0, width, x, y) == pytest.approx(l2, rel=1e-5)
+        assert _ora_dist(1, width, x, y) == pytest.approx(cos, rel=1e-5, abs=1e-5)
+
+
+def test_algo_line_known_answer(oracle_lib):
+    # Test/src/AlgoTest.cpp:163-201: vec[i] = (i)*10, n = 2000, queries 0/2/4, k = 3, L2
+    # expected id sets {0,1,2}, {2,1,3}, {4,3,5}; distances 0, 10, 40
+    path = os.path.join(GOLDEN, "algo_line_bkt.npz")
+    g = np.load(path)
+    files = reflib.IndexFiles.__new__(reflib.IndexFiles)
+    _files_from_npz(files, g)
+    o = reflib.OracleIndex(files)
+    q = np.array([[0] * 10, [2] * 10, [4] * 10], np.float32)
+    ids, dists, _ = o.search(q, 3)
+    assert [set(r) for r in ids.tolist()] == [{0, 1, 2}, {2, 1, 3}, {4, 3, 5}]
+    assert dists.tolist() == [[0, 10, 40], [0, 10, 10], [0, 10, 10]]
+
+
+# ---------------------------------------------------------------------------------------------
+# committed golden vectors (index arrays + the reference's outputs on them)
+# ---------------------------------------------------------------------------------------------
+def _files_from_npz(files, g):
+    files.folder = None
+    files.params = {k: str(v) for k, v in zip(g["param_names"].tolist(), g["param_values"].tolist())}
+    files.algo = files.params["IndexAlgoType"]
+    files.value_type = reflib.VT_OF_NAME[files.params["ValueType"]]
+    files.metric = reflib.METRIC_OF_NAME[files.params["DistCalcMethod"]]
+    files.vectors = np.ascontiguousarray(g["vectors"])
+    files.n, files.dim = files.vectors.shape
+    files.graph = np.ascontiguousarray(g["graph"])
+    files.degree = files.graph.shape[1]
+    files.tree_starts = np.ascontiguousarray(g["tree_starts"])
+    files.tree_num = files.tree_starts.shape[0]
+    files.nodes = np.ascontiguousarray(g["nodes"])
+    files.node_count = files.nodes.shape[0]
+    files.deleted = np.ascontiguousarray(g["deleted"]) if "deleted" in g.files else None
+    files.num_deleted = int(g["num_deleted"]) if "num_deleted" in g.files else 0
+
+
+def golden_cases():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_oracle_matches_golden_reference_outputs(oracle_lib, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    files = reflib.IndexFiles.__new__(reflib.IndexFiles)
+    _files_from_npz(files, g)
+    q = g["queries"]
+    for i, mc in enumerate(g["max_checks"].tolist()):
+        o = reflib.OracleIndex(files)
+        o.max_check = int(mc)
+        k = int(g["k"])
+        ids, dists, stats = o.search(q, k)
+        assert np.array_equal(ids, g["ref_ids"][i]), (name, mc)
+        assert np.array_equal(dists.view(np.int32), g["ref_dists"][i].view(np.int32)), (name, mc)
+        # WorkSpace counters of the reference (m_iNumberOfCheckedLeaves, NGQueue/SPTQueue sizes)
+        assert np.array_equal(stats[:, reflib.ST_CHECKED], g["ref_stats"][i][:, 0]), (name, mc)
+        assert np.array_equal(stats[:, reflib.ST_NG_LEFT], g["ref_stats"][i][:, 2]), (name, mc)
+        assert np.array_equal(stats[:, reflib.ST_SPT_LEFT], g["ref_stats"][i][:, 3]), (name, mc)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference itself
+# ---------------------------------------------------------------------------------------------
+@needs_ref
+@pytest.mark.parametrize("metric", [0, 1])
+def test_distance_bit_exact_vs_reference_all_trees(oracle_lib, metric):
+    rng = np.random.default_rng(7)
+    R = reflib.ref()
+    for dim in [1, 2, 3, 4, 5, 7, 8, 9, 12, 15, 16, 17, 20, 24, 28, 31, 32, 33, 48, 63, 64, 100, 127, 128, 131, 200,
+                256, 384, 768, 960, 1000, 1024]:
+        n = 300
+        a = rng.standard_normal((n, dim), dtype=np.float32)
+        b = rng.standard_normal((n, dim), dtype=np.float32)
+        for isa, width in [(512, 16), (256, 8), (128, 4), (0, 1)]:
+            out_r = np.empty(n, np.float32)
+            out_o = np.empty(n, np.float32)
+            R.ref_distance_f32_many(isa, metric, a.ctypes.data, b.ctypes.data, dim, n, out_r.ctypes.data)
+            oracle_lib.ora_distance_f32_many(metric, width, a.ctypes.data, b.ctypes.data, dim, n, out_o.ctypes.data)
+            assert np.array_equal(out_r.view(np.int32), out_o.view(np.int32)), (dim, isa)
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["algo_line_bkt", "bkt_l2_20k_32", "bkt_cos_10k_128", "bkt_l2_5k_100",
+                                  "bkt_l2_3k_30", "bkt_l2_dups", "kdt_l2_10k_64"])
+def test_search_bit_exact_vs_reference(oracle_lib, name):
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))
+    r = reflib.RefIndex.load(folder)
+    width = {512: 16, 256: 8, 128: 4, 0: 1}[reflib.ref().ref_isa()]
+    k = 10 if files.n > 100 and name != "algo_line_bkt" else 3
+    for mc in [8192, 2048, 512, 64]:
+        r.set_param("MaxCheck", mc)
+        ids_r, d_r, _ = r.search(q, k, threads=4)
+        o = reflib.OracleIndex(files, simd_width=width)
+        o.max_check = mc
+        ids_o, d_o, _ = o.search(q, k, threads=4)
+        assert np.array_equal(ids_r, ids_o), (name, mc)
+        assert np.array_equal(d_r.view(np.int32), d_o.view(np.int32)), (name, mc)
+
+
+@needs_ref
+def test_counters_match_reference_workspace(oracle_lib):
+    folder = data_folder("bkt_l2_20k_32")
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:40]
+    r = reflib.RefIndex.load(folder)
+    assert r.enable_stats() == 0
+    for mc in [4096, 256]:
+        r.set_param("MaxCheck", mc)
+        o = reflib.OracleIndex(files)
+        o.max_check = mc
+        _, _, st = o.search(q, 10)
+        for i in range(q.shape[0]):
+            _, _, rs = r.search_one_stats(q[i], 10)
+            assert rs[0] == st[i, reflib.ST_CHECKED]
+            assert rs[2] == st[i, reflib.ST_NG_LEFT]
+            assert rs[3] == st[i, reflib.ST_SPT_LEFT]
