@@ -1,0 +1,333 @@
+"""GPU index builder for bench/test SET-UP (not part of the search hot path, not shipped in the
+C-ABI library).
+
+The reference's own builder (BKT::Index::BuildIndex: balanced k-means tree + TP-tree KNN + refine,
+BKTIndex.cpp:739-772) needs hours for 1M x 768 on a few host cores, so the
+bench cannot build its index with it inside one GPU lease.  This module builds, with plain torch
+ops on the GPU, an index with the SAME data structures the reference searches and persists:
+
+  * a BKT (BKTree.h:25-32, :546-627): every data point is exactly one tree node; internal nodes hold
+    the member nearest to a k-means centroid (K = BKTKmeansK = 32), sets <= BKTLeafSize (8) become leaf
+    children, the root has centerid = N, a (-1,-1,-1) sentinel ends the array;
+  * a fixed-degree relative-neighbourhood graph (RelativeNeighborhoodGraph.h:18-35 prune rule applied
+    to the `cand` nearest neighbours of every point), rows -1 padded (NeighborhoodGraph.h:626-649);
+
+and writes them in the reference's on-disk format (indexloader.ini, vectors.bin, tree.bin, graph.bin,
+deletes.bin: VectorIndex.cpp:197-222, Dataset.h:146-180, BKTree.h:635-645, NeighborhoodGraph.h:606-615,
+Labelset.h:78-83), so the UNMODIFIED reference loads the very same folder (VectorIndex::LoadIndex) for
+the CPU baseline.  Parity is defined on identical index files, so any index the reference can load is
+a legitimate input; this one is merely fast to make.
+"""
+import math
+import os
+import time
+
+import numpy as np
+import torch
+
+
+def _sq_norms(x):
+    return (x.float() ** 2).sum(1)
+
+
+# ---------------------------------------------------------------------------------------------
+# BKT
+# ---------------------------------------------------------------------------------------------
+def _assign_dense(x, xn, pts, slot, cent, centn, K, chunk_cols_budget=1 << 27):
+    """For points `pts` (ids) whose group slot is `slot`, return argmin over the K centroids of that
+    slot and the distance.  cent: [P*K, dim] (slot-major).  Dense GEMM against all P*K centroids,
+    then each point gathers its own K columns."""
+    P = cent.shape[0] // K
+    n = pts.shape[0]
+    best = torch.empty(n, dtype=torch.int64, device=x.device)
+    bestd = torch.empty(n, dtype=torch.float32, device=x.device)
+    chunk = max(256, min(n, chunk_cols_budget // max(1, P * K)))
+    ar = torch.arange(K, device=x.device)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        ids = pts[s:e]
+        xs = x[ids]
+        if P == 1:
+            d = xn[ids][:, None] - 2.0 * (xs @ cent.t()) + centn[None, :]
+        else:
+            full = xs @ cent.t()  # [c, P*K]
+            cols = slot[s:e, None] * K + ar[None, :]
+            d = xn[ids][:, None] - 2.0 * torch.gather(full, 1, cols) + centn[cols]
+            del full
+        dm, am = d.min(dim=1)
+        best[s:e] = am
+        bestd[s:e] = dm
+    return best, bestd
+
+
+def build_bkt(x, kmeans_k=32, leaf_size=8, iters=2, seed=0, log=None):
+    """Returns (nodes int32 [N+2, 3] on CPU, tree_starts int32 [1])."""
+    dev = x.device
+    N = x.shape[0]
+    K = kmeans_k
+    final_t = K * (leaf_size + 1)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    xn = _sq_norms(x)
+    nodes = torch.full((N + 2, 3), -1, dtype=torch.int32, device=dev)
+    nodes[0, 0] = N
+    next_free = 1
+    # open groups: parent node index per group, members sorted by group, offsets
+    grp_parent = torch.zeros(1, dtype=torch.int64, device=dev)
+    members = torch.randperm(N, generator=g, device=dev)
+    offsets = torch.tensor([0, N], dtype=torch.int64, device=dev)
+    level = 0
+    while grp_parent.numel() > 0:
+        P = grp_parent.numel()
+        sizes = offsets[1:] - offsets[:-1]
+        gid = torch.repeat_interleave(torch.arange(P, device=dev), sizes)  # group of each member
+        pos = torch.arange(members.numel(), device=dev) - offsets[:-1][gid]  # position inside its group
+        small = sizes <= leaf_size
+        big = sizes > final_t
+        mid = ~small & ~big
+
+        # number of children per group
+        nchild = torch.zeros(P, dtype=torch.int64, device=dev)
+        nchild[small] = sizes[small]
+        nchild[mid] = (sizes[mid] + leaf_size) // (leaf_size + 1)
+
+        # ---- big groups: k-means with K centroids, centre = member nearest its centroid ----
+        child_of_member = torch.full_like(members, -1)  # local child rank (0..nchild-1) of each member
+        is_center = torch.zeros_like(members, dtype=torch.bool)
+        if big.any():
+            bslot_of_group = torch.full((P,), -1, dtype=torch.int64, device=dev)
+            bidx = torch.nonzero(big).flatten()
+            Pb = bidx.numel()
+            bslot_of_group[bidx] = torch.arange(Pb, device=dev)
+            msel = big[gid]
+            bm = members[msel]
+            bslot = bslot_of_group[gid[msel]]
+            bpos = pos[msel]
+            # init: the first K members of each (already shuffled) group
+            cent = torch.zeros((Pb * K, x.shape[1]), dtype=torch.float32, device=dev)
+            init = bpos < K
+            cent[bslot[init] * K + bpos[init]] = x[bm[init]].float()
+            for it in range(iters + 1):
+                centn = _sq_norms(cent)
+                a, ad = _assign_dense(x, xn, bm, bslot, cent, centn, K)
+                key = bslot * K + a
+                if it == iters:
+                    break
+                cnt = torch.bincount(key, minlength=Pb * K).float()
+                newc = torch.zeros_like(cent)
+                newc.index_add_(0, key, x[bm].float())
+                nz = cnt > 0
+                cent[nz] = newc[nz] / cnt[nz, None]
+            cnt = torch.bincount(key, minlength=Pb * K)
+            # centre of each non-empty cluster = member with the smallest distance to the centroid
+            mind = torch.full((Pb * K,), float("inf"), device=dev)
+            mind.scatter_reduce_(0, key, ad, reduce="amin")
+            cand = torch.nonzero(ad <= mind[key]).flatten()
+            first = torch.full((Pb * K,), bm.numel(), dtype=torch.int64, device=dev)
+            first.scatter_reduce_(0, key[cand], cand, reduce="amin")
+            nonempty = cnt > 0
+            # local child rank of each cluster inside its group
+            rank = (torch.cumsum(nonempty.view(Pb, K).long(), dim=1) - 1).view(-1)
+            nchild[bidx] = nonempty.view(Pb, K).sum(1)
+            midx = torch.nonzero(msel).flatten()
+            child_of_member[midx] = rank[key]
+            cpos = first[nonempty]
+            is_center[midx[cpos]] = True
+
+        # ---- mid groups: ceil(s / (leaf+1)) children, first c members are centres, rest round-robin ----
+        if mid.any():
+            msel = mid[gid]
+            c = nchild[gid[msel]]
+            p = pos[msel]
+            midx = torch.nonzero(msel).flatten()
+            child_of_member[midx] = p % c
+            is_center[midx[p < c]] = True
+
+        # ---- small groups: every member is a leaf child ----
+        if small.any():
+            msel = small[gid]
+            midx = torch.nonzero(msel).flatten()
+            child_of_member[midx] = pos[msel]
+            is_center[midx] = True
+
+        # ---- allocate child nodes (contiguous per parent) ----
+        cstart = next_free + torch.cumsum(nchild, 0) - nchild
+        nodes[grp_parent, 1] = cstart.int()
+        nodes[grp_parent, 2] = (cstart + nchild).int()
+        total_children = int(nchild.sum().item())
+        child_node = cstart[gid] + child_of_member  # node index of the child each member falls under
+        cm = torch.nonzero(is_center).flatten()
+        nodes[child_node[cm], 0] = members[cm].int()
+        next_free += total_children
+
+        # ---- next level: non-centre members grouped by child node ----
+        rest = torch.nonzero(~is_center).flatten()
+        if rest.numel() == 0:
+            break
+        ckey = child_node[rest]
+        order = torch.argsort(ckey, stable=True)
+        ckey = ckey[order]
+        members = members[rest][order]
+        uniq, counts = torch.unique_consecutive(ckey, return_counts=True)
+        grp_parent = uniq
+        offsets = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(counts, 0)])
+        if log:
+            log("bkt level %d: %d groups, %d nodes so far" % (level, P, next_free))
+        level += 1
+    assert next_free == N + 1, (next_free, N)
+    return nodes.cpu().numpy(), np.array([0], np.int32)
+
+
+# ---------------------------------------------------------------------------------------------
+# relative-neighbourhood graph
+# ---------------------------------------------------------------------------------------------
+def build_rng_graph(x, degree=32, cand=64, rng_factor=1.0, fill=True, row_chunk=None, log=None):
+    """Exact `cand`-nearest neighbours by brute force, then the RNG prune rule of
+    RelativeNeighborhoodGraph::RebuildNeighbors; with fill=True the rows are then topped up with the
+    nearest rejected candidates (the reference prunes ~1000 candidates per node and ends with rows that
+    are ~90% full; pruning only `cand` would leave rows a third full, which is not the workload the
+    reference's searches see).  Returns int32 [N, degree] on CPU (-1 padded)."""
+    dev = x.device
+    N, dim = x.shape
+    cand = min(cand, N - 1)
+    xn = _sq_norms(x)
+    graph = torch.full((N, degree), -1, dtype=torch.int32, device=dev)
+    if row_chunk is None:
+        row_chunk = max(64, min(8192, (1 << 31) // max(1, N)))  # <= 8 GiB of fp32 scores per chunk
+    sub = max(64, min(row_chunk, (1 << 28) // max(1, cand * dim)))  # gather chunk: <= 1 GiB fp32
+    t0 = time.time()
+    for s in range(0, N, row_chunk):
+        e = min(N, s + row_chunk)
+        d = xn[s:e, None] - 2.0 * (x[s:e] @ x.t()) + xn[None, :]
+        d[torch.arange(e - s, device=dev), torch.arange(s, e, device=dev)] = float("inf")
+        dn, idx = torch.topk(d, cand, dim=1, largest=False, sorted=True)
+        del d
+        for ss in range(0, e - s, sub):
+            ee = min(e - s, ss + sub)
+            ci = idx[ss:ee]                       # [b, cand]
+            cd = dn[ss:ee]
+            cv = x[ci.reshape(-1)].view(ee - ss, cand, dim)
+            cn = xn[ci]
+            pd = cn[:, :, None] - 2.0 * torch.bmm(cv, cv.transpose(1, 2)) + cn[:, None, :]
+            del cv
+            acc = torch.zeros((ee - ss, cand), dtype=torch.bool, device=dev)
+            count = torch.zeros(ee - ss, dtype=torch.int64, device=dev)
+            out = torch.full((ee - ss, degree), -1, dtype=torch.int32, device=dev)
+            rows = torch.arange(ee - ss, device=dev)
+            for j in range(cand):
+                bad = ((pd[:, :, j] * rng_factor < cd[:, j, None]) & acc).any(dim=1)
+                ok = ~bad & (count < degree)
+                acc[:, j] = ok
+                r = rows[ok]
+                out[r, count[ok]] = ci[ok, j].int()
+                count += ok.long()
+            if fill:
+                for j in range(cand):
+                    ok = ~acc[:, j] & (count < degree)
+                    r = rows[ok]
+                    out[r, count[ok]] = ci[ok, j].int()
+                    count += ok.long()
+            graph[s + ss:s + ee] = out
+        if log and (s // row_chunk) % 16 == 0:
+            log("graph rows %d/%d (%.1fs)" % (e, N, time.time() - t0))
+    return graph.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# folder writer (reference on-disk format) and exact ground truth
+# ---------------------------------------------------------------------------------------------
+INI_TEMPLATE = """[Index]
+IndexAlgoType=BKT
+ValueType=Float
+
+TreeFilePath=tree.bin
+GraphFilePath=graph.bin
+VectorFilePath=vectors.bin
+DeleteVectorFilePath=deletes.bin
+EnableBfs=0
+BKTNumber=1
+BKTKmeansK={kmeans_k}
+BKTLeafSize={leaf_size}
+Samples=1000
+BKTLambdaFactor=100.000000
+TPTNumber=32
+TPTLeafSize=2000
+NumTopDimensionTpTreeSplit=5
+NeighborhoodSize={degree}
+GraphNeighborhoodScale=2.000000
+GraphCEFScale=2.000000
+RefineIterations=2
+EnableRebuild=0
+CEF=1000
+AddCEF=500
+MaxCheckForRefineGraph=8192
+RNGFactor=1.000000
+GPUGraphType=2
+GPURefineSteps=0
+GPURefineDepth=30
+GPULeafSize=500
+HeadNumGPUs=1
+TPTBalanceFactor=2
+NumberOfThreads={threads}
+DistCalcMethod={metric}
+DeletePercentageForRefine=0.400000
+AddCountForRebuild=1000
+MaxCheck=8192
+ThresholdOfNumberOfContinuousNoBetterPropagation=3
+NumberOfInitialDynamicPivots=50
+NumberOfOtherDynamicPivots=4
+HashTableExponent=2
+DataBlockSize=1048576
+DataCapacity=2147483647
+MetaRecordSize=10
+"""
+
+
+def save_index_folder(folder, vectors, graph, nodes, tree_starts, metric, kmeans_k=32, leaf_size=8):
+    """vectors: float32 numpy [N, dim] (already normalised for cosine)."""
+    os.makedirs(folder, exist_ok=True)
+    N, dim = vectors.shape
+    with open(os.path.join(folder, "vectors.bin"), "wb") as f:
+        np.array([N, dim], np.int32).tofile(f)
+        np.ascontiguousarray(vectors, np.float32).tofile(f)
+    with open(os.path.join(folder, "graph.bin"), "wb") as f:
+        np.array([N, graph.shape[1]], np.int32).tofile(f)
+        np.ascontiguousarray(graph, np.int32).tofile(f)
+    with open(os.path.join(folder, "tree.bin"), "wb") as f:
+        np.array([tree_starts.shape[0]], np.int32).tofile(f)
+        np.ascontiguousarray(tree_starts, np.int32).tofile(f)
+        np.array([nodes.shape[0]], np.int32).tofile(f)
+        np.ascontiguousarray(nodes, np.int32).tofile(f)
+    with open(os.path.join(folder, "deletes.bin"), "wb") as f:
+        np.array([0, N, 1], np.int32).tofile(f)  # Labelset: deleted count, then Dataset<int8>(N x 1)
+        np.zeros(N, np.int8).tofile(f)
+    with open(os.path.join(folder, "indexloader.ini"), "w") as f:
+        f.write(INI_TEMPLATE.format(kmeans_k=kmeans_k, leaf_size=leaf_size, degree=graph.shape[1],
+                                    threads=os.cpu_count() or 1, metric=metric))
+
+
+def exact_topk(x, q, k, metric, chunk=2048):
+    """Exact ground truth ids [nq, k] (L2: squared distance; Cosine: 1 - dot on unit vectors)."""
+    out = []
+    xn = _sq_norms(x)
+    for s in range(0, q.shape[0], chunk):
+        qs = q[s:s + chunk]
+        if metric == "L2":
+            d = (qs ** 2).sum(1)[:, None] - 2.0 * (qs @ x.t()) + xn[None, :]
+        else:
+            d = 1.0 - qs @ x.t()
+        out.append(torch.topk(d, k, dim=1, largest=False).indices)
+    return torch.cat(out).cpu().numpy()
+
+
+def build_index(x, metric="L2", degree=32, cand=64, kmeans_k=32, leaf_size=8, seed=0, log=None):
+    """x: float32 tensor [N, dim] on the build device (unit rows for Cosine). Returns numpy arrays."""
+    t = time.time()
+    nodes, starts = build_bkt(x, kmeans_k=kmeans_k, leaf_size=leaf_size, seed=seed, log=log)
+    t_tree = time.time() - t
+    t = time.time()
+    graph = build_rng_graph(x, degree=degree, cand=cand, log=log)
+    t_graph = time.time() - t
+    if log:
+        log("index built: tree %.1fs, graph %.1fs" % (t_tree, t_graph))
+    return nodes, starts, graph
