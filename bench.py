@@ -348,8 +348,8 @@ def main():
 
     gathered_ids = gathered_d = m_ids = m_d = None
     if args.mode == "shard" and world > 1:
-        gathered_ids = torch.empty((world, args.nq, args.k), dtype=torch.int32, device=dev)
-        gathered_d = torch.empty((world, args.nq, args.k), dtype=torch.float32, device=dev)
+        gathered_ids = torch.empty((world * args.nq, args.k), dtype=torch.int32, device=dev)
+        gathered_d = torch.empty((world * args.nq, args.k), dtype=torch.float32, device=dev)
         m_ids = torch.empty_like(d_ids)
         m_d = torch.empty_like(d_dists)
 
@@ -460,7 +460,7 @@ def main():
     kernel_ms = float(np.mean(kms))
     achieved = alg_bytes / (kernel_ms / 1000.0) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "bkt_search_kernel", "kernel_ms": kernel_ms,
+                "traffic": None, "kernel": "search_kernel<%d,%s,BKT>" % (args.dim if args.dim in (128, 768) else 0, args.metric), "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "share_of_step": kernel_ms / ms_step}
 

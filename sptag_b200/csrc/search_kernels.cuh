@@ -358,6 +358,7 @@ struct WarpSearch {
     QueryRegs<DIM> qr;
     // counters
     int checked, ndist, nexpand, ntree;
+    int tree_checked, no_better;  // KDT: m_iNumberOfTreeCheckedLeaves, m_iNumOfContinuousNoBetterPropagation
     unsigned phase_bits;
 
     __device__ __forceinline__ WarpSearch(const SearchParams& p_, int lane_)
@@ -560,13 +561,112 @@ struct WarpSearch {
             if (heap_top_dist(ng) > heap_top_dist(spt)) search_trees(p.other_pivots + checked);
         }
     }
+
+    // ------------------------------------------------------------------------------------
+    // KDT flavour: KDTree::KDTSearch (KDTree.h:233-271, tail recursion as a loop),
+    // InitSearchTrees/SearchTrees (KDTree.h:213-231), KDT::Index<T>::Search (KDTIndex.cpp:182-241)
+    // ------------------------------------------------------------------------------------
+    __device__ __forceinline__ void kdt_search_node(int node, float distBound) {
+        for (;;) {
+            if (node < 0) {
+                const int index = -node - 1;
+                if (index >= p.n) return;
+                if (check_and_set_uniform(index)) return;
+                ++tree_checked;
+                ++checked;
+                __syncwarp();
+                if (lane == 0) cand_id[0] = index;
+                compute_dists(1);
+                heap_insert(ng, index, cand_dist[0], lane);
+                return;
+            }
+            const int4 tn = __ldg(reinterpret_cast<const int4*>(p.nodes) + node);  // {left, right, split_dim, split_value}
+            ntree++;
+            // the split test reads the raw query (KDTree.h:255); `distBound + diff*diff` is one FMA in the
+            // reference's g++ -O3 build (see oracle/sptag_oracle.c kdt_search_node)
+            const float diff = __fsub_rn(qs[tn.z], __int_as_float(tn.w));
+            const float distanceBound = __fmaf_rn(diff, diff, distBound);
+            int otherChild, bestChild;
+            if (diff < 0) {
+                bestChild = tn.x;
+                otherChild = tn.y;
+            } else {
+                otherChild = tn.x;
+                bestChild = tn.y;
+            }
+            heap_insert(spt, otherChild, distanceBound, lane);
+            node = bestChild;
+        }
+    }
+
+    __device__ __forceinline__ void kdt_search_trees(int limit) {
+        while (spt.count != 0 && checked < limit) {
+            const int2 tcell = heap_pop(spt, lane);
+            kdt_search_node(tcell.x, pair_dist(tcell));
+        }
+    }
+
+    __device__ __forceinline__ void kdt_search() {
+        for (int t = 0; t < p.tree_num; ++t) kdt_search_node(p.tree_starts[t], 0.0f);
+        kdt_search_trees(p.initial_pivots);
+        while (ng.count != 0) {
+            const int2 gnode = heap_pop(ng, lane);
+            const float gdist = pair_dist(gnode);
+            const int* node = p.graph + (size_t)gnode.x * p.degree;
+            nexpand++;
+            int nn = (lane < p.degree) ? node[lane] : -1;
+            if (not_deleted(gnode.x)) {
+                if (!add_point(gnode.x, gdist) && checked > p.max_check) return;
+            }
+            const float upperBound = fmaxf(worst_d, gdist);
+            bool bLocalOpt = true;
+            for (int cbase = 0; cbase < p.degree; cbase += 32) {
+                if (cbase > 0) nn = (cbase + lane < p.degree) ? node[cbase + lane] : -1;
+                const bool in_row = (cbase + lane < p.degree);
+                const unsigned negmask = __ballot_sync(kFull, in_row && nn < 0) | ~__ballot_sync(kFull, in_row);
+                const int first_neg = negmask ? (__ffs(negmask) - 1) : 32;
+                const bool active = lane < first_neg;
+                const unsigned same = __match_any_sync(kFull, active ? nn : (-1 - lane));
+                const bool leader = active && ((__ffs(same) - 1) == lane);
+                bool fresh = false;
+                if (leader) {
+                    const unsigned bit = 1u << (nn & 31);
+                    const unsigned old = atomicOr(&visited[nn >> 5], bit);
+                    fresh = (old & bit) == 0;
+                }
+                const unsigned freshmask = __ballot_sync(kFull, fresh);
+                const int cnt = __popc(freshmask);
+                __syncwarp();
+                if (fresh) cand_id[__popc(freshmask & ((1u << lane) - 1u))] = nn;
+                compute_dists(cnt);
+                for (int r = 0; r < cnt; ++r) {
+                    const float d = cand_dist[r];
+                    if (d <= upperBound) bLocalOpt = false;
+                    checked++;
+                    heap_insert(ng, cand_id[r], d, lane);
+                }
+                if (first_neg < 32) break;
+            }
+            if (bLocalOpt)
+                no_better++;
+            else
+                no_better = 0;
+            if (no_better > p.no_better_threshold) {
+                if (tree_checked <= checked / 10) {
+                    kdt_search_trees(p.other_pivots + checked);
+                } else if (gdist > worst_d) {
+                    break;
+                }
+            }
+        }
+    }
 };
 
 // ------------------------------------------------------------------------------------------
 // kernel: persistent warps pull queries from a global counter
 // ------------------------------------------------------------------------------------------
-template <int DIM, bool COSINE, int RPL>
-__global__ void __launch_bounds__(32) bkt_search_kernel(const SearchParams p) {
+template <int DIM, bool COSINE, int RPL, bool KDT>
+__global__ void __launch_bounds__(32) search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x;
     WarpSearch<DIM, COSINE, RPL> w(p, lane);
@@ -616,6 +716,7 @@ __global__ void __launch_bounds__(32) bkt_search_kernel(const SearchParams p) {
         w.worst_d = SPTAG_B200_MAXDIST;
         w.worst_id = -1;
         w.checked = w.ndist = w.nexpand = w.ntree = 0;
+        w.tree_checked = w.no_better = 0;
         // query -> shared memory (+ registers for the static-DIM variants)
         {
             const float* qg = reinterpret_cast<const float*>(p.queries + (size_t)q * p.query_stride_bytes);
@@ -628,7 +729,10 @@ __global__ void __launch_bounds__(32) bkt_search_kernel(const SearchParams p) {
         }
         __syncwarp();
 
-        w.bkt_search();
+        if (KDT)
+            w.kdt_search();
+        else
+            w.bkt_search();
 
         // ---- QueryResultSet::SortResult: the register list is already ascending by (dist, id) ----
         if (lane < p.k) {
@@ -639,7 +743,7 @@ __global__ void __launch_bounds__(32) bkt_search_kernel(const SearchParams p) {
         if (p.out_stats != nullptr && lane == 0) {
             int* s = p.out_stats + (size_t)q * kStatsPerQuery;
             s[0] = w.checked;
-            s[1] = 0;
+            s[1] = w.tree_checked;
             s[2] = w.ng.count;
             s[3] = w.spt.count;
             s[4] = w.ndist;

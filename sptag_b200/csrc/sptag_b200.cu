@@ -96,7 +96,9 @@ struct sptag_b200_index {
     int queries_per_sm = 0;  // 0 = auto
     int stage_rows = 0;      // 0 = auto
     int stages = 2;
-    int h_ng = 1024, h_spt = 512;
+    // Small queue caches + a small ring: the kernel is latency-bound per warp, so resident queries per
+    // SM matter more than on-chip queue capacity (sweep in profiles/r01_sweep_c2.txt)
+    int h_ng = 128, h_spt = 64;
     int simd_width = 16;
     // scratch
     DeviceBuffer d_visited, d_ng_spill, d_spt_spill, d_counter;
@@ -115,9 +117,9 @@ int heap_lastlevel(int size) {
     return (int)std::pow(2.0, std::floor(std::log2((float)size)));
 }
 
-template <int DIM, bool COSINE, int RPL>
-int launch_bkt(const SearchParams& p, int grid, size_t smem, cudaStream_t stream) {
-    auto kern = bkt_search_kernel<DIM, COSINE, RPL>;
+template <int DIM, bool COSINE, int RPL, bool KDT>
+int launch_search(const SearchParams& p, int grid, size_t smem, cudaStream_t stream) {
+    auto kern = search_kernel<DIM, COSINE, RPL, KDT>;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, 32, smem, stream>>>(p);
     g_launches++;
@@ -126,25 +128,26 @@ int launch_bkt(const SearchParams& p, int grid, size_t smem, cudaStream_t stream
 }
 
 template <int DIM, bool COSINE>
-int launch_bkt_rpl(const SearchParams& p, int grid, size_t smem, cudaStream_t stream) {
-    if (p.mres_cap <= 32 * 16) return launch_bkt<DIM, COSINE, 16>(p, grid, smem, stream);
-    if (p.mres_cap <= 32 * 32) return launch_bkt<DIM, COSINE, 32>(p, grid, smem, stream);
+int launch_rpl(const SearchParams& p, bool kdt, int grid, size_t smem, cudaStream_t stream) {
+    if (kdt) return launch_search<DIM, COSINE, 16, true>(p, grid, smem, stream);  // KDT has no m_Results gate
+    if (p.mres_cap <= 32 * 16) return launch_search<DIM, COSINE, 16, false>(p, grid, smem, stream);
+    if (p.mres_cap <= 32 * 32) return launch_search<DIM, COSINE, 32, false>(p, grid, smem, stream);
     return fail(SPTAG_B200_LACK_OF_INPUTS, "max(MaxCheck/16, K) = %d exceeds the supported 1024", p.mres_cap);
 }
 
 template <bool COSINE>
-int launch_bkt_dim(const SearchParams& p, int grid, size_t smem, cudaStream_t stream) {
+int launch_dim(const SearchParams& p, bool kdt, int grid, size_t smem, cudaStream_t stream) {
     switch (p.dim) {
-    case 128: return launch_bkt_rpl<128, COSINE>(p, grid, smem, stream);
-    case 768: return launch_bkt_rpl<768, COSINE>(p, grid, smem, stream);
-    default: return launch_bkt_rpl<0, COSINE>(p, grid, smem, stream);
+    case 128: return launch_rpl<128, COSINE>(p, kdt, grid, smem, stream);
+    case 768: return launch_rpl<768, COSINE>(p, kdt, grid, smem, stream);
+    default: return launch_rpl<0, COSINE>(p, kdt, grid, smem, stream);
     }
 }
 
 // Fill SearchParams + launch geometry for this handle.  Allocates per-slot scratch.
 int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& smem, int nq) {
-    if (h->algo != SPTAG_B200_ALGO_BKT)
-        return fail(SPTAG_B200_LACK_OF_INPUTS, "only BKT indexes are searchable in this build");
+    if (h->algo != SPTAG_B200_ALGO_BKT && h->algo != SPTAG_B200_ALGO_KDT)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "unsupported index algorithm %d", h->algo);
     if (h->value_type != SPTAG_B200_VT_FLOAT)
         return fail(SPTAG_B200_LACK_OF_INPUTS, "only float vectors are searchable in this build");
     if (h->simd_width != 16)
@@ -182,7 +185,7 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     // ---- shared-memory layout ----
     int stage_rows = h->stage_rows;
     if (stage_rows <= 0) {
-        stage_rows = (int)(12288 / h->row_stride);
+        stage_rows = (int)(6400 / round_up(h->row_stride + 64, 128));
         stage_rows = std::max(2, std::min(16, stage_rows));
     }
     stage_rows &= ~1;
@@ -211,7 +214,7 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
 
     int per_sm = h->queries_per_sm;
     const int fit = (int)std::min<size_t>(32, (228 * 1024) / (smem + 1024));
-    if (per_sm <= 0) per_sm = std::min(fit, 16);
+    if (per_sm <= 0) per_sm = std::min(fit, 12);  // 12 = register-file limit of the 768-d instantiation
     per_sm = std::max(1, std::min(per_sm, fit));
     grid = std::max(1, std::min(nq, h->num_sms * per_sm));
 
@@ -249,8 +252,9 @@ int search_device_impl(sptag_b200_index* h, const void* d_queries, int nq, int k
     p.out_stats = d_stats;
     CUDA_OK(cudaMemsetAsync(p.work_counter, 0, 4, stream));
     CUDA_OK(cudaEventRecord(h->ev_start, stream));
-    int rc = (h->metric == SPTAG_B200_METRIC_L2) ? launch_bkt_dim<false>(p, grid, smem, stream)
-                                                 : launch_bkt_dim<true>(p, grid, smem, stream);
+    const bool kdt = (h->algo == SPTAG_B200_ALGO_KDT);
+    int rc = (h->metric == SPTAG_B200_METRIC_L2) ? launch_dim<false>(p, kdt, grid, smem, stream)
+                                                 : launch_dim<true>(p, kdt, grid, smem, stream);
     if (rc) return rc;
     CUDA_OK(cudaEventRecord(h->ev_stop, stream));
     h->timed = true;

@@ -1,0 +1,144 @@
+// vector_index_adapter.hpp -- C++ host-side mirror of the reference's search interface on top of the
+// C ABI (include/sptag_b200.h).  Header-only; links only against libsptag_b200.so.
+//
+// It mirrors, for the search path only, the reference types a caller touches:
+//   SPTAG::BasicResult    AnnService/inc/Core/SearchResult.h:65-78   (VID, Dist; Meta stays on the host side)
+//   SPTAG::QueryResult    AnnService/inc/Core/SearchQuery.h:15-254   (target pointer, K results)
+//   SPTAG::VectorIndex    AnnService/inc/Core/VectorIndex.h:41,103   (the two SearchIndex overloads,
+//                         LoadIndex, SetParameter/GetParameter, GetNumSamples/GetFeatureDim)
+//   SPTAG::ErrorCode      AnnService/inc/Core/DefinitionList.h:54-68 (same numeric values)
+// with the same names, argument meaning and error behaviour, so existing call sites
+// (Wrappers/src/CoreInterface.cpp:206-238, IndexSearcher/main.cpp:194-217) compile against it by
+// switching the namespace.  INTEGRATION.md shows the three-line patch that makes the reference's own
+// VectorIndex subclass forward to this adapter instead.
+#pragma once
+
+#include <cfloat>
+#include <limits>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/sptag_b200.h"
+
+namespace SPTAG_B200 {
+
+typedef std::int32_t SizeType;
+typedef std::int32_t DimensionType;
+const float MaxDist = (std::numeric_limits<float>::max)() / 10;  // Common.h:122
+
+enum class ErrorCode : std::uint16_t {
+    Success = 0x0000,
+    Fail = 0x0001,
+    FailedOpenFile = 0x0002,
+    ParamNotFound = 0x0010,
+    FailedParseValue = 0x0011,
+    MemoryOverFlow = 0x0012,
+    LackOfInputs = 0x0013,
+    EmptyIndex = 0x0015,
+    DimensionSizeMismatch = 0x0017,
+};
+
+// SearchResult.h:65-78 without the metadata blob (metadata never crosses the device boundary;
+// a wrapping VectorIndex fills it from its own MetadataSet exactly as BKTIndex.cpp:611-618 does)
+struct BasicResult {
+    SizeType VID;
+    float Dist;
+    BasicResult() : VID(-1), Dist(MaxDist) {}
+    BasicResult(SizeType p_vid, float p_dist) : VID(p_vid), Dist(p_dist) {}
+};
+
+// SearchQuery.h:15-254: a target plus K result slots (owning or viewing a caller buffer)
+class QueryResult {
+public:
+    QueryResult(const void* p_target, int p_resultNum, bool /*p_withMeta*/ = false)
+        : m_target(p_target), m_resultNum(p_resultNum), m_own(p_resultNum), m_results(m_own.data()) {}
+    QueryResult(const void* p_target, int p_resultNum, bool /*p_withMeta*/, BasicResult* p_results)
+        : m_target(p_target), m_resultNum(p_resultNum), m_results(p_results) {}
+    const void* GetTarget() const { return m_target; }
+    void SetTarget(const void* p_target) { m_target = p_target; }
+    int GetResultNum() const { return m_resultNum; }
+    BasicResult* GetResult(int i) const { return i < m_resultNum ? m_results + i : nullptr; }
+    BasicResult* GetResults() const { return m_results; }
+    void Reset() {
+        for (int i = 0; i < m_resultNum; ++i) m_results[i] = BasicResult();
+    }
+
+private:
+    const void* m_target;
+    int m_resultNum;
+    std::vector<BasicResult> m_own;
+    BasicResult* m_results;
+};
+
+class VectorIndex {
+public:
+    ~VectorIndex() { sptag_b200_destroy(m_handle); }
+    VectorIndex(const VectorIndex&) = delete;
+    VectorIndex& operator=(const VectorIndex&) = delete;
+
+    // VectorIndex::LoadIndex(folder, index) (VectorIndex.cpp:617-681)
+    static ErrorCode LoadIndex(const std::string& p_loaderFilePath, std::shared_ptr<VectorIndex>& p_vectorIndex,
+                               int device = -1, SizeType idOffset = 0) {
+        sptag_b200_handle h = nullptr;
+        int rc = sptag_b200_load(p_loaderFilePath.c_str(), device, idOffset, &h);
+        if (rc != 0) return static_cast<ErrorCode>(rc);
+        p_vectorIndex.reset(new VectorIndex(h));
+        return ErrorCode::Success;
+    }
+
+    // From arrays already in host memory (what BKT::Index<T> holds after BuildIndex/LoadIndexData)
+    static ErrorCode Create(const sptag_b200_index_desc& desc, std::shared_ptr<VectorIndex>& p_vectorIndex) {
+        sptag_b200_handle h = nullptr;
+        int rc = sptag_b200_create(&desc, &h);
+        if (rc != 0) return static_cast<ErrorCode>(rc);
+        p_vectorIndex.reset(new VectorIndex(h));
+        return ErrorCode::Success;
+    }
+
+    // VectorIndex::SearchIndex(QueryResult&, bool) (VectorIndex.h:41; BKTIndex.cpp:595-620).
+    // One query is one tiny batch on the device; prefer the batched overload.
+    ErrorCode SearchIndex(QueryResult& p_query, bool /*p_searchDeleted*/ = false) const {
+        return SearchIndex(p_query.GetTarget(), 1, p_query.GetResultNum(), false, p_query.GetResults());
+    }
+
+    // VectorIndex::SearchIndex(const void*, int, int, bool, BasicResult*) (VectorIndex.h:103,
+    // VectorIndex.cpp:454-463).  p_results is caller-owned [p_vectorCount x p_neighborCount].
+    ErrorCode SearchIndex(const void* p_vector, int p_vectorCount, int p_neighborCount, bool /*p_withMeta*/,
+                          BasicResult* p_results) const {
+        if (!m_handle) return ErrorCode::EmptyIndex;
+        const size_t n = static_cast<size_t>(p_vectorCount) * p_neighborCount;
+        std::vector<std::int32_t> ids(n);
+        std::vector<float> dists(n);
+        int rc = sptag_b200_search(m_handle, p_vector, p_vectorCount, p_neighborCount, ids.data(), dists.data(),
+                                   nullptr);
+        if (rc != 0) return static_cast<ErrorCode>(rc);
+        for (size_t i = 0; i < n; ++i) {  // scatter the POD SoA into the caller's AoS
+            p_results[i].VID = ids[i];
+            p_results[i].Dist = dists[i];
+        }
+        return ErrorCode::Success;
+    }
+
+    // VectorIndex::SetParameter / GetParameter (BKTIndex.cpp:980-1025)
+    ErrorCode SetParameter(const char* p_param, const char* p_value, const char* /*p_section*/ = nullptr) {
+        return static_cast<ErrorCode>(sptag_b200_set_param(m_handle, p_param, p_value));
+    }
+    std::string GetParameter(const char* p_param, const char* /*p_section*/ = nullptr) const {
+        char buf[64] = {0};
+        if (sptag_b200_get_param(m_handle, p_param, buf, sizeof(buf)) != 0) return std::string();
+        return std::string(buf);
+    }
+    SizeType GetNumSamples() const { return sptag_b200_num_vectors(m_handle); }
+    DimensionType GetFeatureDim() const { return sptag_b200_dim(m_handle); }
+    bool IsReady() const { return m_handle != nullptr; }
+    sptag_b200_handle Handle() const { return m_handle; }
+
+private:
+    explicit VectorIndex(sptag_b200_handle h) : m_handle(h) {}
+    sptag_b200_handle m_handle;
+};
+
+}  // namespace SPTAG_B200

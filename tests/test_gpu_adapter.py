@@ -1,0 +1,35 @@
+"""GPU test: the C++ host-side mirror of VectorIndex/QueryResult/BasicResult (vector_index_adapter.hpp)
+returns exactly what the oracle returns, when driven the way the reference's callers drive VectorIndex."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import reflib
+from conftest import data_folder
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cpp_adapter_matches_oracle():
+    import __graft_entry__
+    exe = __graft_entry__.build_adapter_test()
+    folder = data_folder("bkt_cos_10k_128")
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:64]
+    k, mc = 10, 1024
+    with tempfile.TemporaryDirectory() as tmp:
+        qf, of = os.path.join(tmp, "q.f32"), os.path.join(tmp, "out.bin")
+        q.astype(np.float32).tofile(qf)
+        subprocess.check_call([exe, folder, qf, str(q.shape[0]), str(q.shape[1]), str(k), str(mc), of])
+        raw = np.fromfile(of, dtype=np.int32).reshape(q.shape[0], k, 2)
+    ids = raw[:, :, 0]
+    dist_bits = raw[:, :, 1]
+    o = reflib.OracleIndex(files)
+    o.max_check = mc
+    ids_o, d_o, _ = o.search(q, k)
+    assert np.array_equal(ids, ids_o)
+    assert np.array_equal(dist_bits, d_o.view(np.int32))

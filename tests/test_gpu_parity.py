@@ -27,7 +27,8 @@ def _compare(idx, files, q, k, mc, tag):
     assert bad.size == 0, "%s MaxCheck=%d: %d/%d queries differ, first %d: gpu %s oracle %s" % (
         tag, mc, bad.size, q.shape[0], bad[0], ids[bad[0]], ids_o[bad[0]])
     assert np.array_equal(dists.view(np.int32), d_o.view(np.int32)), (tag, mc)
-    for a, b in [(capi.ST_CHECKED, reflib.ST_CHECKED), (capi.ST_NG_LEFT, reflib.ST_NG_LEFT),
+    for a, b in [(capi.ST_CHECKED, reflib.ST_CHECKED), (capi.ST_TREE_CHECKED, reflib.ST_TREE_CHECKED),
+                 (capi.ST_NG_LEFT, reflib.ST_NG_LEFT),
                  (capi.ST_SPT_LEFT, reflib.ST_SPT_LEFT), (capi.ST_NDIST, reflib.ST_NDIST),
                  (capi.ST_NEXPAND, reflib.ST_NEXPAND), (capi.ST_NTREE, reflib.ST_NTREE)]:
         assert np.array_equal(stats[:, a], st_o[:, b]), (tag, mc, "stat", a)
@@ -45,6 +46,22 @@ def test_bkt_search_bit_exact(name):
     try:
         for mc in [8192, 1024, 64]:
             _compare(idx, files, q, k, mc, name)
+    finally:
+        idx.close()
+
+
+@pytest.mark.parametrize("name", ["kdt_l2_10k_64"])
+def test_kdt_search_bit_exact(name):
+    from sptag_b200 import B200Index
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))
+    idx = B200Index.load(folder)
+    try:
+        for mc in [8192, 1024, 64]:
+            _compare(idx, files, q, 10, mc, name)
+        idx.set_param("B200.NGCacheEntries", 8)  # KDT keeps ~MaxCheck entries in NGQueue: force the HBM spill
+        _compare(idx, files, q, 10, 2048, name + " spill")
     finally:
         idx.close()
 
