@@ -133,42 +133,65 @@ struct QueryRegs {
     float q[DIM / 16 > 0 ? DIM / 16 : 1];
 };
 
-// Distance of the query to one row staged in shared memory, computed by a half-warp.
+// Distance of the query to NR rows staged in shared memory, computed by a half-warp (NR independent
+// accumulator chains per lane for instruction-level parallelism; each chain is exactly the reference's).
 // Lane j (0..15) owns accumulator j of ComputeL2Distance_AVX512 / ComputeCosineDistance_AVX512;
 // the folds 16 -> 8 -> 4 -> 1 and the 8-/4-wide/scalar tails follow DistanceUtils.cpp:650-682.
-// The result is valid in lane j == 0 of the half-warp.  Must be called by all 32 lanes.
+// Results are valid in lane j == 0 of the half-warp.  Must be called by all 32 lanes.
+template <int DIM, bool COSINE, int NR>
+__device__ __forceinline__ void half_warp_distance_n(const float* const (&row)[NR], const QueryRegs<DIM>& qr,
+                                                     const float* __restrict__ qs, int dim, int j, float (&out)[NR]) {
+    float acc[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) acc[r] = 0.0f;
+    if (DIM > 0) {
+#pragma unroll
+        for (int c = 0; c < DIM / 16; ++c) {
+            const float q = qr.q[c];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc[r] = __fadd_rn(acc[r], dist_term<COSINE>(q, row[r][16 * c + j]));
+        }
+    } else {
+        const int nch = dim >> 4;
+        for (int c = 0; c < nch; ++c) {
+            const float q = qs[16 * c + j];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc[r] = __fadd_rn(acc[r], dist_term<COSINE>(q, row[r][16 * c + j]));
+        }
+    }
+    const int d = (DIM > 0) ? DIM : dim;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        int off = (d >> 4) << 4;
+        // diff256 = lo(diff512) + hi(diff512)
+        float a8 = __fadd_rn(acc[r], __shfl_down_sync(kFull, acc[r], 8, 16));
+        if (d & 8) {
+            if (j < 8) a8 = __fadd_rn(a8, dist_term<COSINE>(qs[off + j], row[r][off + j]));
+            off += 8;
+        }
+        // diff128 = lo(diff256) + hi(diff256)
+        float a4 = __fadd_rn(a8, __shfl_down_sync(kFull, a8, 4, 16));
+        if (d & 4) {
+            if (j < 4) a4 = __fadd_rn(a4, dist_term<COSINE>(qs[off + j], row[r][off + j]));
+            off += 4;
+        }
+        // DIFF128[0] + DIFF128[1] + DIFF128[2] + DIFF128[3], left to right
+        const float a1 = __shfl_sync(kFull, a4, 1, 16);
+        const float a2 = __shfl_sync(kFull, a4, 2, 16);
+        const float a3 = __shfl_sync(kFull, a4, 3, 16);
+        float sum = __fadd_rn(__fadd_rn(__fadd_rn(a4, a1), a2), a3);
+        for (int i = off; i < d; ++i) sum = dist_tail<COSINE>(qs[i], row[r][i], sum);
+        out[r] = COSINE ? __fsub_rn(1.0f, sum) : sum;
+    }
+}
+
 template <int DIM, bool COSINE>
 __device__ __forceinline__ float half_warp_distance(const float* __restrict__ row, const QueryRegs<DIM>& qr,
                                                     const float* __restrict__ qs, int dim, int j) {
-    float acc = 0.0f;
-    if (DIM > 0) {
-#pragma unroll
-        for (int c = 0; c < DIM / 16; ++c) acc = __fadd_rn(acc, dist_term<COSINE>(qr.q[c], row[16 * c + j]));
-    } else {
-        const int nch = dim >> 4;
-        for (int c = 0; c < nch; ++c) acc = __fadd_rn(acc, dist_term<COSINE>(qs[16 * c + j], row[16 * c + j]));
-    }
-    const int d = (DIM > 0) ? DIM : dim;
-    int off = (d >> 4) << 4;
-    // diff256 = lo(diff512) + hi(diff512)
-    float a8 = __fadd_rn(acc, __shfl_down_sync(kFull, acc, 8, 16));
-    if (d & 8) {
-        if (j < 8) a8 = __fadd_rn(a8, dist_term<COSINE>(qs[off + j], row[off + j]));
-        off += 8;
-    }
-    // diff128 = lo(diff256) + hi(diff256)
-    float a4 = __fadd_rn(a8, __shfl_down_sync(kFull, a8, 4, 16));
-    if (d & 4) {
-        if (j < 4) a4 = __fadd_rn(a4, dist_term<COSINE>(qs[off + j], row[off + j]));
-        off += 4;
-    }
-    // DIFF128[0] + DIFF128[1] + DIFF128[2] + DIFF128[3], left to right
-    const float a1 = __shfl_sync(kFull, a4, 1, 16);
-    const float a2 = __shfl_sync(kFull, a4, 2, 16);
-    const float a3 = __shfl_sync(kFull, a4, 3, 16);
-    float s = __fadd_rn(__fadd_rn(__fadd_rn(a4, a1), a2), a3);
-    for (int i = off; i < d; ++i) s = dist_tail<COSINE>(qs[i], row[i], s);
-    return COSINE ? __fsub_rn(1.0f, s) : s;
+    const float* const rows[1] = {row};
+    float out[1];
+    half_warp_distance_n<DIM, COSINE, 1>(rows, qr, qs, dim, j, out);
+    return out[0];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -430,7 +453,19 @@ struct WarpSearch {
             phase_bits ^= (1u << st);
             const int base = t * p.stage_rows;
             const int rows = min(p.stage_rows, cnt - base);
-            for (int pr = 0; 2 * pr < rows; ++pr) {
+            int pr = 0;
+            for (; 2 * pr + 2 < rows; pr += 2) {  // two row pairs per pass: 2 independent chains per lane
+                const int r0 = 2 * pr + half, r1 = r0 + 2;
+                const float* const rws[2] = {reinterpret_cast<const float*>(slot_ptr(st * p.stage_rows + r0)),
+                                             reinterpret_cast<const float*>(slot_ptr(st * p.stage_rows + r1))};
+                float d2[2];
+                half_warp_distance_n<DIM, COSINE, 2>(rws, qr, qs, p.dim, j, d2);
+                if (j == 0) {
+                    cand_dist[base + r0] = d2[0];
+                    if (r1 < rows) cand_dist[base + r1] = d2[1];
+                }
+            }
+            for (; 2 * pr < rows; ++pr) {
                 const int r = 2 * pr + half;
                 const float* row = reinterpret_cast<const float*>(slot_ptr(st * p.stage_rows + r));
                 const float d = half_warp_distance<DIM, COSINE>(row, qr, qs, p.dim, j);
@@ -551,10 +586,18 @@ struct WarpSearch {
                 __syncwarp();
                 if (fresh) cand_id[__popc(freshmask & ((1u << lane) - 1u))] = nn;
                 compute_dists(cnt);
-                for (int r = 0; r < cnt; ++r) {
-                    const float d = cand_dist[r];
-                    checked++;
-                    if (mres.insert(d, lane)) heap_insert(ng, cand_id[r], d, lane);
+                // m_Results.worst() never increases, so a candidate above the current worst is rejected
+                // whenever its turn comes; only the others are replayed in neighbour order (BKTIndex.cpp:338-344)
+                const float myd = (lane < cnt) ? cand_dist[lane] : SPTAG_B200_MAXDIST;
+                const int myid = (lane < cnt) ? cand_id[lane] : -1;
+                checked += cnt;
+                unsigned maybe = __ballot_sync(kFull, lane < cnt && !(myd > mres.worst));
+                while (maybe) {
+                    const int r = __ffs(maybe) - 1;
+                    maybe &= maybe - 1;
+                    const float d = __shfl_sync(kFull, myd, r);
+                    const int id = __shfl_sync(kFull, myid, r);
+                    if (mres.insert(d, lane)) heap_insert(ng, id, d, lane);
                 }
                 if (first_neg < 32) break;
             }
