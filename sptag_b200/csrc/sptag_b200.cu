@@ -117,35 +117,34 @@ int heap_lastlevel(int size) {
     return (int)std::pow(2.0, std::floor(std::log2((float)size)));
 }
 
-template <int DIM, bool COSINE, int RPL, bool KDT>
-int launch_search(const SearchParams& p, int grid, size_t smem, cudaStream_t stream) {
-    auto kern = search_kernel<DIM, COSINE, RPL, KDT>;
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 32, smem, stream>>>(p);
-    g_launches++;
-    CUDA_OK(cudaGetLastError());
-    return 0;
-}
+typedef void (*SearchKernelFn)(const SearchParams);
 
 template <int DIM, bool COSINE>
-int launch_rpl(const SearchParams& p, bool kdt, int grid, size_t smem, cudaStream_t stream) {
-    if (kdt) return launch_search<DIM, COSINE, 16, true>(p, grid, smem, stream);  // KDT has no m_Results gate
-    if (p.mres_cap <= 32 * 16) return launch_search<DIM, COSINE, 16, false>(p, grid, smem, stream);
-    if (p.mres_cap <= 32 * 32) return launch_search<DIM, COSINE, 32, false>(p, grid, smem, stream);
-    return fail(SPTAG_B200_LACK_OF_INPUTS, "max(MaxCheck/16, K) = %d exceeds the supported 1024", p.mres_cap);
+SearchKernelFn pick_rpl(int mres_cap, bool kdt) {
+    if (kdt) return search_kernel<DIM, COSINE, 16, true>;  // KDT has no m_Results gate
+    if (mres_cap <= 32 * 16) return search_kernel<DIM, COSINE, 16, false>;
+    if (mres_cap <= 32 * 32) return search_kernel<DIM, COSINE, 32, false>;
+    return nullptr;
 }
 
 template <bool COSINE>
-int launch_dim(const SearchParams& p, bool kdt, int grid, size_t smem, cudaStream_t stream) {
-    switch (p.dim) {
-    case 128: return launch_rpl<128, COSINE>(p, kdt, grid, smem, stream);
-    case 768: return launch_rpl<768, COSINE>(p, kdt, grid, smem, stream);
-    default: return launch_rpl<0, COSINE>(p, kdt, grid, smem, stream);
+SearchKernelFn pick_dim(int dim, int mres_cap, bool kdt) {
+    switch (dim) {
+    case 128: return pick_rpl<128, COSINE>(mres_cap, kdt);
+    case 768: return pick_rpl<768, COSINE>(mres_cap, kdt);
+    default: return pick_rpl<0, COSINE>(mres_cap, kdt);
     }
 }
 
+// The kernel instantiation for this index / parameter set (nullptr: unsupported m_Results capacity)
+SearchKernelFn pick_kernel(const sptag_b200_index* h, int mres_cap) {
+    const bool kdt = (h->algo == SPTAG_B200_ALGO_KDT);
+    return (h->metric == SPTAG_B200_METRIC_L2) ? pick_dim<false>(h->dim, mres_cap, kdt)
+                                                : pick_dim<true>(h->dim, mres_cap, kdt);
+}
+
 // Fill SearchParams + launch geometry for this handle.  Allocates per-slot scratch.
-int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& smem, int nq) {
+int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& smem, int nq, SearchKernelFn& kern) {
     if (h->algo != SPTAG_B200_ALGO_BKT && h->algo != SPTAG_B200_ALGO_KDT)
         return fail(SPTAG_B200_LACK_OF_INPUTS, "unsupported index algorithm %d", h->algo);
     if (h->value_type != SPTAG_B200_VT_FLOAT)
@@ -185,7 +184,7 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     // ---- shared-memory layout ----
     int stage_rows = h->stage_rows;
     if (stage_rows <= 0) {
-        stage_rows = (int)(6400 / round_up(h->row_stride + 64, 128));
+        stage_rows = (int)(5120 / round_up(h->row_stride + 64, 128));
         stage_rows = std::max(2, std::min(16, stage_rows));
     }
     stage_rows &= ~1;
@@ -212,9 +211,16 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     if (smem > h->smem_optin)
         return fail(SPTAG_B200_MEMORY_OVERFLOW, "shared memory per query slot %zu exceeds %zu", smem, h->smem_optin);
 
+    kern = pick_kernel(h, p.mres_cap);
+    if (!kern)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "max(MaxCheck/16, K) = %d exceeds the supported 1024", p.mres_cap);
+    CUDA_OK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // resident single-warp CTAs per SM allowed by registers + shared memory for this instantiation
+    int fit = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, (const void*)kern, 32, smem));
+    if (fit < 1) return fail(SPTAG_B200_MEMORY_OVERFLOW, "search kernel does not fit on an SM (smem %zu)", smem);
     int per_sm = h->queries_per_sm;
-    const int fit = (int)std::min<size_t>(32, (228 * 1024) / (smem + 1024));
-    if (per_sm <= 0) per_sm = std::min(fit, 12);  // 12 = register-file limit of the 768-d instantiation
+    if (per_sm <= 0) per_sm = std::min(fit, 16);  // the kernel is latency-bound per warp: fill the SM
     per_sm = std::max(1, std::min(per_sm, fit));
     grid = std::max(1, std::min(nq, h->num_sms * per_sm));
 
@@ -243,7 +249,8 @@ int search_device_impl(sptag_b200_index* h, const void* d_queries, int nq, int k
     SearchParams p;
     int grid = 0;
     size_t smem = 0;
-    if (int rc = configure(h, k, p, grid, smem, nq)) return rc;
+    SearchKernelFn kern = nullptr;
+    if (int rc = configure(h, k, p, grid, smem, nq, kern)) return rc;
     p.queries = (const unsigned char*)d_queries;
     p.query_stride_bytes = (size_t)h->dim * value_size(h->value_type);
     p.nq = nq;
@@ -252,10 +259,9 @@ int search_device_impl(sptag_b200_index* h, const void* d_queries, int nq, int k
     p.out_stats = d_stats;
     CUDA_OK(cudaMemsetAsync(p.work_counter, 0, 4, stream));
     CUDA_OK(cudaEventRecord(h->ev_start, stream));
-    const bool kdt = (h->algo == SPTAG_B200_ALGO_KDT);
-    int rc = (h->metric == SPTAG_B200_METRIC_L2) ? launch_dim<false>(p, kdt, grid, smem, stream)
-                                                 : launch_dim<true>(p, kdt, grid, smem, stream);
-    if (rc) return rc;
+    kern<<<grid, 32, smem, stream>>>(p);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(h->ev_stop, stream));
     h->timed = true;
     return SPTAG_B200_SUCCESS;
