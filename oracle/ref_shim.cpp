@@ -15,6 +15,7 @@
 #include "inc/Core/Common/DistanceUtils.h"
 #include "inc/Core/Common/InstructionUtils.h"
 #include "inc/Core/Common/WorkSpace.h"
+#include "inc/Core/Common/IQuantizer.h"
 #include "inc/Helper/Logging.h"
 
 #include <omp.h>
@@ -163,6 +164,70 @@ int ref_search_batch(void* h, const void* queries, int nq, int k, int threads,
         dists[i] = res[i].Dist;
     }
     return (int)ec;
+}
+
+// ---- quantized indexes (PQ / OPQ): IQuantizer.h, PQQuantizer.h:110-180, OPQQuantizer.h:96-121 ----
+
+// Build a BKT/KDT index over uint8 PQ codes with the quantizer loaded from `quantizer_file`
+// (VectorIndex::LoadQuantizer, VectorIndex.cpp:548-563; the file format is PQQuantizer::SaveQuantizer /
+// OPQQuantizer::SaveQuantizer).  codes: n x M uint8.
+void* ref_build_quantized(int algo, int metric, const char* quantizer_file, const void* codes, int n, int m,
+                          int threads, const char* params) {
+    auto idx = VectorIndex::CreateInstance((IndexAlgoType)algo, VectorValueType::UInt8);
+    if (!idx) return nullptr;
+    if (idx->LoadQuantizer(std::string(quantizer_file)) != ErrorCode::Success) return nullptr;
+    idx->SetParameter("DistCalcMethod", metric == 0 ? "L2" : "Cosine");
+    idx->SetParameter("NumberOfThreads", std::to_string(threads).c_str());
+    apply_params(idx.get(), params);
+    // SetParameter("DistCalcMethod") re-selects m_fComputeDistance from the quantizer (BKTIndex.cpp:1001)
+    if (idx->BuildIndex(codes, n, m) != ErrorCode::Success) return nullptr;
+    auto* h = new RefHandle();
+    h->index = idx;
+    return h;
+}
+
+// Stand-alone quantizer (no index): returns an opaque handle holding shared_ptr<IQuantizer>
+void* ref_quantizer_load(const char* quantizer_file) {
+    auto ptr = SPTAG::f_createIO();
+    if (!ptr->Initialize(quantizer_file, std::ios::binary | std::ios::in)) return nullptr;
+    auto q = COMMON::IQuantizer::LoadIQuantizer(ptr);
+    if (!q) return nullptr;
+    return new std::shared_ptr<COMMON::IQuantizer>(q);
+}
+int ref_quantizer_m(void* q) { return (*(std::shared_ptr<COMMON::IQuantizer>*)q)->GetNumSubvectors(); }
+int ref_quantizer_reconstruct_dim(void* q) { return (*(std::shared_ptr<COMMON::IQuantizer>*)q)->ReconstructDim(); }
+// IQuantizer::QuantizeVector(vec, out, ADC=false): raw vectors (ReconstructSize() bytes each) -> M code bytes each
+void ref_quantizer_encode(void* q, const void* raw, int nvec, unsigned char* out) {
+    auto& quant = *(std::shared_ptr<COMMON::IQuantizer>*)q;
+    const size_t rs = quant->ReconstructSize(), m = quant->GetNumSubvectors();
+#pragma omp parallel for
+    for (int i = 0; i < nvec; ++i) quant->QuantizeVector((const std::uint8_t*)raw + i * rs, out + i * m, false);
+}
+// IQuantizer::L2Distance on two code vectors (SDC table lookups when ADC is off, PQQuantizer.h:110-128)
+float ref_quantizer_l2(void* q, const unsigned char* a, const unsigned char* b) {
+    return (*(std::shared_ptr<COMMON::IQuantizer>*)q)->L2Distance(a, b);
+}
+
+// Per-query overload over a batch of RAW queries (what IndexSearcher does for quantized indexes,
+// IndexSearcher/main.cpp:179-206; the batched overload strides by code bytes and is not usable here,
+// SURVEY.md 8b).  stride_bytes = bytes between consecutive raw queries.
+int ref_search_each(void* h, const void* queries, int nq, long long stride_bytes, int k, int threads,
+                    int* ids, float* dists, double* seconds) {
+    auto& idx = ((RefHandle*)h)->index;
+    if (threads > 0) omp_set_num_threads(threads);
+    auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 10)
+    for (int i = 0; i < nq; ++i) {
+        QueryResult res((const char*)queries + (size_t)i * stride_bytes, k, false);
+        idx->SearchIndex(res);
+        for (int j = 0; j < k; ++j) {
+            ids[(size_t)i * k + j] = res.GetResult(j)->VID;
+            dists[(size_t)i * k + j] = res.GetResult(j)->Dist;
+        }
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    return 0;
 }
 
 // Install the counter-reading factory (single-query stats below need it). Irreversible for h.

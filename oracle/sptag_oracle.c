@@ -131,6 +131,90 @@ void ora_distance_f32_many(int32_t metric, int32_t simd_width, const float* a, c
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* PQ / OPQ quantizer  (PQQuantizer.h:110-180, :333-348; OPQQuantizer.h:96-121, :198-206)      */
+/* ------------------------------------------------------------------------------------------ */
+
+void ora_quantizer_init(ora_quantizer* q)
+{
+    /* InitializeDistanceTables: table[i][j][k] = L2(codebook[i][j], codebook[i][k]) via the selected
+     * DistanceUtils float variant */
+    const int m = q->m, ks = q->ks, d = q->dsub;
+    for (int i = 0; i < m; i++) {
+        const float* base = q->codebooks + (size_t)i * ks * d;
+        for (int j = 0; j < ks; j++)
+            for (int k = 0; k < ks; k++)
+                q->sdc[((size_t)i * ks + j) * ks + k] = dist_f32(0, q->simd_width, base + (size_t)j * d, base + (size_t)k * d, d);
+    }
+    if (q->qtype == ORA_Q_OPQ) {
+        const int dim = m * d;
+        for (int i = 0; i < dim; i++)
+            for (int j = 0; j < dim; j++) q->rotation_t[(size_t)i * dim + j] = q->rotation[(size_t)j * dim + i];
+    }
+}
+
+static float raw_elem(const void* raw, int rtype, size_t i)
+{
+    switch (rtype) {
+    case ORA_INT8: return (float)((const int8_t*)raw)[i];
+    case ORA_UINT8: return (float)((const uint8_t*)raw)[i];
+    case ORA_INT16: return (float)((const int16_t*)raw)[i];
+    default: return ((const float*)raw)[i];
+    }
+}
+
+static void quantize_one(const ora_quantizer* q, const void* raw, uint8_t* out, float* tmp /* 2*dim */)
+{
+    const int m = q->m, ks = q->ks, d = q->dsub, dim = m * d;
+    float* vec = tmp;
+    float* rot = tmp + dim;
+    for (int i = 0; i < dim; i++) vec[i] = raw_elem(raw, q->rtype, (size_t)i);
+    const float* src = vec;
+    if (q->qtype == ORA_Q_OPQ) {
+        /* m_VectorMatrixMultiply(m_OPQMatrix_T, vec, out): out[i] = m_base - m_fdot(vec, row_i), m_base = 1,
+         * m_fdot = float cosine distance = 1 - dot (OPQQuantizer.h:198-206) */
+        for (int i = 0; i < dim; i++)
+            rot[i] = 1 - dist_f32(1, q->simd_width, vec, q->rotation_t + (size_t)i * dim, dim);
+        src = rot;
+    }
+    /* PQQuantizer::QuantizeVector, ADC off: first codeword with the strictly smallest L2 distance */
+    for (int i = 0; i < m; i++) {
+        int best = -1;
+        float mind = INFINITY;
+        const float* cb = q->codebooks + (size_t)i * ks * d;
+        for (int j = 0; j < ks; j++) {
+            float dist = dist_f32(0, q->simd_width, src + (size_t)i * d, cb + (size_t)j * d, d);
+            if (dist < mind) {
+                best = j;
+                mind = dist;
+            }
+        }
+        out[i] = (uint8_t)best;
+    }
+}
+
+void ora_quantizer_encode(const ora_quantizer* q, const void* raw, int32_t n, uint8_t* out)
+{
+    static const size_t elem[4] = {1, 1, 2, 4};
+    const int dim = q->m * q->dsub;
+    const size_t rs = elem[q->rtype] * (size_t)dim;
+#pragma omp parallel
+    {
+        float* tmp = (float*)malloc(sizeof(float) * 2 * (size_t)dim);
+#pragma omp for
+        for (int32_t i = 0; i < n; i++)
+            quantize_one(q, (const char*)raw + (size_t)i * rs, out + (size_t)i * q->m, tmp);
+        free(tmp);
+    }
+}
+
+float ora_quantizer_l2(const ora_quantizer* q, const uint8_t* x, const uint8_t* y)
+{
+    float out = 0;
+    for (int i = 0; i < q->m; i++) out += q->sdc[((size_t)i * q->ks + x[i]) * q->ks + y[i]];
+    return out;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* Heap<NodeDistPair>  (Heap.h:13-106, SearchResult.h:11-27)                                   */
 /* ------------------------------------------------------------------------------------------ */
 
@@ -402,6 +486,8 @@ static inline float qdist(const qctx_t* c, ws_t* ws, int32_t id)
 {
     ws->ndist++;
     const char* row = (const char*)c->idx->vectors + (size_t)id * c->row_bytes;
+    if (c->idx->quantizer) /* m_fComputeDistance = quantizer L2Distance (BKTIndex.cpp:34-50, IQuantizer.cpp:103-114) */
+        return ora_quantizer_l2(c->idx->quantizer, (const uint8_t*)c->query, (const uint8_t*)row);
     return ora_distance(c->idx->metric, c->idx->value_type, c->idx->simd_width, c->query, row, c->idx->dim);
 }
 
@@ -613,6 +699,9 @@ int ora_search_batch(const ora_index* idx, const void* queries, int32_t nq, int3
 {
     static const size_t elem[4] = {1, 1, 2, 4};
     const size_t row_bytes = elem[idx->value_type] * (size_t)idx->dim;
+    const ora_quantizer* quant = idx->quantizer;
+    if (quant && idx->tree_kind != ORA_BKT) return 1; /* quantized KDT not restated */
+    const size_t query_bytes = quant ? elem[quant->rtype] * (size_t)(quant->m * quant->dsub) : row_bytes;
     /* a fresh thread's work space: Initialize(max(MaxCheck, MaxCheckForRefineGraph)) then
      * Reset(MaxCheck, K) (BKTIndex.cpp:600-605) */
     const int alloc_check = idx->max_check > idx->max_check_refine ? idx->max_check : idx->max_check_refine;
@@ -626,9 +715,15 @@ int ora_search_batch(const ora_index* idx, const void* queries, int32_t nq, int3
         ws_t ws;
         ws_init(&ws, idx->n, alloc_check);
         res_t* res = (res_t*)malloc(sizeof(res_t) * (size_t)(k > 0 ? k : 1));
+        uint8_t* qcode = quant ? (uint8_t*)malloc((size_t)quant->m) : NULL;
+        float* qtmp = quant ? (float*)malloc(sizeof(float) * 2 * (size_t)(quant->m * quant->dsub)) : NULL;
 #pragma omp for schedule(dynamic, 10)
         for (int32_t q = 0; q < nq; q++) {
-            qctx_t c = {idx, (const char*)queries + (size_t)q * row_bytes, row_bytes, idx->metric != ORA_L2};
+            qctx_t c = {idx, (const char*)queries + (size_t)q * query_bytes, row_bytes, idx->metric != ORA_L2};
+            if (quant) { /* QueryResultSet::SetTarget -> QuantizeVector (QueryResultSet.h:46-60) */
+                quantize_one(quant, c.query, qcode, qtmp);
+                c.query = qcode;
+            }
             for (int i = 0; i < k; i++) {
                 res[i].vid = -1;
                 res[i].dist = kMaxDist();
@@ -655,6 +750,8 @@ int ora_search_batch(const ora_index* idx, const void* queries, int32_t nq, int3
             }
         }
         free(res);
+        free(qcode);
+        free(qtmp);
         ws_free(&ws);
     }
     return 0;

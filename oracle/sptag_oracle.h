@@ -22,6 +22,20 @@ typedef struct {
     float split_value; /* KDTree.h:22-28 */
 } ora_kdt_node;
 
+/* PQ / OPQ quantizer (PQQuantizer.h, OPQQuantizer.h; file layout PQQuantizer.h:226-239, OPQQuantizer.h:133-147).
+ * Supported: PQQuantizer<float>, OPQQuantizer<T> (codebooks and rotation are float for every T). */
+enum { ORA_Q_NONE = 0, ORA_Q_PQ = 1, ORA_Q_OPQ = 2 };
+typedef struct {
+    int32_t qtype;          /* ORA_Q_* (DefinitionList.h:44-46 order) */
+    int32_t rtype;          /* reconstruct type = element type of raw queries (ORA_INT8 ... ORA_FLOAT) */
+    int32_t m, ks, dsub;    /* NumSubvectors, KsPerSubvector, DimPerSubvector */
+    int32_t simd_width;     /* DistanceUtils variant used for the tables / encoding */
+    const float* codebooks; /* m * ks * dsub */
+    const float* rotation;  /* OPQ: (m*dsub)^2 floats as stored (m_OPQMatrix); NULL for PQ */
+    float* sdc;             /* m * ks * ks, caller-allocated, filled by ora_quantizer_init */
+    float* rotation_t;      /* OPQ: caller-allocated (m*dsub)^2, filled by ora_quantizer_init */
+} ora_quantizer;
+
 typedef struct {
     /* vectors.bin (Dataset.h:146-180): row-major n x dim, no padding */
     int32_t n, dim;
@@ -45,6 +59,9 @@ typedef struct {
     int32_t no_better_threshold;     /* ThresholdOfNumberOfContinuousNoBetterPropagation (KDT) */
     /* which DistanceUtils variant to restate: 16 = AVX512, 8 = AVX/AVX2, 4 = SSE, 1 = scalar template */
     int32_t simd_width;
+    /* non-NULL: the index holds uint8 PQ codes (value_type ORA_UINT8, dim = m) and queries are RAW vectors of
+     * quantizer->rtype with m*dsub elements (BKTIndex.cpp:463-469, QueryResultSet.h:46-60) */
+    const ora_quantizer* quantizer;
 } ora_index;
 
 /* per-query counters, all int32 */
@@ -66,6 +83,13 @@ float ora_distance(int32_t metric, int32_t value_type, int32_t simd_width,
 
 void ora_distance_f32_many(int32_t metric, int32_t simd_width, const float* a, const float* b,
                            int32_t dim, int32_t n, float* out);
+
+/* PQQuantizer::InitializeDistanceTables (PQQuantizer.h:333-348) + OPQQuantizer::m_InitMatrixTranspose */
+void ora_quantizer_init(ora_quantizer* q);
+/* IQuantizer::QuantizeVector(vec, out, ADC=false): n raw vectors -> n x m code bytes */
+void ora_quantizer_encode(const ora_quantizer* q, const void* raw, int32_t n, uint8_t* out);
+/* PQQuantizer::L2Distance with ADC off (SDC table sum, PQQuantizer.h:110-128) */
+float ora_quantizer_l2(const ora_quantizer* q, const uint8_t* x, const uint8_t* y);
 
 /* Restatement of VectorIndex::SearchIndex(batch) (VectorIndex.cpp:454-463): nq queries of `dim`
  * elements of the index value type, k results each; ids/dists are [nq*k]; stats is [nq*ORA_ST_COUNT]

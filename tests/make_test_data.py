@@ -45,7 +45,47 @@ SPECS = {
 }
 
 
+def _int8_lowrank(n, dim, rank, seed):
+    # SPACEV-style int8 raw vectors: clamp(round(32 * x), -127, 127)
+    return np.clip(np.round(32.0 * reflib.gen_lowrank(n, dim, rank, seed)), -127, 127).astype(np.int8)
+
+
+# quantized indexes: name -> (raw data gen, raw query gen, M, opq, reconstruct type)
+QSPECS = {
+    "bkt_pq_6k_32": (lambda: reflib.gen_lowrank(6000, 32, 8, 41), lambda: reflib.gen_lowrank(200, 32, 8, 42), 8, False,
+                     reflib.VT_FLOAT),
+    "bkt_opq_6k_48": (lambda: reflib.gen_lowrank(6000, 48, 10, 43), lambda: reflib.gen_lowrank(200, 48, 10, 44), 16, True,
+                      reflib.VT_FLOAT),
+    "bkt_opq_i8_8k_100": (lambda: _int8_lowrank(8000, 100, 16, 45), lambda: _int8_lowrank(200, 100, 16, 46), 50, True,
+                          reflib.VT_INT8),
+}
+
+
+def make_quantized(name, force=False):
+    folder = os.path.join(reflib.DATA_DIR, name)
+    if os.path.exists(os.path.join(folder, "indexloader.ini")) and os.path.exists(
+            os.path.join(folder, "queries.npy")) and not force:
+        return folder
+    if not reflib.have_ref():
+        raise RuntimeError("oracle/_ref/libsptag_ref.so missing")
+    gen_data, gen_q, m, opq, rtype = QSPECS[name]
+    raw = np.ascontiguousarray(gen_data())
+    t = time.time()
+    os.makedirs(folder, exist_ok=True)
+    qz = reflib.train_quantizer(raw.astype(np.float32), m=m, ks=256, opq=opq, rtype=rtype, seed=5, iters=4)
+    qpath = os.path.join(folder, "quantizer_src.bin")
+    qz.write(qpath)
+    codes = reflib.RefQuantizer(qpath).encode(raw)          # the reference's own QuantizeVector
+    idx = reflib.RefIndex.build_quantized("BKT", codes, "L2", qpath, threads=os.cpu_count() or 8)
+    idx.save(folder)                                         # writes quantizer.bin + [Quantizer] ini section
+    np.save(os.path.join(folder, "queries.npy"), np.ascontiguousarray(gen_q()))
+    print("built %-18s n=%d raw dim=%d M=%d in %.1fs" % (name, raw.shape[0], raw.shape[1], m, time.time() - t), flush=True)
+    return folder
+
+
 def make(name, force=False):
+    if name in QSPECS:
+        return make_quantized(name, force)
     folder = os.path.join(reflib.DATA_DIR, name)
     if os.path.exists(os.path.join(folder, "indexloader.ini")) and os.path.exists(
             os.path.join(folder, "queries.npy")) and not force:
@@ -63,6 +103,6 @@ def make(name, force=False):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(SPECS)
+    names = sys.argv[1:] or (list(SPECS) + list(QSPECS))
     for nm in names:
         make(nm)

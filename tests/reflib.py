@@ -65,6 +65,17 @@ def ref():
         L.ref_distance_f32_isa.restype = C.c_float
         L.ref_distance_f32_isa.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.ref_distance_f32_many.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ref_build_quantized.restype = C.c_void_p
+        L.ref_build_quantized.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p]
+        L.ref_quantizer_load.restype = C.c_void_p
+        L.ref_quantizer_load.argtypes = [C.c_char_p]
+        L.ref_quantizer_m.argtypes = [C.c_void_p]
+        L.ref_quantizer_reconstruct_dim.argtypes = [C.c_void_p]
+        L.ref_quantizer_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_quantizer_l2.restype = C.c_float
+        L.ref_quantizer_l2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_search_each.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_quiet(3)  # warnings and errors only
         _ref = L
     return _ref
@@ -110,6 +121,24 @@ class RefIndex:
                                     dists.ctypes.data, C.byref(sec))
         if rc != 0:
             raise RuntimeError("reference SearchIndex failed: %d" % rc)
+        return ids, dists, sec.value
+
+    @classmethod
+    def build_quantized(cls, algo, codes, metric, quantizer_file, threads=8, params=""):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        h = ref().ref_build_quantized(ALGO_OF_NAME[algo], METRIC_OF_NAME[metric], quantizer_file.encode(),
+                                      codes.ctypes.data, codes.shape[0], codes.shape[1], threads, params.encode())
+        return cls(h)
+
+    def search_each(self, queries, k, threads=0):
+        """Per-query overload on RAW queries (needed for quantized indexes)."""
+        queries = np.ascontiguousarray(queries)
+        nq = queries.shape[0]
+        ids = np.empty((nq, k), np.int32)
+        dists = np.empty((nq, k), np.float32)
+        sec = C.c_double()
+        ref().ref_search_each(self.h, queries.ctypes.data, nq, queries.strides[0], k, threads, ids.ctypes.data,
+                              dists.ctypes.data, C.byref(sec))
         return ids, dists, sec.value
 
     def enable_stats(self):
@@ -178,13 +207,151 @@ class IndexFiles:
             rows = int(raw[4:8].view(np.int32)[0])
             self.deleted = np.ascontiguousarray(raw[12:12 + rows].view(np.int8))
 
+        self.quantizer = None
+        qf = p.get("QuantizerFilePath")
+        if qf and os.path.exists(os.path.join(folder, qf)):
+            self.quantizer = Quantizer.read(os.path.join(folder, qf))
+
     def int_param(self, name, default):
         return int(self.params.get(name, default))
 
 
 # ------------------------------------------------------------------------------------------------
+# quantizer.bin (PQQuantizer::SaveQuantizer, PQQuantizer.h:226-239; OPQQuantizer::SaveQuantizer,
+# OPQQuantizer.h:133-147): uint8 qtype, uint8 rtype, int32 M, int32 Ks, int32 dimPerSub, codebooks, [rotation]
+# ------------------------------------------------------------------------------------------------
+Q_NONE, Q_PQ, Q_OPQ = 0, 1, 2
+
+
+class Quantizer:
+    def __init__(self, qtype, rtype, codebooks, rotation=None):
+        self.qtype, self.rtype = qtype, rtype
+        self.codebooks = np.ascontiguousarray(codebooks, np.float32)   # [M, Ks, dsub]
+        self.m, self.ks, self.dsub = self.codebooks.shape
+        self.rotation = None if rotation is None else np.ascontiguousarray(rotation, np.float32)
+        self.dim = self.m * self.dsub
+
+    def write(self, path):
+        with open(path, "wb") as f:
+            np.array([self.qtype, self.rtype], np.uint8).tofile(f)
+            np.array([self.m, self.ks, self.dsub], np.int32).tofile(f)
+            self.codebooks.tofile(f)
+            if self.qtype == Q_OPQ:
+                self.rotation.tofile(f)
+
+    @classmethod
+    def read(cls, path):
+        raw = np.fromfile(path, dtype=np.uint8)
+        qtype, rtype = int(raw[0]), int(raw[1])
+        m, ks, dsub = (int(v) for v in raw[2:14].view(np.int32))
+        if qtype == Q_PQ and rtype != VT_FLOAT:
+            raise NotImplementedError("PQQuantizer<%d>: only float codebooks are handled" % rtype)
+        n = m * ks * dsub
+        cb = raw[14:14 + 4 * n].view(np.float32).reshape(m, ks, dsub)
+        rot = None
+        if qtype == Q_OPQ:
+            d = m * dsub
+            rot = raw[14 + 4 * n:14 + 4 * n + 4 * d * d].view(np.float32).reshape(d, d)
+        return cls(qtype, rtype, cb.copy(), None if rot is None else rot.copy())
+
+    def blob(self):
+        import io
+        b = io.BytesIO()
+        b.write(np.array([self.qtype, self.rtype], np.uint8).tobytes())
+        b.write(np.array([self.m, self.ks, self.dsub], np.int32).tobytes())
+        b.write(self.codebooks.tobytes())
+        if self.qtype == Q_OPQ:
+            b.write(self.rotation.tobytes())
+        return b.getvalue()
+
+
+def train_quantizer(data, m, ks=256, opq=False, rtype=VT_FLOAT, seed=0, iters=6):
+    """Synthetic quantizer for tests/bench: per-subspace k-means codebooks (+ a random orthonormal rotation
+    for OPQ).  The reference cannot train OPQ natively (Quantizer/main.cpp:157-163), so SURVEY.md section 7
+    prescribes exactly this synthesis."""
+    rng = np.random.default_rng(seed)
+    x = np.asarray(data, np.float32)
+    dim = x.shape[1]
+    dsub = dim // m
+    assert dsub * m == dim
+    rot = None
+    if opq:
+        qm, _ = np.linalg.qr(rng.standard_normal((dim, dim)))
+        rot = qm.astype(np.float32)
+        x = x @ rot  # vec . R: the reference computes out[i] = dot(vec, R^T row i) = sum_j vec[j] R[j][i]
+    sample = x[rng.choice(x.shape[0], min(x.shape[0], 20000), replace=False)]
+    cb = np.zeros((m, ks, dsub), np.float32)
+    for i in range(m):
+        sub = sample[:, i * dsub:(i + 1) * dsub]
+        c = sub[rng.choice(sub.shape[0], ks, replace=sub.shape[0] < ks)].copy()
+        for _ in range(iters):
+            d = ((sub[:, None, :] - c[None, :, :]) ** 2).sum(-1)
+            a = d.argmin(1)
+            for j in range(ks):
+                sel = sub[a == j]
+                if sel.shape[0]:
+                    c[j] = sel.mean(0)
+        cb[i] = c
+    return Quantizer(Q_OPQ if opq else Q_PQ, rtype, cb, rot)
+
+
+class RefQuantizer:
+    def __init__(self, path):
+        self.h = C.c_void_p(ref().ref_quantizer_load(path.encode()))
+        if not self.h:
+            raise RuntimeError("reference could not load quantizer " + path)
+        self.m = ref().ref_quantizer_m(self.h)
+        self.dim = ref().ref_quantizer_reconstruct_dim(self.h)
+
+    def encode(self, raw):
+        raw = np.ascontiguousarray(raw)
+        out = np.empty((raw.shape[0], self.m), np.uint8)
+        ref().ref_quantizer_encode(self.h, raw.ctypes.data, raw.shape[0], out.ctypes.data)
+        return out
+
+    def l2(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8)
+        b = np.ascontiguousarray(b, np.uint8)
+        return ref().ref_quantizer_l2(self.h, a.ctypes.data, b.ctypes.data)
+
+
+# ------------------------------------------------------------------------------------------------
 # C restatement
 # ------------------------------------------------------------------------------------------------
+class _OraQuantizer(C.Structure):
+    _fields_ = [("qtype", C.c_int32), ("rtype", C.c_int32), ("m", C.c_int32), ("ks", C.c_int32),
+                ("dsub", C.c_int32), ("simd_width", C.c_int32), ("codebooks", C.c_void_p),
+                ("rotation", C.c_void_p), ("sdc", C.c_void_p), ("rotation_t", C.c_void_p)]
+
+
+class OracleQuantizer:
+    """oracle/sptag_oracle.c quantizer over a Quantizer (tables built by ora_quantizer_init)."""
+
+    def __init__(self, quant, simd_width=16):
+        self.q = quant
+        self.sdc = np.empty((quant.m, quant.ks, quant.ks), np.float32)
+        self.rot_t = np.empty((quant.dim, quant.dim), np.float32) if quant.qtype == Q_OPQ else None
+        s = _OraQuantizer()
+        s.qtype, s.rtype, s.m, s.ks, s.dsub, s.simd_width = quant.qtype, quant.rtype, quant.m, quant.ks, quant.dsub, simd_width
+        s.codebooks = quant.codebooks.ctypes.data
+        s.rotation = quant.rotation.ctypes.data if quant.rotation is not None else None
+        s.sdc = self.sdc.ctypes.data
+        s.rotation_t = self.rot_t.ctypes.data if self.rot_t is not None else None
+        self.struct = s
+        ora().ora_quantizer_init(C.byref(s))
+
+    def encode(self, raw):
+        raw = np.ascontiguousarray(raw)
+        out = np.empty((raw.shape[0], self.q.m), np.uint8)
+        ora().ora_quantizer_encode(C.byref(self.struct), raw.ctypes.data, raw.shape[0], out.ctypes.data)
+        return out
+
+    def l2(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8)
+        b = np.ascontiguousarray(b, np.uint8)
+        return ora().ora_quantizer_l2(C.byref(self.struct), a.ctypes.data, b.ctypes.data)
+
+
 class _OraIndex(C.Structure):
     _fields_ = [("n", C.c_int32), ("dim", C.c_int32), ("value_type", C.c_int32), ("metric", C.c_int32),
                 ("vectors", C.c_void_p), ("degree", C.c_int32), ("graph", C.c_void_p),
@@ -192,7 +359,7 @@ class _OraIndex(C.Structure):
                 ("tree_starts", C.c_void_p), ("nodes", C.c_void_p), ("deleted", C.c_void_p),
                 ("num_deleted", C.c_int32), ("max_check", C.c_int32), ("max_check_refine", C.c_int32),
                 ("initial_pivots", C.c_int32), ("other_pivots", C.c_int32),
-                ("no_better_threshold", C.c_int32), ("simd_width", C.c_int32)]
+                ("no_better_threshold", C.c_int32), ("simd_width", C.c_int32), ("quantizer", C.c_void_p)]
 
 
 _ora = None
@@ -211,6 +378,10 @@ def ora():
                                             C.c_int32, C.c_void_p]
         L.ora_search_batch.argtypes = [C.POINTER(_OraIndex), C.c_void_p, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        L.ora_quantizer_init.argtypes = [C.POINTER(_OraQuantizer)]
+        L.ora_quantizer_encode.argtypes = [C.POINTER(_OraQuantizer), C.c_void_p, C.c_int32, C.c_void_p]
+        L.ora_quantizer_l2.restype = C.c_float
+        L.ora_quantizer_l2.argtypes = [C.POINTER(_OraQuantizer), C.c_void_p, C.c_void_p]
         _ora = L
     return _ora
 
@@ -226,6 +397,7 @@ class OracleIndex:
         self.initial_pivots = files.int_param("NumberOfInitialDynamicPivots", 50)
         self.other_pivots = files.int_param("NumberOfOtherDynamicPivots", 4)
         self.no_better_threshold = files.int_param("ThresholdOfNumberOfContinuousNoBetterPropagation", 3)
+        self.oq = OracleQuantizer(files.quantizer, simd_width) if getattr(files, "quantizer", None) is not None else None
 
     def _struct(self):
         f = self.files
@@ -247,6 +419,7 @@ class OracleIndex:
         s.other_pivots = self.other_pivots
         s.no_better_threshold = self.no_better_threshold
         s.simd_width = self.simd_width
+        s.quantizer = C.addressof(self.oq.struct) if self.oq is not None else None
         return s
 
     def search(self, queries, k, threads=0, want_stats=True):

@@ -173,3 +173,41 @@ def test_counters_match_reference_workspace(oracle_lib):
             assert rs[0] == st[i, reflib.ST_CHECKED]
             assert rs[2] == st[i, reflib.ST_NG_LEFT]
             assert rs[3] == st[i, reflib.ST_SPT_LEFT]
+
+
+# ---------------------------------------------------------------------------------------------
+# PQ / OPQ quantized indexes
+# ---------------------------------------------------------------------------------------------
+@needs_ref
+@pytest.mark.parametrize("opq,rtype", [(False, reflib.VT_FLOAT), (True, reflib.VT_FLOAT), (True, reflib.VT_INT8)])
+def test_quantizer_bit_exact_vs_reference(oracle_lib, tmp_path, opq, rtype):
+    x = reflib.gen_lowrank(3000, 24, 6, 51)
+    xs = x if rtype == reflib.VT_FLOAT else np.clip(np.round(x * 32), -127, 127).astype(np.int8)
+    qz = reflib.train_quantizer(xs.astype(np.float32), m=6, ks=256, opq=opq, rtype=rtype, iters=2)
+    path = str(tmp_path / "q.bin")
+    qz.write(path)
+    rq = reflib.RefQuantizer(path)
+    oq = reflib.OracleQuantizer(reflib.Quantizer.read(path))
+    cr, co = rq.encode(xs), oq.encode(xs)
+    assert np.array_equal(cr, co)                       # QuantizeVector (incl. the OPQ rotation)
+    dr = np.array([rq.l2(cr[i], cr[i + 1]) for i in range(500)], np.float32)
+    do = np.array([oq.l2(co[i], co[i + 1]) for i in range(500)], np.float32)
+    assert np.array_equal(dr.view(np.int32), do.view(np.int32))   # SDC table sum
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["bkt_pq_6k_32", "bkt_opq_6k_48", "bkt_opq_i8_8k_100"])
+def test_quantized_search_bit_exact_vs_reference(oracle_lib, name):
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    assert files.quantizer is not None and files.value_type == reflib.VT_UINT8
+    q = np.load(os.path.join(folder, "queries.npy"))
+    r = reflib.RefIndex.load(folder)
+    for mc in [8192, 1024, 128]:
+        r.set_param("MaxCheck", mc)
+        ids_r, d_r, _ = r.search_each(q, 10, threads=4)   # per-query overload on RAW queries
+        o = reflib.OracleIndex(files)
+        o.max_check = mc
+        ids_o, d_o, _ = o.search(q, 10, threads=4)
+        assert np.array_equal(ids_r, ids_o), (name, mc)
+        assert np.array_equal(d_r.view(np.int32), d_o.view(np.int32)), (name, mc)
