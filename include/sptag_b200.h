@@ -90,6 +90,22 @@ int sptag_b200_create(const sptag_b200_index_desc* desc, sptag_b200_handle* out)
  * indexloader.ini and the four binary files of a reference index folder and uploads them. */
 int sptag_b200_load(const char* folder, int32_t device, int32_t id_offset, sptag_b200_handle* out);
 
+/* Replaces: VectorIndex::LoadQuantizer / SetQuantizer (VectorIndex.cpp:548-563, BKTIndex.cpp:34-50) for an
+ * index whose value type is UInt8 PQ codes.  `blob` is the content of a quantizer file exactly as
+ * PQQuantizer::SaveQuantizer / OPQQuantizer::SaveQuantizer write it (PQQuantizer.h:226-239,
+ * OPQQuantizer.h:133-147): uint8 quantizer type (1 PQ, 2 OPQ), uint8 reconstruct type, int32 M, int32 Ks,
+ * int32 DimPerSubvector, codebooks[M*Ks*Dsub], OPQ only: rotation[(M*Dsub)^2].  Supported: PQQuantizer<float>
+ * and OPQQuantizer<T> for every T (its codebooks/rotation are float).  After this call the search entry
+ * points take RAW query vectors (M*Dsub elements of the reconstruct type), quantize them on the device
+ * exactly like QueryResultSet::SetTarget -> IQuantizer::QuantizeVector (QueryResultSet.h:46-60) and compute
+ * distances by SDC table look-ups (PQQuantizer::L2Distance, ADC off = the reference's default).
+ * sptag_b200_load calls it automatically when indexloader.ini has a [Quantizer] section. */
+int sptag_b200_set_quantizer(sptag_b200_handle h, const void* blob, int64_t blob_bytes);
+
+/* Replaces: VectorIndex::QuantizeVector (VectorIndex.h:146-153): num raw vectors -> num x M code bytes.
+ * Host buffers; blocking. */
+int sptag_b200_quantize(sptag_b200_handle h, const void* raw_vectors, int32_t num, uint8_t* codes_out);
+
 /* Replaces: VectorIndex destructor. */
 void sptag_b200_destroy(sptag_b200_handle h);
 

@@ -20,7 +20,8 @@ METRIC_L2, METRIC_COSINE, METRIC_IP = 0, 1, 2
 ALGO_BKT, ALGO_KDT = 0, 1
 
 EXPORTS = [
-    "sptag_b200_create", "sptag_b200_load", "sptag_b200_destroy", "sptag_b200_set_param",
+    "sptag_b200_create", "sptag_b200_load", "sptag_b200_destroy", "sptag_b200_set_param", "sptag_b200_set_quantizer",
+    "sptag_b200_quantize",
     "sptag_b200_get_param", "sptag_b200_search", "sptag_b200_search_device", "sptag_b200_distance_batch",
     "sptag_b200_merge_topk", "sptag_b200_last_kernel_ms", "sptag_b200_launch_count",
     "sptag_b200_num_vectors", "sptag_b200_dim", "sptag_b200_value_type", "sptag_b200_metric",
@@ -56,6 +57,8 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.sptag_b200_create.argtypes = [C.POINTER(IndexDesc), C.POINTER(C.c_void_p)]
         L.sptag_b200_load.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.sptag_b200_set_quantizer.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.sptag_b200_quantize.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.sptag_b200_destroy.argtypes = [C.c_void_p]
         L.sptag_b200_destroy.restype = None
         L.sptag_b200_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
@@ -149,6 +152,18 @@ class B200Index:
     def set_param(self, name, value):
         """VectorIndex::SetParameter (same names as the reference's ini file)."""
         _check(lib().sptag_b200_set_param(self._h, name.encode(), str(value).encode()))
+
+    def set_quantizer(self, blob):
+        """VectorIndex::LoadQuantizer: blob = bytes of a reference quantizer file."""
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        _check(lib().sptag_b200_set_quantizer(self._h, buf, len(blob)))
+
+    def quantize(self, raw, m):
+        """VectorIndex::QuantizeVector: raw vectors -> [n, m] uint8 codes."""
+        raw = np.ascontiguousarray(raw)
+        out = np.empty((raw.shape[0], m), np.uint8)
+        _check(lib().sptag_b200_quantize(self._h, raw.ctypes.data, raw.shape[0], out.ctypes.data))
+        return out
 
     def get_param(self, name):
         buf = C.create_string_buffer(64)

@@ -64,6 +64,10 @@ struct SearchParams {
     int stage_rows, stages, slot_stride;
     int h_ng, h_spt;
     int off_ng, off_spt, off_cand, off_bar, off_query;
+    // PQ / OPQ quantized index (PQQuantizer.h:110-128, ADC off): rows are M code bytes, the query is M code
+    // bytes too and distance = sum_i sdc[(i*Ks + x_i)*Ks + y_i]
+    const float* sdc;
+    int pq_m, pq_ks;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -357,7 +361,7 @@ struct BktNodeDev {
     int centerid, childStart, childEnd;
 };
 
-template <int DIM, bool COSINE, int RPL>
+template <int DIM, bool COSINE, int RPL, bool PQ>
 struct WarpSearch {
     const SearchParams& p;
     const int lane, half, j;
@@ -440,8 +444,45 @@ struct WarpSearch {
     }
 
     // distances of the query to cand_id[0..cnt) -> cand_dist[0..cnt).  cnt <= 32.
+    // PQ rows: all (<= 32) code rows of the step are staged by one TMA batch, then lane r sums the M
+    // table entries of candidate r in subvector order -- the reference's single float accumulator
+    // (PQQuantizer::L2Distance, PQQuantizer.h:110-128), one candidate per lane.
+    __device__ __forceinline__ void compute_dists_pq(int cnt) {
+        __syncwarp();
+        fence_proxy_async();
+        if (lane == 0) mbar_arrive_expect_tx(&bars[0], (uint32_t)cnt * (uint32_t)p.row_bytes);
+        __syncwarp();
+        if (lane < cnt)
+            tma_load_1d(ring + (size_t)lane * p.slot_stride, p.vectors + (size_t)cand_id[lane] * p.row_stride_bytes,
+                        (uint32_t)p.row_bytes, &bars[0]);
+        mbar_wait(&bars[0], phase_bits & 1u);
+        phase_bits ^= 1u;
+        if (lane < cnt) {
+            const unsigned char* row = ring + (size_t)lane * p.slot_stride;
+            const int* qoff = reinterpret_cast<const int*>(qs);
+            float acc = 0.0f;
+            const int m4 = p.pq_m & ~3;
+            int i = 0;
+            for (; i < m4; i += 4) {
+                const unsigned w = *reinterpret_cast<const unsigned*>(row + i);
+                acc = __fadd_rn(acc, __ldg(p.sdc + qoff[i] + (w & 255u)));
+                acc = __fadd_rn(acc, __ldg(p.sdc + qoff[i + 1] + ((w >> 8) & 255u)));
+                acc = __fadd_rn(acc, __ldg(p.sdc + qoff[i + 2] + ((w >> 16) & 255u)));
+                acc = __fadd_rn(acc, __ldg(p.sdc + qoff[i + 3] + (w >> 24)));
+            }
+            for (; i < p.pq_m; ++i) acc = __fadd_rn(acc, __ldg(p.sdc + qoff[i] + row[i]));
+            cand_dist[lane] = acc;
+        }
+        __syncwarp();
+        ndist += cnt;
+    }
+
     __device__ __forceinline__ void compute_dists(int cnt) {
         if (cnt <= 0) return;
+        if (PQ) {
+            compute_dists_pq(cnt);
+            return;
+        }
         __syncwarp();
         fence_proxy_async();  // earlier generic-proxy reads of the ring precede the async writes
         const int nst = (cnt + p.stage_rows - 1) / p.stage_rows;
@@ -708,11 +749,11 @@ struct WarpSearch {
 // ------------------------------------------------------------------------------------------
 // kernel: persistent warps pull queries from a global counter
 // ------------------------------------------------------------------------------------------
-template <int DIM, bool COSINE, int RPL, bool KDT>
+template <int DIM, bool COSINE, int RPL, bool KDT, bool PQ = false>
 __global__ void __launch_bounds__(32) search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x;
-    WarpSearch<DIM, COSINE, RPL> w(p, lane);
+    WarpSearch<DIM, COSINE, RPL, PQ> w(p, lane);
     w.ring = smem;
     w.cand_id = reinterpret_cast<int*>(smem + p.off_cand);
     w.cand_dist = reinterpret_cast<float*>(smem + p.off_cand + 128);
@@ -761,7 +802,12 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p) {
         w.checked = w.ndist = w.nexpand = w.ntree = 0;
         w.tree_checked = w.no_better = 0;
         // query -> shared memory (+ registers for the static-DIM variants)
-        {
+        if (PQ) {
+            // the (already quantized) query: M code bytes -> row offsets of its SDC table rows
+            const unsigned char* qc = p.queries + (size_t)q * p.query_stride_bytes;
+            int* qoff = reinterpret_cast<int*>(w.qs);
+            for (int i = lane; i < p.pq_m; i += 32) qoff[i] = (i * p.pq_ks + (int)qc[i]) * p.pq_ks;
+        } else {
             const float* qg = reinterpret_cast<const float*>(p.queries + (size_t)q * p.query_stride_bytes);
             for (int i = lane; i < p.dim; i += 32) w.qs[i] = qg[i];
             __syncwarp();
@@ -823,6 +869,112 @@ __global__ void distance_batch_kernel(const unsigned char* vectors, unsigned lon
     QueryRegs<0> qr;
     const float d = half_warp_distance<0, COSINE>(row, qr, qv, dim, j);
     if (valid && j == 0) out[item] = ok ? d : SPTAG_B200_MAXDIST;
+}
+
+// ------------------------------------------------------------------------------------------
+// PQ / OPQ quantizer kernels (query side + tables; PQQuantizer.h:138-180, :333-348, OPQQuantizer.h:96-121)
+// ------------------------------------------------------------------------------------------
+
+// The reference's float AVX-512 summation tree evaluated by ONE thread (any length d): used where the
+// operands are tiny (sub-vectors of a codebook) or where one thread owns one output (rotation rows).
+template <bool COSINE>
+__device__ float exact_dist_thread(const float* __restrict__ x, const float* __restrict__ y, int d) {
+    float a16[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a16[j] = 0.0f;
+    int i = 0;
+    for (; i + 16 <= d; i += 16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a16[j] = __fadd_rn(a16[j], dist_term<COSINE>(x[i + j], y[i + j]));
+    }
+    float a8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a8[j] = __fadd_rn(a16[j], a16[j + 8]);
+    if (d & 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a8[j] = __fadd_rn(a8[j], dist_term<COSINE>(x[i + j], y[i + j]));
+        i += 8;
+    }
+    float a4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a4[j] = __fadd_rn(a8[j], a8[j + 4]);
+    if (d & 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a4[j] = __fadd_rn(a4[j], dist_term<COSINE>(x[i + j], y[i + j]));
+        i += 4;
+    }
+    float s = __fadd_rn(__fadd_rn(__fadd_rn(a4[0], a4[1]), a4[2]), a4[3]);
+    for (; i < d; ++i) s = dist_tail<COSINE>(x[i], y[i], s);
+    return COSINE ? __fsub_rn(1.0f, s) : s;
+}
+
+// PQQuantizer::InitializeDistanceTables (PQQuantizer.h:333-348): sdc[i][j][k] = L2(codebook[i][j], codebook[i][k])
+__global__ void sdc_table_kernel(const float* __restrict__ codebooks, int m, int ks, int dsub, float* __restrict__ sdc) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)m * ks * ks;
+    if (t >= total) return;
+    const int k = (int)(t % ks);
+    const int j = (int)((t / ks) % ks);
+    const int i = (int)(t / ((long long)ks * ks));
+    const float* base = codebooks + (size_t)i * ks * dsub;
+    sdc[t] = exact_dist_thread<false>(base + (size_t)j * dsub, base + (size_t)k * dsub, dsub);
+}
+
+// IQuantizer::QuantizeVector(raw, codes, ADC=false) for a batch: one CTA per raw vector.
+//   OPQ: rot[i] = m_base - m_fdot(vec, OPQMatrix_T row i) with m_base = 1 and m_fdot = float cosine distance
+//        (OPQQuantizer.h:96-121, :198-206); PQ: rot = vec.
+//   then per sub-vector the first codeword with the strictly smallest L2 distance (PQQuantizer.h:158-179).
+// raw_type: 0 int8, 1 uint8, 2 int16, 3 float (the quantizer's reconstruct type).
+__global__ void pq_quantize_kernel(const unsigned char* __restrict__ raw, int raw_type, long long raw_stride_bytes,
+                                   int nvec, const float* __restrict__ codebooks, const float* __restrict__ rotation_t,
+                                   int m, int ks, int dsub, unsigned char* __restrict__ codes) {
+    extern __shared__ float qsm[];  // vec[dim] | rot[dim]
+    const int dim = m * dsub;
+    float* vec = qsm;
+    float* rot = qsm + dim;
+    const int v = blockIdx.x;
+    if (v >= nvec) return;
+    const unsigned char* src = raw + (size_t)v * raw_stride_bytes;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+        float f;
+        switch (raw_type) {
+        case 0: f = (float)reinterpret_cast<const signed char*>(src)[i]; break;
+        case 1: f = (float)src[i]; break;
+        case 2: f = (float)reinterpret_cast<const short*>(src)[i]; break;
+        default: f = reinterpret_cast<const float*>(src)[i]; break;
+        }
+        vec[i] = f;
+    }
+    __syncthreads();
+    const float* q = vec;
+    if (rotation_t != nullptr) {
+        for (int i = threadIdx.x; i < dim; i += blockDim.x)
+            rot[i] = __fsub_rn(1.0f, exact_dist_thread<true>(vec, rotation_t + (size_t)i * dim, dim));
+        __syncthreads();
+        q = rot;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int i = warp; i < m; i += nwarps) {
+        float best = INFINITY;
+        int bestj = 0x7fffffff;
+        for (int j = lane; j < ks; j += 32) {
+            const float d = exact_dist_thread<false>(q + (size_t)i * dsub, codebooks + ((size_t)i * ks + j) * dsub, dsub);
+            if (d < best) {  // increasing j per lane: strict '<' keeps the first minimum
+                best = d;
+                bestj = j;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(kFull, best, o);
+            const int oj = __shfl_xor_sync(kFull, bestj, o);
+            if (ob < best || (ob == best && oj < bestj)) {
+                best = ob;
+                bestj = oj;
+            }
+        }
+        if (lane == 0) codes[(size_t)v * m + i] = (unsigned char)bestj;
+    }
 }
 
 // ------------------------------------------------------------------------------------------

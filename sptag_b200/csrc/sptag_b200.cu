@@ -100,6 +100,9 @@ struct sptag_b200_index {
     // SM matter more than on-chip queue capacity (sweep in profiles/r01_sweep_c2.txt)
     int h_ng = 128, h_spt = 64;
     int simd_width = 16;
+    // PQ / OPQ quantizer (null when q_type == 0)
+    int q_type = 0, q_rtype = SPTAG_B200_VT_FLOAT, q_m = 0, q_ks = 0, q_dsub = 0;
+    DeviceBuffer d_codebooks, d_rotation_t, d_sdc, d_codes, d_raw;
     // scratch
     DeviceBuffer d_visited, d_ng_spill, d_spt_spill, d_counter;
     DeviceBuffer d_queries, d_ids, d_dists, d_stats;  // staging for the host-buffer entry point
@@ -139,6 +142,11 @@ SearchKernelFn pick_dim(int dim, int mres_cap, bool kdt) {
 // The kernel instantiation for this index / parameter set (nullptr: unsupported m_Results capacity)
 SearchKernelFn pick_kernel(const sptag_b200_index* h, int mres_cap) {
     const bool kdt = (h->algo == SPTAG_B200_ALGO_KDT);
+    if (h->q_type != 0) {  // quantized: BKT + L2 only (the quantizer has no cosine distance, PQQuantizer.h:130-136)
+        if (mres_cap <= 32 * 16) return search_kernel<0, false, 16, false, true>;
+        if (mres_cap <= 32 * 32) return search_kernel<0, false, 32, false, true>;
+        return nullptr;
+    }
     return (h->metric == SPTAG_B200_METRIC_L2) ? pick_dim<false>(h->dim, mres_cap, kdt)
                                                 : pick_dim<true>(h->dim, mres_cap, kdt);
 }
@@ -147,8 +155,17 @@ SearchKernelFn pick_kernel(const sptag_b200_index* h, int mres_cap) {
 int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& smem, int nq, SearchKernelFn& kern) {
     if (h->algo != SPTAG_B200_ALGO_BKT && h->algo != SPTAG_B200_ALGO_KDT)
         return fail(SPTAG_B200_LACK_OF_INPUTS, "unsupported index algorithm %d", h->algo);
-    if (h->value_type != SPTAG_B200_VT_FLOAT)
-        return fail(SPTAG_B200_LACK_OF_INPUTS, "only float vectors are searchable in this build");
+    const bool pq = (h->q_type != 0);
+    if (pq) {
+        if (h->value_type != SPTAG_B200_VT_UINT8 || h->dim != h->q_m)
+            return fail(SPTAG_B200_DIMENSION_MISMATCH, "quantizer has %d sub-vectors but the index rows are %d x type %d",
+                        h->q_m, h->dim, h->value_type);
+        if (h->algo != SPTAG_B200_ALGO_BKT || h->metric != SPTAG_B200_METRIC_L2)
+            return fail(SPTAG_B200_LACK_OF_INPUTS, "quantized indexes are searchable as BKT + L2 only");
+    } else if (h->value_type != SPTAG_B200_VT_FLOAT) {
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "value type %d needs a quantizer (integer DistanceUtils variants are not built)",
+                    h->value_type);
+    }
     if (h->simd_width != 16)
         return fail(SPTAG_B200_LACK_OF_INPUTS, "B200.SimdWidth %d not built (16 only)", h->simd_width);
     if (k < 1 || k > 32) return fail(SPTAG_B200_LACK_OF_INPUTS, "k = %d outside the supported range [1, 32]", k);
@@ -180,6 +197,9 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     p.spt_length = alloc_check * 10;
     p.spt_lastlevel = heap_lastlevel(p.spt_length);
     p.mres_cap = std::max(h->max_check / 16, k);
+    p.sdc = (const float*)h->d_sdc.ptr;
+    p.pq_m = h->q_m;
+    p.pq_ks = h->q_ks;
 
     // ---- shared-memory layout ----
     int stage_rows = h->stage_rows;
@@ -190,10 +210,15 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     stage_rows &= ~1;
     if (stage_rows < 2) stage_rows = 2;
     if (stage_rows > 32) stage_rows = 32;
-    const int stages = std::max(1, std::min(8, h->stages));
+    int stages = std::max(1, std::min(8, h->stages));
+    p.slot_stride = (int)round_up(h->row_stride + 64, 128);
+    if (pq) {  // every candidate row of a step in one TMA batch; rows are M bytes
+        stage_rows = 32;
+        stages = 1;
+        p.slot_stride = (int)h->row_stride + ((h->row_stride % 128 == 0) ? 16 : 0);
+    }
     p.stage_rows = stage_rows;
     p.stages = stages;
-    p.slot_stride = (int)round_up(h->row_stride + 64, 128);
     p.h_ng = std::max(1, h->h_ng);
     p.h_spt = std::max(1, h->h_spt);
     size_t off = (size_t)stage_rows * stages * p.slot_stride;
@@ -206,7 +231,7 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     p.off_bar = (int)off;
     off += round_up((size_t)stages * 8, 16);
     p.off_query = (int)off;
-    off += round_up((size_t)h->dim * 4 + 16, 16);
+    off += round_up((size_t)h->dim * 4 + 16, 16);  // float query, or M row offsets (int) for PQ
     smem = round_up(off, 128);
     if (smem > h->smem_optin)
         return fail(SPTAG_B200_MEMORY_OVERFLOW, "shared memory per query slot %zu exceeds %zu", smem, h->smem_optin);
@@ -243,6 +268,25 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     return 0;
 }
 
+size_t query_bytes(const sptag_b200_index* h) {
+    if (h->q_type != 0) return (size_t)h->q_m * h->q_dsub * value_size(h->q_rtype);
+    return (size_t)h->dim * value_size(h->value_type);
+}
+
+int quantize_device(sptag_b200_index* h, const void* d_raw, int n, unsigned char* d_codes, cudaStream_t stream) {
+    const int dim = h->q_m * h->q_dsub;
+    const size_t smem = (size_t)dim * 2 * sizeof(float);
+    if (smem > 48 * 1024)
+        CUDA_OK(cudaFuncSetAttribute(pq_quantize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pq_quantize_kernel<<<n, 128, smem, stream>>>((const unsigned char*)d_raw, h->q_rtype, (long long)query_bytes(h), n,
+                                                  (const float*)h->d_codebooks.ptr,
+                                                  h->q_type == 2 ? (const float*)h->d_rotation_t.ptr : nullptr, h->q_m,
+                                                  h->q_ks, h->q_dsub, d_codes);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int search_device_impl(sptag_b200_index* h, const void* d_queries, int nq, int k, int* d_ids, float* d_dists,
                        int* d_stats, cudaStream_t stream) {
     if (nq <= 0) return SPTAG_B200_SUCCESS;
@@ -253,6 +297,13 @@ int search_device_impl(sptag_b200_index* h, const void* d_queries, int nq, int k
     if (int rc = configure(h, k, p, grid, smem, nq, kern)) return rc;
     p.queries = (const unsigned char*)d_queries;
     p.query_stride_bytes = (size_t)h->dim * value_size(h->value_type);
+    if (h->q_type != 0) {
+        // QueryResultSet::SetTarget -> IQuantizer::QuantizeVector (QueryResultSet.h:46-60): raw -> M code bytes
+        if (int rc = h->d_codes.ensure((size_t)nq * h->q_m)) return rc;
+        if (int rc = quantize_device(h, d_queries, nq, (unsigned char*)h->d_codes.ptr, stream)) return rc;
+        p.queries = (const unsigned char*)h->d_codes.ptr;
+        p.query_stride_bytes = (size_t)h->q_m;
+    }
     p.nq = nq;
     p.out_ids = d_ids;
     p.out_dists = d_dists;
@@ -384,6 +435,11 @@ void sptag_b200_destroy(sptag_b200_handle h) {
     h->d_nodes.release();
     h->d_tree_starts.release();
     h->d_deleted.release();
+    h->d_codebooks.release();
+    h->d_rotation_t.release();
+    h->d_sdc.release();
+    h->d_codes.release();
+    h->d_raw.release();
     h->d_visited.release();
     h->d_ng_spill.release();
     h->d_spt_spill.release();
@@ -484,6 +540,20 @@ int sptag_b200_load(const char* folder, int32_t device, int32_t id_offset, sptag
     }
     sptag_b200_handle h = nullptr;
     if (int rc = sptag_b200_create(&d, &h)) return rc;
+    {
+        auto it = kv.find("QuantizerFilePath");  // [Quantizer] section (VectorIndex.cpp:188-192)
+        if (it != kv.end() && !it->second.empty()) {
+            std::vector<char> qb;
+            if (!read_file(dir + "/" + it->second, qb)) {
+                sptag_b200_destroy(h);
+                return fail(SPTAG_B200_FAILED_OPEN_FILE, "cannot read quantizer file %s", it->second.c_str());
+            }
+            if (int rc = sptag_b200_set_quantizer(h, qb.data(), (int64_t)qb.size())) {
+                sptag_b200_destroy(h);
+                return rc;
+            }
+        }
+    }
     static const char* names[] = {"MaxCheck", "MaxCheckForRefineGraph", "NumberOfInitialDynamicPivots",
                                   "NumberOfOtherDynamicPivots", "ThresholdOfNumberOfContinuousNoBetterPropagation"};
     for (const char* nm : names) {
@@ -491,6 +561,70 @@ int sptag_b200_load(const char* folder, int32_t device, int32_t id_offset, sptag
         if (it != kv.end()) sptag_b200_set_param(h, nm, it->second.c_str());
     }
     *out = h;
+    return SPTAG_B200_SUCCESS;
+}
+
+int sptag_b200_set_quantizer(sptag_b200_handle h, const void* blob, int64_t blob_bytes) {
+    if (!h || !blob || blob_bytes < 14) return fail(SPTAG_B200_LACK_OF_INPUTS, "null or short quantizer blob");
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceGuard guard(h->device);
+    const unsigned char* b = (const unsigned char*)blob;
+    const int qtype = b[0], rtype = b[1];
+    int32_t hdr[3];
+    memcpy(hdr, b + 2, 12);
+    const int m = hdr[0], ks = hdr[1], dsub = hdr[2];
+    if (qtype != 1 && qtype != 2) return fail(SPTAG_B200_LACK_OF_INPUTS, "unknown quantizer type %d", qtype);
+    if (qtype == 1 && rtype != SPTAG_B200_VT_FLOAT)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "PQQuantizer<T> is supported for T = float only (reconstruct type %d)", rtype);
+    if (rtype < 0 || rtype > 3 || m <= 0 || ks <= 0 || ks > 256 || dsub <= 0)
+        return fail(SPTAG_B200_FAILED_PARSE_VALUE, "bad quantizer header (M %d Ks %d Dsub %d type %d)", m, ks, dsub, rtype);
+    const size_t dim = (size_t)m * dsub;
+    const size_t cb_bytes = (size_t)m * ks * dsub * 4;
+    const size_t need = 14 + cb_bytes + (qtype == 2 ? dim * dim * 4 : 0);
+    if ((size_t)blob_bytes < need) return fail(SPTAG_B200_FAILED_PARSE_VALUE, "quantizer blob truncated (%lld < %zu)",
+                                              (long long)blob_bytes, need);
+    if (int rc = h->d_codebooks.ensure(cb_bytes)) return rc;
+    CUDA_OK(cudaMemcpy(h->d_codebooks.ptr, b + 14, cb_bytes, cudaMemcpyHostToDevice));
+    if (qtype == 2) {
+        // m_InitMatrixTranspose (OPQQuantizer.h:84-94): the rows the query is multiplied with
+        const float* rot = (const float*)(b + 14 + cb_bytes);
+        std::vector<float> rt(dim * dim);
+        for (size_t i = 0; i < dim; ++i)
+            for (size_t j = 0; j < dim; ++j) {
+                float v;
+                memcpy(&v, (const char*)rot + (j * dim + i) * 4, 4);
+                rt[i * dim + j] = v;
+            }
+        if (int rc = h->d_rotation_t.ensure(dim * dim * 4)) return rc;
+        CUDA_OK(cudaMemcpy(h->d_rotation_t.ptr, rt.data(), dim * dim * 4, cudaMemcpyHostToDevice));
+    }
+    // InitializeDistanceTables (PQQuantizer.h:333-348) on the device, same summation tree as the reference
+    const size_t entries = (size_t)m * ks * ks;
+    if (int rc = h->d_sdc.ensure(entries * 4)) return rc;
+    sdc_table_kernel<<<(unsigned)((entries + 255) / 256), 256>>>((const float*)h->d_codebooks.ptr, m, ks, dsub,
+                                                                (float*)h->d_sdc.ptr);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaDeviceSynchronize());
+    h->q_type = qtype;
+    h->q_rtype = rtype;
+    h->q_m = m;
+    h->q_ks = ks;
+    h->q_dsub = dsub;
+    return SPTAG_B200_SUCCESS;
+}
+
+int sptag_b200_quantize(sptag_b200_handle h, const void* raw_vectors, int32_t num, uint8_t* codes_out) {
+    if (!h || !raw_vectors || !codes_out || num <= 0) return fail(SPTAG_B200_LACK_OF_INPUTS, "null buffer");
+    if (h->q_type == 0) return fail(SPTAG_B200_LACK_OF_INPUTS, "index has no quantizer");
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceGuard guard(h->device);
+    const size_t rbytes = (size_t)num * query_bytes(h);
+    if (int rc = h->d_raw.ensure(rbytes)) return rc;
+    if (int rc = h->d_codes.ensure((size_t)num * h->q_m)) return rc;
+    CUDA_OK(cudaMemcpy(h->d_raw.ptr, raw_vectors, rbytes, cudaMemcpyHostToDevice));
+    if (int rc = quantize_device(h, h->d_raw.ptr, num, (unsigned char*)h->d_codes.ptr, nullptr)) return rc;
+    CUDA_OK(cudaMemcpy(codes_out, h->d_codes.ptr, (size_t)num * h->q_m, cudaMemcpyDeviceToHost));
     return SPTAG_B200_SUCCESS;
 }
 
@@ -556,7 +690,7 @@ int sptag_b200_search(sptag_b200_handle h, const void* queries, int32_t num_quer
     if (num_queries == 0) return SPTAG_B200_SUCCESS;
     std::lock_guard<std::mutex> lock(h->mu);
     DeviceGuard guard(h->device);
-    const size_t qbytes = (size_t)num_queries * h->dim * value_size(h->value_type);
+    const size_t qbytes = (size_t)num_queries * query_bytes(h);
     const size_t rn = (size_t)num_queries * k;
     if (int rc = h->d_queries.ensure(qbytes)) return rc;
     if (int rc = h->d_ids.ensure(rn * 4)) return rc;

@@ -230,3 +230,39 @@ def test_merge_topk_matches_comparator():
         exp = cand[:k]
         assert o_ids[i].tolist() == [c[1] for c in exp]
         assert o_d[i].tolist() == [c[0] for c in exp]
+
+
+# ---------------------------------------------------------------------------------------------
+# PQ / OPQ quantized indexes: raw queries in, device-side QuantizeVector,
+# SDC table distances -- all bit-exact against the oracle (itself pinned to the reference)
+# ---------------------------------------------------------------------------------------------
+QUANT_SETS = ["bkt_pq_6k_32", "bkt_opq_6k_48", "bkt_opq_i8_8k_100"]
+
+
+@pytest.mark.parametrize("name", QUANT_SETS)
+def test_quantize_vector_bit_exact(name):
+    from sptag_b200 import B200Index
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))
+    idx = B200Index.load(folder)          # picks up [Quantizer] QuantizerFilePath
+    try:
+        codes = idx.quantize(q, files.quantizer.m)
+        exp = reflib.OracleQuantizer(files.quantizer).encode(q)
+        assert np.array_equal(codes, exp)
+    finally:
+        idx.close()
+
+
+@pytest.mark.parametrize("name", QUANT_SETS)
+def test_quantized_bkt_search_bit_exact(name):
+    from sptag_b200 import B200Index
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))
+    idx = B200Index.load(folder)
+    try:
+        for mc in [8192, 1024, 128]:
+            _compare(idx, files, q, 10, mc, name)
+    finally:
+        idx.close()
