@@ -63,6 +63,11 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--param", action="append", default=[], help="Name=Value passed to sptag_b200_set_param")
+    ap.add_argument("--algo", default="bkt", choices=["bkt", "kdt"], help="space-partition tree of the index")
+    ap.add_argument("--quantizer", default="none", choices=["none", "pq", "opq"],
+                    help="index holds uint8 PQ codes (BASELINE config 4 shape: --quantizer opq --raw-type int8 --dim 100 --pq-m 50)")
+    ap.add_argument("--pq-m", type=int, default=50, help="number of PQ sub-vectors")
+    ap.add_argument("--raw-type", default="float", choices=["float", "int8"], help="element type of raw vectors/queries")
     return ap.parse_args()
 
 
@@ -84,6 +89,9 @@ def gen_data(args, n, seed, device):
         z = torch.randn((n, r), generator=g, device=device, dtype=torch.float32)
         x = z @ A
         x += 0.1 * torch.randn((n, args.dim), generator=g, device=device, dtype=torch.float32)
+    if args.raw_type == "int8":
+        # SPACEV-style int8 raw vectors: clamp(round(32 x), -127, 127), kept as float values here
+        x = torch.clamp(torch.round(32.0 * x), -127, 127)
     if args.metric == "Cosine":
         # the reference normalises base vectors at build time (BKTIndex.cpp:749-756) and expects
         # unit-norm queries from the caller
@@ -92,8 +100,10 @@ def gen_data(args, n, seed, device):
 
 
 def index_folder(args, shard):
-    key = "bkt_%s_%dx%d_%s_r%d_s%d_shard%d_v%d" % (args.metric, args.n, args.dim, args.data, args.rank_dim,
+    key = "%s_%s_%dx%d_%s_r%d_s%d_shard%d_v%d" % (args.algo, args.metric, args.n, args.dim, args.data, args.rank_dim,
                                                    args.seed, shard, BUILDER_VERSION)
+    if args.quantizer != "none":
+        key += "_%s%d_%s" % (args.quantizer, args.pq_m, args.raw_type)
     return os.path.join(args.cache, key)
 
 
@@ -108,8 +118,14 @@ def ensure_index(args, shard, device):
     t0 = time.time()
     torch.backends.cuda.matmul.allow_tf32 = True
     x = gen_data(args, args.n, args.seed + 1000 * (shard + 1), device)
-    nodes, starts, graph = B.build_index(x, args.metric, seed=args.seed + shard, log=log)
-    B.save_index_folder(folder, x.cpu().numpy(), graph, nodes, starts, args.metric)
+    nodes, starts, graph = B.build_index(x, args.metric, seed=args.seed + shard, log=log, algo=args.algo.upper())
+    if args.quantizer != "none":
+        cb, rot = B.train_quantizer_gpu(x, args.pq_m, opq=(args.quantizer == "opq"), seed=args.seed)
+        codes = B.encode_gpu(x, cb, rot)
+        blob = B.quantizer_blob(cb, rot, 0 if args.raw_type == "int8" else 3)
+        B.save_index_folder(folder, codes.cpu().numpy(), graph, nodes, starts, args.metric, quantizer=blob)
+    else:
+        B.save_index_folder(folder, x.cpu().numpy(), graph, nodes, starts, args.metric, algo=args.algo.upper())
     torch.backends.cuda.matmul.allow_tf32 = False
     with open(done, "w") as f:
         f.write("ok\n")
@@ -191,7 +207,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # reference / cpu baseline leg (the ONLY place the oracle is executed by bench.py)
 # ---------------------------------------------------------------------------------------------
-def cpu_search_leg(folder, queries_np, k, maxcheck, threads, sample, repeats=1):
+def cpu_search_leg(folder, queries_np, k, maxcheck, threads, sample, repeats=1, each=False):
     """Times the reference's CPU SearchIndex(batch) on `sample` queries. Returns dict + ids for a parity check."""
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -201,10 +217,12 @@ def cpu_search_leg(folder, queries_np, k, maxcheck, threads, sample, repeats=1):
         kind = "reference"
         idx = reflib.RefIndex.load(folder)
         idx.set_param("MaxCheck", maxcheck)
-        idx.search(q[:min(256, sample)], k, threads=threads)  # creates the per-thread work spaces
+        # quantized indexes: the per-query overload on raw queries, as IndexSearcher does
+        run = idx.search_each if each else idx.search
+        run(q[:min(256, sample)], k, threads=threads)  # creates the per-thread work spaces
         best = None
         for _ in range(repeats):
-            ids, dists, sec = idx.search(q, k, threads=threads)
+            ids, dists, sec = run(q, k, threads=threads)
             best = sec if best is None else min(best, sec)
         isa = reflib.ref().ref_isa()
     else:
@@ -225,14 +243,14 @@ def cpu_search_leg(folder, queries_np, k, maxcheck, threads, sample, repeats=1):
             "seconds": best}, ids, dists
 
 
-def best_cpu_threads(folder, queries_np, k, maxcheck):
+def best_cpu_threads(folder, queries_np, k, maxcheck, each=False):
     """The reference gets every host thread it can use; on SMT boxes one thread per physical core is
     sometimes faster for this DRAM-bound loop, so probe both and keep the faster."""
     n = os.cpu_count() or 1
     cands = sorted({n, max(1, n // 2)}, reverse=True)
     best_t, best_v = n, -1.0
     for t in cands:
-        r, _, _ = cpu_search_leg(folder, queries_np, k, maxcheck, t, min(queries_np.shape[0], 1024))
+        r, _, _ = cpu_search_leg(folder, queries_np, k, maxcheck, t, min(queries_np.shape[0], 1024), each=each)
         if r["value"] > best_v:
             best_t, best_v = t, r["value"]
     return best_t
@@ -255,13 +273,19 @@ def main():
     if world != args.gpus and world > 1:
         args.gpus = world
 
-    workload = "SPTAG-BKT, %dx%d float32 %s, batch %d queries, k=%d, MaxCheck=%d, %s synthetic" % (
-        args.n, args.dim, args.metric.lower(), args.nq, args.k, args.maxcheck, args.data)
-    config = {"workload": workload, "index": "BKT+RNG(degree 32)", "n": args.n, "dim": args.dim,
+    quantized = args.quantizer != "none"
+    if quantized:
+        args.metric = "L2"  # the reference's quantizers have no cosine distance (PQQuantizer.h:130-136)
+    workload = "SPTAG-%s, %dx%d %s %s, batch %d queries, k=%d, MaxCheck=%d, %s synthetic" % (
+        args.algo.upper(), args.n, args.dim, "float32" if args.raw_type == "float" else "int8", args.metric.lower(), args.nq, args.k,
+        args.maxcheck, args.data)
+    if quantized:
+        workload += ", %s uint8 codes M=%d Ks=256 (SDC)" % (args.quantizer.upper(), args.pq_m)
+    config = {"workload": workload, "index": "%s+RNG(degree 32)" % args.algo.upper(), "n": args.n, "dim": args.dim,
               "metric": args.metric, "batch": args.nq, "k": args.k, "max_check": args.maxcheck,
               "parallelism": ("%s x%d" % (args.mode, args.gpus)) if args.gpus > 1 else "single GPU",
-              "l2_policy": "index (%.1f GB) and per-step traffic are larger than L2; no explicit flush"
-                           % (args.n * args.dim * 4 / 1e9)}
+              "l2_policy": "index (%.2f GB of vector rows) and per-step traffic are larger than L2; no explicit flush"
+                           % (args.n * (args.pq_m if quantized else args.dim * 4) / 1e9)}
 
     # ------------------------------ reference arm ------------------------------
     if args.impl == "reference":
@@ -275,9 +299,11 @@ def main():
             return 0
         folder = ensure_index(args, 0, dev) if dev is not None else index_folder(args, 0)
         q = gen_data(args, args.nq, args.seed + 7, dev if dev is not None else "cpu").cpu().numpy()
-        threads = best_cpu_threads(folder, q, args.k, args.maxcheck)
+        if args.raw_type == "int8":
+            q = q.astype(np.int8)
+        threads = best_cpu_threads(folder, q, args.k, args.maxcheck, each=quantized)
         # bounded sample per step: probe the speed, then size a step to ~3 s of CPU work
-        probe, _, _ = cpu_search_leg(folder, q, args.k, args.maxcheck, threads, min(args.nq, 512))
+        probe, _, _ = cpu_search_leg(folder, q, args.k, args.maxcheck, threads, min(args.nq, 512), each=quantized)
         sample = int(max(256, min(args.nq, probe["value"] * 3.0)))
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import reflib
@@ -287,7 +313,7 @@ def main():
             idx.set_param("MaxCheck", args.maxcheck)
             kind = "reference"
             for s in range(args.warmup + args.steps):
-                _, _, sec = idx.search(q[:sample], args.k, threads=threads)
+                _, _, sec = (idx.search_each if quantized else idx.search)(q[:sample], args.k, threads=threads)
                 if s >= args.warmup:
                     secs.append(sec)
         else:
@@ -340,9 +366,11 @@ def main():
     files = load_folder_arrays(folder)
     id_offset = shard * args.n if args.mode == "shard" else 0
     t0 = time.time()
-    idx = B200Index.create(algo=capi.ALGO_BKT, value_type=capi.VT_FLOAT, metric=files.metric, vectors=files.vectors,
+    idx = B200Index.create(algo=capi.ALGO_KDT if args.algo == "kdt" else capi.ALGO_BKT, value_type=files.value_type, metric=files.metric, vectors=files.vectors,
                            graph=files.graph, tree_starts=files.tree_starts, tree_nodes=files.nodes,
                            device=local_rank, id_offset=id_offset)
+    if quantized:
+        idx.set_quantizer(files.quantizer.blob())
     idx.set_param("MaxCheck", args.maxcheck)
     for kv in args.param:
         nm, v = kv.split("=", 1)
@@ -350,8 +378,10 @@ def main():
     log("index uploaded to HBM in %.1fs" % (time.time() - t0))
 
     qseed = args.seed + 7 + (rank if args.mode == "replica" else 0)
-    d_q = gen_data(args, args.nq, qseed, dev)
-    h_q = torch.empty((args.nq, args.dim), dtype=torch.float32, pin_memory=True)
+    d_q_f32 = gen_data(args, args.nq, qseed, dev)
+    qdtype = torch.int8 if args.raw_type == "int8" else torch.float32
+    d_q = d_q_f32.to(qdtype).contiguous()
+    h_q = torch.empty((args.nq, args.dim), dtype=qdtype, pin_memory=True)
     h_q.copy_(d_q)
     d_ids = torch.empty((args.nq, args.k), dtype=torch.int32, device=dev)
     d_dists = torch.empty((args.nq, args.k), dtype=torch.float32, device=dev)
@@ -390,9 +420,9 @@ def main():
     step_device(with_stats=True)
     torch.cuda.synchronize()
     st = d_stats.cpu().numpy().astype(np.int64)
-    row_bytes = args.dim * 4
+    row_bytes = files.vectors.shape[1] * files.vectors.itemsize  # dim*4, or M code bytes when quantized
     alg_bytes = int((st[:, capi.ST_NDIST] * row_bytes + st[:, capi.ST_NEXPAND] * files.degree * 4
-                     + st[:, capi.ST_NTREE] * 12).sum())
+                     + st[:, capi.ST_NTREE] * (16 if args.algo == "kdt" else 12)).sum())
     res_ids = (m_ids if m_ids is not None else d_ids).cpu().numpy()
     shard_merge_check = None
     if gathered_ids is not None:
@@ -409,8 +439,11 @@ def main():
     recall = None
     if args.mode == "replica" or world == 1:
         from tools import gpu_index_builder as B
-        x_dev = torch.from_numpy(files.vectors).to(dev)
-        truth = B.exact_topk(x_dev, d_q, args.k, args.metric)
+        if quantized:  # ground truth on the raw vectors (regenerated: the folder only holds codes)
+            x_dev = gen_data(args, args.n, args.seed + 1000 * (shard + 1), dev)
+        else:
+            x_dev = torch.from_numpy(files.vectors).to(dev)
+        truth = B.exact_topk(x_dev, d_q_f32, args.k, args.metric)
         del x_dev
         torch.cuda.empty_cache()
         recall = recall_at_k(res_ids, truth, args.k)
@@ -484,7 +517,8 @@ def main():
     kernel_ms = float(np.mean(kms))
     achieved = alg_bytes / (kernel_ms / 1000.0) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "search_kernel<%d,%s,BKT>" % (args.dim if args.dim in (128, 768) else 0, args.metric), "kernel_ms": kernel_ms,
+                "traffic": None, "kernel": ("search_kernel<PQ,L2,BKT>" if quantized else
+                           "search_kernel<%d,%s,%s>" % (args.dim if args.dim in (128, 768) else 0, args.metric, args.algo.upper())), "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "share_of_step": kernel_ms / ms_step}
 
@@ -493,19 +527,20 @@ def main():
     parity = None
     if args.gpus == 1 and not args.no_cpu_baseline:
         qn = h_q.numpy()
-        threads = best_cpu_threads(folder, qn, args.k, args.maxcheck)
-        probe, _, _ = cpu_search_leg(folder, qn, args.k, args.maxcheck, threads, min(args.nq, 512))
+        threads = best_cpu_threads(folder, qn, args.k, args.maxcheck, each=quantized)
+        probe, _, _ = cpu_search_leg(folder, qn, args.k, args.maxcheck, threads, min(args.nq, 512), each=quantized)
         sample = args.cpu_sample or int(max(512, min(args.nq, probe["value"] * 5.0)))
-        cpu_baseline, cpu_ids, cpu_d = cpu_search_leg(folder, qn, args.k, args.maxcheck, threads, sample, repeats=3)
+        cpu_baseline, cpu_ids, cpu_d = cpu_search_leg(folder, qn, args.k, args.maxcheck, threads, sample, repeats=3,
+                                                      each=quantized)
         same = int((cpu_ids == res_ids[:sample]).all(axis=1).sum())
         parity = {"queries_compared": sample, "identical_id_lists": same}
         cpu_baseline.pop("seconds", None)
 
     line = {"metric": "queries_per_second", "value": value, "unit": "queries/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if not quantized else "u8 codes, f32 SDC sums", "data": "synthetic", "config": config,
             "recall_at_10": recall, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": args.nq * args.dim * 4,
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": args.nq * args.dim * h_q.element_size(),
                     "d2h_bytes_per_step": args.nq * args.k * 8},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "parity_vs_reference": parity, "shard_merge_check": shard_merge_check}

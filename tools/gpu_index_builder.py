@@ -179,6 +179,75 @@ def build_bkt(x, kmeans_k=32, leaf_size=8, iters=2, seed=0, log=None):
 
 
 # ---------------------------------------------------------------------------------------------
+# KD-tree (KDTree.h:22-28 node, :61-446 build): split on the dimension of largest variance at the mean,
+# values < split go left (Subdivide, KDTree.h:401-446), an all-equal node is split evenly, single points
+# become leaves encoded as -(id)-1.  Level-synchronous on the GPU.
+# ---------------------------------------------------------------------------------------------
+def build_kdt(x, log=None):
+    """Returns (nodes [N, 4] as int32 view {left, right, split_dim, split_value bits}, tree_starts [1])."""
+    dev = x.device
+    N, dim = x.shape
+    left = torch.zeros(N, dtype=torch.int32, device=dev)
+    right = torch.zeros(N, dtype=torch.int32, device=dev)
+    sdim = torch.zeros(N, dtype=torch.int32, device=dev)
+    sval = torch.zeros(N, dtype=torch.float32, device=dev)
+    perm = torch.arange(N, device=dev)
+    seg_node = torch.zeros(1, dtype=torch.int64, device=dev)        # tree node index of each open segment
+    sizes = torch.tensor([N], dtype=torch.int64, device=dev)
+    next_free = 1
+    level = 0
+    while seg_node.numel() > 0:
+        S = seg_node.numel()
+        seg = torch.repeat_interleave(torch.arange(S, device=dev), sizes)
+        offs = torch.cumsum(sizes, 0) - sizes
+        pos = torch.arange(perm.numel(), device=dev) - offs[seg]
+        xs = x[perm]
+        cnt = sizes.float()[:, None]
+        mean = torch.zeros((S, dim), device=dev).index_add_(0, seg, xs) / cnt
+        var = torch.zeros((S, dim), device=dev).index_add_(0, seg, xs * xs) / cnt - mean * mean
+        sd = var.argmax(1)
+        sv = mean[torch.arange(S, device=dev), sd]
+        val = xs[torch.arange(xs.shape[0], device=dev), sd[seg]]
+        go_right = val >= sv[seg]
+        nright = torch.zeros(S, dtype=torch.int64, device=dev).index_add_(0, seg, go_right.long())
+        degenerate = (nright == 0) | (nright == sizes)
+        if degenerate.any():  # all equal along the split dimension: split evenly (KDTree.h:438-443)
+            half = (sizes // 2)[seg]
+            go_right = torch.where(degenerate[seg], pos >= half, go_right)
+            nright = torch.zeros(S, dtype=torch.int64, device=dev).index_add_(0, seg, go_right.long())
+        nleft = sizes - nright
+        sdim[seg_node] = sd.int()
+        sval[seg_node] = sv
+        # order members: by segment, left side first
+        order = torch.argsort(seg * 2 + go_right.long(), stable=True)
+        perm = perm[order]
+        child_sizes = torch.stack([nleft, nright], 1).reshape(-1)    # [2S] in (seg, side) order
+        child_first = torch.cumsum(child_sizes, 0) - child_sizes
+        is_leaf = child_sizes == 1
+        internal = ~is_leaf
+        n_int = int(internal.sum().item())
+        child_index = torch.full((2 * S,), -1, dtype=torch.int64, device=dev)
+        child_index[internal] = next_free + torch.arange(n_int, device=dev)
+        child_index[is_leaf] = -perm[child_first[is_leaf]] - 1
+        ci = child_index.view(S, 2)
+        left[seg_node] = ci[:, 0].int()
+        right[seg_node] = ci[:, 1].int()
+        next_free += n_int
+        # next level: members of internal children, in order
+        keep_child = internal
+        child_of_pos = torch.repeat_interleave(torch.arange(2 * S, device=dev), child_sizes)
+        keep = keep_child[child_of_pos]
+        perm = perm[keep]
+        seg_node = child_index[internal]
+        sizes = child_sizes[internal]
+        if log and level % 4 == 0:
+            log("kdt level %d: %d segments" % (level, S))
+        level += 1
+    nodes = torch.stack([left, right, sdim, sval.view(torch.int32)], 1).contiguous()
+    return nodes.cpu().numpy(), np.array([0], np.int32)
+
+
+# ---------------------------------------------------------------------------------------------
 # relative-neighbourhood graph
 # ---------------------------------------------------------------------------------------------
 def build_rng_graph(x, degree=32, cand=64, rng_factor=1.0, fill=True, row_chunk=None, log=None):
@@ -283,13 +352,99 @@ MetaRecordSize=10
 """
 
 
-def save_index_folder(folder, vectors, graph, nodes, tree_starts, metric, kmeans_k=32, leaf_size=8):
-    """vectors: float32 numpy [N, dim] (already normalised for cosine)."""
+# ---------------------------------------------------------------------------------------------
+# synthetic PQ / OPQ quantizer (the reference cannot train OPQ natively, so the
+# codebooks are plain per-subspace k-means and the rotation a random orthonormal matrix, written in the
+# reference's SaveQuantizer format so the reference loads the same file)
+# ---------------------------------------------------------------------------------------------
+def train_quantizer_gpu(x, m, ks=256, opq=True, seed=0, iters=8, sample=200000):
+    """x: float32 [N, dim] on the device. Returns (codebooks [m, ks, dsub], rotation [dim, dim] or None);
+    the rotation is applied as x @ rotation (OPQQuantizer::m_VectorMatrixMultiply with the transposed matrix)."""
+    dev = x.device
+    N, dim = x.shape
+    dsub = dim // m
+    assert dsub * m == dim
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    rot = None
+    if opq:
+        a = torch.randn((dim, dim), generator=g, device=dev, dtype=torch.float32)
+        rot, _ = torch.linalg.qr(a)
+        rot = rot.contiguous()
+    idx = torch.randperm(N, generator=g, device=dev)[:min(N, sample)]
+    s = x[idx]
+    if rot is not None:
+        s = s @ rot
+    s = s.view(-1, m, dsub).transpose(0, 1).contiguous()            # [m, S, dsub]
+    S = s.shape[1]
+    cb = s[:, torch.randperm(S, generator=g, device=dev)[:ks], :].clone()   # [m, ks, dsub]
+    if cb.shape[1] < ks:
+        cb = torch.cat([cb, cb[:, :ks - cb.shape[1]]], 1)
+    for _ in range(iters):
+        d = (s * s).sum(2)[:, :, None] - 2.0 * torch.bmm(s, cb.transpose(1, 2)) + (cb * cb).sum(2)[:, None, :]
+        a = d.argmin(2)                                              # [m, S]
+        onehot = torch.zeros((m, S, ks), device=dev, dtype=torch.float32).scatter_(2, a[:, :, None], 1.0)
+        cnt = onehot.sum(1)                                          # [m, ks]
+        newc = torch.bmm(onehot.transpose(1, 2), s)                  # [m, ks, dsub]
+        nz = cnt > 0
+        cb[nz] = newc[nz] / cnt[nz][:, None]
+    return cb.contiguous(), rot
+
+
+def encode_gpu(x, codebooks, rotation, chunk=262144):
+    """Nearest codeword per sub-vector (plain fp32; the stored codes are just data for the index)."""
+    m, ks, dsub = codebooks.shape
+    out = torch.empty((x.shape[0], m), dtype=torch.uint8, device=x.device)
+    cn = (codebooks * codebooks).sum(2)
+    for s in range(0, x.shape[0], chunk):
+        xs = x[s:s + chunk]
+        if rotation is not None:
+            xs = xs @ rotation
+        xs = xs.view(-1, m, dsub).transpose(0, 1)                    # [m, c, dsub]
+        d = -2.0 * torch.bmm(xs, codebooks.transpose(1, 2)) + cn[:, None, :]
+        out[s:s + chunk] = d.argmin(2).transpose(0, 1).to(torch.uint8)
+    return out
+
+
+def quantizer_blob(codebooks, rotation, rtype):
+    """PQQuantizer::SaveQuantizer / OPQQuantizer::SaveQuantizer layout. rtype: 0 int8, 1 uint8, 2 int16, 3 float."""
+    m, ks, dsub = codebooks.shape
+    qtype = 2 if rotation is not None else 1
+    b = np.array([qtype, rtype], np.uint8).tobytes() + np.array([m, ks, dsub], np.int32).tobytes()
+    b += np.ascontiguousarray(codebooks.cpu().numpy(), np.float32).tobytes()
+    if rotation is not None:
+        b += np.ascontiguousarray(rotation.cpu().numpy(), np.float32).tobytes()
+    return b
+
+
+KDT_INI_HEAD = """[Index]
+IndexAlgoType=KDT
+ValueType=Float
+
+TreeFilePath=tree.bin
+GraphFilePath=graph.bin
+VectorFilePath=vectors.bin
+DeleteVectorFilePath=deletes.bin
+KDTNumber=1
+NumTopDimensionKDTSplit=5
+Samples=100
+IsOldVersion=false
+"""
+
+
+def save_index_folder(folder, vectors, graph, nodes, tree_starts, metric, kmeans_k=32, leaf_size=8,
+                      quantizer=None, algo="BKT"):
+    """vectors: float32 numpy [N, dim] (already normalised for cosine), or uint8 PQ codes [N, M] together with
+    `quantizer` = bytes of the quantizer file."""
     os.makedirs(folder, exist_ok=True)
     N, dim = vectors.shape
+    quantized = quantizer is not None
     with open(os.path.join(folder, "vectors.bin"), "wb") as f:
         np.array([N, dim], np.int32).tofile(f)
-        np.ascontiguousarray(vectors, np.float32).tofile(f)
+        np.ascontiguousarray(vectors, np.uint8 if quantized else np.float32).tofile(f)
+    if quantized:
+        with open(os.path.join(folder, "quantizer.bin"), "wb") as f:
+            f.write(quantizer)
     with open(os.path.join(folder, "graph.bin"), "wb") as f:
         np.array([N, graph.shape[1]], np.int32).tofile(f)
         np.ascontiguousarray(graph, np.int32).tofile(f)
@@ -302,7 +457,14 @@ def save_index_folder(folder, vectors, graph, nodes, tree_starts, metric, kmeans
         np.array([0, N, 1], np.int32).tofile(f)  # Labelset: deleted count, then Dataset<int8>(N x 1)
         np.zeros(N, np.int8).tofile(f)
     with open(os.path.join(folder, "indexloader.ini"), "w") as f:
-        f.write(INI_TEMPLATE.format(kmeans_k=kmeans_k, leaf_size=leaf_size, degree=graph.shape[1],
+        text = INI_TEMPLATE
+        if algo == "KDT":
+            # same [Index] body with the KD-tree parameters in place of the BKT ones (KDT/ParameterDefinitionList.h)
+            body = INI_TEMPLATE.split("TPTNumber=32", 1)[1]
+            text = KDT_INI_HEAD + "TPTNumber=32" + body.replace("NumTopDimensionTpTreeSplit", "NumTopDimensionTPTSplit")
+        if quantized:
+            text = "[Quantizer]\nQuantizerFilePath=quantizer.bin\n\n" + text.replace("ValueType=Float", "ValueType=UInt8")
+        f.write(text.format(kmeans_k=kmeans_k, leaf_size=leaf_size, degree=graph.shape[1],
                                     threads=os.cpu_count() or 1, metric=metric))
 
 
@@ -320,10 +482,13 @@ def exact_topk(x, q, k, metric, chunk=2048):
     return torch.cat(out).cpu().numpy()
 
 
-def build_index(x, metric="L2", degree=32, cand=64, kmeans_k=32, leaf_size=8, seed=0, log=None):
+def build_index(x, metric="L2", degree=32, cand=64, kmeans_k=32, leaf_size=8, seed=0, log=None, algo="BKT"):
     """x: float32 tensor [N, dim] on the build device (unit rows for Cosine). Returns numpy arrays."""
     t = time.time()
-    nodes, starts = build_bkt(x, kmeans_k=kmeans_k, leaf_size=leaf_size, seed=seed, log=log)
+    if algo == "KDT":
+        nodes, starts = build_kdt(x, log=log)
+    else:
+        nodes, starts = build_bkt(x, kmeans_k=kmeans_k, leaf_size=leaf_size, seed=seed, log=log)
     t_tree = time.time() - t
     t = time.time()
     graph = build_rng_graph(x, degree=degree, cand=cand, log=log)
