@@ -60,6 +60,9 @@ struct SearchParams {
     int2* spt_spill;
     unsigned long long spt_spill_entries;  // per slot
     unsigned int* work_counter;
+    // large N: instead of clearing the whole bitmap per query, log the words that were set and clear only those
+    unsigned int* vlog;                    // per slot, vlog_entries words; nullptr = clear the bitmap per query
+    unsigned long long vlog_entries;
     // shared-memory layout (bytes from the dynamic smem base)
     int stage_rows, stages, slot_stride;
     int h_ng, h_spt;
@@ -373,6 +376,8 @@ struct WarpSearch {
     float* qs;
     // HBM scratch of this slot
     unsigned int* visited;
+    unsigned int* vlog;  // nullptr when the bitmap is cleared wholesale
+    int vlog_count;
     // queues
     WarpHeap ng, spt;
     MResults<RPL> mres;
@@ -400,7 +405,13 @@ struct WarpSearch {
         const unsigned w = __ldcg(&visited[id >> 5]);
         const unsigned bit = 1u << (id & 31);
         const bool was = (w & bit) != 0;
-        if (!was && lane == 0) visited[id >> 5] = w | bit;
+        if (!was) {
+            if (lane == 0) {
+                visited[id >> 5] = w | bit;
+                if (vlog != nullptr && vlog_count < (int)p.vlog_entries) vlog[vlog_count] = (unsigned)(id >> 5);
+            }
+            vlog_count++;
+        }
         __syncwarp();
         return was;
     }
@@ -625,7 +636,12 @@ struct WarpSearch {
                 const unsigned freshmask = __ballot_sync(kFull, fresh);
                 const int cnt = __popc(freshmask);
                 __syncwarp();
-                if (fresh) cand_id[__popc(freshmask & ((1u << lane) - 1u))] = nn;
+                if (fresh) {
+                    const int rank = __popc(freshmask & ((1u << lane) - 1u));
+                    cand_id[rank] = nn;
+                    if (vlog != nullptr && vlog_count + rank < (int)p.vlog_entries) vlog[vlog_count + rank] = (unsigned)(nn >> 5);
+                }
+                vlog_count += cnt;
                 compute_dists(cnt);
                 // m_Results.worst() never increases, so a candidate above the current worst is rejected
                 // whenever its turn comes; only the others are replayed in neighbour order (BKTIndex.cpp:338-344)
@@ -721,7 +737,12 @@ struct WarpSearch {
                 const unsigned freshmask = __ballot_sync(kFull, fresh);
                 const int cnt = __popc(freshmask);
                 __syncwarp();
-                if (fresh) cand_id[__popc(freshmask & ((1u << lane) - 1u))] = nn;
+                if (fresh) {
+                    const int rank = __popc(freshmask & ((1u << lane) - 1u));
+                    cand_id[rank] = nn;
+                    if (vlog != nullptr && vlog_count + rank < (int)p.vlog_entries) vlog[vlog_count + rank] = (unsigned)(nn >> 5);
+                }
+                vlog_count += cnt;
                 compute_dists(cnt);
                 for (int r = 0; r < cnt; ++r) {
                     const float d = cand_dist[r];
@@ -760,6 +781,7 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p) {
     w.bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
     w.qs = reinterpret_cast<float*>(smem + p.off_query);
     w.visited = p.visited + (size_t)blockIdx.x * p.visited_words;
+    w.vlog = p.vlog ? p.vlog + (size_t)blockIdx.x * p.vlog_entries : nullptr;
     w.ng.s = reinterpret_cast<int2*>(smem + p.off_ng);
     w.ng.g = p.ng_spill + (size_t)blockIdx.x * p.ng_spill_entries;
     w.ng.H = p.h_ng;
@@ -787,11 +809,12 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p) {
         if (q >= p.nq) break;
 
         // ---- WorkSpace::Reset (WorkSpace.h:265-278) ----
-        {
+        if (w.vlog == nullptr) {
             uint4* v4 = reinterpret_cast<uint4*>(w.visited);
             const size_t n4 = p.visited_words >> 2;
             for (size_t i = lane; i < n4; i += 32) v4[i] = make_uint4(0, 0, 0, 0);
         }
+        w.vlog_count = 0;
         w.ng.count = 0;
         w.spt.count = 0;
         w.mres.reset(p.mres_cap, lane);
@@ -823,6 +846,18 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p) {
         else
             w.bkt_search();
 
+        // log mode: leave the bitmap clean for the next query of this slot
+        if (w.vlog != nullptr) {
+            __syncwarp();
+            if (w.vlog_count <= (int)p.vlog_entries) {
+                for (int i = lane; i < w.vlog_count; i += 32) w.visited[w.vlog[i]] = 0u;
+            } else {  // the log overflowed: clear everything
+                uint4* v4 = reinterpret_cast<uint4*>(w.visited);
+                const size_t n4 = p.visited_words >> 2;
+                for (size_t i = lane; i < n4; i += 32) v4[i] = make_uint4(0, 0, 0, 0);
+            }
+            __syncwarp();
+        }
         // ---- QueryResultSet::SortResult: the register list is already ascending by (dist, id) ----
         if (lane < p.k) {
             const int id = w.tk_id;

@@ -100,11 +100,14 @@ struct sptag_b200_index {
     // SM matter more than on-chip queue capacity (sweep in profiles/r01_sweep_c2.txt)
     int h_ng = 128, h_spt = 64;
     int simd_width = 16;
+    int visited_log = -1;         // -1 auto (bitmap > 256 KB per slot), 0 clear per query, 1 log + selective clear
+    int visited_log_entries = 0;  // 0 = auto
+    bool visited_clean = false;   // the whole d_visited buffer is known to be zero
     // PQ / OPQ quantizer (null when q_type == 0)
     int q_type = 0, q_rtype = SPTAG_B200_VT_FLOAT, q_m = 0, q_ks = 0, q_dsub = 0;
     DeviceBuffer d_codebooks, d_rotation_t, d_sdc, d_codes, d_raw;
     // scratch
-    DeviceBuffer d_visited, d_ng_spill, d_spt_spill, d_counter;
+    DeviceBuffer d_visited, d_ng_spill, d_spt_spill, d_counter, d_vlog;
     DeviceBuffer d_queries, d_ids, d_dists, d_stats;  // staging for the host-buffer entry point
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool timed = false;
@@ -257,7 +260,28 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     const size_t use_slots = std::min(slots, (size_t)std::max(grid, 1));
     (void)use_slots;
     const size_t alloc_slots = (size_t)h->num_sms * per_sm;
-    if (int rc = h->d_visited.ensure(alloc_slots * p.visited_words * 4)) return rc;
+    {
+        const size_t before = h->d_visited.bytes;
+        if (int rc = h->d_visited.ensure(alloc_slots * p.visited_words * 4)) return rc;
+        if (h->d_visited.bytes != before) h->visited_clean = false;
+    }
+    const bool use_log = h->visited_log < 0 ? (p.visited_words * 4 > 256 * 1024) : (h->visited_log != 0);
+    if (use_log) {
+        size_t entries = h->visited_log_entries > 0 ? (size_t)h->visited_log_entries
+                                                    : (size_t)std::max(65536, 8 * alloc_check);
+        entries = std::min(entries, (size_t)h->n + 2);
+        p.vlog_entries = entries;
+        if (int rc = h->d_vlog.ensure(alloc_slots * entries * 4)) return rc;
+        p.vlog = (unsigned int*)h->d_vlog.ptr;
+        if (!h->visited_clean) {  // log mode relies on every query leaving its bitmap zeroed
+            CUDA_OK(cudaMemset(h->d_visited.ptr, 0, h->d_visited.bytes));
+            h->visited_clean = true;
+        }
+    } else {
+        p.vlog = nullptr;
+        p.vlog_entries = 0;
+        h->visited_clean = false;  // clear-per-query mode leaves the last query's bits behind
+    }
     if (int rc = h->d_ng_spill.ensure(alloc_slots * p.ng_spill_entries * 8)) return rc;
     if (int rc = h->d_spt_spill.ensure(alloc_slots * p.spt_spill_entries * 8)) return rc;
     if (int rc = h->d_counter.ensure(256)) return rc;
@@ -441,6 +465,7 @@ void sptag_b200_destroy(sptag_b200_handle h) {
     h->d_codes.release();
     h->d_raw.release();
     h->d_visited.release();
+    h->d_vlog.release();
     h->d_ng_spill.release();
     h->d_spt_spill.release();
     h->d_counter.release();
@@ -646,6 +671,8 @@ int sptag_b200_set_param(sptag_b200_handle h, const char* name, const char* valu
     else if (n == "B200.NGCacheEntries") h->h_ng = (int)v;
     else if (n == "B200.SPTCacheEntries") h->h_spt = (int)v;
     else if (n == "B200.SimdWidth") h->simd_width = (int)v;
+    else if (n == "B200.VisitedLog") h->visited_log = (int)v;
+    else if (n == "B200.VisitedLogEntries") h->visited_log_entries = (int)v;
     else return fail(SPTAG_B200_PARAM_NOT_FOUND, "unknown parameter %s", name);
     return SPTAG_B200_SUCCESS;
 }
@@ -666,6 +693,8 @@ int sptag_b200_get_param(sptag_b200_handle h, const char* name, char* value_out,
     else if (n == "B200.NGCacheEntries") v = h->h_ng;
     else if (n == "B200.SPTCacheEntries") v = h->h_spt;
     else if (n == "B200.SimdWidth") v = h->simd_width;
+    else if (n == "B200.VisitedLog") v = h->visited_log;
+    else if (n == "B200.VisitedLogEntries") v = h->visited_log_entries;
     else return fail(SPTAG_B200_PARAM_NOT_FOUND, "unknown parameter %s", name);
     snprintf(value_out, (size_t)capacity, "%ld", v);
     return SPTAG_B200_SUCCESS;

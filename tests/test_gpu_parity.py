@@ -85,6 +85,8 @@ def test_algo_line_known_answer_on_gpu():
     {"B200.NGCacheEntries": 64, "B200.SPTCacheEntries": 4096},
     {"B200.QueriesPerSM": 1},
     {"B200.QueriesPerSM": 16},
+    {"B200.VisitedLog": 1},                                     # log + selective clear of the visited bitmap
+    {"B200.VisitedLog": 1, "B200.VisitedLogEntries": 300},      # log overflow -> full clear
 ])
 def test_tuning_knobs_do_not_change_results(knobs):
     from sptag_b200 import B200Index
@@ -264,5 +266,42 @@ def test_quantized_bkt_search_bit_exact(name):
     try:
         for mc in [8192, 1024, 128]:
             _compare(idx, files, q, 10, mc, name)
+    finally:
+        idx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# the committed golden fixtures (tests/golden/*.npz): reference-built indexes + the REFERENCE'S OWN outputs.
+# These need nothing but the repository (no tests/_data, no oracle/_ref), so they pin the device path to the
+# reference even on a box that only has a fresh checkout.
+# ---------------------------------------------------------------------------------------------
+def _golden_names():
+    import glob
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(g))
+
+
+@pytest.mark.parametrize("name", _golden_names())
+def test_gpu_matches_reference_golden_outputs(name):
+    from sptag_b200 import B200Index, capi
+    import test_oracle_pin as pin
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    files = reflib.IndexFiles.__new__(reflib.IndexFiles)
+    pin._files_from_npz(files, g)
+    idx = B200Index.create(algo=capi.ALGO_KDT if files.algo == "KDT" else capi.ALGO_BKT, value_type=capi.VT_FLOAT,
+                           metric=files.metric, vectors=files.vectors, graph=files.graph,
+                           tree_starts=files.tree_starts, tree_nodes=files.nodes)
+    try:
+        q = np.ascontiguousarray(g["queries"])
+        k = int(g["k"])
+        for i, mc in enumerate(g["max_checks"].tolist()):
+            idx.set_param("MaxCheck", int(mc))
+            ids, dists, stats = idx.search(q, k, want_stats=True)
+            assert np.array_equal(ids, g["ref_ids"][i]), (name, mc)
+            assert np.array_equal(dists.view(np.int32), g["ref_dists"][i].view(np.int32)), (name, mc)
+            # the reference's WorkSpace counters: checked leaves, tree-checked leaves, queue sizes at exit
+            assert np.array_equal(stats[:, capi.ST_CHECKED], g["ref_stats"][i][:, 0]), (name, mc)
+            assert np.array_equal(stats[:, capi.ST_NG_LEFT], g["ref_stats"][i][:, 2]), (name, mc)
+            assert np.array_equal(stats[:, capi.ST_SPT_LEFT], g["ref_stats"][i][:, 3]), (name, mc)
     finally:
         idx.close()
