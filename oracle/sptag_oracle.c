@@ -113,13 +113,79 @@ static float dist_f32(int cosine, int width, const float* x, const float* y, int
     return cosine ? 1 - diff : diff;
 }
 
+/* int8 / uint8 variants (DistanceUtils.cpp:305-558 L2, :684-874 cosine; helpers :17-296).
+ * One SIMD step over 4*W bytes yields W float lanes; lane t = (128-bit lane L = t/4, position p = t%4) holds the
+ * EXACT int32 sum of the four terms at byte offsets 16L + 2p + {0, 1, 8, 9} (unpacklo/unpackhi_epi8 interleave +
+ * madd_epi16 + add_epi32), converted with cvtepi32_ps and accumulated in fp32 like the float kernels. */
+static inline int elem_i8u8(const void* p, int is_unsigned, int i)
+{
+    return is_unsigned ? (int)((const uint8_t*)p)[i] : (int)((const int8_t*)p)[i];
+}
+
+static inline float lane_term_i8(int cosine, int is_unsigned, const void* x, const void* y, int base, int t)
+{
+    static const int add[4] = {0, 1, 8, 9};
+    const int off = base + 16 * (t / 4) + 2 * (t % 4);
+    int32_t s = 0;
+    for (int k = 0; k < 4; k++) {
+        int a = elem_i8u8(x, is_unsigned, off + add[k]), b = elem_i8u8(y, is_unsigned, off + add[k]);
+        s += cosine ? a * b : (a - b) * (a - b);
+    }
+    return (float)s;
+}
+
+static float dist_i8u8(int cosine, int width, int is_unsigned, const void* x, const void* y, int len)
+{
+    int i = 0, j;
+    float diff;
+    float a16[16], a8[8], a4[4];
+    if (width == 16) {
+        for (j = 0; j < 16; j++) a16[j] = 0.0f;
+        for (; i + 64 <= len; i += 64)
+            for (j = 0; j < 16; j++) a16[j] = a16[j] + lane_term_i8(cosine, is_unsigned, x, y, i, j);
+        for (j = 0; j < 8; j++) a8[j] = a16[j] + a16[j + 8];
+        for (; i + 32 <= len; i += 32)
+            for (j = 0; j < 8; j++) a8[j] = a8[j] + lane_term_i8(cosine, is_unsigned, x, y, i, j);
+        for (j = 0; j < 4; j++) a4[j] = a8[j] + a8[j + 4];
+        for (; i + 16 <= len; i += 16)
+            for (j = 0; j < 4; j++) a4[j] = a4[j] + lane_term_i8(cosine, is_unsigned, x, y, i, j);
+        diff = a4[0] + a4[1] + a4[2] + a4[3];
+    } else if (width == 8) {
+        for (j = 0; j < 8; j++) a8[j] = 0.0f;
+        for (; i + 32 <= len; i += 32)
+            for (j = 0; j < 8; j++) a8[j] = a8[j] + lane_term_i8(cosine, is_unsigned, x, y, i, j);
+        for (j = 0; j < 4; j++) a4[j] = a8[j] + a8[j + 4];
+        for (; i + 16 <= len; i += 16)
+            for (j = 0; j < 4; j++) a4[j] = a4[j] + lane_term_i8(cosine, is_unsigned, x, y, i, j);
+        diff = a4[0] + a4[1] + a4[2] + a4[3];
+    } else if (width == 4) {
+        for (j = 0; j < 4; j++) a4[j] = 0.0f;
+        for (; i + 16 <= len; i += 16)
+            for (j = 0; j < 4; j++) a4[j] = a4[j] + lane_term_i8(cosine, is_unsigned, x, y, i, j);
+        diff = a4[0] + a4[1] + a4[2] + a4[3];
+    } else {
+        diff = 0.0f;
+    }
+    /* plain-C tails on (float) casts; every value here is an integer far below 2^24 for the supported
+     * dimensions, so the 4-unrolled / FMA-contracted distinction of the float kernels cannot change a bit */
+    for (; i + 4 <= len; i += 4)
+        for (j = 0; j < 4; j++)
+            diff = diff + term_f32(cosine, (float)elem_i8u8(x, is_unsigned, i + j), (float)elem_i8u8(y, is_unsigned, i + j));
+    for (; i < len; i++)
+        diff = tail_f32(cosine, (float)elem_i8u8(x, is_unsigned, i), (float)elem_i8u8(y, is_unsigned, i), diff);
+    /* base^2 - dot: 127^2 = 16129 (int8), 255^2 = 65025 (uint8) (DistanceUtils.cpp:775, :869) */
+    return cosine ? (float)(is_unsigned ? 65025 : 16129) - diff : diff;
+}
+
 float ora_distance(int32_t metric, int32_t value_type, int32_t simd_width,
                    const void* x, const void* y, int32_t dim)
 {
     int cosine = (metric != ORA_L2);
     if (value_type == ORA_FLOAT)
         return dist_f32(cosine, simd_width, (const float*)x, (const float*)y, dim);
-    return NAN; /* integer element types: not on the float configs; added with the int8 row */
+    if (value_type == ORA_INT8 || value_type == ORA_UINT8)
+        return dist_i8u8(cosine, simd_width, value_type == ORA_UINT8, x, y, dim);
+    return NAN; /* int16: not restated */
 }
 
 void ora_distance_f32_many(int32_t metric, int32_t simd_width, const float* a, const float* b,
@@ -625,7 +691,7 @@ static void kdt_search_node(const qctx_t* c, ws_t* ws, int32_t node, float distB
         const ora_kdt_node* tnode = &nodes[node];
         ws->ntree++;
         /* split test reads the raw (un-quantized) query, KDTree.h:255 */
-        float diff = ((const float*)c->query)[tnode->split_dim] - tnode->split_value;
+        float diff = raw_elem(c->query, c->idx->value_type, (size_t)tnode->split_dim) - tnode->split_value;
         /* `distBound + diff * diff` is FMA-contracted in the reference's g++ -O3 build on an FMA
          * target (one vfmadd in KDTree::KDTSearch, checked by disassembly) */
         float distanceBound = fmaf(diff, diff, distBound);

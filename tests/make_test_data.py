@@ -41,8 +41,25 @@ SPECS = {
     "bkt_cos_3k_768": ("BKT", "Cosine", lambda: reflib.gen_lowrank(3000, 768, 32, 9),
                        lambda: reflib.normalize_rows(reflib.gen_lowrank(100, 768, 32, 10)), ""),
     "bkt_l2_dups": ("BKT", "L2", _dup_data, lambda: reflib.gen_iid(200, 24, 13), ""),
+    # integer element types (DistanceUtils int8 / uint8 variants; PerfTest.cpp uses int8 cosine)
+    "bkt_i8_cos_6k_64": ("BKT", "Cosine", lambda: _int8_lowrank(6000, 64, 10, 61), lambda: _norm_i8(_int8_lowrank(200, 64, 10, 62)), ""),
+    "bkt_u8_l2_6k_128": ("BKT", "L2", lambda: _uint8_lowrank(6000, 128, 12, 63), lambda: _uint8_lowrank(200, 128, 12, 64), ""),
+    "bkt_i8_l2_5k_100": ("BKT", "L2", lambda: _int8_lowrank(5000, 100, 12, 65), lambda: _int8_lowrank(200, 100, 12, 66), ""),
+    "kdt_i8_l2_6k_32": ("KDT", "L2", lambda: _int8_lowrank(6000, 32, 8, 67), lambda: _int8_lowrank(200, 32, 8, 68), ""),
     "kdt_l2_10k_64": ("KDT", "L2", lambda: reflib.gen_iid(10000, 64, 14), lambda: reflib.gen_iid(300, 64, 15), ""),
 }
+
+
+def _uint8_lowrank(n, dim, rank, seed):
+    return np.clip(np.round(40.0 * reflib.gen_lowrank(n, dim, rank, seed) + 128), 0, 255).astype(np.uint8)
+
+
+def _norm_i8(x):
+    # the caller-side normalisation the reference expects for cosine queries: Utils::Normalize (CommonUtils.h:62-76),
+    # arr[j] = (T)(arr[j] / |arr| * base), base = 127, C cast = truncation toward zero
+    v = x.astype(np.float64)
+    n = np.sqrt((v * v).sum(1, keepdims=True))
+    return np.trunc(v / n * 127).astype(np.int8)
 
 
 def _int8_lowrank(n, dim, rank, seed):

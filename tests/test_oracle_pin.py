@@ -211,3 +211,40 @@ def test_quantized_search_bit_exact_vs_reference(oracle_lib, name):
         ids_o, d_o, _ = o.search(q, 10, threads=4)
         assert np.array_equal(ids_r, ids_o), (name, mc)
         assert np.array_equal(d_r.view(np.int32), d_o.view(np.int32)), (name, mc)
+
+
+# ---------------------------------------------------------------------------------------------
+# int8 / uint8 element types (DistanceUtils.cpp:305-558, :684-874)
+# ---------------------------------------------------------------------------------------------
+@needs_ref
+@pytest.mark.parametrize("vt,dt,lo,hi", [(reflib.VT_INT8, np.int8, -127, 128), (reflib.VT_UINT8, np.uint8, 0, 256)])
+def test_integer_distance_bit_exact_vs_reference(oracle_lib, vt, dt, lo, hi):
+    rng = np.random.default_rng(9)
+    width = {512: 16, 256: 8, 128: 4, 0: 1}[reflib.ref().ref_isa()]
+    for metric in (0, 1):
+        for dim in [1, 3, 4, 5, 15, 16, 17, 31, 32, 33, 47, 48, 63, 64, 65, 79, 80, 95, 96, 100, 127, 128, 131, 192,
+                    200, 256, 258]:
+            for _ in range(25):
+                a = rng.integers(lo, hi, dim).astype(dt)
+                b = rng.integers(lo, hi, dim).astype(dt)
+                r = np.float32(reflib.ref().ref_distance(metric, vt, a.ctypes.data, b.ctypes.data, dim))
+                o = np.float32(oracle_lib.ora_distance(metric, vt, width, a.ctypes.data, b.ctypes.data, dim))
+                assert r.view(np.int32) == o.view(np.int32), (vt, metric, dim)
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["bkt_i8_cos_6k_64", "bkt_u8_l2_6k_128", "bkt_i8_l2_5k_100", "kdt_i8_l2_6k_32"])
+def test_integer_index_search_bit_exact_vs_reference(oracle_lib, name):
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))
+    r = reflib.RefIndex.load(folder)
+    width = {512: 16, 256: 8, 128: 4, 0: 1}[reflib.ref().ref_isa()]
+    for mc in [8192, 1024, 128]:
+        r.set_param("MaxCheck", mc)
+        ids_r, d_r, _ = r.search(q, 10, threads=4)
+        o = reflib.OracleIndex(files, simd_width=width)
+        o.max_check = mc
+        ids_o, d_o, _ = o.search(q, 10, threads=4)
+        assert np.array_equal(ids_r, ids_o), (name, mc)
+        assert np.array_equal(d_r.view(np.int32), d_o.view(np.int32)), (name, mc)
