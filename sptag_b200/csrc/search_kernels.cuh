@@ -202,6 +202,68 @@ __device__ __forceinline__ float half_warp_distance(const float* __restrict__ ro
 }
 
 // ------------------------------------------------------------------------------------------
+// int8 / uint8 rows (DistanceUtils.cpp:363-400, :460-496 L2; :744-780, :838-874 cosine; helpers :195-263).
+// One AVX-512 step covers 64 bytes and yields 16 float lanes; lane t = (128-bit lane L = t/4, position p = t%4) is
+// the EXACT int32 sum of the four terms at byte offsets 16L + 2p + {0,1,8,9} (unpacklo/hi_epi8 + madd_epi16 +
+// add_epi32), converted by cvtepi32_ps and accumulated in fp32; 32- and 16-byte steps do the same on 8 / 4 lanes.
+// ------------------------------------------------------------------------------------------
+template <bool UNSIGNED>
+__device__ __forceinline__ int byte_val(unsigned v) {
+    return UNSIGNED ? (int)(v & 255u) : (int)(signed char)(v & 255u);
+}
+template <bool COSINE, bool UNSIGNED>
+__device__ __forceinline__ float int_lane_term(const unsigned char* __restrict__ x, const unsigned char* __restrict__ y,
+                                               int off) {
+    const unsigned x0 = *reinterpret_cast<const unsigned short*>(x + off);
+    const unsigned x1 = *reinterpret_cast<const unsigned short*>(x + off + 8);
+    const unsigned y0 = *reinterpret_cast<const unsigned short*>(y + off);
+    const unsigned y1 = *reinterpret_cast<const unsigned short*>(y + off + 8);
+    const int a0 = byte_val<UNSIGNED>(x0), a1 = byte_val<UNSIGNED>(x0 >> 8), a2 = byte_val<UNSIGNED>(x1),
+              a3 = byte_val<UNSIGNED>(x1 >> 8);
+    const int b0 = byte_val<UNSIGNED>(y0), b1 = byte_val<UNSIGNED>(y0 >> 8), b2 = byte_val<UNSIGNED>(y1),
+              b3 = byte_val<UNSIGNED>(y1 >> 8);
+    int s;
+    if (COSINE) {
+        s = a0 * b0 + a1 * b1 + a2 * b2 + a3 * b3;
+    } else {
+        const int d0 = a0 - b0, d1 = a1 - b1, d2 = a2 - b2, d3 = a3 - b3;
+        s = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    return (float)s;
+}
+
+// x = query bytes, row = vector bytes (both 2-byte aligned); result valid in lane j == 0 of the half-warp
+template <bool COSINE, bool UNSIGNED>
+__device__ __forceinline__ float half_warp_distance_int(const unsigned char* __restrict__ row,
+                                                        const unsigned char* __restrict__ x, int dim, int j) {
+    float acc = 0.0f;
+    int i = 0;
+    const int lane_off = 16 * (j >> 2) + 2 * (j & 3);
+    for (; i + 64 <= dim; i += 64) acc = __fadd_rn(acc, int_lane_term<COSINE, UNSIGNED>(x, row, i + lane_off));
+    float a8 = __fadd_rn(acc, __shfl_down_sync(kFull, acc, 8, 16));
+    if (dim & 32) {
+        if (j < 8) a8 = __fadd_rn(a8, int_lane_term<COSINE, UNSIGNED>(x, row, i + lane_off));
+        i += 32;
+    }
+    float a4 = __fadd_rn(a8, __shfl_down_sync(kFull, a8, 4, 16));
+    if (dim & 16) {
+        if (j < 4) a4 = __fadd_rn(a4, int_lane_term<COSINE, UNSIGNED>(x, row, i + lane_off));
+        i += 16;
+    }
+    const float a1 = __shfl_sync(kFull, a4, 1, 16);
+    const float a2 = __shfl_sync(kFull, a4, 2, 16);
+    const float a3 = __shfl_sync(kFull, a4, 3, 16);
+    float s = __fadd_rn(__fadd_rn(__fadd_rn(a4, a1), a2), a3);
+    for (; i + 4 <= dim; i += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            s = __fadd_rn(s, dist_term<COSINE>((float)byte_val<UNSIGNED>(x[i + k]), (float)byte_val<UNSIGNED>(row[i + k])));
+    }
+    for (; i < dim; ++i) s = dist_tail<COSINE>((float)byte_val<UNSIGNED>(x[i]), (float)byte_val<UNSIGNED>(row[i]), s);
+    return COSINE ? __fsub_rn(UNSIGNED ? 65025.0f : 16129.0f, s) : s;
+}
+
+// ------------------------------------------------------------------------------------------
 // Heap<NodeDistPair>: exact emulation of Heap.h:13-106.  entry = (node, distance bits) as int2.
 // Index 0 holds the default pair (-1, MaxDist); indices 1..H live in shared memory, the rest of
 // the array in the per-slot HBM arena.
@@ -364,7 +426,7 @@ struct BktNodeDev {
     int centerid, childStart, childEnd;
 };
 
-template <int DIM, bool COSINE, int RPL, bool PQ>
+template <int DIM, bool COSINE, int RPL, bool PQ, int ELEM>
 struct WarpSearch {
     const SearchParams& p;
     const int lane, half, j;
@@ -506,7 +568,7 @@ struct WarpSearch {
             const int base = t * p.stage_rows;
             const int rows = min(p.stage_rows, cnt - base);
             int pr = 0;
-            for (; 2 * pr + 2 < rows; pr += 2) {  // two row pairs per pass: 2 independent chains per lane
+            for (; ELEM == 0 && 2 * pr + 2 < rows; pr += 2) {  // two row pairs per pass: 2 independent chains per lane
                 const int r0 = 2 * pr + half, r1 = r0 + 2;
                 const float* const rws[2] = {reinterpret_cast<const float*>(slot_ptr(st * p.stage_rows + r0)),
                                              reinterpret_cast<const float*>(slot_ptr(st * p.stage_rows + r1))};
@@ -519,8 +581,14 @@ struct WarpSearch {
             }
             for (; 2 * pr < rows; ++pr) {
                 const int r = 2 * pr + half;
-                const float* row = reinterpret_cast<const float*>(slot_ptr(st * p.stage_rows + r));
-                const float d = half_warp_distance<DIM, COSINE>(row, qr, qs, p.dim, j);
+                float d;
+                if (ELEM == 0) {
+                    const float* row = reinterpret_cast<const float*>(slot_ptr(st * p.stage_rows + r));
+                    d = half_warp_distance<DIM, COSINE>(row, qr, qs, p.dim, j);
+                } else {
+                    d = half_warp_distance_int<COSINE, ELEM == 2>(slot_ptr(st * p.stage_rows + r),
+                                                                  reinterpret_cast<const unsigned char*>(qs), p.dim, j);
+                }
                 if (j == 0 && r < rows) cand_dist[base + r] = d;
             }
             __syncwarp();
@@ -684,7 +752,12 @@ struct WarpSearch {
             ntree++;
             // the split test reads the raw query (KDTree.h:255); `distBound + diff*diff` is one FMA in the
             // reference's g++ -O3 build (see oracle/sptag_oracle.c kdt_search_node)
-            const float diff = __fsub_rn(qs[tn.z], __int_as_float(tn.w));
+            float qv;
+            if (ELEM == 0)
+                qv = qs[tn.z];
+            else
+                qv = (float)byte_val<ELEM == 2>(reinterpret_cast<const unsigned char*>(qs)[tn.z]);
+            const float diff = __fsub_rn(qv, __int_as_float(tn.w));
             const float distanceBound = __fmaf_rn(diff, diff, distBound);
             int otherChild, bestChild;
             if (diff < 0) {
@@ -770,11 +843,11 @@ struct WarpSearch {
 // ------------------------------------------------------------------------------------------
 // kernel: persistent warps pull queries from a global counter
 // ------------------------------------------------------------------------------------------
-template <int DIM, bool COSINE, int RPL, bool KDT, bool PQ = false>
+template <int DIM, bool COSINE, int RPL, bool KDT, bool PQ = false, int ELEM = 0>
 __global__ void __launch_bounds__(32) search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x;
-    WarpSearch<DIM, COSINE, RPL, PQ> w(p, lane);
+    WarpSearch<DIM, COSINE, RPL, PQ, ELEM> w(p, lane);
     w.ring = smem;
     w.cand_id = reinterpret_cast<int*>(smem + p.off_cand);
     w.cand_dist = reinterpret_cast<float*>(smem + p.off_cand + 128);
@@ -830,6 +903,10 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p) {
             const unsigned char* qc = p.queries + (size_t)q * p.query_stride_bytes;
             int* qoff = reinterpret_cast<int*>(w.qs);
             for (int i = lane; i < p.pq_m; i += 32) qoff[i] = (i * p.pq_ks + (int)qc[i]) * p.pq_ks;
+        } else if (ELEM != 0) {
+            const unsigned char* qb = p.queries + (size_t)q * p.query_stride_bytes;
+            unsigned char* qd = reinterpret_cast<unsigned char*>(w.qs);
+            for (int i = lane; i < p.dim; i += 32) qd[i] = qb[i];
         } else {
             const float* qg = reinterpret_cast<const float*>(p.queries + (size_t)q * p.query_stride_bytes);
             for (int i = lane; i < p.dim; i += 32) w.qs[i] = qg[i];
@@ -882,9 +959,9 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p) {
 // ------------------------------------------------------------------------------------------
 // stand-alone batched distance kernel (inner-loop parity): one half-warp per (query, id)
 // ------------------------------------------------------------------------------------------
-template <bool COSINE>
+template <bool COSINE, int ELEM>
 __global__ void distance_batch_kernel(const unsigned char* vectors, unsigned long long row_stride_bytes, int n,
-                                      int dim, const float* queries, int nq, const int* ids, int ids_per_query,
+                                      int dim, const void* queries_v, int nq, const int* ids, int ids_per_query,
                                       float* out) {
     const int lane = threadIdx.x & 31;
     const int j = lane & 15;
@@ -899,10 +976,17 @@ __global__ void distance_batch_kernel(const unsigned char* vectors, unsigned lon
     const int q = (int)(item / ids_per_query);
     const int id = ids[item];
     const bool ok = (id >= 0 && id < n);
-    const float* row = reinterpret_cast<const float*>(vectors + (size_t)(ok ? id : 0) * row_stride_bytes);
-    const float* qv = queries + (size_t)q * dim;
-    QueryRegs<0> qr;
-    const float d = half_warp_distance<0, COSINE>(row, qr, qv, dim, j);
+    float d;
+    if (ELEM == 0) {
+        const float* row = reinterpret_cast<const float*>(vectors + (size_t)(ok ? id : 0) * row_stride_bytes);
+        const float* qv = reinterpret_cast<const float*>(queries_v) + (size_t)q * dim;
+        QueryRegs<0> qr;
+        d = half_warp_distance<0, COSINE>(row, qr, qv, dim, j);
+    } else {
+        // odd dims would make the second query of a pair 1-byte aligned; the host pads the query stride to even
+        const unsigned char* qv = reinterpret_cast<const unsigned char*>(queries_v) + (size_t)q * ((dim + 1) & ~1);
+        d = half_warp_distance_int<COSINE, ELEM == 2>(vectors + (size_t)(ok ? id : 0) * row_stride_bytes, qv, dim, j);
+    }
     if (valid && j == 0) out[item] = ok ? d : SPTAG_B200_MAXDIST;
 }
 

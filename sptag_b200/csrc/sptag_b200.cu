@@ -143,6 +143,14 @@ SearchKernelFn pick_dim(int dim, int mres_cap, bool kdt) {
 }
 
 // The kernel instantiation for this index / parameter set (nullptr: unsupported m_Results capacity)
+template <bool COSINE, int ELEM>
+SearchKernelFn pick_int(int mres_cap, bool kdt) {
+    if (kdt) return search_kernel<0, COSINE, 16, true, false, ELEM>;
+    if (mres_cap <= 32 * 16) return search_kernel<0, COSINE, 16, false, false, ELEM>;
+    if (mres_cap <= 32 * 32) return search_kernel<0, COSINE, 32, false, false, ELEM>;
+    return nullptr;
+}
+
 SearchKernelFn pick_kernel(const sptag_b200_index* h, int mres_cap) {
     const bool kdt = (h->algo == SPTAG_B200_ALGO_KDT);
     if (h->q_type != 0) {  // quantized: BKT + L2 only (the quantizer has no cosine distance, PQQuantizer.h:130-136)
@@ -150,8 +158,10 @@ SearchKernelFn pick_kernel(const sptag_b200_index* h, int mres_cap) {
         if (mres_cap <= 32 * 32) return search_kernel<0, false, 32, false, true>;
         return nullptr;
     }
-    return (h->metric == SPTAG_B200_METRIC_L2) ? pick_dim<false>(h->dim, mres_cap, kdt)
-                                                : pick_dim<true>(h->dim, mres_cap, kdt);
+    const bool l2 = (h->metric == SPTAG_B200_METRIC_L2);
+    if (h->value_type == SPTAG_B200_VT_INT8) return l2 ? pick_int<false, 1>(mres_cap, kdt) : pick_int<true, 1>(mres_cap, kdt);
+    if (h->value_type == SPTAG_B200_VT_UINT8) return l2 ? pick_int<false, 2>(mres_cap, kdt) : pick_int<true, 2>(mres_cap, kdt);
+    return l2 ? pick_dim<false>(h->dim, mres_cap, kdt) : pick_dim<true>(h->dim, mres_cap, kdt);
 }
 
 // Fill SearchParams + launch geometry for this handle.  Allocates per-slot scratch.
@@ -165,9 +175,15 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
                         h->q_m, h->dim, h->value_type);
         if (h->algo != SPTAG_B200_ALGO_BKT || h->metric != SPTAG_B200_METRIC_L2)
             return fail(SPTAG_B200_LACK_OF_INPUTS, "quantized indexes are searchable as BKT + L2 only");
+    } else if (h->value_type == SPTAG_B200_VT_INT16) {
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "int16 vectors are not supported (DistanceUtils int16 variants are not built)");
     } else if (h->value_type != SPTAG_B200_VT_FLOAT) {
-        return fail(SPTAG_B200_LACK_OF_INPUTS, "value type %d needs a quantizer (integer DistanceUtils variants are not built)",
-                    h->value_type);
+        // int8 / uint8: every partial sum must stay an exactly representable integer for the kernel's and the
+        // reference's summation orders to be interchangeable in the scalar tails; true for the supported range
+        const int maxterm = (h->value_type == SPTAG_B200_VT_INT8) ? (h->metric == SPTAG_B200_METRIC_L2 ? 254 * 254 : 127 * 127)
+                                                                   : 255 * 255;
+        if ((long long)h->dim * maxterm >= (1ll << 31))
+            return fail(SPTAG_B200_LACK_OF_INPUTS, "dimension %d too large for the integer distance kernels", h->dim);
     }
     if (h->simd_width != 16)
         return fail(SPTAG_B200_LACK_OF_INPUTS, "B200.SimdWidth %d not built (16 only)", h->simd_width);
@@ -745,11 +761,13 @@ int sptag_b200_distance_batch(sptag_b200_handle h, const void* queries, int32_t 
     if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
     if (!queries || !ids || !out || num_queries <= 0 || ids_per_query <= 0)
         return fail(SPTAG_B200_LACK_OF_INPUTS, "null buffer");
-    if (h->value_type != SPTAG_B200_VT_FLOAT)
-        return fail(SPTAG_B200_LACK_OF_INPUTS, "only float vectors are supported in this build");
+    if (h->q_type != 0 || h->value_type == SPTAG_B200_VT_INT16)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "distance_batch handles float / int8 / uint8 vectors without a quantizer");
     std::lock_guard<std::mutex> lock(h->mu);
     DeviceGuard guard(h->device);
-    const size_t qbytes = (size_t)num_queries * h->dim * 4;
+    const bool is_float = (h->value_type == SPTAG_B200_VT_FLOAT);
+    const size_t qstride = is_float ? (size_t)h->dim * 4 : (size_t)((h->dim + 1) & ~1);  // integer rows: even stride
+    const size_t qbytes = (size_t)num_queries * qstride;
     const size_t total = (size_t)num_queries * ids_per_query;
     DeviceBuffer dq, di, dout;
     int rc = 0;
@@ -757,21 +775,29 @@ int sptag_b200_distance_batch(sptag_b200_handle h, const void* queries, int32_t 
         dq.release(); di.release(); dout.release();
         return rc;
     }
-    cudaMemcpy(dq.ptr, queries, qbytes, cudaMemcpyHostToDevice);
+    if (is_float || (h->dim & 1) == 0)
+        cudaMemcpy(dq.ptr, queries, qbytes, cudaMemcpyHostToDevice);
+    else
+        cudaMemcpy2D(dq.ptr, qstride, queries, (size_t)h->dim, (size_t)h->dim, (size_t)num_queries, cudaMemcpyHostToDevice);
     cudaMemcpy(di.ptr, ids, total * 4, cudaMemcpyHostToDevice);
     const long long halfwarps = (long long)((total + 1) / 2) * 2;
     const int threads = 256;
     const long long blocks = (halfwarps * 16 + threads - 1) / threads;
-    if (h->metric == SPTAG_B200_METRIC_L2)
-        distance_batch_kernel<false><<<(unsigned)blocks, threads>>>((const unsigned char*)h->d_vectors.ptr,
-                                                                   h->row_stride, h->n, h->dim, (const float*)dq.ptr,
-                                                                   num_queries, (const int*)di.ptr, ids_per_query,
-                                                                   (float*)dout.ptr);
-    else
-        distance_batch_kernel<true><<<(unsigned)blocks, threads>>>((const unsigned char*)h->d_vectors.ptr,
-                                                                  h->row_stride, h->n, h->dim, (const float*)dq.ptr,
-                                                                  num_queries, (const int*)di.ptr, ids_per_query,
-                                                                  (float*)dout.ptr);
+    {
+        const unsigned char* dv = (const unsigned char*)h->d_vectors.ptr;
+        const bool l2 = (h->metric == SPTAG_B200_METRIC_L2);
+#define SPTAG_B200_DB(COS, EL)                                                                                        \
+    distance_batch_kernel<COS, EL><<<(unsigned)blocks, threads>>>(dv, h->row_stride, h->n, h->dim, dq.ptr, num_queries, \
+                                                                  (const int*)di.ptr, ids_per_query, (float*)dout.ptr)
+        if (h->value_type == SPTAG_B200_VT_FLOAT) {
+            if (l2) SPTAG_B200_DB(false, 0); else SPTAG_B200_DB(true, 0);
+        } else if (h->value_type == SPTAG_B200_VT_INT8) {
+            if (l2) SPTAG_B200_DB(false, 1); else SPTAG_B200_DB(true, 1);
+        } else {
+            if (l2) SPTAG_B200_DB(false, 2); else SPTAG_B200_DB(true, 2);
+        }
+#undef SPTAG_B200_DB
+    }
     g_launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(out, dout.ptr, total * 4, cudaMemcpyDeviceToHost);

@@ -305,3 +305,48 @@ def test_gpu_matches_reference_golden_outputs(name):
             assert np.array_equal(stats[:, capi.ST_SPT_LEFT], g["ref_stats"][i][:, 3]), (name, mc)
     finally:
         idx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# int8 / uint8 element types (DistanceUtils integer variants)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["bkt_i8_cos_6k_64", "bkt_u8_l2_6k_128", "bkt_i8_l2_5k_100", "kdt_i8_l2_6k_32"])
+def test_integer_index_search_bit_exact(name):
+    from sptag_b200 import B200Index
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))
+    idx = B200Index.load(folder)
+    try:
+        for mc in [8192, 1024, 128]:
+            _compare(idx, files, q, 10, mc, name)
+    finally:
+        idx.close()
+
+
+@pytest.mark.parametrize("vt,dt,lo,hi", [(0, np.int8, -127, 128), (1, np.uint8, 0, 256)])
+@pytest.mark.parametrize("metric", [0, 1])
+def test_integer_distance_kernel_bit_exact_all_dims(vt, dt, lo, hi, metric):
+    from sptag_b200 import B200Index, capi
+    rng = np.random.default_rng(13)
+    L = reflib.ora()
+    for dim in [1, 3, 4, 5, 15, 16, 17, 31, 32, 33, 48, 63, 64, 65, 80, 96, 100, 127, 128, 131, 200, 256, 258]:
+        n, nq, per = 129, 7, 21
+        x = rng.integers(lo, hi, (n, dim)).astype(dt)
+        q = rng.integers(lo, hi, (nq, dim)).astype(dt)
+        graph = np.full((n, 4), -1, np.int32)
+        nodes = np.array([[n, 1, 2], [0, -1, -1], [-1, -1, -1]], np.int32)
+        idx = B200Index.create(algo=capi.ALGO_BKT, value_type=vt, metric=metric, vectors=x, graph=graph,
+                               tree_starts=np.array([0], np.int32), tree_nodes=nodes)
+        ids = rng.integers(0, n, (nq, per)).astype(np.int32)
+        qc = np.ascontiguousarray(q)
+        out = np.empty(ids.shape, np.float32)
+        capi._check(capi.lib().sptag_b200_distance_batch(idx._h, qc.ctypes.data, nq, ids.ctypes.data, per, out.ctypes.data))
+        exp = np.empty_like(out)
+        for i in range(nq):
+            for jj in range(per):
+                a = np.ascontiguousarray(q[i])
+                b = np.ascontiguousarray(x[ids[i, jj]])
+                exp[i, jj] = L.ora_distance(metric, vt, 16, a.ctypes.data, b.ctypes.data, dim)
+        assert np.array_equal(out.view(np.int32), exp.view(np.int32)), (vt, metric, dim)
+        idx.close()
