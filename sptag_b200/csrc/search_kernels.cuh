@@ -534,14 +534,28 @@ struct WarpSearch {
             const unsigned char* row = ring + (size_t)lane * p.slot_stride;
             const int* qoff = reinterpret_cast<const int*>(qs);
             float acc = 0.0f;
-            const int m4 = p.pq_m & ~3;
+            // 16 look-ups in flight per lane (their addresses do not depend on the running sum), then the sum in
+            // sub-vector order
+            const int m16 = p.pq_m & ~15;
             int i = 0;
+            for (; i < m16; i += 16) {
+                const uint4 w = *reinterpret_cast<const uint4*>(row + i);
+                const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+                float t[16];
+#pragma unroll
+                for (int b = 0; b < 16; ++b)
+                    t[b] = __ldg(p.sdc + qoff[i + b] + ((ws[b >> 2] >> (8 * (b & 3))) & 255u));
+#pragma unroll
+                for (int b = 0; b < 16; ++b) acc = __fadd_rn(acc, t[b]);
+            }
+            const int m4 = p.pq_m & ~3;
             for (; i < m4; i += 4) {
                 const unsigned w = *reinterpret_cast<const unsigned*>(row + i);
-                acc = __fadd_rn(acc, __ldg(p.sdc + qoff[i] + (w & 255u)));
-                acc = __fadd_rn(acc, __ldg(p.sdc + qoff[i + 1] + ((w >> 8) & 255u)));
-                acc = __fadd_rn(acc, __ldg(p.sdc + qoff[i + 2] + ((w >> 16) & 255u)));
-                acc = __fadd_rn(acc, __ldg(p.sdc + qoff[i + 3] + (w >> 24)));
+                const float t0 = __ldg(p.sdc + qoff[i] + (w & 255u));
+                const float t1 = __ldg(p.sdc + qoff[i + 1] + ((w >> 8) & 255u));
+                const float t2 = __ldg(p.sdc + qoff[i + 2] + ((w >> 16) & 255u));
+                const float t3 = __ldg(p.sdc + qoff[i + 3] + (w >> 24));
+                acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, t0), t1), t2), t3);
             }
             for (; i < p.pq_m; ++i) acc = __fadd_rn(acc, __ldg(p.sdc + qoff[i] + row[i]));
             cand_dist[lane] = acc;
