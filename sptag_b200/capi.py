@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsptag_b200.so")
+LIB_PATH = os.environ.get("SPTAG_B200_LIB", os.path.join(_HERE, "lib", "libsptag_b200.so"))
 
 STATS_PER_QUERY = 8
 ST_CHECKED, ST_TREE_CHECKED, ST_NG_LEFT, ST_SPT_LEFT, ST_NDIST, ST_NEXPAND, ST_NTREE, ST_FLAGS = range(8)

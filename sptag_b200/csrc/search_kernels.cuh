@@ -857,8 +857,10 @@ struct WarpSearch {
 // ------------------------------------------------------------------------------------------
 // kernel: persistent warps pull queries from a global counter
 // ------------------------------------------------------------------------------------------
-template <int DIM, bool COSINE, int RPL, bool KDT, bool PQ = false, int ELEM = 0>
-__global__ void __launch_bounds__(32) search_kernel(const SearchParams p) {
+// MINB = minimum resident single-warp CTAs per SM the compiler must allow (caps registers): the PQ variant is
+// bound by per-step latency, so more resident queries win (80 registers, 24 per SM: +32 % QPS, profiles/r01_sweep_c2.txt)
+template <int DIM, bool COSINE, int RPL, bool KDT, bool PQ = false, int ELEM = 0, int MINB = 1>
+__global__ void __launch_bounds__(32, MINB) search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x;
     WarpSearch<DIM, COSINE, RPL, PQ, ELEM> w(p, lane);

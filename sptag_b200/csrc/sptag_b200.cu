@@ -154,8 +154,8 @@ SearchKernelFn pick_int(int mres_cap, bool kdt) {
 SearchKernelFn pick_kernel(const sptag_b200_index* h, int mres_cap) {
     const bool kdt = (h->algo == SPTAG_B200_ALGO_KDT);
     if (h->q_type != 0) {  // quantized: BKT + L2 only (the quantizer has no cosine distance, PQQuantizer.h:130-136)
-        if (mres_cap <= 32 * 16) return search_kernel<0, false, 16, false, true>;
-        if (mres_cap <= 32 * 32) return search_kernel<0, false, 32, false, true>;
+        if (mres_cap <= 32 * 16) return search_kernel<0, false, 16, false, true, 0, 24>;
+        if (mres_cap <= 32 * 32) return search_kernel<0, false, 32, false, true, 0, 16>;
         return nullptr;
     }
     const bool l2 = (h->metric == SPTAG_B200_METRIC_L2);
@@ -223,7 +223,7 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     // ---- shared-memory layout ----
     int stage_rows = h->stage_rows;
     if (stage_rows <= 0) {
-        stage_rows = (int)(5120 / round_up(h->row_stride + 64, 128));
+        stage_rows = (int)(3840 / round_up(h->row_stride + 64, 128));  // 768-d: 2 rows, 128-d: 6 rows (sweeps)
         stage_rows = std::max(2, std::min(16, stage_rows));
     }
     stage_rows &= ~1;
@@ -264,7 +264,7 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, (const void*)kern, 32, smem));
     if (fit < 1) return fail(SPTAG_B200_MEMORY_OVERFLOW, "search kernel does not fit on an SM (smem %zu)", smem);
     int per_sm = h->queries_per_sm;
-    if (per_sm <= 0) per_sm = std::min(fit, 16);  // the kernel is latency-bound per warp: fill the SM
+    if (per_sm <= 0) per_sm = fit;  // the kernel is latency-bound per warp: fill the SM
     per_sm = std::max(1, std::min(per_sm, fit));
     grid = std::max(1, std::min(nq, h->num_sms * per_sm));
 
