@@ -65,6 +65,7 @@ struct SearchParams {
     unsigned long long vlog_entries;
     // shared-memory layout (bytes from the dynamic smem base)
     int stage_rows, stages, slot_stride;
+    int slot_stagger;  // 1: odd ring slots start 64 B later (stride is a multiple of 128); 0: stride = 64 mod 128
     int h_ng, h_spt;
     int off_ng, off_spt, off_cand, off_bar, off_query;
     // PQ / OPQ quantized index (PQQuantizer.h:110-128, ADC off): rows are M code bytes, the query is M code
@@ -459,7 +460,7 @@ struct WarpSearch {
         : p(p_), lane(lane_), half(lane_ >> 4), j(lane_ & 15) {}
 
     __device__ __forceinline__ unsigned char* slot_ptr(int s) const {
-        return ring + (size_t)s * p.slot_stride + ((s & 1) << 6);
+        return ring + (size_t)s * p.slot_stride + (p.slot_stagger ? ((s & 1) << 6) : 0);
     }
 
     // OptHashPosVector::CheckAndSet for a warp-uniform id: true if already present
@@ -925,11 +926,16 @@ __global__ void __launch_bounds__(32, MINB) search_kernel(const SearchParams p) 
             for (int i = lane; i < p.dim; i += 32) qd[i] = qb[i];
         } else {
             const float* qg = reinterpret_cast<const float*>(p.queries + (size_t)q * p.query_stride_bytes);
-            for (int i = lane; i < p.dim; i += 32) w.qs[i] = qg[i];
-            __syncwarp();
+            // static dims that are multiples of 16 never read the shared copy in the BKT flavour (no tails, no
+            // KD split test), so those instantiations keep the query in registers only and give the 3 KB back
+            constexpr bool kRegsOnly = (DIM > 0) && (DIM % 16 == 0) && !KDT;
+            if (!kRegsOnly) {
+                for (int i = lane; i < p.dim; i += 32) w.qs[i] = qg[i];
+                __syncwarp();
+            }
             if (DIM > 0) {
 #pragma unroll
-                for (int c = 0; c < DIM / 16; ++c) w.qr.q[c] = w.qs[16 * c + (lane & 15)];
+                for (int c = 0; c < DIM / 16; ++c) w.qr.q[c] = __ldg(qg + 16 * c + (lane & 15));
             }
         }
         __syncwarp();

@@ -97,8 +97,8 @@ struct sptag_b200_index {
     int stage_rows = 0;      // 0 = auto
     int stages = 2;
     // Small queue caches + a small ring: the kernel is latency-bound per warp, so resident queries per
-    // SM matter more than on-chip queue capacity (sweep in profiles/r01_sweep_c2.txt)
-    int h_ng = 128, h_spt = 64;
+    // SM matter more than on-chip queue capacity (sweep in profiles/r01_sweep_c2.txt).  0 = auto.
+    int h_ng = 0, h_spt = 0;
     int simd_width = 16;
     int visited_log = -1;         // -1 auto (bitmap > 256 KB per slot), 0 clear per query, 1 log + selective clear
     int visited_log_entries = 0;  // 0 = auto
@@ -137,7 +137,10 @@ template <bool COSINE>
 SearchKernelFn pick_dim(int dim, int mres_cap, bool kdt) {
     switch (dim) {
     case 128: return pick_rpl<128, COSINE>(mres_cap, kdt);
-    case 768: return pick_rpl<768, COSINE>(mres_cap, kdt);
+    case 768:
+        // 15 resident queries per SM (127 registers, no spills) when the m_Results file is the 16-register one
+        if (!kdt && mres_cap <= 32 * 16) return search_kernel<768, COSINE, 16, false, false, 0, 15>;
+        return pick_rpl<768, COSINE>(mres_cap, kdt);
     default: return pick_rpl<0, COSINE>(mres_cap, kdt);
     }
 }
@@ -230,16 +233,24 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     if (stage_rows < 2) stage_rows = 2;
     if (stage_rows > 32) stage_rows = 32;
     int stages = std::max(1, std::min(8, h->stages));
-    p.slot_stride = (int)round_up(h->row_stride + 64, 128);
+    // ring slot stride: the two rows of a pair must start 64 B apart modulo 128 (disjoint banks for the two
+    // half-warps); either a 128-multiple stride with odd slots staggered, or a stride that is 64 mod 128
+    {
+        const size_t a = round_up(h->row_stride + 64, 128), b = round_up(h->row_stride, 128) + 64;
+        p.slot_stagger = (a <= b) ? 1 : 0;
+        p.slot_stride = (int)std::min(a, b);
+    }
     if (pq) {  // every candidate row of a step in one TMA batch; rows are M bytes
         stage_rows = 32;
         stages = 1;
         p.slot_stride = (int)h->row_stride + ((h->row_stride % 128 == 0) ? 16 : 0);
+        p.slot_stagger = 0;
     }
     p.stage_rows = stage_rows;
     p.stages = stages;
-    p.h_ng = std::max(1, h->h_ng);
-    p.h_spt = std::max(1, h->h_spt);
+    const bool big_rows = h->row_stride >= 2048;
+    p.h_ng = h->h_ng > 0 ? h->h_ng : (big_rows ? 64 : 128);
+    p.h_spt = h->h_spt > 0 ? h->h_spt : (big_rows ? 32 : 64);
     size_t off = (size_t)stage_rows * stages * p.slot_stride;
     p.off_ng = (int)off;
     off += round_up((size_t)(p.h_ng + 1) * 8, 16);
@@ -250,7 +261,9 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     p.off_bar = (int)off;
     off += round_up((size_t)stages * 8, 16);
     p.off_query = (int)off;
-    off += round_up((size_t)h->dim * 4 + 16, 16);  // float query, or M row offsets (int) for PQ
+    const bool query_in_regs_only = !pq && h->value_type == SPTAG_B200_VT_FLOAT && h->algo == SPTAG_B200_ALGO_BKT &&
+                                    (h->dim == 128 || h->dim == 768);  // must mirror kRegsOnly in search_kernel
+    off += query_in_regs_only ? 16 : round_up((size_t)h->dim * 4 + 16, 16);  // float query, or M row offsets for PQ
     smem = round_up(off, 128);
     if (smem > h->smem_optin)
         return fail(SPTAG_B200_MEMORY_OVERFLOW, "shared memory per query slot %zu exceeds %zu", smem, h->smem_optin);
