@@ -389,31 +389,53 @@ __device__ __forceinline__ float key_float(unsigned k) {
 
 template <int RPL>
 struct MResults {
+    static constexpr int G = RPL / 4;  // four groups per lane so the owner rescans one group, not the whole lane
     float m[RPL];
+    float g[4];   // maximum of each group of this lane
     float lmax;   // this lane's maximum
     float worst;  // warp-wide maximum (uniform)
 
     __device__ __forceinline__ void reset(int cap, int lane) {
 #pragma unroll
         for (int r = 0; r < RPL; ++r) m[r] = (r * 32 + lane < cap) ? SPTAG_B200_MAXDIST : -INFINITY;
-        lmax = m[0];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float v = -INFINITY;
+#pragma unroll
+            for (int r = 0; r < G; ++r) v = fmaxf(v, m[k * G + r]);
+            g[k] = v;
+        }
+        lmax = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
         worst = SPTAG_B200_MAXDIST;
+    }
+    template <int K>
+    __device__ __forceinline__ void replace_in_group(float d) {
+        bool done = false;
+        float nm = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < G; ++r) {
+            if (!done && m[K * G + r] == lmax) {
+                m[K * G + r] = d;
+                done = true;
+            }
+            nm = fmaxf(nm, m[K * G + r]);
+        }
+        g[K] = nm;
     }
     __device__ __forceinline__ bool insert(float d, int lane) {
         if (d > worst) return false;
         const int owner = __ffs(__ballot_sync(kFull, lmax == worst)) - 1;
         if (lane == owner) {
-            bool done = false;
-            float nm = -INFINITY;
-#pragma unroll
-            for (int r = 0; r < RPL; ++r) {
-                if (!done && m[r] == lmax) {
-                    m[r] = d;
-                    done = true;
-                }
-                nm = fmaxf(nm, m[r]);
-            }
-            lmax = nm;
+            // replace ONE maximum: the first group whose maximum is the lane maximum (any one is equivalent)
+            if (g[0] == lmax)
+                replace_in_group<0>(d);
+            else if (g[1] == lmax)
+                replace_in_group<1>(d);
+            else if (g[2] == lmax)
+                replace_in_group<2>(d);
+            else
+                replace_in_group<3>(d);
+            lmax = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
         }
         worst = key_float(__reduce_max_sync(kFull, float_key(lmax)));
         return true;
@@ -507,7 +529,7 @@ struct WarpSearch {
     __device__ __forceinline__ void issue_stage(int t, int cnt) {
         const int base = t * p.stage_rows;
         const int rows = min(p.stage_rows, cnt - base);
-        const int st = t % p.stages;
+        const int st = t & (p.stages - 1);  // the host keeps `stages` a power of two
         if (lane == 0) mbar_arrive_expect_tx(&bars[st], (uint32_t)rows * (uint32_t)p.row_bytes);
         __syncwarp();
         if (lane < rows) {
@@ -577,7 +599,7 @@ struct WarpSearch {
         const int pre = min(nst, p.stages);
         for (int t = 0; t < pre; ++t) issue_stage(t, cnt);
         for (int t = 0; t < nst; ++t) {
-            const int st = t % p.stages;
+            const int st = t & (p.stages - 1);  // the host keeps `stages` a power of two
             mbar_wait(&bars[st], (phase_bits >> st) & 1u);
             phase_bits ^= (1u << st);
             const int base = t * p.stage_rows;

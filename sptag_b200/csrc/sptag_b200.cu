@@ -100,6 +100,7 @@ struct sptag_b200_index {
     // SM matter more than on-chip queue capacity (sweep in profiles/r01_sweep_c2.txt).  0 = auto.
     int h_ng = 0, h_spt = 0;
     int simd_width = 16;
+    int slot_scheme = 0;          // 0 auto, 1 = 128-multiple stride + staggered odd slots, 2 = stride 64 mod 128
     int visited_log = -1;         // -1 auto (bitmap > 256 KB per slot), 0 clear per query, 1 log + selective clear
     int visited_log_entries = 0;  // 0 = auto
     bool visited_clean = false;   // the whole d_visited buffer is known to be zero
@@ -233,12 +234,15 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     if (stage_rows < 2) stage_rows = 2;
     if (stage_rows > 32) stage_rows = 32;
     int stages = std::max(1, std::min(8, h->stages));
+    while (stages & (stages - 1)) stages &= stages - 1;  // power of two (the kernel masks instead of dividing)
     // ring slot stride: the two rows of a pair must start 64 B apart modulo 128 (disjoint banks for the two
     // half-warps); either a 128-multiple stride with odd slots staggered, or a stride that is 64 mod 128
     {
         const size_t a = round_up(h->row_stride + 64, 128), b = round_up(h->row_stride, 128) + 64;
         p.slot_stagger = (a <= b) ? 1 : 0;
-        p.slot_stride = (int)std::min(a, b);
+        if (h->slot_scheme == 1) p.slot_stagger = 1;
+        if (h->slot_scheme == 2) p.slot_stagger = 0;
+        p.slot_stride = (int)(p.slot_stagger ? a : b);
     }
     if (pq) {  // every candidate row of a step in one TMA batch; rows are M bytes
         stage_rows = 32;
@@ -249,8 +253,12 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     p.stage_rows = stage_rows;
     p.stages = stages;
     const bool big_rows = h->row_stride >= 2048;
-    p.h_ng = h->h_ng > 0 ? h->h_ng : (big_rows ? 64 : 128);
-    p.h_spt = h->h_spt > 0 ? h->h_spt : (big_rows ? 32 : 64);
+    int extra_ng = 0, extra_spt = 0;
+    bool relayout_done = false;
+    int fit = 0;
+relayout:
+    p.h_ng = (h->h_ng > 0 ? h->h_ng : (big_rows ? 64 : 128)) + extra_ng;
+    p.h_spt = (h->h_spt > 0 ? h->h_spt : (big_rows ? 32 : 64)) + extra_spt;
     size_t off = (size_t)stage_rows * stages * p.slot_stride;
     p.off_ng = (int)off;
     off += round_up((size_t)(p.h_ng + 1) * 8, 16);
@@ -273,12 +281,26 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
         return fail(SPTAG_B200_LACK_OF_INPUTS, "max(MaxCheck/16, K) = %d exceeds the supported 1024", p.mres_cap);
     CUDA_OK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // resident single-warp CTAs per SM allowed by registers + shared memory for this instantiation
-    int fit = 0;
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, (const void*)kern, 32, smem));
     if (fit < 1) return fail(SPTAG_B200_MEMORY_OVERFLOW, "search kernel does not fit on an SM (smem %zu)", smem);
     int per_sm = h->queries_per_sm;
     if (per_sm <= 0) per_sm = fit;  // the kernel is latency-bound per warp: fill the SM
     per_sm = std::max(1, std::min(per_sm, fit));
+    if (h->h_ng <= 0 && h->h_spt <= 0 && !relayout_done) {
+        // Spare shared memory of a slot (at this residency) goes to the queue heads: 3/4 NGQueue, 1/4 SPTQueue
+        const size_t per_slot = (size_t)(227 * 1024) / per_sm - 1024;
+        if (per_slot > smem + 512) {
+            const size_t spare_entries = (per_slot - smem) / 8;
+            extra_ng = (int)std::min<size_t>(spare_entries * 3 / 4, 4096);
+            extra_spt = (int)std::min<size_t>(spare_entries / 4, 2048);
+            extra_ng &= ~1;
+            extra_spt &= ~1;
+            if (extra_ng + extra_spt >= 64) {
+                relayout_done = true;
+                goto relayout;
+            }
+        }
+    }
     grid = std::max(1, std::min(nq, h->num_sms * per_sm));
 
     // ---- per-slot scratch ----
@@ -702,6 +724,7 @@ int sptag_b200_set_param(sptag_b200_handle h, const char* name, const char* valu
     else if (n == "B200.SimdWidth") h->simd_width = (int)v;
     else if (n == "B200.VisitedLog") h->visited_log = (int)v;
     else if (n == "B200.VisitedLogEntries") h->visited_log_entries = (int)v;
+    else if (n == "B200.SlotScheme") h->slot_scheme = (int)v;
     else return fail(SPTAG_B200_PARAM_NOT_FOUND, "unknown parameter %s", name);
     return SPTAG_B200_SUCCESS;
 }
@@ -724,6 +747,7 @@ int sptag_b200_get_param(sptag_b200_handle h, const char* name, char* value_out,
     else if (n == "B200.SimdWidth") v = h->simd_width;
     else if (n == "B200.VisitedLog") v = h->visited_log;
     else if (n == "B200.VisitedLogEntries") v = h->visited_log_entries;
+    else if (n == "B200.SlotScheme") v = h->slot_scheme;
     else return fail(SPTAG_B200_PARAM_NOT_FOUND, "unknown parameter %s", name);
     snprintf(value_out, (size_t)capacity, "%ld", v);
     return SPTAG_B200_SUCCESS;
