@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--cache", default=os.environ.get("SPTAG_B200_CACHE", "/tmp/sptag_b200_cache"))
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="debug: do not sample nvidia-smi during the timed region")
     ap.add_argument("--param", action="append", default=[], help="Name=Value passed to sptag_b200_set_param")
     ap.add_argument("--algo", default="bkt", choices=["bkt", "kdt"], help="space-partition tree of the index")
     ap.add_argument("--quantizer", default="none", choices=["none", "pq", "opq"],
@@ -452,7 +453,7 @@ def main():
 
     # ---- timed region 1: inputs resident in HBM (value, roofline) ----
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         sampler.start()
         time.sleep(0.3)
     for _ in range(args.warmup):
@@ -519,6 +520,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": ("search_kernel<PQ,L2,BKT>" if quantized else
                            "search_kernel<%d,%s,%s>" % (args.dim if args.dim in (128, 768) else 0, args.metric, args.algo.upper())), "kernel_ms": kernel_ms,
+                "kernel_ms_samples": [round(v, 3) for v in kms],
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "share_of_step": kernel_ms / ms_step}
 

@@ -227,7 +227,7 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     // ---- shared-memory layout ----
     int stage_rows = h->stage_rows;
     if (stage_rows <= 0) {
-        stage_rows = (int)(3840 / round_up(h->row_stride + 64, 128));  // 768-d: 2 rows, 128-d: 6 rows (sweeps)
+        stage_rows = (int)(5120 / round_up(h->row_stride + 64, 128));  // 768-d: 2 rows, 128-d: 8 rows (sweeps)
         stage_rows = std::max(2, std::min(16, stage_rows));
     }
     stage_rows &= ~1;
@@ -285,6 +285,7 @@ relayout:
     if (fit < 1) return fail(SPTAG_B200_MEMORY_OVERFLOW, "search kernel does not fit on an SM (smem %zu)", smem);
     int per_sm = h->queries_per_sm;
     if (per_sm <= 0) per_sm = fit;  // the kernel is latency-bound per warp: fill the SM
+    if (h->queries_per_sm <= 0 && big_rows) per_sm = std::min(per_sm, 14);  // 3 KB rows: 14 beats 15 (HBM-bound, sweep)
     per_sm = std::max(1, std::min(per_sm, fit));
     if (h->h_ng <= 0 && h->h_spt <= 0 && !relayout_done) {
         // Spare shared memory of a slot (at this residency) goes to the queue heads: 3/4 NGQueue, 1/4 SPTQueue
