@@ -46,6 +46,9 @@ SPECS = {
     "bkt_u8_l2_6k_128": ("BKT", "L2", lambda: _uint8_lowrank(6000, 128, 12, 63), lambda: _uint8_lowrank(200, 128, 12, 64), ""),
     "bkt_i8_l2_5k_100": ("BKT", "L2", lambda: _int8_lowrank(5000, 100, 12, 65), lambda: _int8_lowrank(200, 100, 12, 66), ""),
     "kdt_i8_l2_6k_32": ("KDT", "L2", lambda: _int8_lowrank(6000, 32, 8, 67), lambda: _int8_lowrank(200, 32, 8, 68), ""),
+    # more than one space-partition tree (BKTNumber / KDTNumber; the reference's ReconstructIndexSimilarityTest uses KDTNumber=2)
+    "bkt2_l2_6k_32": ("BKT", "L2", lambda: reflib.gen_iid(6000, 32, 71), lambda: reflib.gen_iid(200, 32, 72), "BKTNumber=2"),
+    "kdt2_l2_6k_32": ("KDT", "L2", lambda: reflib.gen_iid(6000, 32, 73), lambda: reflib.gen_iid(200, 32, 74), "KDTNumber=2"),
     "kdt_l2_10k_64": ("KDT", "L2", lambda: reflib.gen_iid(10000, 64, 14), lambda: reflib.gen_iid(300, 64, 15), ""),
 }
 

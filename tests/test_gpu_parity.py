@@ -13,7 +13,7 @@ from conftest import data_folder
 pytestmark = pytest.mark.gpu
 
 BKT_SETS = ["algo_line_bkt", "bkt_l2_20k_32", "bkt_cos_10k_128", "bkt_l2_10k_128", "bkt_l2_5k_100",
-            "bkt_l2_3k_30", "bkt_cos_3k_768", "bkt_l2_dups"]
+            "bkt_l2_3k_30", "bkt_cos_3k_768", "bkt_l2_dups", "bkt2_l2_6k_32"]
 
 
 def _compare(idx, files, q, k, mc, tag):
@@ -50,7 +50,7 @@ def test_bkt_search_bit_exact(name):
         idx.close()
 
 
-@pytest.mark.parametrize("name", ["kdt_l2_10k_64"])
+@pytest.mark.parametrize("name", ["kdt_l2_10k_64", "kdt2_l2_6k_32"])
 def test_kdt_search_bit_exact(name):
     from sptag_b200 import B200Index
     folder = data_folder(name)
@@ -349,4 +349,59 @@ def test_integer_distance_kernel_bit_exact_all_dims(vt, dt, lo, hi, metric):
                 b = np.ascontiguousarray(x[ids[i, jj]])
                 exp[i, jj] = L.ora_distance(metric, vt, 16, a.ctypes.data, b.ctypes.data, dim)
         assert np.array_equal(out.view(np.int32), exp.view(np.int32)), (vt, metric, dim)
+        idx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties of the result lists (what the full-size bench run also relies on)
+# ---------------------------------------------------------------------------------------------
+def test_result_list_properties():
+    from sptag_b200 import B200Index
+    folder = data_folder("bkt_l2_20k_32")
+    q = np.load(os.path.join(folder, "queries.npy"))
+    idx = B200Index.load(folder)
+    try:
+        idx.set_param("MaxCheck", 2048)
+        ids, dists = idx.search(q, 10)
+        # ascending by (dist, id), ids unique and in range, no unfilled slot on a 20k index
+        assert (np.diff(dists, axis=1) >= 0).all()
+        ties = np.diff(dists, axis=1) == 0
+        assert (np.diff(ids, axis=1)[ties] > 0).all()
+        assert (ids >= 0).all() and (ids < idx.num_vectors).all()
+        assert all(len(set(r)) == len(r) for r in ids.tolist())
+        # reported distance == the inner loop evaluated on (query, id): the list is self-consistent
+        assert np.array_equal(idx.distance_batch(q, ids).view(np.int32), dists.view(np.int32))
+        # a query's result does not depend on its position in the batch or on its neighbours in the batch
+        perm = np.random.default_rng(1).permutation(q.shape[0])
+        ids_p, dists_p = idx.search(q[perm], 10)
+        assert np.array_equal(ids_p, ids[perm]) and np.array_equal(dists_p, dists[perm])
+        rep = np.repeat(q[:7], 5, axis=0)
+        ids_r, _ = idx.search(rep, 10)
+        assert np.array_equal(ids_r, np.repeat(ids[:7], 5, axis=0))
+        # idempotence: the same batch again gives the same bits
+        ids2, dists2 = idx.search(q, 10)
+        assert np.array_equal(ids2, ids) and np.array_equal(dists2.view(np.int32), dists.view(np.int32))
+        # a larger budget never returns a worse k-th distance on this data
+        idx.set_param("MaxCheck", 8192)
+        _, dists_big = idx.search(q, 10)
+        assert (dists_big[:, -1] <= dists[:, -1]).mean() > 0.99
+    finally:
+        idx.close()
+
+
+def test_empty_and_single_query_batches():
+    from sptag_b200 import B200Index, capi
+    folder = data_folder("bkt_l2_3k_30")
+    q = np.load(os.path.join(folder, "queries.npy"))
+    idx = B200Index.load(folder)
+    try:
+        assert capi.lib().sptag_b200_search(idx._h, None, 0, 10, None, None, None) == 0   # empty batch is a no-op
+        one_ids, one_d = idx.search(q[:1], 10)
+        all_ids, all_d = idx.search(q, 10)
+        assert np.array_equal(one_ids[0], all_ids[0]) and np.array_equal(one_d[0], all_d[0])
+        with pytest.raises(capi.SptagB200Error):
+            idx.search(q, 33)            # K > 32 is rejected loudly, not truncated
+        with pytest.raises(capi.SptagB200Error):
+            idx.set_param("NoSuchParameter", 1)
+    finally:
         idx.close()

@@ -138,7 +138,7 @@ def test_distance_bit_exact_vs_reference_all_trees(oracle_lib, metric):
 
 @needs_ref
 @pytest.mark.parametrize("name", ["algo_line_bkt", "bkt_l2_20k_32", "bkt_cos_10k_128", "bkt_l2_5k_100",
-                                  "bkt_l2_3k_30", "bkt_l2_dups", "kdt_l2_10k_64"])
+                                  "bkt_l2_3k_30", "bkt_l2_dups", "kdt_l2_10k_64", "bkt2_l2_6k_32", "kdt2_l2_6k_32"])
 def test_search_bit_exact_vs_reference(oracle_lib, name):
     folder = data_folder(name)
     files = reflib.IndexFiles(folder)
