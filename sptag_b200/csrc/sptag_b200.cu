@@ -308,9 +308,6 @@ relayout:
     p.visited_words = round_up(((size_t)h->n + 1 + 31) / 32, 4);
     p.ng_spill_entries = (size_t)std::min<long long>((long long)p.ng_length, (long long)h->n + 2) + 2;
     p.spt_spill_entries = (size_t)std::min<long long>((long long)p.spt_length, (long long)h->node_count + 2) + 2;
-    const size_t slots = (size_t)h->num_sms * 32;  // upper bound on grid so re-configuration never reallocates
-    const size_t use_slots = std::min(slots, (size_t)std::max(grid, 1));
-    (void)use_slots;
     const size_t alloc_slots = (size_t)h->num_sms * per_sm;
     {
         const size_t before = h->d_visited.bytes;
