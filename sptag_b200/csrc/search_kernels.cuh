@@ -72,6 +72,8 @@ struct SearchParams {
     // bytes too and distance = sum_i sdc[(i*Ks + x_i)*Ks + y_i]
     const float* sdc;
     int pq_m, pq_ks;
+    // 1: small float rows are loaded straight from HBM into registers (no TMA ring) in the static-DIM kernels
+    int direct_load;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -449,7 +451,7 @@ struct BktNodeDev {
     int centerid, childStart, childEnd;
 };
 
-template <int DIM, bool COSINE, int RPL, bool PQ, int ELEM>
+template <int DIM, bool COSINE, int RPL, bool PQ, int ELEM, bool DIRECT>
 struct WarpSearch {
     const SearchParams& p;
     const int lane, half, j;
@@ -587,10 +589,55 @@ struct WarpSearch {
         ndist += cnt;
     }
 
+    // Small rows (<= 1 KB): the per-row TMA descriptor/mbarrier round trip costs more than it hides, so each
+    // half-warp lane loads "its" element of every 16-chunk (element 16c + j, the accumulator it owns in the
+    // reference's summation tree) of NR rows straight from HBM into registers, then runs the NR chains.
+    template <int NR>
+    __device__ __forceinline__ void compute_dists_direct(int cnt) {
+        constexpr int NCH = (DIM > 0) ? DIM / 16 : 1;
+        __syncwarp();
+        for (int base = 0; base < cnt; base += 2 * NR) {
+            float v[NR][NCH];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int ri = min(base + 2 * r + half, cnt - 1);
+                const float* row = reinterpret_cast<const float*>(p.vectors + (size_t)cand_id[ri] * p.row_stride_bytes);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) v[r][c] = __ldcs(row + 16 * c + j);
+            }
+            float acc[NR];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc[r] = 0.0f;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const float q = qr.q[c];
+#pragma unroll
+                for (int r = 0; r < NR; ++r) acc[r] = __fadd_rn(acc[r], dist_term<COSINE>(q, v[r][c]));
+            }
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const float a8 = __fadd_rn(acc[r], __shfl_down_sync(kFull, acc[r], 8, 16));
+                const float a4 = __fadd_rn(a8, __shfl_down_sync(kFull, a8, 4, 16));
+                const float a1 = __shfl_sync(kFull, a4, 1, 16);
+                const float a2 = __shfl_sync(kFull, a4, 2, 16);
+                const float a3 = __shfl_sync(kFull, a4, 3, 16);
+                const float sum = __fadd_rn(__fadd_rn(__fadd_rn(a4, a1), a2), a3);
+                const int ri = base + 2 * r + half;
+                if (j == 0 && ri < cnt) cand_dist[ri] = COSINE ? __fsub_rn(1.0f, sum) : sum;
+            }
+        }
+        __syncwarp();
+        ndist += cnt;
+    }
+
     __device__ __forceinline__ void compute_dists(int cnt) {
         if (cnt <= 0) return;
         if (PQ) {
             compute_dists_pq(cnt);
+            return;
+        }
+        if (DIRECT) {  // compile-time: the TMA path below is not even instantiated for these kernels
+            compute_dists_direct<2>(cnt);
             return;
         }
         __syncwarp();
@@ -882,11 +929,12 @@ struct WarpSearch {
 // ------------------------------------------------------------------------------------------
 // MINB = minimum resident single-warp CTAs per SM the compiler must allow (caps registers): the PQ variant is
 // bound by per-step latency, so more resident queries win (80 registers, 24 per SM: +32 % QPS, profiles/r01_sweep_c2.txt)
-template <int DIM, bool COSINE, int RPL, bool KDT, bool PQ = false, int ELEM = 0, int MINB = 1>
+template <int DIM, bool COSINE, int RPL, bool KDT, bool PQ = false, int ELEM = 0, int MINB = 1, bool DIRECT = false>
 __global__ void __launch_bounds__(32, MINB) search_kernel(const SearchParams p) {
+    static_assert(!DIRECT || (DIM > 0 && DIM <= 256 && DIM % 16 == 0 && ELEM == 0 && !PQ), "direct loads: small static float rows");
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x;
-    WarpSearch<DIM, COSINE, RPL, PQ, ELEM> w(p, lane);
+    WarpSearch<DIM, COSINE, RPL, PQ, ELEM, DIRECT> w(p, lane);
     w.ring = smem;
     w.cand_id = reinterpret_cast<int*>(smem + p.off_cand);
     w.cand_dist = reinterpret_cast<float*>(smem + p.off_cand + 128);

@@ -100,6 +100,7 @@ struct sptag_b200_index {
     // SM matter more than on-chip queue capacity (sweep in profiles/r01_sweep_c2.txt).  0 = auto.
     int h_ng = 0, h_spt = 0;
     int simd_width = 16;
+    int direct_load = 0;          // 1: <=1 KB float rows bypass the TMA ring (static-DIM kernels only)
     int slot_scheme = 0;          // 0 auto, 1 = 128-multiple stride + staggered odd slots, 2 = stride 64 mod 128
     int visited_log = -1;         // -1 auto (bitmap > 256 KB per slot), 0 clear per query, 1 log + selective clear
     int visited_log_entries = 0;  // 0 = auto
@@ -135,9 +136,12 @@ SearchKernelFn pick_rpl(int mres_cap, bool kdt) {
 }
 
 template <bool COSINE>
-SearchKernelFn pick_dim(int dim, int mres_cap, bool kdt) {
+SearchKernelFn pick_dim(int dim, int mres_cap, bool kdt, bool direct) {
     switch (dim) {
-    case 128: return pick_rpl<128, COSINE>(mres_cap, kdt);
+    case 128:
+        if (direct && !kdt && mres_cap <= 32 * 16) return search_kernel<128, COSINE, 16, false, false, 0, 16, true>;
+        if (!kdt && mres_cap <= 32 * 16) return search_kernel<128, COSINE, 16, false, false, 0, 16>;  // 128 regs, 16/SM
+        return pick_rpl<128, COSINE>(mres_cap, kdt);
     case 768:
         // 15 resident queries per SM (127 registers, no spills) when the m_Results file is the 16-register one
         if (!kdt && mres_cap <= 32 * 16) return search_kernel<768, COSINE, 16, false, false, 0, 15>;
@@ -165,7 +169,8 @@ SearchKernelFn pick_kernel(const sptag_b200_index* h, int mres_cap) {
     const bool l2 = (h->metric == SPTAG_B200_METRIC_L2);
     if (h->value_type == SPTAG_B200_VT_INT8) return l2 ? pick_int<false, 1>(mres_cap, kdt) : pick_int<true, 1>(mres_cap, kdt);
     if (h->value_type == SPTAG_B200_VT_UINT8) return l2 ? pick_int<false, 2>(mres_cap, kdt) : pick_int<true, 2>(mres_cap, kdt);
-    return l2 ? pick_dim<false>(h->dim, mres_cap, kdt) : pick_dim<true>(h->dim, mres_cap, kdt);
+    const bool direct = (h->direct_load != 0);
+    return l2 ? pick_dim<false>(h->dim, mres_cap, kdt, direct) : pick_dim<true>(h->dim, mres_cap, kdt, direct);
 }
 
 // Fill SearchParams + launch geometry for this handle.  Allocates per-slot scratch.
@@ -220,6 +225,9 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     p.spt_length = alloc_check * 10;
     p.spt_lastlevel = heap_lastlevel(p.spt_length);
     p.mres_cap = std::max(h->max_check / 16, k);
+    // must mirror pick_dim: the direct-load instantiation exists for 128-d float BKT with the 16-register m_Results file
+    p.direct_load = (h->direct_load != 0 && !pq && h->value_type == SPTAG_B200_VT_FLOAT && h->dim == 128 &&
+                     h->algo == SPTAG_B200_ALGO_BKT && std::max(h->max_check / 16, k) <= 512) ? 1 : 0;
     p.sdc = (const float*)h->d_sdc.ptr;
     p.pq_m = h->q_m;
     p.pq_ks = h->q_ks;
@@ -243,6 +251,10 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
         if (h->slot_scheme == 1) p.slot_stagger = 1;
         if (h->slot_scheme == 2) p.slot_stagger = 0;
         p.slot_stride = (int)(p.slot_stagger ? a : b);
+    }
+    if (p.direct_load) {  // the ring is not used: keep the minimum
+        stage_rows = 2;
+        stages = 1;
     }
     if (pq) {  // every candidate row of a step in one TMA batch; rows are M bytes
         stage_rows = 32;
@@ -723,6 +735,7 @@ int sptag_b200_set_param(sptag_b200_handle h, const char* name, const char* valu
     else if (n == "B200.VisitedLog") h->visited_log = (int)v;
     else if (n == "B200.VisitedLogEntries") h->visited_log_entries = (int)v;
     else if (n == "B200.SlotScheme") h->slot_scheme = (int)v;
+    else if (n == "B200.DirectLoad") h->direct_load = (int)v;
     else return fail(SPTAG_B200_PARAM_NOT_FOUND, "unknown parameter %s", name);
     return SPTAG_B200_SUCCESS;
 }
@@ -746,6 +759,7 @@ int sptag_b200_get_param(sptag_b200_handle h, const char* name, char* value_out,
     else if (n == "B200.VisitedLog") v = h->visited_log;
     else if (n == "B200.VisitedLogEntries") v = h->visited_log_entries;
     else if (n == "B200.SlotScheme") v = h->slot_scheme;
+    else if (n == "B200.DirectLoad") v = h->direct_load;
     else return fail(SPTAG_B200_PARAM_NOT_FOUND, "unknown parameter %s", name);
     snprintf(value_out, (size_t)capacity, "%ld", v);
     return SPTAG_B200_SUCCESS;
