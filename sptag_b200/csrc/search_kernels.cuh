@@ -642,7 +642,9 @@ struct WarpSearch {
         }
         __syncwarp();
         fence_proxy_async();  // earlier generic-proxy reads of the ring precede the async writes
-        const int nst = (cnt + p.stage_rows - 1) / p.stage_rows;
+        // stage count without an integer division (runtime divisor = a ~20-instruction emulation on the step's critical path)
+        int nst = 0;
+        for (int covered = 0; covered < cnt; covered += p.stage_rows) ++nst;
         const int pre = min(nst, p.stages);
         for (int t = 0; t < pre; ++t) issue_stage(t, cnt);
         for (int t = 0; t < nst; ++t) {
