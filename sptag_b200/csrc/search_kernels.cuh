@@ -74,6 +74,8 @@ struct SearchParams {
     int pq_m, pq_ks;
     // 1: small float rows are loaded straight from HBM into registers (no TMA ring) in the static-DIM kernels
     int direct_load;
+    // K > 32: the result set is the reference's own max-heap (QueryResultSet.h:77-120) in a per-slot HBM arena
+    int2* topk;                            // per slot, k entries (id, distance bits); nullptr when k <= 32
 };
 
 // ------------------------------------------------------------------------------------------
@@ -468,7 +470,8 @@ struct WarpSearch {
     // queues
     WarpHeap ng, spt;
     MResults<RPL> mres;
-    // top-K: lane i holds the i-th best (dist, id)
+    // top-K: lane i holds the i-th best (dist, id) (k <= 32); larger k: heap in HBM
+    int2* tk;
     float tk_d;
     int tk_id;
     float worst_d;
@@ -503,9 +506,66 @@ struct WarpSearch {
         return was;
     }
 
+    // ---- K > 32: QueryResultSet as the reference keeps it, a max-heap on (Dist, VID) in the slot's arena ----
+    static __device__ __forceinline__ bool res_less(int2 a, int2 b) {  // QueryResultSet.h:17-20
+        const float da = __int_as_float(a.y), db = __int_as_float(b.y);
+        return (da < db) || ((da == db) && (a.x < b.x));
+    }
+    // QueryResultSet::Heapify(count) with `cur` being the value sitting at the root (QueryResultSet.h:101-116);
+    // executed redundantly by all lanes (uniform loads), lane 0 stores
+    __device__ __forceinline__ void res_heapify(int2 cur, int count) {
+        int parent = 0, next = 1;
+        const int maxidx = count - 1;
+        while (next < maxidx) {
+            int2 a = tk[next];
+            const int2 b = tk[next + 1];
+            if (res_less(a, b)) {
+                next++;
+                a = b;
+            }
+            if (res_less(cur, a)) {
+                if (lane == 0) tk[parent] = a;
+                parent = next;
+                next = (parent << 1) + 1;
+            } else
+                break;
+        }
+        if (next == maxidx) {
+            const int2 a = tk[next];
+            if (res_less(cur, a)) {
+                if (lane == 0) tk[parent] = a;
+                parent = next;
+            }
+        }
+        if (lane == 0 && count > 0) tk[parent] = cur;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void res_reset() {
+        for (int i = lane; i < p.k; i += 32) tk[i] = make_pair(-1, SPTAG_B200_MAXDIST);
+        __syncwarp();
+    }
+    // QueryResultSet::SortResult (QueryResultSet.h:89-96): heap-sort ascending in place
+    __device__ __forceinline__ void res_sort() {
+        for (int i = p.k - 1; i >= 0; i--) {
+            const int2 root = tk[0];
+            const int2 last = tk[i];
+            __syncwarp();
+            if (lane == 0) tk[i] = root;
+            __syncwarp();
+            res_heapify(last, i);
+        }
+    }
+
     // QueryResultSet::AddPoint (QueryResultSet.h:77-87) on the sorted register list
     __device__ __forceinline__ bool add_point(int id, float d) {
         if (!(d < worst_d || (d == worst_d && id < worst_id))) return false;
+        if (tk != nullptr) {
+            res_heapify(make_pair(id, d), p.k);
+            const int2 root = tk[0];
+            worst_d = __int_as_float(root.y);
+            worst_id = root.x;
+            return true;
+        }
         const bool less = (lane < p.k) && ((tk_d < d) || (tk_d == d && tk_id < id));
         const int pos = __popc(__ballot_sync(kFull, less));
         const float pd = __shfl_up_sync(kFull, tk_d, 1);
@@ -944,6 +1004,7 @@ __global__ void __launch_bounds__(32, MINB) search_kernel(const SearchParams p) 
     w.qs = reinterpret_cast<float*>(smem + p.off_query);
     w.visited = p.visited + (size_t)blockIdx.x * p.visited_words;
     w.vlog = p.vlog ? p.vlog + (size_t)blockIdx.x * p.vlog_entries : nullptr;
+    w.tk = p.topk ? p.topk + (size_t)blockIdx.x * p.k : nullptr;
     w.ng.s = reinterpret_cast<int2*>(smem + p.off_ng);
     w.ng.g = p.ng_spill + (size_t)blockIdx.x * p.ng_spill_entries;
     w.ng.H = p.h_ng;
@@ -984,6 +1045,7 @@ __global__ void __launch_bounds__(32, MINB) search_kernel(const SearchParams p) 
         w.tk_id = -1;
         w.worst_d = SPTAG_B200_MAXDIST;
         w.worst_id = -1;
+        if (w.tk != nullptr) w.res_reset();
         w.checked = w.ndist = w.nexpand = w.ntree = 0;
         w.tree_checked = w.no_better = 0;
         // query -> shared memory (+ registers for the static-DIM variants)
@@ -1030,7 +1092,14 @@ __global__ void __launch_bounds__(32, MINB) search_kernel(const SearchParams p) 
             __syncwarp();
         }
         // ---- QueryResultSet::SortResult: the register list is already ascending by (dist, id) ----
-        if (lane < p.k) {
+        if (w.tk != nullptr) {
+            w.res_sort();
+            for (int i = lane; i < p.k; i += 32) {
+                const int2 e = w.tk[i];
+                p.out_ids[(size_t)q * p.k + i] = (e.x >= 0) ? e.x + p.id_offset : e.x;
+                p.out_dists[(size_t)q * p.k + i] = __int_as_float(e.y);
+            }
+        } else if (lane < p.k) {
             const int id = w.tk_id;
             p.out_ids[(size_t)q * p.k + lane] = (id >= 0) ? id + p.id_offset : id;
             p.out_dists[(size_t)q * p.k + lane] = w.tk_d;

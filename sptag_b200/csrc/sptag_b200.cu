@@ -109,7 +109,7 @@ struct sptag_b200_index {
     int q_type = 0, q_rtype = SPTAG_B200_VT_FLOAT, q_m = 0, q_ks = 0, q_dsub = 0;
     DeviceBuffer d_codebooks, d_rotation_t, d_sdc, d_codes, d_raw;
     // scratch
-    DeviceBuffer d_visited, d_ng_spill, d_spt_spill, d_counter, d_vlog;
+    DeviceBuffer d_visited, d_ng_spill, d_spt_spill, d_counter, d_vlog, d_topk;
     DeviceBuffer d_queries, d_ids, d_dists, d_stats;  // staging for the host-buffer entry point
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool timed = false;
@@ -196,7 +196,7 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     }
     if (h->simd_width != 16)
         return fail(SPTAG_B200_LACK_OF_INPUTS, "B200.SimdWidth %d not built (16 only)", h->simd_width);
-    if (k < 1 || k > 32) return fail(SPTAG_B200_LACK_OF_INPUTS, "k = %d outside the supported range [1, 32]", k);
+    if (k < 1 || k > 1024) return fail(SPTAG_B200_LACK_OF_INPUTS, "k = %d outside the supported range [1, 1024]", k);
 
     memset(&p, 0, sizeof(p));
     p.vectors = (const unsigned char*)h->d_vectors.ptr;
@@ -346,6 +346,11 @@ relayout:
     if (int rc = h->d_ng_spill.ensure(alloc_slots * p.ng_spill_entries * 8)) return rc;
     if (int rc = h->d_spt_spill.ensure(alloc_slots * p.spt_spill_entries * 8)) return rc;
     if (int rc = h->d_counter.ensure(256)) return rc;
+    p.topk = nullptr;
+    if (k > 32) {  // result heap of the reference in HBM, one arena per slot
+        if (int rc = h->d_topk.ensure(alloc_slots * (size_t)k * 8)) return rc;
+        p.topk = (int2*)h->d_topk.ptr;
+    }
     p.visited = (unsigned int*)h->d_visited.ptr;
     p.ng_spill = (int2*)h->d_ng_spill.ptr;
     p.spt_spill = (int2*)h->d_spt_spill.ptr;
@@ -527,6 +532,7 @@ void sptag_b200_destroy(sptag_b200_handle h) {
     h->d_raw.release();
     h->d_visited.release();
     h->d_vlog.release();
+    h->d_topk.release();
     h->d_ng_spill.release();
     h->d_spt_spill.release();
     h->d_counter.release();

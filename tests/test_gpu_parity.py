@@ -103,7 +103,7 @@ def test_tuning_knobs_do_not_change_results(knobs):
         idx.close()
 
 
-@pytest.mark.parametrize("k", [1, 5, 32])
+@pytest.mark.parametrize("k", [1, 5, 32, 33, 100, 500])
 def test_result_counts(k):
     from sptag_b200 import B200Index
     folder = data_folder("bkt_l2_10k_128")
@@ -400,7 +400,7 @@ def test_empty_and_single_query_batches():
         all_ids, all_d = idx.search(q, 10)
         assert np.array_equal(one_ids[0], all_ids[0]) and np.array_equal(one_d[0], all_d[0])
         with pytest.raises(capi.SptagB200Error):
-            idx.search(q, 33)            # K > 32 is rejected loudly, not truncated
+            idx.search(q, 1025)          # K > 1024 is rejected loudly, not truncated
         with pytest.raises(capi.SptagB200Error):
             idx.set_param("NoSuchParameter", 1)
     finally:
