@@ -112,7 +112,8 @@ void sptag_b200_destroy(sptag_b200_handle h);
 /* Replaces: VectorIndex::SetParameter / GetParameter (BKTIndex.cpp:980-1025) for the search-time
  * parameters, same names as the ini file: MaxCheck, MaxCheckForRefineGraph,
  * NumberOfInitialDynamicPivots, NumberOfOtherDynamicPivots,
- * ThresholdOfNumberOfContinuousNoBetterPropagation.  Additional B200 tuning knobs (not in the
+ * ThresholdOfNumberOfContinuousNoBetterPropagation; "EnableADC" = VectorIndex::SetQuantizerADC
+ * (VectorIndex.h:136-138) for quantized indexes.  Additional B200 tuning knobs (not in the
  * reference) are prefixed "B200.": B200.QueriesPerSM, B200.StageRows, B200.Stages,
  * B200.NGCacheEntries, B200.SPTCacheEntries, B200.SimdWidth (16/8/4: which DistanceUtils
  * summation tree to reproduce bit-exactly; default 16 = AVX-512), B200.VisitedLog (-1 auto, 0 clear the

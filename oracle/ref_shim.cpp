@@ -208,6 +208,10 @@ float ref_quantizer_l2(void* q, const unsigned char* a, const unsigned char* b) 
     return (*(std::shared_ptr<COMMON::IQuantizer>*)q)->L2Distance(a, b);
 }
 
+// VectorIndex::SetQuantizerADC (VectorIndex.h:136-138): asymmetric distance (query -> per-sub-vector distance table,
+// PQQuantizer.h:114-119, :141-157) instead of the default symmetric SDC table look-up.  Not serialized with the index.
+void ref_set_adc(void* h, int enable) { ((RefHandle*)h)->index->SetQuantizerADC(enable != 0); }
+
 // Per-query overload over a batch of RAW queries (what IndexSearcher does for quantized indexes,
 // IndexSearcher/main.cpp:179-206; the batched overload strides by code bytes and is not usable here,
 // SURVEY.md 8b).  stride_bytes = bytes between consecutive raw queries.

@@ -258,6 +258,34 @@ static void quantize_one(const ora_quantizer* q, const void* raw, uint8_t* out, 
     }
 }
 
+/* PQQuantizer::QuantizeVector with ADC enabled (PQQuantizer.h:141-157): table[i][j] = L2(subvector_i, codeword_ij);
+ * OPQ rotates first (OPQQuantizer.h:96-121) */
+static void adc_table_one(const ora_quantizer* q, const void* raw, float* table, float* tmp /* 2*dim */)
+{
+    const int m = q->m, ks = q->ks, d = q->dsub, dim = m * d;
+    float* vec = tmp;
+    float* rot = tmp + dim;
+    for (int i = 0; i < dim; i++) vec[i] = raw_elem(raw, q->rtype, (size_t)i);
+    const float* src = vec;
+    if (q->qtype == ORA_Q_OPQ) {
+        for (int i = 0; i < dim; i++)
+            rot[i] = 1 - dist_f32(1, q->simd_width, vec, q->rotation_t + (size_t)i * dim, dim);
+        src = rot;
+    }
+    for (int i = 0; i < m; i++)
+        for (int j = 0; j < ks; j++)
+            table[(size_t)i * ks + j] = dist_f32(0, q->simd_width, src + (size_t)i * d,
+                                                 q->codebooks + ((size_t)i * ks + j) * d, d);
+}
+
+/* PQQuantizer::L2Distance, ADC branch (PQQuantizer.h:114-119): pX is the query's table */
+static float adc_l2(const ora_quantizer* q, const float* table, const uint8_t* y)
+{
+    float out = 0;
+    for (int i = 0; i < q->m; i++) out += table[(size_t)i * q->ks + y[i]];
+    return out;
+}
+
 void ora_quantizer_encode(const ora_quantizer* q, const void* raw, int32_t n, uint8_t* out)
 {
     static const size_t elem[4] = {1, 1, 2, 4};
@@ -552,8 +580,10 @@ static inline float qdist(const qctx_t* c, ws_t* ws, int32_t id)
 {
     ws->ndist++;
     const char* row = (const char*)c->idx->vectors + (size_t)id * c->row_bytes;
-    if (c->idx->quantizer) /* m_fComputeDistance = quantizer L2Distance (BKTIndex.cpp:34-50, IQuantizer.cpp:103-114) */
+    if (c->idx->quantizer) { /* m_fComputeDistance = quantizer L2Distance (BKTIndex.cpp:34-50, IQuantizer.cpp:103-114) */
+        if (c->idx->quantizer->enable_adc) return adc_l2(c->idx->quantizer, (const float*)c->query, (const uint8_t*)row);
         return ora_quantizer_l2(c->idx->quantizer, (const uint8_t*)c->query, (const uint8_t*)row);
+    }
     return ora_distance(c->idx->metric, c->idx->value_type, c->idx->simd_width, c->query, row, c->idx->dim);
 }
 
@@ -782,13 +812,19 @@ int ora_search_batch(const ora_index* idx, const void* queries, int32_t nq, int3
         ws_init(&ws, idx->n, alloc_check);
         res_t* res = (res_t*)malloc(sizeof(res_t) * (size_t)(k > 0 ? k : 1));
         uint8_t* qcode = quant ? (uint8_t*)malloc((size_t)quant->m) : NULL;
+        float* qtable = (quant && quant->enable_adc) ? (float*)malloc(sizeof(float) * (size_t)quant->m * quant->ks) : NULL;
         float* qtmp = quant ? (float*)malloc(sizeof(float) * 2 * (size_t)(quant->m * quant->dsub)) : NULL;
 #pragma omp for schedule(dynamic, 10)
         for (int32_t q = 0; q < nq; q++) {
             qctx_t c = {idx, (const char*)queries + (size_t)q * query_bytes, row_bytes, idx->metric != ORA_L2};
             if (quant) { /* QueryResultSet::SetTarget -> QuantizeVector (QueryResultSet.h:46-60) */
-                quantize_one(quant, c.query, qcode, qtmp);
-                c.query = qcode;
+                if (quant->enable_adc) {
+                    adc_table_one(quant, c.query, qtable, qtmp);
+                    c.query = qtable;
+                } else {
+                    quantize_one(quant, c.query, qcode, qtmp);
+                    c.query = qcode;
+                }
             }
             for (int i = 0; i < k; i++) {
                 res[i].vid = -1;
@@ -817,6 +853,7 @@ int ora_search_batch(const ora_index* idx, const void* queries, int32_t nq, int3
         }
         free(res);
         free(qcode);
+        free(qtable);
         free(qtmp);
         ws_free(&ws);
     }

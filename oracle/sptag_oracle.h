@@ -30,6 +30,7 @@ typedef struct {
     int32_t rtype;          /* reconstruct type = element type of raw queries (ORA_INT8 ... ORA_FLOAT) */
     int32_t m, ks, dsub;    /* NumSubvectors, KsPerSubvector, DimPerSubvector */
     int32_t simd_width;     /* DistanceUtils variant used for the tables / encoding */
+    int32_t enable_adc;     /* IQuantizer::SetEnableADC: queries become M*Ks distance tables (PQQuantizer.h:114-119) */
     const float* codebooks; /* m * ks * dsub */
     const float* rotation;  /* OPQ: (m*dsub)^2 floats as stored (m_OPQMatrix); NULL for PQ */
     float* sdc;             /* m * ks * ks, caller-allocated, filled by ora_quantizer_init */

@@ -72,6 +72,11 @@ struct SearchParams {
     // bytes too and distance = sum_i sdc[(i*Ks + x_i)*Ks + y_i]
     const float* sdc;
     int pq_m, pq_ks;
+    // ADC mode (IQuantizer::SetEnableADC, PQQuantizer.h:114-119, :141-157): the query is a rotated float vector,
+    // each warp builds its M*Ks distance table in its slot of `adc_tables` and sums table[i*Ks + y_i]
+    int pq_adc, pq_dsub;
+    const float* codebooks;
+    float* adc_tables;                     // per slot, pq_m * pq_ks floats
     // 1: small float rows are loaded straight from HBM into registers (no TMA ring) in the static-DIM kernels
     int direct_load;
     // K > 32: the result set is the reference's own max-heap (QueryResultSet.h:77-120) in a per-slot HBM arena
@@ -136,6 +141,39 @@ __device__ __forceinline__ float dist_tail(float x, float y, float acc) {
     if (COSINE) return __fmaf_rn(x, y, acc);
     float d = __fsub_rn(x, y);
     return __fmaf_rn(d, d, acc);
+}
+
+// The reference's float AVX-512 summation tree evaluated by ONE thread (any length d): used where the
+// operands are tiny (sub-vectors of a codebook) or where one thread owns one output (rotation rows).
+template <bool COSINE>
+__device__ float exact_dist_thread(const float* __restrict__ x, const float* __restrict__ y, int d) {
+    float a16[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a16[j] = 0.0f;
+    int i = 0;
+    for (; i + 16 <= d; i += 16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a16[j] = __fadd_rn(a16[j], dist_term<COSINE>(x[i + j], y[i + j]));
+    }
+    float a8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a8[j] = __fadd_rn(a16[j], a16[j + 8]);
+    if (d & 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a8[j] = __fadd_rn(a8[j], dist_term<COSINE>(x[i + j], y[i + j]));
+        i += 8;
+    }
+    float a4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a4[j] = __fadd_rn(a8[j], a8[j + 4]);
+    if (d & 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a4[j] = __fadd_rn(a4[j], dist_term<COSINE>(x[i + j], y[i + j]));
+        i += 4;
+    }
+    float s = __fadd_rn(__fadd_rn(__fadd_rn(a4[0], a4[1]), a4[2]), a4[3]);
+    for (; i < d; ++i) s = dist_tail<COSINE>(x[i], y[i], s);
+    return COSINE ? __fsub_rn(1.0f, s) : s;
 }
 
 // Registers holding this lane's slice of the query: element 16c + (lane & 15) for every full
@@ -602,6 +640,11 @@ struct WarpSearch {
     }
 
     // distances of the query to cand_id[0..cnt) -> cand_dist[0..cnt).  cnt <= 32.
+    const float* pq_table;
+    // the SDC table is read-only for the whole kernel (non-coherent path is fine); an ADC table was written by
+    // this warp a moment ago, so it is read with ordinary loads
+    __device__ __forceinline__ float pq_ld(const float* a) const { return p.pq_adc ? *a : __ldg(a); }
+
     // PQ rows: all (<= 32) code rows of the step are staged by one TMA batch, then lane r sums the M
     // table entries of candidate r in subvector order -- the reference's single float accumulator
     // (PQQuantizer::L2Distance, PQQuantizer.h:110-128), one candidate per lane.
@@ -618,6 +661,7 @@ struct WarpSearch {
         if (lane < cnt) {
             const unsigned char* row = ring + (size_t)lane * p.slot_stride;
             const int* qoff = reinterpret_cast<const int*>(qs);
+            const float* tb = pq_table;  // the shared SDC table, or this slot's ADC table of the current query
             float acc = 0.0f;
             // 16 look-ups in flight per lane (their addresses do not depend on the running sum), then the sum in
             // sub-vector order
@@ -629,20 +673,20 @@ struct WarpSearch {
                 float t[16];
 #pragma unroll
                 for (int b = 0; b < 16; ++b)
-                    t[b] = __ldg(p.sdc + qoff[i + b] + ((ws[b >> 2] >> (8 * (b & 3))) & 255u));
+                    t[b] = pq_ld(tb + qoff[i + b] + ((ws[b >> 2] >> (8 * (b & 3))) & 255u));
 #pragma unroll
                 for (int b = 0; b < 16; ++b) acc = __fadd_rn(acc, t[b]);
             }
             const int m4 = p.pq_m & ~3;
             for (; i < m4; i += 4) {
                 const unsigned w = *reinterpret_cast<const unsigned*>(row + i);
-                const float t0 = __ldg(p.sdc + qoff[i] + (w & 255u));
-                const float t1 = __ldg(p.sdc + qoff[i + 1] + ((w >> 8) & 255u));
-                const float t2 = __ldg(p.sdc + qoff[i + 2] + ((w >> 16) & 255u));
-                const float t3 = __ldg(p.sdc + qoff[i + 3] + (w >> 24));
+                const float t0 = pq_ld(tb + qoff[i] + (w & 255u));
+                const float t1 = pq_ld(tb + qoff[i + 1] + ((w >> 8) & 255u));
+                const float t2 = pq_ld(tb + qoff[i + 2] + ((w >> 16) & 255u));
+                const float t3 = pq_ld(tb + qoff[i + 3] + (w >> 24));
                 acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, t0), t1), t2), t3);
             }
-            for (; i < p.pq_m; ++i) acc = __fadd_rn(acc, __ldg(p.sdc + qoff[i] + row[i]));
+            for (; i < p.pq_m; ++i) acc = __fadd_rn(acc, pq_ld(tb + qoff[i] + row[i]));
             cand_dist[lane] = acc;
         }
         __syncwarp();
@@ -1049,11 +1093,25 @@ __global__ void __launch_bounds__(32, MINB) search_kernel(const SearchParams p) 
         w.checked = w.ndist = w.nexpand = w.ntree = 0;
         w.tree_checked = w.no_better = 0;
         // query -> shared memory (+ registers for the static-DIM variants)
-        if (PQ) {
+        if (PQ && p.pq_adc) {
+            // PQQuantizer::QuantizeVector with ADC on (PQQuantizer.h:141-157): table[i][j] = L2(query sub-vector i,
+            // codeword j of sub-space i), built by the warp into its slot's arena
+            const float* qrot = reinterpret_cast<const float*>(p.queries + (size_t)q * p.query_stride_bytes);
+            float* table = p.adc_tables + (size_t)blockIdx.x * p.pq_m * p.pq_ks;
+            const int total = p.pq_m * p.pq_ks;
+            for (int t = lane; t < total; t += 32) {
+                const int i = t / p.pq_ks;
+                table[t] = exact_dist_thread<false>(qrot + (size_t)i * p.pq_dsub, p.codebooks + (size_t)t * p.pq_dsub, p.pq_dsub);
+            }
+            int* qoff = reinterpret_cast<int*>(w.qs);
+            for (int i = lane; i < p.pq_m; i += 32) qoff[i] = i * p.pq_ks;
+            w.pq_table = table;
+        } else if (PQ) {
             // the (already quantized) query: M code bytes -> row offsets of its SDC table rows
             const unsigned char* qc = p.queries + (size_t)q * p.query_stride_bytes;
             int* qoff = reinterpret_cast<int*>(w.qs);
             for (int i = lane; i < p.pq_m; i += 32) qoff[i] = (i * p.pq_ks + (int)qc[i]) * p.pq_ks;
+            w.pq_table = p.sdc;
         } else if (ELEM != 0) {
             const unsigned char* qb = p.queries + (size_t)q * p.query_stride_bytes;
             unsigned char* qd = reinterpret_cast<unsigned char*>(w.qs);
@@ -1157,39 +1215,6 @@ __global__ void distance_batch_kernel(const unsigned char* vectors, unsigned lon
 // PQ / OPQ quantizer kernels (query side + tables; PQQuantizer.h:138-180, :333-348, OPQQuantizer.h:96-121)
 // ------------------------------------------------------------------------------------------
 
-// The reference's float AVX-512 summation tree evaluated by ONE thread (any length d): used where the
-// operands are tiny (sub-vectors of a codebook) or where one thread owns one output (rotation rows).
-template <bool COSINE>
-__device__ float exact_dist_thread(const float* __restrict__ x, const float* __restrict__ y, int d) {
-    float a16[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) a16[j] = 0.0f;
-    int i = 0;
-    for (; i + 16 <= d; i += 16) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) a16[j] = __fadd_rn(a16[j], dist_term<COSINE>(x[i + j], y[i + j]));
-    }
-    float a8[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a8[j] = __fadd_rn(a16[j], a16[j + 8]);
-    if (d & 8) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a8[j] = __fadd_rn(a8[j], dist_term<COSINE>(x[i + j], y[i + j]));
-        i += 8;
-    }
-    float a4[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) a4[j] = __fadd_rn(a8[j], a8[j + 4]);
-    if (d & 4) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) a4[j] = __fadd_rn(a4[j], dist_term<COSINE>(x[i + j], y[i + j]));
-        i += 4;
-    }
-    float s = __fadd_rn(__fadd_rn(__fadd_rn(a4[0], a4[1]), a4[2]), a4[3]);
-    for (; i < d; ++i) s = dist_tail<COSINE>(x[i], y[i], s);
-    return COSINE ? __fsub_rn(1.0f, s) : s;
-}
-
 // PQQuantizer::InitializeDistanceTables (PQQuantizer.h:333-348): sdc[i][j][k] = L2(codebook[i][j], codebook[i][k])
 __global__ void sdc_table_kernel(const float* __restrict__ codebooks, int m, int ks, int dsub, float* __restrict__ sdc) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1209,7 +1234,8 @@ __global__ void sdc_table_kernel(const float* __restrict__ codebooks, int m, int
 // raw_type: 0 int8, 1 uint8, 2 int16, 3 float (the quantizer's reconstruct type).
 __global__ void pq_quantize_kernel(const unsigned char* __restrict__ raw, int raw_type, long long raw_stride_bytes,
                                    int nvec, const float* __restrict__ codebooks, const float* __restrict__ rotation_t,
-                                   int m, int ks, int dsub, unsigned char* __restrict__ codes) {
+                                   int m, int ks, int dsub, unsigned char* __restrict__ codes,
+                                   float* __restrict__ rotated_out) {
     extern __shared__ float qsm[];  // vec[dim] | rot[dim]
     const int dim = m * dsub;
     float* vec = qsm;
@@ -1234,6 +1260,10 @@ __global__ void pq_quantize_kernel(const unsigned char* __restrict__ raw, int ra
             rot[i] = __fsub_rn(1.0f, exact_dist_thread<true>(vec, rotation_t + (size_t)i * dim, dim));
         __syncthreads();
         q = rot;
+    }
+    if (rotated_out != nullptr) {  // ADC mode: the search kernel builds the distance table from the rotated vector
+        for (int i = threadIdx.x; i < dim; i += blockDim.x) rotated_out[(size_t)v * dim + i] = q[i];
+        return;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int i = warp; i < m; i += nwarps) {

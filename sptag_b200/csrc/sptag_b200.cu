@@ -107,7 +107,8 @@ struct sptag_b200_index {
     bool visited_clean = false;   // the whole d_visited buffer is known to be zero
     // PQ / OPQ quantizer (null when q_type == 0)
     int q_type = 0, q_rtype = SPTAG_B200_VT_FLOAT, q_m = 0, q_ks = 0, q_dsub = 0;
-    DeviceBuffer d_codebooks, d_rotation_t, d_sdc, d_codes, d_raw;
+    int q_adc = 0;  // IQuantizer::SetEnableADC (not serialized by the reference either)
+    DeviceBuffer d_codebooks, d_rotation_t, d_sdc, d_codes, d_raw, d_adc;
     // scratch
     DeviceBuffer d_visited, d_ng_spill, d_spt_spill, d_counter, d_vlog, d_topk;
     DeviceBuffer d_queries, d_ids, d_dists, d_stats;  // staging for the host-buffer entry point
@@ -231,6 +232,9 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     p.sdc = (const float*)h->d_sdc.ptr;
     p.pq_m = h->q_m;
     p.pq_ks = h->q_ks;
+    p.pq_adc = (pq && h->q_adc) ? 1 : 0;
+    p.pq_dsub = h->q_dsub;
+    p.codebooks = (const float*)h->d_codebooks.ptr;
 
     // ---- shared-memory layout ----
     int stage_rows = h->stage_rows;
@@ -346,6 +350,11 @@ relayout:
     if (int rc = h->d_ng_spill.ensure(alloc_slots * p.ng_spill_entries * 8)) return rc;
     if (int rc = h->d_spt_spill.ensure(alloc_slots * p.spt_spill_entries * 8)) return rc;
     if (int rc = h->d_counter.ensure(256)) return rc;
+    p.adc_tables = nullptr;
+    if (p.pq_adc) {  // one M x Ks fp32 table per resident query
+        if (int rc = h->d_adc.ensure(alloc_slots * (size_t)h->q_m * h->q_ks * 4)) return rc;
+        p.adc_tables = (float*)h->d_adc.ptr;
+    }
     p.topk = nullptr;
     if (k > 32) {  // result heap of the reference in HBM, one arena per slot
         if (int rc = h->d_topk.ensure(alloc_slots * (size_t)k * 8)) return rc;
@@ -363,7 +372,8 @@ size_t query_bytes(const sptag_b200_index* h) {
     return (size_t)h->dim * value_size(h->value_type);
 }
 
-int quantize_device(sptag_b200_index* h, const void* d_raw, int n, unsigned char* d_codes, cudaStream_t stream) {
+int quantize_device(sptag_b200_index* h, const void* d_raw, int n, unsigned char* d_codes, cudaStream_t stream,
+                    float* d_rotated = nullptr) {
     const int dim = h->q_m * h->q_dsub;
     const size_t smem = (size_t)dim * 2 * sizeof(float);
     if (smem > 48 * 1024)
@@ -371,7 +381,7 @@ int quantize_device(sptag_b200_index* h, const void* d_raw, int n, unsigned char
     pq_quantize_kernel<<<n, 128, smem, stream>>>((const unsigned char*)d_raw, h->q_rtype, (long long)query_bytes(h), n,
                                                   (const float*)h->d_codebooks.ptr,
                                                   h->q_type == 2 ? (const float*)h->d_rotation_t.ptr : nullptr, h->q_m,
-                                                  h->q_ks, h->q_dsub, d_codes);
+                                                  h->q_ks, h->q_dsub, d_codes, d_rotated);
     g_launches++;
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -389,10 +399,18 @@ int search_device_impl(sptag_b200_index* h, const void* d_queries, int nq, int k
     p.query_stride_bytes = (size_t)h->dim * value_size(h->value_type);
     if (h->q_type != 0) {
         // QueryResultSet::SetTarget -> IQuantizer::QuantizeVector (QueryResultSet.h:46-60): raw -> M code bytes
-        if (int rc = h->d_codes.ensure((size_t)nq * h->q_m)) return rc;
-        if (int rc = quantize_device(h, d_queries, nq, (unsigned char*)h->d_codes.ptr, stream)) return rc;
-        p.queries = (const unsigned char*)h->d_codes.ptr;
-        p.query_stride_bytes = (size_t)h->q_m;
+        if (h->q_adc) {  // ADC: the kernel needs the rotated float vector, not codes
+            const size_t dimq = (size_t)h->q_m * h->q_dsub;
+            if (int rc = h->d_codes.ensure((size_t)nq * dimq * 4)) return rc;
+            if (int rc = quantize_device(h, d_queries, nq, nullptr, stream, (float*)h->d_codes.ptr)) return rc;
+            p.queries = (const unsigned char*)h->d_codes.ptr;
+            p.query_stride_bytes = dimq * 4;
+        } else {
+            if (int rc = h->d_codes.ensure((size_t)nq * h->q_m)) return rc;
+            if (int rc = quantize_device(h, d_queries, nq, (unsigned char*)h->d_codes.ptr, stream)) return rc;
+            p.queries = (const unsigned char*)h->d_codes.ptr;
+            p.query_stride_bytes = (size_t)h->q_m;
+        }
     }
     p.nq = nq;
     p.out_ids = d_ids;
@@ -530,6 +548,7 @@ void sptag_b200_destroy(sptag_b200_handle h) {
     h->d_sdc.release();
     h->d_codes.release();
     h->d_raw.release();
+    h->d_adc.release();
     h->d_visited.release();
     h->d_vlog.release();
     h->d_topk.release();
@@ -742,6 +761,7 @@ int sptag_b200_set_param(sptag_b200_handle h, const char* name, const char* valu
     else if (n == "B200.VisitedLogEntries") h->visited_log_entries = (int)v;
     else if (n == "B200.SlotScheme") h->slot_scheme = (int)v;
     else if (n == "B200.DirectLoad") h->direct_load = (int)v;
+    else if (n == "EnableADC") h->q_adc = (v != 0);  // VectorIndex::SetQuantizerADC (VectorIndex.h:136-138)
     else return fail(SPTAG_B200_PARAM_NOT_FOUND, "unknown parameter %s", name);
     return SPTAG_B200_SUCCESS;
 }
@@ -766,6 +786,7 @@ int sptag_b200_get_param(sptag_b200_handle h, const char* name, char* value_out,
     else if (n == "B200.VisitedLogEntries") v = h->visited_log_entries;
     else if (n == "B200.SlotScheme") v = h->slot_scheme;
     else if (n == "B200.DirectLoad") v = h->direct_load;
+    else if (n == "EnableADC") v = h->q_adc;
     else return fail(SPTAG_B200_PARAM_NOT_FOUND, "unknown parameter %s", name);
     snprintf(value_out, (size_t)capacity, "%ld", v);
     return SPTAG_B200_SUCCESS;

@@ -74,6 +74,7 @@ def ref():
         L.ref_quantizer_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_quantizer_l2.restype = C.c_float
         L.ref_quantizer_l2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_set_adc.argtypes = [C.c_void_p, C.c_int]
         L.ref_search_each.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_quiet(3)  # warnings and errors only
@@ -129,6 +130,9 @@ class RefIndex:
         h = ref().ref_build_quantized(ALGO_OF_NAME[algo], METRIC_OF_NAME[metric], quantizer_file.encode(),
                                       codes.ctypes.data, codes.shape[0], codes.shape[1], threads, params.encode())
         return cls(h)
+
+    def set_adc(self, enable):
+        ref().ref_set_adc(self.h, 1 if enable else 0)
 
     def search_each(self, queries, k, threads=0):
         """Per-query overload on RAW queries (needed for quantized indexes)."""
@@ -320,7 +324,7 @@ class RefQuantizer:
 # ------------------------------------------------------------------------------------------------
 class _OraQuantizer(C.Structure):
     _fields_ = [("qtype", C.c_int32), ("rtype", C.c_int32), ("m", C.c_int32), ("ks", C.c_int32),
-                ("dsub", C.c_int32), ("simd_width", C.c_int32), ("codebooks", C.c_void_p),
+                ("dsub", C.c_int32), ("simd_width", C.c_int32), ("enable_adc", C.c_int32), ("codebooks", C.c_void_p),
                 ("rotation", C.c_void_p), ("sdc", C.c_void_p), ("rotation_t", C.c_void_p)]
 
 
@@ -333,6 +337,7 @@ class OracleQuantizer:
         self.rot_t = np.empty((quant.dim, quant.dim), np.float32) if quant.qtype == Q_OPQ else None
         s = _OraQuantizer()
         s.qtype, s.rtype, s.m, s.ks, s.dsub, s.simd_width = quant.qtype, quant.rtype, quant.m, quant.ks, quant.dsub, simd_width
+        s.enable_adc = 0
         s.codebooks = quant.codebooks.ctypes.data
         s.rotation = quant.rotation.ctypes.data if quant.rotation is not None else None
         s.sdc = self.sdc.ctypes.data
@@ -398,6 +403,7 @@ class OracleIndex:
         self.other_pivots = files.int_param("NumberOfOtherDynamicPivots", 4)
         self.no_better_threshold = files.int_param("ThresholdOfNumberOfContinuousNoBetterPropagation", 3)
         self.oq = OracleQuantizer(files.quantizer, simd_width) if getattr(files, "quantizer", None) is not None else None
+        self.enable_adc = False
 
     def _struct(self):
         f = self.files
@@ -419,6 +425,8 @@ class OracleIndex:
         s.other_pivots = self.other_pivots
         s.no_better_threshold = self.no_better_threshold
         s.simd_width = self.simd_width
+        if self.oq is not None:
+            self.oq.struct.enable_adc = 1 if self.enable_adc else 0
         s.quantizer = C.addressof(self.oq.struct) if self.oq is not None else None
         return s
 

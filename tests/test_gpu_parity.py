@@ -405,3 +405,29 @@ def test_empty_and_single_query_batches():
             idx.set_param("NoSuchParameter", 1)
     finally:
         idx.close()
+
+
+@pytest.mark.parametrize("name", QUANT_SETS)
+def test_quantized_adc_search_bit_exact(name):
+    # VectorIndex::SetQuantizerADC(true): per-query asymmetric distance tables instead of the SDC table
+    from sptag_b200 import B200Index, capi
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))
+    idx = B200Index.load(folder)
+    try:
+        idx.set_param("EnableADC", 1)
+        for mc in [8192, 256]:
+            idx.set_param("MaxCheck", mc)
+            ids, dists, stats = idx.search(q, 10, want_stats=True)
+            o = reflib.OracleIndex(files)
+            o.max_check = mc
+            o.enable_adc = True
+            ids_o, d_o, st_o = o.search(q, 10)
+            assert np.array_equal(ids, ids_o), (name, mc)
+            assert np.array_equal(dists.view(np.int32), d_o.view(np.int32)), (name, mc)
+            assert np.array_equal(stats[:, capi.ST_NDIST], st_o[:, reflib.ST_NDIST])
+        idx.set_param("EnableADC", 0)       # and back to SDC on the same handle
+        _compare(idx, files, q, 10, 1024, name + " sdc-after-adc")
+    finally:
+        idx.close()

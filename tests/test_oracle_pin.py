@@ -248,3 +248,23 @@ def test_integer_index_search_bit_exact_vs_reference(oracle_lib, name):
         ids_o, d_o, _ = o.search(q, 10, threads=4)
         assert np.array_equal(ids_r, ids_o), (name, mc)
         assert np.array_equal(d_r.view(np.int32), d_o.view(np.int32)), (name, mc)
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["bkt_pq_6k_32", "bkt_opq_6k_48", "bkt_opq_i8_8k_100"])
+def test_quantized_adc_search_bit_exact_vs_reference(oracle_lib, name):
+    # VectorIndex::SetQuantizerADC(true): asymmetric distance tables (PQQuantizer.h:114-119, :141-157)
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))
+    r = reflib.RefIndex.load(folder)
+    r.set_adc(True)
+    for mc in [8192, 256]:
+        r.set_param("MaxCheck", mc)
+        ids_r, d_r, _ = r.search_each(q, 10, threads=4)
+        o = reflib.OracleIndex(files)
+        o.max_check = mc
+        o.enable_adc = True
+        ids_o, d_o, _ = o.search(q, 10, threads=4)
+        assert np.array_equal(ids_r, ids_o), (name, mc)
+        assert np.array_equal(d_r.view(np.int32), d_o.view(np.int32)), (name, mc)
