@@ -303,6 +303,143 @@ def build_rng_graph(x, degree=32, cand=64, rng_factor=1.0, fill=True, row_chunk=
 
 
 # ---------------------------------------------------------------------------------------------
+# kNN candidates at scale: random-projection partition trees with brute force inside the leaves -- the
+# reference's own recipe for the initial graph (NeighborhoodGraph.h:126-360: TPTNumber trees, leaves <= TPTLeafSize,
+# all-pairs inside a leaf, keep the best), level-synchronous on the GPU.  O(trees * N * leaf * dim) instead of O(N^2).
+# ---------------------------------------------------------------------------------------------
+def _tpt_leaves(x, leaf, gen):
+    """One balanced random-projection tree. Returns perm (ids ordered by leaf) and the leaf size (last leaf padded)."""
+    dev = x.device
+    N, dim = x.shape
+    perm = torch.randperm(N, generator=gen, device=dev)
+    seg_len = N
+    nseg = 1
+    while seg_len > leaf:
+        # every segment splits at the median of the projection on the direction between two of its random members
+        offs = (torch.arange(nseg, device=dev) * seg_len)
+        a = perm[offs + torch.randint(0, seg_len, (nseg,), generator=gen, device=dev).clamp_max(seg_len - 1)]
+        b = perm[offs + torch.randint(0, seg_len, (nseg,), generator=gen, device=dev).clamp_max(seg_len - 1)]
+        dirs = (x[a] - x[b])                                            # [nseg, dim]
+        n_full = nseg * seg_len
+        proj = torch.empty(N, device=dev)
+        chunk = max(1, (1 << 26) // dim)
+        segid = torch.arange(N, device=dev) // seg_len
+        segid.clamp_(max=nseg - 1)
+        for s in range(0, N, chunk):
+            e = min(N, s + chunk)
+            proj[s:e] = (x[perm[s:e]] * dirs[segid[s:e]]).sum(1)
+        # sort inside segments: key = segment, then projection
+        order = torch.argsort(proj, stable=True)
+        order = order[torch.argsort(segid[order], stable=True)]
+        perm = perm[order]
+        seg_len = (seg_len + 1) // 2
+        nseg *= 2
+        # after the split the two halves of every old segment are [0, ceil(len/2)) and the rest; with N not a power of
+        # two the tail segments are a little shorter, which only means slightly unbalanced leaves
+        if nseg * seg_len < N:
+            seg_len += 1
+    return perm, seg_len
+
+
+def build_knn_tpt(x, k=48, trees=8, leaf=1024, seed=0, log=None):
+    """Approximate k nearest neighbours of every point. Returns (ids [N,k] int64, dists [N,k]) sorted by distance."""
+    dev = x.device
+    N, dim = x.shape
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed + 77)
+    xn = _sq_norms(x)
+    best_d = torch.full((N, k), float("inf"), device=dev)
+    best_i = torch.full((N, k), -1, dtype=torch.int64, device=dev)
+    t0 = time.time()
+    for t in range(trees):
+        perm, m = _tpt_leaves(x, leaf, g)
+        nleaf = (N + m - 1) // m
+        pad = nleaf * m - N
+        if pad:
+            perm = torch.cat([perm, perm[:pad]])                      # pad the last leaf with repeats (masked below)
+        lchunk = max(1, (1 << 28) // (m * m))
+        kk = min(k, m - 1)
+        for ls in range(0, nleaf, lchunk):
+            le = min(nleaf, ls + lchunk)
+            ids = perm[ls * m:le * m].view(le - ls, m)                  # [L, m]
+            xl = x[ids.reshape(-1)].view(le - ls, m, dim)
+            nl = xn[ids]
+            d = nl[:, :, None] - 2.0 * torch.bmm(xl, xl.transpose(1, 2)) + nl[:, None, :]
+            del xl
+            d.diagonal(dim1=1, dim2=2).fill_(float("inf"))
+            if pad and le == nleaf:                                   # padded duplicates of the last leaf: never candidates
+                d[-1, :, m - pad:] = float("inf")
+            cd, ci = torch.topk(d, kk, dim=2, largest=False)            # [L, m, kk]
+            del d
+            cand_ids = torch.gather(ids[:, None, :].expand(-1, m, -1), 2, ci)
+            rows = ids.reshape(-1)
+            cd = cd.reshape(-1, kk)
+            cand_ids = cand_ids.reshape(-1, kk)
+            if pad and le == nleaf:
+                keep = torch.ones(rows.numel(), dtype=torch.bool, device=dev)
+                keep[-pad:] = False
+                rows, cd, cand_ids = rows[keep], cd[keep], cand_ids[keep]
+            # merge with the running best of those rows: concatenate, drop duplicate ids, keep the k smallest
+            md = torch.cat([best_d[rows], cd], 1)
+            mi = torch.cat([best_i[rows], cand_ids], 1)
+            o = torch.argsort(mi, dim=1, stable=True)
+            mi_s = torch.gather(mi, 1, o)
+            md_s = torch.gather(md, 1, o)
+            dup = torch.zeros_like(mi_s, dtype=torch.bool)
+            dup[:, 1:] = (mi_s[:, 1:] == mi_s[:, :-1]) & (mi_s[:, 1:] >= 0)
+            md_s[dup] = float("inf")
+            nd, no = torch.topk(md_s, k, dim=1, largest=False)
+            best_d[rows] = nd
+            best_i[rows] = torch.gather(mi_s, 1, no)
+        if log:
+            log("tpt tree %d/%d done (%.1fs)" % (t + 1, trees, time.time() - t0))
+    best_i[torch.isinf(best_d)] = -1
+    return best_i, best_d
+
+
+def build_rng_graph_from_candidates(x, cand_i, cand_d, degree=32, rng_factor=1.0, fill=True, log=None):
+    """RNG prune (RelativeNeighborhoodGraph::RebuildNeighbors) of given sorted candidate lists. int32 [N, degree] on CPU."""
+    dev = x.device
+    N, dim = x.shape
+    cand = cand_i.shape[1]
+    xn = _sq_norms(x)
+    graph = torch.full((N, degree), -1, dtype=torch.int32, device=dev)
+    sub = max(64, min(65536, (1 << 28) // max(1, cand * dim)))
+    t0 = time.time()
+    for s in range(0, N, sub):
+        e = min(N, s + sub)
+        ci = cand_i[s:e]
+        cd = cand_d[s:e]
+        valid = ci >= 0
+        cis = ci.clamp_min(0)
+        cv = x[cis.reshape(-1)].view(e - s, cand, dim)
+        cn = xn[cis]
+        pd = cn[:, :, None] - 2.0 * torch.bmm(cv, cv.transpose(1, 2)) + cn[:, None, :]
+        del cv
+        acc = torch.zeros((e - s, cand), dtype=torch.bool, device=dev)
+        count = torch.zeros(e - s, dtype=torch.int64, device=dev)
+        out = torch.full((e - s, degree), -1, dtype=torch.int32, device=dev)
+        rows = torch.arange(e - s, device=dev)
+        for j in range(cand):
+            bad = ((pd[:, :, j] * rng_factor < cd[:, j, None]) & acc).any(dim=1)
+            ok = ~bad & (count < degree) & valid[:, j]
+            acc[:, j] = ok
+            r = rows[ok]
+            out[r, count[ok]] = ci[ok, j].int()
+            count += ok.long()
+        if fill:
+            for j in range(cand):
+                ok = ~acc[:, j] & (count < degree) & valid[:, j]
+                r = rows[ok]
+                out[r, count[ok]] = ci[ok, j].int()
+                count += ok.long()
+        graph[s:e] = out
+        if log and (s // sub) % 32 == 0:
+            log("rng rows %d/%d (%.1fs)" % (e, N, time.time() - t0))
+    return graph.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------
 # folder writer (reference on-disk format) and exact ground truth
 # ---------------------------------------------------------------------------------------------
 INI_TEMPLATE = """[Index]
@@ -472,6 +609,7 @@ def exact_topk(x, q, k, metric, chunk=2048):
     """Exact ground truth ids [nq, k] (L2: squared distance; Cosine: 1 - dot on unit vectors)."""
     out = []
     xn = _sq_norms(x)
+    chunk = max(32, min(chunk, (1 << 31) // max(1, x.shape[0])))  # <= 8 GiB of fp32 scores at a time
     for s in range(0, q.shape[0], chunk):
         qs = q[s:s + chunk]
         if metric == "L2":
@@ -482,7 +620,8 @@ def exact_topk(x, q, k, metric, chunk=2048):
     return torch.cat(out).cpu().numpy()
 
 
-def build_index(x, metric="L2", degree=32, cand=64, kmeans_k=32, leaf_size=8, seed=0, log=None, algo="BKT"):
+def build_index(x, metric="L2", degree=32, cand=64, kmeans_k=32, leaf_size=8, seed=0, log=None, algo="BKT",
+                tpt_above=2500000, tpt_trees=8):
     """x: float32 tensor [N, dim] on the build device (unit rows for Cosine). Returns numpy arrays."""
     t = time.time()
     if algo == "KDT":
@@ -491,7 +630,12 @@ def build_index(x, metric="L2", degree=32, cand=64, kmeans_k=32, leaf_size=8, se
         nodes, starts = build_bkt(x, kmeans_k=kmeans_k, leaf_size=leaf_size, seed=seed, log=log)
     t_tree = time.time() - t
     t = time.time()
-    graph = build_rng_graph(x, degree=degree, cand=cand, log=log)
+    if x.shape[0] > tpt_above:   # brute force is O(N^2): beyond a few million points use the partition-tree candidates
+        ci, cdist = build_knn_tpt(x, k=min(cand, 48), trees=tpt_trees, leaf=1024, seed=seed, log=log)
+        graph = build_rng_graph_from_candidates(x, ci, cdist, degree=degree, log=log)
+        del ci, cdist
+    else:
+        graph = build_rng_graph(x, degree=degree, cand=cand, log=log)
     t_graph = time.time() - t
     if log:
         log("index built: tree %.1fs, graph %.1fs" % (t_tree, t_graph))
