@@ -131,6 +131,17 @@ int sptag_b200_get_param(sptag_b200_handle h, const char* name, char* value_out,
 int sptag_b200_search(sptag_b200_handle h, const void* queries, int32_t num_queries, int32_t k,
                       int32_t* out_ids, float* out_dists, int32_t* out_stats);
 
+/* Replaces: VectorIndex::SearchIndexWithFilter(QueryResult&, std::function<bool(const ByteArray&)> filterFunc,
+ * int maxCheck, bool) (VectorIndex.h:57, BKTIndex.cpp:622-647) for a batch.  The reference evaluates `filterFunc` on
+ * the metadata of every vector it is about to add to the results; a device cannot call back into host code, so the
+ * caller (or the C++ adapter) evaluates its predicate once per vector into `allowed` (HOST buffer, one byte per
+ * vector, 0 = filtered out).  Filtered vectors are still traversed, exactly as in the reference.  max_check: 0 = the
+ * index's MaxCheck, otherwise this call's budget.  BKT only ("Not Support Filter on KDT Index!", KDTIndex.cpp:361-365
+ * -> Fail). */
+int sptag_b200_search_filtered(sptag_b200_handle h, const void* queries, int32_t num_queries, int32_t k,
+                               const uint8_t* allowed, int32_t max_check, int32_t* out_ids, float* out_dists,
+                               int32_t* out_stats);
+
 /* Same call with every buffer already resident in HBM on the index's device (device pointers) and
  * stream-ordered on `cuda_stream` (a cudaStream_t; NULL = default stream).  Does not synchronise. */
 int sptag_b200_search_device(sptag_b200_handle h, const void* d_queries, int32_t num_queries, int32_t k,

@@ -16,6 +16,7 @@
 #include "inc/Core/Common/InstructionUtils.h"
 #include "inc/Core/Common/WorkSpace.h"
 #include "inc/Core/Common/IQuantizer.h"
+#include "inc/Core/MetadataSet.h"
 #include "inc/Helper/Logging.h"
 
 #include <omp.h>
@@ -232,6 +233,42 @@ int ref_search_each(void* h, const void* queries, int nq, long long stride_bytes
     auto t1 = std::chrono::steady_clock::now();
     if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
     return 0;
+}
+
+// VectorIndex::SearchIndexWithFilter (BKTIndex.cpp:622-647) with a filter over per-vector metadata.  The shim attaches
+// a MemMetadataSet whose record i is the 4-byte id i (VectorIndex::SetMetadata), and the filter callback looks the id
+// up in `allowed` (1 = may be returned).  max_check 0 = the index's MaxCheck, as in the reference.
+int ref_search_filtered(void* h, const void* queries, int nq, long long stride_bytes, int k, const unsigned char* allowed,
+                        int max_check, int threads, int* ids, float* dists) {
+    auto& idx = ((RefHandle*)h)->index;
+    const int n = idx->GetNumSamples();
+    if (idx->GetMetadata() == nullptr) {
+        ByteArray meta = ByteArray::Alloc((size_t)n * 4);
+        ByteArray offs = ByteArray::Alloc(((size_t)n + 1) * sizeof(std::uint64_t));
+        for (int i = 0; i < n; ++i) {
+            std::memcpy(meta.Data() + (size_t)i * 4, &i, 4);
+            ((std::uint64_t*)offs.Data())[i] = (std::uint64_t)i * 4;
+        }
+        ((std::uint64_t*)offs.Data())[n] = (std::uint64_t)n * 4;
+        idx->SetMetadata(new MemMetadataSet(meta, offs, n));
+    }
+    std::function<bool(const ByteArray&)> f = [allowed](const ByteArray& m) -> bool {
+        int id;
+        std::memcpy(&id, m.Data(), 4);
+        return allowed[id] != 0;
+    };
+    if (threads > 0) omp_set_num_threads(threads);
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 10) reduction(+ : bad)
+    for (int i = 0; i < nq; ++i) {
+        QueryResult res((const char*)queries + (size_t)i * stride_bytes, k, false);
+        if (idx->SearchIndexWithFilter(res, f, max_check) != ErrorCode::Success) bad++;
+        for (int j = 0; j < k; ++j) {
+            ids[(size_t)i * k + j] = res.GetResult(j)->VID;
+            dists[(size_t)i * k + j] = res.GetResult(j)->Dist;
+        }
+    }
+    return bad;
 }
 
 // Install the counter-reading factory (single-query stats below need it). Irreversible for h.

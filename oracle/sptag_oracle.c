@@ -587,6 +587,9 @@ static inline float qdist(const qctx_t* c, ws_t* ws, int32_t id)
     return ora_distance(c->idx->metric, c->idx->value_type, c->idx->simd_width, c->query, row, c->idx->dim);
 }
 
+/* StaticDispatch::CheckFilter / AlwaysTrue (BKTIndex.cpp:455-458, :471-507) */
+static inline int check_filter(const ora_index* idx, int32_t id) { return idx->filter == NULL || idx->filter[id] != 0; }
+
 static inline int not_deleted(const ora_index* idx, int32_t id)
 {
     /* StaticDispatch::CheckIfNotDeleted / AlwaysTrue (BKTIndex.cpp:437-440, :471-507) */
@@ -668,13 +671,17 @@ static void bkt_search(const qctx_t* c, ws_t* ws, res_t* res, int k)
                 int32_t i = -tnode->childStart;
                 do {
                     if (not_deleted(idx, tmpNode)) {
-                        if (!res_add_point(res, k, tmpNode, gnode.distance)) break; /* CheckDup */
+                        if (check_filter(idx, tmpNode)) {
+                            if (!res_add_point(res, k, tmpNode, gnode.distance)) break; /* CheckDup */
+                        }
                     }
                     if (i <= 0) break;
                     tmpNode = nodes[i].centerid;
                 } while (i++ < tnode->childEnd);
             } else {
-                if (not_deleted(idx, tmpNode)) res_add_point(res, k, tmpNode, gnode.distance);
+                if (not_deleted(idx, tmpNode)) {
+                    if (check_filter(idx, tmpNode)) res_add_point(res, k, tmpNode, gnode.distance);
+                }
             }
         } else {
             if (not_deleted(idx, tmpNode)) {
@@ -797,6 +804,7 @@ int ora_search_batch(const ora_index* idx, const void* queries, int32_t nq, int3
     const size_t row_bytes = elem[idx->value_type] * (size_t)idx->dim;
     const ora_quantizer* quant = idx->quantizer;
     if (quant && idx->tree_kind != ORA_BKT) return 1; /* quantized KDT not restated */
+    if (idx->filter && idx->tree_kind != ORA_BKT) return 1; /* "Not Support Filter on KDT Index!" (KDTIndex.cpp:361-365) */
     const size_t query_bytes = quant ? elem[quant->rtype] * (size_t)(quant->m * quant->dsub) : row_bytes;
     /* a fresh thread's work space: Initialize(max(MaxCheck, MaxCheckForRefineGraph)) then
      * Reset(MaxCheck, K) (BKTIndex.cpp:600-605) */

@@ -63,6 +63,9 @@ typedef struct {
     /* non-NULL: the index holds uint8 PQ codes (value_type ORA_UINT8, dim = m) and queries are RAW vectors of
      * quantizer->rtype with m*dsub elements (BKTIndex.cpp:463-469, QueryResultSet.h:46-60) */
     const ora_quantizer* quantizer;
+    /* SearchIndexWithFilter (BKTIndex.cpp:622-647): non-NULL = one byte per vector, 0 = the filter callback
+     * rejects it (it is still traversed, only never added to the results); BKT only */
+    const uint8_t* filter;
 } ora_index;
 
 /* per-query counters, all int32 */

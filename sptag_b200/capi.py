@@ -21,7 +21,7 @@ ALGO_BKT, ALGO_KDT = 0, 1
 
 EXPORTS = [
     "sptag_b200_create", "sptag_b200_load", "sptag_b200_destroy", "sptag_b200_set_param", "sptag_b200_set_quantizer",
-    "sptag_b200_quantize",
+    "sptag_b200_quantize", "sptag_b200_search_filtered",
     "sptag_b200_get_param", "sptag_b200_search", "sptag_b200_search_device", "sptag_b200_distance_batch",
     "sptag_b200_merge_topk", "sptag_b200_last_kernel_ms", "sptag_b200_launch_count",
     "sptag_b200_num_vectors", "sptag_b200_dim", "sptag_b200_value_type", "sptag_b200_metric",
@@ -64,6 +64,8 @@ def lib():
         L.sptag_b200_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.sptag_b200_get_param.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int32]
         L.sptag_b200_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sptag_b200_search_filtered.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p]
         L.sptag_b200_search_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p]
         L.sptag_b200_distance_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
@@ -180,6 +182,19 @@ class B200Index:
         stats = np.zeros((nq, STATS_PER_QUERY), np.int32) if want_stats else None
         _check(lib().sptag_b200_search(self._h, queries.ctypes.data, nq, k, ids.ctypes.data, dists.ctypes.data,
                                        stats.ctypes.data if want_stats else None))
+        return (ids, dists, stats) if want_stats else (ids, dists)
+
+    def search_filtered(self, queries, k, allowed, max_check=0, want_stats=False):
+        """VectorIndex::SearchIndexWithFilter for a batch; allowed = uint8 [N], 0 = filtered out."""
+        queries = np.ascontiguousarray(queries)
+        allowed = np.ascontiguousarray(allowed, dtype=np.uint8)
+        nq = queries.shape[0]
+        ids = np.empty((nq, k), np.int32)
+        dists = np.empty((nq, k), np.float32)
+        stats = np.zeros((nq, STATS_PER_QUERY), np.int32) if want_stats else None
+        _check(lib().sptag_b200_search_filtered(self._h, queries.ctypes.data, nq, k, allowed.ctypes.data, max_check,
+                                                ids.ctypes.data, dists.ctypes.data,
+                                                stats.ctypes.data if want_stats else None))
         return (ids, dists, stats) if want_stats else (ids, dists)
 
     def search_device(self, d_queries_ptr, nq, k, d_ids_ptr, d_dists_ptr, d_stats_ptr=0, stream=0):

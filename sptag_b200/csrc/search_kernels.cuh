@@ -40,6 +40,7 @@ struct SearchParams {
     const int* tree_starts;
     int tree_num, node_count;
     const signed char* deleted;            // nullptr when there are no tombstones
+    const unsigned char* filter;           // SearchIndexWithFilter: 0 = never added to the results; nullptr = no filter
     // queries / outputs (device)
     const unsigned char* queries;
     unsigned long long query_stride_bytes;
@@ -625,6 +626,8 @@ struct WarpSearch {
     __device__ __forceinline__ bool not_deleted(int id) const {
         return p.deleted == nullptr || p.deleted[id] != 1;
     }
+    // StaticDispatch::CheckFilter (BKTIndex.cpp:455-458): the host evaluated the callback into one byte per vector
+    __device__ __forceinline__ bool check_filter(int id) const { return p.filter == nullptr || p.filter[id] != 0; }
 
     __device__ __forceinline__ void issue_stage(int t, int cnt) {
         const int base = t * p.stage_rows;
@@ -861,13 +864,15 @@ struct WarpSearch {
                     int i = -tcs;
                     do {
                         if (not_deleted(tmpNode)) {
-                            if (!add_point(tmpNode, gdist)) break;
+                            if (check_filter(tmpNode)) {
+                                if (!add_point(tmpNode, gdist)) break;
+                            }
                         }
                         if (i <= 0) break;
                         tmpNode = p.nodes[3 * i];
                     } while (i++ < tce);
                 } else {
-                    if (not_deleted(tmpNode)) add_point(tmpNode, gdist);
+                    if (not_deleted(tmpNode) && check_filter(tmpNode)) add_point(tmpNode, gdist);
                 }
             } else {
                 if (not_deleted(tmpNode)) {

@@ -89,7 +89,8 @@ struct sptag_b200_index {
     int n = 0, dim = 0, degree = 0, tree_num = 0, node_count = 0, num_deleted = 0, id_offset = 0;
     size_t row_stride = 0;  // bytes, multiple of 16
     // device-resident index
-    DeviceBuffer d_vectors, d_graph, d_nodes, d_tree_starts, d_deleted;
+    DeviceBuffer d_vectors, d_graph, d_nodes, d_tree_starts, d_deleted, d_filter;
+    bool use_filter = false;  // set for the duration of a sptag_b200_search_filtered call
     // search parameters (reference names)
     int max_check = 8192, max_check_refine = 8192, initial_pivots = 50, other_pivots = 4, no_better_threshold = 3;
     // B200 tuning knobs
@@ -212,6 +213,7 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     p.tree_num = h->tree_num;
     p.node_count = h->node_count;
     p.deleted = (h->num_deleted > 0) ? (const signed char*)h->d_deleted.ptr : nullptr;
+    p.filter = h->use_filter ? (const unsigned char*)h->d_filter.ptr : nullptr;
     p.k = k;
     p.id_offset = h->id_offset;
     p.max_check = h->max_check;
@@ -543,6 +545,7 @@ void sptag_b200_destroy(sptag_b200_handle h) {
     h->d_nodes.release();
     h->d_tree_starts.release();
     h->d_deleted.release();
+    h->d_filter.release();
     h->d_codebooks.release();
     h->d_rotation_t.release();
     h->d_sdc.release();
@@ -830,6 +833,31 @@ int sptag_b200_search(sptag_b200_handle h, const void* queries, int32_t num_quer
                                 cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
     return SPTAG_B200_SUCCESS;
+}
+
+int sptag_b200_search_filtered(sptag_b200_handle h, const void* queries, int32_t num_queries, int32_t k,
+                               const uint8_t* allowed, int32_t max_check, int32_t* out_ids, float* out_dists,
+                               int32_t* out_stats) {
+    if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
+    if (!allowed) return fail(SPTAG_B200_LACK_OF_INPUTS, "null filter map");
+    if (h->algo != SPTAG_B200_ALGO_BKT) return fail(SPTAG_B200_FAIL, "Not Support Filter on KDT Index!");
+    int saved_check;
+    {
+        std::lock_guard<std::mutex> lock(h->mu);
+        DeviceGuard guard(h->device);
+        if (int rc = h->d_filter.ensure((size_t)h->n)) return rc;
+        CUDA_OK(cudaMemcpy(h->d_filter.ptr, allowed, (size_t)h->n, cudaMemcpyHostToDevice));
+        saved_check = h->max_check;
+        if (max_check > 0) h->max_check = max_check;  // workSpace->Reset(maxCheck == 0 ? m_iMaxCheck : maxCheck, K)
+        h->use_filter = true;
+    }
+    const int rc = sptag_b200_search(h, queries, num_queries, k, out_ids, out_dists, out_stats);
+    {
+        std::lock_guard<std::mutex> lock(h->mu);
+        h->use_filter = false;
+        h->max_check = saved_check;
+    }
+    return rc;
 }
 
 int sptag_b200_distance_batch(sptag_b200_handle h, const void* queries, int32_t num_queries, const int32_t* ids,

@@ -122,6 +122,28 @@ public:
         return ErrorCode::Success;
     }
 
+    // VectorIndex::SearchIndexWithFilter (VectorIndex.h:57, BKTIndex.cpp:622-647).  The reference's callback sees the
+    // vector's metadata; here the predicate receives the vector id (the caller owns the id -> metadata mapping) and is
+    // evaluated once per vector on the host before the batch runs on the device.
+    template <typename Pred>
+    ErrorCode SearchIndexWithFilter(QueryResult& p_query, Pred p_allowed, int maxCheck = 0, bool /*p_searchDeleted*/ = false) const {
+        if (!m_handle) return ErrorCode::EmptyIndex;
+        const SizeType n = GetNumSamples();
+        std::vector<std::uint8_t> allowed((size_t)n);
+        for (SizeType i = 0; i < n; ++i) allowed[(size_t)i] = p_allowed(i) ? 1 : 0;
+        const int k = p_query.GetResultNum();
+        std::vector<std::int32_t> ids((size_t)k);
+        std::vector<float> dists((size_t)k);
+        int rc = sptag_b200_search_filtered(m_handle, p_query.GetTarget(), 1, k, allowed.data(), maxCheck, ids.data(),
+                                            dists.data(), nullptr);
+        if (rc != 0) return static_cast<ErrorCode>(rc);
+        for (int i = 0; i < k; ++i) {
+            p_query.GetResult(i)->VID = ids[(size_t)i];
+            p_query.GetResult(i)->Dist = dists[(size_t)i];
+        }
+        return ErrorCode::Success;
+    }
+
     // VectorIndex::SetParameter / GetParameter (BKTIndex.cpp:980-1025)
     ErrorCode SetParameter(const char* p_param, const char* p_value, const char* /*p_section*/ = nullptr) {
         return static_cast<ErrorCode>(sptag_b200_set_param(m_handle, p_param, p_value));

@@ -75,6 +75,8 @@ def ref():
         L.ref_quantizer_l2.restype = C.c_float
         L.ref_quantizer_l2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_set_adc.argtypes = [C.c_void_p, C.c_int]
+        L.ref_search_filtered.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_int,
+                                          C.c_int, C.c_void_p, C.c_void_p]
         L.ref_search_each.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_quiet(3)  # warnings and errors only
@@ -130,6 +132,19 @@ class RefIndex:
         h = ref().ref_build_quantized(ALGO_OF_NAME[algo], METRIC_OF_NAME[metric], quantizer_file.encode(),
                                       codes.ctypes.data, codes.shape[0], codes.shape[1], threads, params.encode())
         return cls(h)
+
+    def search_filtered(self, queries, k, allowed, max_check=0, threads=0):
+        """VectorIndex::SearchIndexWithFilter with allowed[id] (uint8) as the predicate."""
+        queries = np.ascontiguousarray(queries)
+        allowed = np.ascontiguousarray(allowed, np.uint8)
+        nq = queries.shape[0]
+        ids = np.empty((nq, k), np.int32)
+        dists = np.empty((nq, k), np.float32)
+        bad = ref().ref_search_filtered(self.h, queries.ctypes.data, nq, queries.strides[0], k, allowed.ctypes.data,
+                                        max_check, threads, ids.ctypes.data, dists.ctypes.data)
+        if bad:
+            raise RuntimeError("SearchIndexWithFilter failed for %d queries" % bad)
+        return ids, dists
 
     def set_adc(self, enable):
         ref().ref_set_adc(self.h, 1 if enable else 0)
@@ -364,7 +379,8 @@ class _OraIndex(C.Structure):
                 ("tree_starts", C.c_void_p), ("nodes", C.c_void_p), ("deleted", C.c_void_p),
                 ("num_deleted", C.c_int32), ("max_check", C.c_int32), ("max_check_refine", C.c_int32),
                 ("initial_pivots", C.c_int32), ("other_pivots", C.c_int32),
-                ("no_better_threshold", C.c_int32), ("simd_width", C.c_int32), ("quantizer", C.c_void_p)]
+                ("no_better_threshold", C.c_int32), ("simd_width", C.c_int32), ("quantizer", C.c_void_p),
+                ("filter", C.c_void_p)]
 
 
 _ora = None
@@ -404,6 +420,7 @@ class OracleIndex:
         self.no_better_threshold = files.int_param("ThresholdOfNumberOfContinuousNoBetterPropagation", 3)
         self.oq = OracleQuantizer(files.quantizer, simd_width) if getattr(files, "quantizer", None) is not None else None
         self.enable_adc = False
+        self.filter = None   # numpy uint8 [n]: SearchIndexWithFilter semantics
 
     def _struct(self):
         f = self.files
@@ -428,6 +445,7 @@ class OracleIndex:
         if self.oq is not None:
             self.oq.struct.enable_adc = 1 if self.enable_adc else 0
         s.quantizer = C.addressof(self.oq.struct) if self.oq is not None else None
+        s.filter = self.filter.ctypes.data if self.filter is not None else None
         return s
 
     def search(self, queries, k, threads=0, want_stats=True):

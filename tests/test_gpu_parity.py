@@ -431,3 +431,51 @@ def test_quantized_adc_search_bit_exact(name):
         _compare(idx, files, q, 10, 1024, name + " sdc-after-adc")
     finally:
         idx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# SearchIndexWithFilter on the device
+# ---------------------------------------------------------------------------------------------
+def test_filter_known_answer_on_gpu():
+    from sptag_b200 import B200Index
+    folder = data_folder("algo_line_bkt")
+    idx = B200Index.load(folder)
+    allowed = np.ones(idx.num_vectors, np.uint8)
+    allowed[2] = 0                                   # FilterTest.cpp:40-60: metadata "2" is rejected
+    ids, _ = idx.search_filtered(np.array([[0] * 10, [2] * 10, [4] * 10], np.float32), 3, allowed)
+    assert ids.tolist() == [[0, 1, 3], [1, 3, 0], [4, 3, 5]]
+    idx.close()
+
+
+@pytest.mark.parametrize("name", ["bkt_l2_20k_32", "bkt_l2_dups", "bkt_cos_10k_128"])
+def test_filtered_search_bit_exact(name):
+    from sptag_b200 import B200Index, capi
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:150]
+    allowed = (np.random.default_rng(5).random(files.n) < 0.5).astype(np.uint8)
+    idx = B200Index.load(folder)
+    try:
+        for mc in [0, 512]:
+            ids, dists, stats = idx.search_filtered(q, 10, allowed, max_check=mc, want_stats=True)
+            o = reflib.OracleIndex(files)
+            o.filter = allowed
+            if mc:
+                o.max_check = mc
+            ids_o, d_o, st_o = o.search(q, 10)
+            assert np.array_equal(ids, ids_o), (name, mc)
+            assert np.array_equal(dists.view(np.int32), d_o.view(np.int32)), (name, mc)
+            assert np.array_equal(stats[:, capi.ST_CHECKED], st_o[:, reflib.ST_CHECKED])
+        _compare(idx, files, q, 10, 1024, name + " unfiltered-after-filtered")   # the override does not stick
+    finally:
+        idx.close()
+
+
+def test_filter_rejected_on_kdt():
+    from sptag_b200 import B200Index, capi
+    folder = data_folder("kdt_l2_10k_64")
+    idx = B200Index.load(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:4]
+    with pytest.raises(capi.SptagB200Error):     # "Not Support Filter on KDT Index!" (KDTIndex.cpp:361-365)
+        idx.search_filtered(q, 10, np.ones(idx.num_vectors, np.uint8))
+    idx.close()

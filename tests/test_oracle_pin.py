@@ -268,3 +268,41 @@ def test_quantized_adc_search_bit_exact_vs_reference(oracle_lib, name):
         ids_o, d_o, _ = o.search(q, 10, threads=4)
         assert np.array_equal(ids_r, ids_o), (name, mc)
         assert np.array_equal(d_r.view(np.int32), d_o.view(np.int32)), (name, mc)
+
+
+# ---------------------------------------------------------------------------------------------
+# SearchIndexWithFilter (Test/src/FilterTest.cpp:40-60)
+# ---------------------------------------------------------------------------------------------
+def test_filter_known_answer(oracle_lib):
+    # FilterTest.cpp: line data, queries (0..),(2..),(4..), k = 3, the filter rejects metadata "2" -> id 2 never returned
+    g = np.load(os.path.join(GOLDEN, "algo_line_bkt.npz"))
+    files = reflib.IndexFiles.__new__(reflib.IndexFiles)
+    _files_from_npz(files, g)
+    allowed = np.ones(files.n, np.uint8)
+    allowed[2] = 0
+    o = reflib.OracleIndex(files)
+    o.filter = allowed
+    ids, _, _ = o.search(np.array([[0] * 10, [2] * 10, [4] * 10], np.float32), 3)
+    assert 2 not in ids.ravel().tolist()
+    assert ids.tolist() == [[0, 1, 3], [1, 3, 0], [4, 3, 5]]
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["algo_line_bkt", "bkt_l2_20k_32", "bkt_l2_dups", "bkt_cos_10k_128"])
+def test_filtered_search_bit_exact_vs_reference(oracle_lib, name):
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:100]
+    allowed = (np.random.default_rng(5).random(files.n) < 0.5).astype(np.uint8)
+    r = reflib.RefIndex.load(folder)
+    k = 3 if name == "algo_line_bkt" else 10
+    for mc in [0, 512]:
+        ids_r, d_r = r.search_filtered(q, k, allowed, max_check=mc, threads=4)
+        o = reflib.OracleIndex(files)
+        o.filter = allowed
+        if mc:
+            o.max_check = mc
+        ids_o, d_o, _ = o.search(q, k, threads=4)
+        assert np.array_equal(ids_r, ids_o), (name, mc)
+        assert np.array_equal(d_r.view(np.int32), d_o.view(np.int32)), (name, mc)
+        assert allowed[ids_r[ids_r >= 0]].all()

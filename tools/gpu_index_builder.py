@@ -317,8 +317,9 @@ def _tpt_leaves(x, leaf, gen):
     while seg_len > leaf:
         # every segment splits at the median of the projection on the direction between two of its random members
         offs = (torch.arange(nseg, device=dev) * seg_len)
-        a = perm[offs + torch.randint(0, seg_len, (nseg,), generator=gen, device=dev).clamp_max(seg_len - 1)]
-        b = perm[offs + torch.randint(0, seg_len, (nseg,), generator=gen, device=dev).clamp_max(seg_len - 1)]
+        # (nseg * seg_len can exceed N by a few elements when N is not a power of two: clamp into the array)
+        a = perm[(offs + torch.randint(0, seg_len, (nseg,), generator=gen, device=dev)).clamp_max(N - 1)]
+        b = perm[(offs + torch.randint(0, seg_len, (nseg,), generator=gen, device=dev)).clamp_max(N - 1)]
         dirs = (x[a] - x[b])                                            # [nseg, dim]
         n_full = nseg * seg_len
         proj = torch.empty(N, device=dev)
