@@ -105,11 +105,14 @@ def index_folder(args, shard):
                                                    args.seed, shard, BUILDER_VERSION)
     if args.quantizer != "none":
         key += "_%s%d_%s" % (args.quantizer, args.pq_m, args.raw_type)
+    elif args.raw_type != "float":
+        key += "_" + args.raw_type
     return os.path.join(args.cache, key)
 
 
 def ensure_index(args, shard, device):
     """Build (GPU, torch) and save the reference-format folder unless it is cached. Returns folder."""
+    import numpy as np
     import torch
     from tools import gpu_index_builder as B
     folder = index_folder(args, shard)
@@ -125,6 +128,9 @@ def ensure_index(args, shard, device):
         codes = B.encode_gpu(x, cb, rot)
         blob = B.quantizer_blob(cb, rot, 0 if args.raw_type == "int8" else 3)
         B.save_index_folder(folder, codes.cpu().numpy(), graph, nodes, starts, args.metric, quantizer=blob)
+    elif args.raw_type == "int8":   # unquantized int8 rows (DistanceUtils int8 variants), e.g. SPACEV / PerfTest.cpp shape
+        B.save_index_folder(folder, x.cpu().numpy().astype(np.int8), graph, nodes, starts, args.metric,
+                            algo=args.algo.upper(), value_type="Int8")
     else:
         B.save_index_folder(folder, x.cpu().numpy(), graph, nodes, starts, args.metric, algo=args.algo.upper())
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -275,8 +281,10 @@ def main():
         args.gpus = world
 
     quantized = args.quantizer != "none"
-    if quantized:
-        args.metric = "L2"  # the reference's quantizers have no cosine distance (PQQuantizer.h:130-136)
+    if quantized or args.raw_type == "int8":
+        # the reference's quantizers have no cosine distance (PQQuantizer.h:130-136); int8 cosine needs base-127
+        # normalised rows, which this synthetic generator does not produce
+        args.metric = "L2"
     workload = "SPTAG-%s, %dx%d %s %s, batch %d queries, k=%d, MaxCheck=%d, %s synthetic" % (
         args.algo.upper(), args.n, args.dim, "float32" if args.raw_type == "float" else "int8", args.metric.lower(), args.nq, args.k,
         args.maxcheck, args.data)
@@ -518,7 +526,8 @@ def main():
     kernel_ms = float(np.mean(kms))
     achieved = alg_bytes / (kernel_ms / 1000.0) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": ("search_kernel<PQ,L2,BKT>" if quantized else
+                "traffic": None, "kernel": ("search_kernel<PQ,L2,BKT>" if quantized else "search_kernel<int8,L2,%s>" % args.algo.upper()
+                           if args.raw_type == "int8" else
                            "search_kernel<%d,%s,%s>" % (args.dim if args.dim in (128, 768) else 0, args.metric, args.algo.upper())), "kernel_ms": kernel_ms,
                 "kernel_ms_samples": [round(v, 3) for v in kms],
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,

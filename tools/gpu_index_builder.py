@@ -571,7 +571,7 @@ IsOldVersion=false
 
 
 def save_index_folder(folder, vectors, graph, nodes, tree_starts, metric, kmeans_k=32, leaf_size=8,
-                      quantizer=None, algo="BKT"):
+                      quantizer=None, algo="BKT", value_type="Float"):
     """vectors: float32 numpy [N, dim] (already normalised for cosine), or uint8 PQ codes [N, M] together with
     `quantizer` = bytes of the quantizer file."""
     os.makedirs(folder, exist_ok=True)
@@ -579,7 +579,8 @@ def save_index_folder(folder, vectors, graph, nodes, tree_starts, metric, kmeans
     quantized = quantizer is not None
     with open(os.path.join(folder, "vectors.bin"), "wb") as f:
         np.array([N, dim], np.int32).tofile(f)
-        np.ascontiguousarray(vectors, np.uint8 if quantized else np.float32).tofile(f)
+        vdt = {"Float": np.float32, "Int8": np.int8, "UInt8": np.uint8}[value_type]
+        np.ascontiguousarray(vectors, np.uint8 if quantized else vdt).tofile(f)
     if quantized:
         with open(os.path.join(folder, "quantizer.bin"), "wb") as f:
             f.write(quantizer)
@@ -602,6 +603,8 @@ def save_index_folder(folder, vectors, graph, nodes, tree_starts, metric, kmeans
             text = KDT_INI_HEAD + "TPTNumber=32" + body.replace("NumTopDimensionTpTreeSplit", "NumTopDimensionTPTSplit")
         if quantized:
             text = "[Quantizer]\nQuantizerFilePath=quantizer.bin\n\n" + text.replace("ValueType=Float", "ValueType=UInt8")
+        elif value_type != "Float":
+            text = text.replace("ValueType=Float", "ValueType=" + value_type)
         f.write(text.format(kmeans_k=kmeans_k, leaf_size=leaf_size, degree=graph.shape[1],
                                     threads=os.cpu_count() or 1, metric=metric))
 
