@@ -76,7 +76,16 @@ def parse_args():
 # synthetic data + index folder (built on the GPU once per box, cached under --cache)
 # ---------------------------------------------------------------------------------------------
 def gen_data(args, n, seed, device):
+    """Synthetic vectors [n, dim] (float32 values; int8-valued when --raw-type int8).  Generated in 10M-row pieces so
+    that 100M-point sets never need more than the result plus one piece of temporaries."""
     import torch
+    piece = 10000000
+    if n > piece:
+        out = torch.empty((n, args.dim), dtype=torch.float32, device=device)
+        for i, s in enumerate(range(0, n, piece)):
+            e = min(n, s + piece)
+            out[s:e] = gen_data(args, e - s, seed * 1000003 + i + 1, device)
+        return out
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     if args.data == "iid":

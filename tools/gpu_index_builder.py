@@ -26,8 +26,14 @@ import numpy as np
 import torch
 
 
-def _sq_norms(x):
-    return (x.float() ** 2).sum(1)
+def _sq_norms(x, chunk=4000000):
+    """Row-wise squared norms without materialising x**2 for the whole array."""
+    if x.shape[0] <= chunk:
+        return (x.float() ** 2).sum(1)
+    out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    for s in range(0, x.shape[0], chunk):
+        out[s:s + chunk] = (x[s:s + chunk].float() ** 2).sum(1)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -173,6 +179,140 @@ def build_bkt(x, kmeans_k=32, leaf_size=8, iters=2, seed=0, log=None):
         offsets = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(counts, 0)])
         if log:
             log("bkt level %d: %d groups, %d nodes so far" % (level, P, next_free))
+        level += 1
+    assert next_free == N + 1, (next_free, N)
+    return nodes.cpu().numpy(), np.array([0], np.int32)
+
+
+# ---------------------------------------------------------------------------------------------
+# BKT for very large N: same node layout, but a big group is cut into its <= 32 children by five rounds of
+# balanced random-direction bisection (O(N dim) per round) instead of k-means against all centroids of the level
+# (O(N * centroids * dim), which stops being practical around 10^7-10^8 points).  The centre of a child is the
+# member nearest to the child's mean, exactly as in build_bkt.
+# ---------------------------------------------------------------------------------------------
+def _segment_stats(seg, nseg):
+    cnt = torch.bincount(seg, minlength=nseg)
+    off = torch.cumsum(cnt, 0) - cnt
+    return cnt, off
+
+
+def build_bkt_balanced(x, kmeans_k=32, leaf_size=8, seed=0, log=None):
+    dev = x.device
+    N, dim = x.shape
+    K = kmeans_k
+    rounds = int(math.log2(K))
+    assert (1 << rounds) == K, "balanced builder needs a power-of-two fan-out"
+    final_t = K * (leaf_size + 1)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    nodes = torch.full((N + 2, 3), -1, dtype=torch.int32, device=dev)
+    nodes[0, 0] = N
+    next_free = 1
+    grp_parent = torch.zeros(1, dtype=torch.int64, device=dev)
+    members = torch.randperm(N, generator=g, device=dev)
+    offsets = torch.tensor([0, N], dtype=torch.int64, device=dev)
+    chunk = max(1, (1 << 26) // dim)
+    level = 0
+    while grp_parent.numel() > 0:
+        P = grp_parent.numel()
+        sizes = offsets[1:] - offsets[:-1]
+        gid = torch.repeat_interleave(torch.arange(P, device=dev), sizes)
+        pos = torch.arange(members.numel(), device=dev) - offsets[:-1][gid]
+        small = sizes <= leaf_size
+        big = sizes > final_t
+        mid = ~small & ~big
+        nchild = torch.zeros(P, dtype=torch.int64, device=dev)
+        nchild[small] = sizes[small]
+        nchild[mid] = (sizes[mid] + leaf_size) // (leaf_size + 1)
+        child_of_member = torch.full_like(members, -1)
+        is_center = torch.zeros_like(members, dtype=torch.bool)
+
+        if big.any():
+            bidx = torch.nonzero(big).flatten()
+            Pb = bidx.numel()
+            brank = torch.full((P,), -1, dtype=torch.int64, device=dev)
+            brank[bidx] = torch.arange(Pb, device=dev)
+            msel = big[gid]
+            midx = torch.nonzero(msel).flatten()          # positions in `members`
+            bm = members[midx]
+            seg = brank[gid[midx]]                          # one segment per big group to start with
+            nseg = Pb
+            for _ in range(rounds):
+                cnt, off = _segment_stats(seg, nseg)
+                # members are kept sorted by segment, so segment s occupies [off[s], off[s]+cnt[s])
+                ra = off + (torch.rand(nseg, generator=g, device=dev) * cnt).long().clamp_max_(1 << 62)
+                rb = off + (torch.rand(nseg, generator=g, device=dev) * cnt).long()
+                ra = torch.minimum(ra, off + cnt - 1)
+                rb = torch.minimum(rb, off + cnt - 1)
+                dirs = x[bm[ra]] - x[bm[rb]]
+                proj = torch.empty(bm.numel(), device=dev)
+                for s0 in range(0, bm.numel(), chunk):
+                    e0 = min(bm.numel(), s0 + chunk)
+                    proj[s0:e0] = (x[bm[s0:e0]] * dirs[seg[s0:e0]]).sum(1)
+                order = torch.argsort(proj, stable=True)
+                order = order[torch.argsort(seg[order], stable=True)]
+                bm = bm[order]
+                midx = midx[order]
+                seg = seg[order]
+                p_in = torch.arange(bm.numel(), device=dev) - off[seg]
+                seg = seg * 2 + (p_in >= (cnt[seg] + 1) // 2).long()
+                nseg *= 2
+            # child segments: mean, centre = member nearest to its segment mean
+            cnt, off = _segment_stats(seg, nseg)
+            mean = torch.zeros((nseg, dim), device=dev)
+            for s0 in range(0, bm.numel(), chunk):
+                e0 = min(bm.numel(), s0 + chunk)
+                mean.index_add_(0, seg[s0:e0], x[bm[s0:e0]])
+            mean /= cnt.clamp_min(1)[:, None].float()
+            dmean = torch.empty(bm.numel(), device=dev)
+            for s0 in range(0, bm.numel(), chunk):
+                e0 = min(bm.numel(), s0 + chunk)
+                dmean[s0:e0] = ((x[bm[s0:e0]] - mean[seg[s0:e0]]) ** 2).sum(1)
+            mind = torch.full((nseg,), float("inf"), device=dev)
+            mind.scatter_reduce_(0, seg, dmean, reduce="amin")
+            candp = torch.nonzero(dmean <= mind[seg]).flatten()
+            first = torch.full((nseg,), bm.numel(), dtype=torch.int64, device=dev)
+            first.scatter_reduce_(0, seg[candp], candp, reduce="amin")
+            nonempty = cnt > 0
+            rank = (torch.cumsum(nonempty.view(Pb, K).long(), dim=1) - 1).view(-1)
+            nchild[bidx] = nonempty.view(Pb, K).sum(1)
+            child_of_member[midx] = rank[seg]
+            is_center[midx[first[nonempty]]] = True
+            # (members/offsets order is irrelevant below: everything is expressed per position in `members`)
+
+        if mid.any():
+            msel = mid[gid]
+            c = nchild[gid[msel]]
+            p_ = pos[msel]
+            mi = torch.nonzero(msel).flatten()
+            child_of_member[mi] = p_ % c
+            is_center[mi[p_ < c]] = True
+        if small.any():
+            msel = small[gid]
+            mi = torch.nonzero(msel).flatten()
+            child_of_member[mi] = pos[msel]
+            is_center[mi] = True
+
+        cstart = next_free + torch.cumsum(nchild, 0) - nchild
+        nodes[grp_parent, 1] = cstart.int()
+        nodes[grp_parent, 2] = (cstart + nchild).int()
+        child_node = cstart[gid] + child_of_member
+        cm = torch.nonzero(is_center).flatten()
+        nodes[child_node[cm], 0] = members[cm].int()
+        next_free += int(nchild.sum().item())
+
+        rest = torch.nonzero(~is_center).flatten()
+        if rest.numel() == 0:
+            break
+        ckey = child_node[rest]
+        order = torch.argsort(ckey, stable=True)
+        ckey = ckey[order]
+        members = members[rest][order]
+        uniq, counts = torch.unique_consecutive(ckey, return_counts=True)
+        grp_parent = uniq
+        offsets = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(counts, 0)])
+        if log:
+            log("bkt(balanced) level %d: %d groups, %d nodes so far" % (level, P, next_free))
         level += 1
     assert next_free == N + 1, (next_free, N)
     return nodes.cpu().numpy(), np.array([0], np.int32)
@@ -532,6 +672,7 @@ def train_quantizer_gpu(x, m, ks=256, opq=True, seed=0, iters=8, sample=200000):
 def encode_gpu(x, codebooks, rotation, chunk=262144):
     """Nearest codeword per sub-vector (plain fp32; the stored codes are just data for the index)."""
     m, ks, dsub = codebooks.shape
+    chunk = max(1024, min(chunk, (1 << 29) // (m * ks)))  # <= 2 GiB for the [m, chunk, ks] distance block
     out = torch.empty((x.shape[0], m), dtype=torch.uint8, device=x.device)
     cn = (codebooks * codebooks).sum(2)
     for s in range(0, x.shape[0], chunk):
@@ -625,17 +766,20 @@ def exact_topk(x, q, k, metric, chunk=2048):
 
 
 def build_index(x, metric="L2", degree=32, cand=64, kmeans_k=32, leaf_size=8, seed=0, log=None, algo="BKT",
-                tpt_above=2500000, tpt_trees=8):
+                tpt_above=2500000, tpt_trees=8, balanced_above=12000000):
     """x: float32 tensor [N, dim] on the build device (unit rows for Cosine). Returns numpy arrays."""
     t = time.time()
     if algo == "KDT":
         nodes, starts = build_kdt(x, log=log)
+    elif x.shape[0] > balanced_above:
+        nodes, starts = build_bkt_balanced(x, kmeans_k=kmeans_k, leaf_size=leaf_size, seed=seed, log=log)
     else:
         nodes, starts = build_bkt(x, kmeans_k=kmeans_k, leaf_size=leaf_size, seed=seed, log=log)
     t_tree = time.time() - t
     t = time.time()
     if x.shape[0] > tpt_above:   # brute force is O(N^2): beyond a few million points use the partition-tree candidates
-        ci, cdist = build_knn_tpt(x, k=min(cand, 48), trees=tpt_trees, leaf=1024, seed=seed, log=log)
+        kc = min(cand, 48) if x.shape[0] <= 50000000 else 32   # candidate lists are N x k x 12 bytes on the device
+        ci, cdist = build_knn_tpt(x, k=kc, trees=tpt_trees, leaf=1024, seed=seed, log=log)
         graph = build_rng_graph_from_candidates(x, ci, cdist, degree=degree, log=log)
         del ci, cdist
     else:
