@@ -64,6 +64,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="debug: do not sample nvidia-smi during the timed region")
     ap.add_argument("--param", action="append", default=[], help="Name=Value passed to sptag_b200_set_param")
+    ap.add_argument("--tpt-above", type=int, default=2500000,
+                    help="builder: above this many vectors use partition-tree kNN candidates instead of brute force")
     ap.add_argument("--algo", default="bkt", choices=["bkt", "kdt"], help="space-partition tree of the index")
     ap.add_argument("--quantizer", default="none", choices=["none", "pq", "opq"],
                     help="index holds uint8 PQ codes (BASELINE config 4 shape: --quantizer opq --raw-type int8 --dim 100 --pq-m 50)")
@@ -112,6 +114,8 @@ def gen_data(args, n, seed, device):
 def index_folder(args, shard):
     key = "%s_%s_%dx%d_%s_r%d_s%d_shard%d_v%d" % (args.algo, args.metric, args.n, args.dim, args.data, args.rank_dim,
                                                    args.seed, shard, BUILDER_VERSION)
+    if args.tpt_above != 2500000:
+        key += "_tpt%d" % args.tpt_above
     if args.quantizer != "none":
         key += "_%s%d_%s" % (args.quantizer, args.pq_m, args.raw_type)
     elif args.raw_type != "float":
@@ -131,7 +135,8 @@ def ensure_index(args, shard, device):
     t0 = time.time()
     torch.backends.cuda.matmul.allow_tf32 = True
     x = gen_data(args, args.n, args.seed + 1000 * (shard + 1), device)
-    nodes, starts, graph = B.build_index(x, args.metric, seed=args.seed + shard, log=log, algo=args.algo.upper())
+    nodes, starts, graph = B.build_index(x, args.metric, seed=args.seed + shard, log=log, algo=args.algo.upper(),
+                                         tpt_above=args.tpt_above)
     if args.quantizer != "none":
         cb, rot = B.train_quantizer_gpu(x, args.pq_m, opq=(args.quantizer == "opq"), seed=args.seed)
         codes = B.encode_gpu(x, cb, rot)
