@@ -156,6 +156,36 @@ def ensure_index(args, shard, device):
     return folder
 
 
+class _InMemoryIndex:
+    """What bench needs from reflib.IndexFiles, for an index that is built and handed to the device without touching
+    the disk (shard mode on many GPUs: eight 8-GB folders would not fit the box's scratch disk)."""
+
+    def __init__(self, vectors, graph, nodes, tree_starts, metric_name):
+        self.vectors, self.graph, self.nodes, self.tree_starts = vectors, graph, nodes, tree_starts
+        self.value_type = 3
+        self.metric = {"L2": 0, "Cosine": 1}[metric_name]
+        self.n, self.dim = vectors.shape
+        self.degree = graph.shape[1]
+        self.quantizer = None
+
+
+def build_in_memory(args, shard, device):
+    import numpy as np
+    import torch
+    from tools import gpu_index_builder as B
+    t0 = time.time()
+    torch.backends.cuda.matmul.allow_tf32 = True
+    x = gen_data(args, args.n, args.seed + 1000 * (shard + 1), device)
+    nodes, starts, graph = B.build_index(x, args.metric, seed=args.seed + shard, log=log, algo=args.algo.upper(),
+                                         tpt_above=args.tpt_above)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    files = _InMemoryIndex(x.cpu().numpy(), graph, nodes, starts, args.metric)
+    del x
+    torch.cuda.empty_cache()
+    log("index shard %d built in memory in %.1fs" % (shard, time.time() - t0))
+    return files
+
+
 def load_folder_arrays(folder):
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -385,8 +415,12 @@ def main():
         if rank == 0:
             ensure_index(args, 0, dev)
         dist.barrier()
-    folder = ensure_index(args, shard, dev)
-    files = load_folder_arrays(folder)
+    if world > 1 and args.mode == "shard" and not quantized and args.raw_type == "float":
+        folder = None
+        files = build_in_memory(args, shard, dev)   # no reference leg in this mode: nothing needs the folder
+    else:
+        folder = ensure_index(args, shard, dev)
+        files = load_folder_arrays(folder)
     id_offset = shard * args.n if args.mode == "shard" else 0
     t0 = time.time()
     idx = B200Index.create(algo=capi.ALGO_KDT if args.algo == "kdt" else capi.ALGO_BKT, value_type=files.value_type, metric=files.metric, vectors=files.vectors,
