@@ -499,7 +499,7 @@ def main():
         if quantized:  # ground truth on the raw vectors (regenerated: the folder only holds codes)
             x_dev = gen_data(args, args.n, args.seed + 1000 * (shard + 1), dev)
         else:
-            x_dev = torch.from_numpy(files.vectors).to(dev)
+            x_dev = torch.from_numpy(files.vectors).to(dev).float()   # int8 rows: exact truth on their float values
         truth = B.exact_topk(x_dev, d_q_f32, args.k, args.metric)
         del x_dev
         torch.cuda.empty_cache()
