@@ -50,7 +50,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="replica", choices=["replica", "shard"])
-    ap.add_argument("--n", type=int, default=1000000)
+    # (--num-vectors: under `python -m torch.distributed.run` a bare --n is swallowed by torchrun's own
+    #  abbreviation matching (--nnodes / --nproc-per-node), so multi-GPU launches must use the long name)
+    ap.add_argument("--n", "--num-vectors", dest="n", type=int, default=1000000)
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--metric", default="Cosine", choices=["Cosine", "L2"])
     ap.add_argument("--nq", type=int, default=10000)
