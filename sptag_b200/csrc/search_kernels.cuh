@@ -2,19 +2,29 @@
 //
 // One warp (one 32-thread CTA) owns one query at a time and runs the reference's whole
 // per-query algorithm on the device:
-//   BKT::Index<T>::Search            (AnnService/src/Core/BKT/BKTIndex.cpp:268-352)
+//   BKT::Index<T>::Search            (AnnService/src/Core/BKT/BKTIndex.cpp:268-352, incl. the filter variant :622-647)
 //   BKTree::InitSearchTrees/SearchTrees (inc/Core/Common/BKTree.h:696-799)
+//   KDT::Index<T>::Search, KDTree::KDTSearch (src/Core/KDT/KDTIndex.cpp:182-241, inc/Core/Common/KDTree.h:213-271)
 //   Heap<NodeDistPair>               (inc/Core/Common/Heap.h:13-106)      -> exact binary-heap emulation
 //   DistPriorityQueue m_Results      (inc/Core/Common/WorkSpace.h:167-225) -> multiset in registers
 //   OptHashPosVector visited set     (inc/Core/Common/WorkSpace.h:43-165) -> exact bitmap in HBM/L2
 //   QueryResultSet top-K             (inc/Core/Common/QueryResultSet.h:17-120) -> sorted list, one entry per lane
-//   DistanceUtils float L2 / cosine  (src/Core/Common/DistanceUtils.cpp:650-682, :1016-1046)
+//                                     (K <= 32) or the reference's own max-heap in HBM (K <= 1024)
+//   DistanceUtils float / int8 / uint8, L2 / cosine (src/Core/Common/DistanceUtils.cpp:305-1046)
 //                                     -> same 16-accumulator summation tree, no FMA, bit-exact
+//   PQQuantizer / OPQQuantizer       (inc/Core/Common/PQQuantizer.h:110-180, OPQQuantizer.h:96-121)
+//                                     -> SDC / ADC table look-ups summed in sub-vector order, device-side QuantizeVector
 //
 // Candidate vectors (graph neighbours / tree-centre rows) are gathered with 1-D TMA bulk copies
 // (cp.async.bulk global->shared, mbarrier complete_tx) into a per-warp shared-memory ring and
 // reduced from there; the two priority queues keep their first entries in shared memory and spill
 // the tail of the array to a per-slot arena in HBM so the emulation stays exact at any size.
+//
+// search_kernel<DIM, COSINE, RPL, KDT, PQ, ELEM, MINB, DIRECT>:
+//   DIM    768 / 128: query slice in registers, fully unrolled; 0: any dimension (query in shared memory)
+//   RPL    registers per lane of the m_Results multiset (16: cap <= 512, 32: cap <= 1024)
+//   KDT    KD-tree flavour of the search loop;  PQ: rows are PQ codes;  ELEM 0 float, 1 int8, 2 uint8
+//   MINB   __launch_bounds__ minimum resident CTAs per SM (register cap);  DIRECT: experimental no-TMA row loads
 #pragma once
 
 #include <cuda_runtime.h>
