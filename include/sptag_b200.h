@@ -155,6 +155,28 @@ int sptag_b200_search_device(sptag_b200_handle h, const void* d_queries, int32_t
 int sptag_b200_distance_batch(sptag_b200_handle h, const void* queries, int32_t num_queries,
                               const int32_t* ids, int32_t ids_per_query, float* out);
 
+/* Replaces: one pass of NeighborhoodGraph::RefineNode(index, node, updateNeighbors=false, searchDeleted=false, CEF)
+ * (NeighborhoodGraph.h:534-545, looped by RefineGraph :459-488) over nodes [first_node, first_node+num_nodes):
+ *   RefineSearchIndex (BKTIndex.cpp:698-711 / KDTIndex.cpp:367-390): the search kernel with the node's own row as the
+ *   query, K = cef+1, MaxCheckForRefineGraph as the budget, searchDuplicated = false;
+ *   RelativeNeighborhoodGraph::RebuildNeighbors (RelativeNeighborhoodGraph.h:20-38) with m_iNeighborhoodSize =
+ *   neighborhood_size and m_fRNGFactor = rng_factor.
+ * Every node is refined against the graph as it is when the call starts (the reference updates rows in place under
+ * OpenMP, so its pass depends on thread timing; this is the deterministic double-buffered form).
+ * out_graph (host, nullable): [num_nodes x neighborhood_size] new rows, -1 padded, local ids.
+ * out_res_ids / out_res_dists (host, nullable): [num_nodes x (cef+1)] the refine-search result lists.
+ * install != 0 (needs a full pass with neighborhood_size == the index's degree): the new rows replace the index's
+ * graph on the device; duplicate-group back-pointers in the last slot are carried over (NeighborhoodGraph.h:395-401).
+ * cef <= 1023.  Not available for quantized indexes. */
+int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num_nodes, int32_t cef,
+                            int32_t neighborhood_size, float rng_factor, int32_t* out_graph, int32_t* out_res_ids,
+                            float* out_res_dists, int32_t install);
+
+/* The index's current graph rows (NeighborhoodGraph::SaveGraph payload, NeighborhoodGraph.h:606-615):
+ * [num_vectors x graph_degree] int32 to a host buffer. */
+int sptag_b200_get_graph(sptag_b200_handle h, int32_t* out_graph);
+int32_t sptag_b200_graph_degree(sptag_b200_handle h);
+
 /* Vector-partition sharding: merges `num_lists` per-shard result lists of a query
  * batch, each [num_queries x k] ascending by (dist,id), into the global top-k with the comparator
  * of QueryResultSet.h:17-26.  All pointers are DEVICE pointers on `device`; lists are laid out

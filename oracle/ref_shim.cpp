@@ -17,6 +17,8 @@
 #include "inc/Core/Common/WorkSpace.h"
 #include "inc/Core/Common/IQuantizer.h"
 #include "inc/Core/MetadataSet.h"
+#include "inc/Core/Common/QueryResultSet.h"
+#include "inc/Core/Common/RelativeNeighborhoodGraph.h"
 #include "inc/Helper/Logging.h"
 
 #include <omp.h>
@@ -91,6 +93,31 @@ void apply_params(VectorIndex* idx, const char* params) {
 }
 
 }  // namespace
+
+// One NeighborhoodGraph::RefineNode(index, node, updateNeighbors=false, searchDeleted=false, CEF) per node
+// (NeighborhoodGraph.h:534-545) WITHOUT writing the index's graph: the reference's own RefineSearchIndex
+// (BKTIndex.cpp:698-711 / KDTIndex.cpp:367-390) on the loaded index, then the reference's own
+// RelativeNeighborhoodGraph::RebuildNeighbors (RelativeNeighborhoodGraph.h:20-38) into out_graph.
+template <typename T>
+static int refine_nodes_t(VectorIndex* idx, int first, int num, int cef, int neighborhood, float rng_factor,
+                          int* out_graph, int* res_ids, float* res_dists) {
+    COMMON::RelativeNeighborhoodGraph rng;
+    rng.m_iNeighborhoodSize = neighborhood;
+    rng.m_fRNGFactor = rng_factor;
+    const int k = cef + 1;
+#pragma omp parallel for schedule(dynamic, 10)
+    for (int i = 0; i < num; ++i) {
+        const int node = first + i;
+        COMMON::QueryResultSet<T> query((const T*)idx->GetSample(node), k);
+        idx->RefineSearchIndex(query, false);
+        rng.RebuildNeighbors(idx, node, out_graph + (size_t)i * neighborhood, query.GetResults(), k);
+        for (int j = 0; j < k; ++j) {
+            if (res_ids) res_ids[(size_t)i * k + j] = query.GetResult(j)->VID;
+            if (res_dists) res_dists[(size_t)i * k + j] = query.GetResult(j)->Dist;
+        }
+    }
+    return 0;
+}
 
 extern "C" {
 
@@ -269,6 +296,18 @@ int ref_search_filtered(void* h, const void* queries, int nq, long long stride_b
         }
     }
     return bad;
+}
+
+int ref_refine_nodes(void* h, int first, int num, int cef, int neighborhood, float rng_factor, int threads,
+                     int* out_graph, int* res_ids, float* res_dists) {
+    auto& idx = ((RefHandle*)h)->index;
+    if (threads > 0) omp_set_num_threads(threads);
+    switch (idx->GetVectorValueType()) {
+    case VectorValueType::Float: return refine_nodes_t<float>(idx.get(), first, num, cef, neighborhood, rng_factor, out_graph, res_ids, res_dists);
+    case VectorValueType::Int8: return refine_nodes_t<std::int8_t>(idx.get(), first, num, cef, neighborhood, rng_factor, out_graph, res_ids, res_dists);
+    case VectorValueType::UInt8: return refine_nodes_t<std::uint8_t>(idx.get(), first, num, cef, neighborhood, rng_factor, out_graph, res_ids, res_dists);
+    default: return 1;
+    }
 }
 
 // Install the counter-reading factory (single-query stats below need it). Irreversible for h.

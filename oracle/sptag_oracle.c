@@ -648,9 +648,10 @@ static void bkt_search_trees(const qctx_t* c, ws_t* ws, int limits)
     }
 }
 
-/* BKT::Index<T>::Search<notDeleted, CheckDup, AlwaysTrue> (BKTIndex.cpp:268-352) as dispatched by the
- * public SearchIndex (searchDuplicated = true, no filter; :463-508, :595-620) */
-static void bkt_search(const qctx_t* c, ws_t* ws, res_t* res, int k)
+/* BKT::Index<T>::Search<notDeleted, isDup, checkFilter> (BKTIndex.cpp:268-352).  never_dup = 0: CheckDup, as
+ * dispatched by the public SearchIndex (searchDuplicated = true; :463-508, :595-620); never_dup = 1: NeverDup, as
+ * dispatched by RefineSearchIndex (searchDuplicated = false; :698-711, StaticDispatch::NeverDup :447-452) */
+static void bkt_search(const qctx_t* c, ws_t* ws, res_t* res, int k, int never_dup)
 {
     const ora_index* idx = c->idx;
     const ora_bkt_node* nodes = (const ora_bkt_node*)idx->nodes;
@@ -672,7 +673,8 @@ static void bkt_search(const qctx_t* c, ws_t* ws, res_t* res, int k)
                 do {
                     if (not_deleted(idx, tmpNode)) {
                         if (check_filter(idx, tmpNode)) {
-                            if (!res_add_point(res, k, tmpNode, gnode.distance)) break; /* CheckDup */
+                            /* CheckDup: stop at the first member that does not enter; NeverDup: add one, stop */
+                            if (!res_add_point(res, k, tmpNode, gnode.distance) || never_dup) break;
                         }
                     }
                     if (i <= 0) break;
@@ -840,7 +842,7 @@ int ora_search_batch(const ora_index* idx, const void* queries, int32_t nq, int3
             }
             ws_reset(&ws, idx->max_check, k);
             if (idx->tree_kind == ORA_BKT)
-                bkt_search(&c, &ws, res, k);
+                bkt_search(&c, &ws, res, k, 0);
             else
                 kdt_search(&c, &ws, res, k);
             for (int i = 0; i < k; i++) {
@@ -863,6 +865,91 @@ int ora_search_batch(const ora_index* idx, const void* queries, int32_t nq, int3
         free(qcode);
         free(qtable);
         free(qtmp);
+        ws_free(&ws);
+    }
+    return 0;
+}
+
+
+/* RelativeNeighborhoodGraph::RebuildNeighbors (RelativeNeighborhoodGraph.h:20-38): walk the ascending result list,
+ * keep a candidate unless an already kept neighbour is closer to it than the node is (RNG rule, factor m_fRNGFactor);
+ * distances between base rows use the index's own ComputeDistance (VectorIndex.h:136-139). */
+static void rebuild_neighbors(const ora_index* idx, int32_t node, int32_t* nodes, const res_t* results, int num_results,
+                              int neighborhood, float rng_factor)
+{
+    static const size_t elem[4] = {1, 1, 2, 4};
+    const size_t row_bytes = elem[idx->value_type] * (size_t)idx->dim;
+    const char* base = (const char*)idx->vectors;
+    int count = 0;
+    for (int j = 0; j < num_results && count < neighborhood; j++) {
+        const res_t* item = &results[j];
+        if (item->vid < 0) break;
+        if (item->vid == node) continue;
+        int good = 1;
+        for (int k = 0; k < count; k++) {
+            float d;
+            if (idx->quantizer)
+                d = ora_quantizer_l2(idx->quantizer, (const uint8_t*)base + (size_t)nodes[k] * row_bytes,
+                                     (const uint8_t*)base + (size_t)item->vid * row_bytes);
+            else
+                d = ora_distance(idx->metric, idx->value_type, idx->simd_width, base + (size_t)nodes[k] * row_bytes,
+                                 base + (size_t)item->vid * row_bytes, idx->dim);
+            if (rng_factor * d < item->dist) {
+                good = 0;
+                break;
+            }
+        }
+        if (good) nodes[count++] = item->vid;
+    }
+    for (int j = count; j < neighborhood; j++) nodes[j] = -1;
+}
+
+/* NeighborhoodGraph::RefineNode(index, node, updateNeighbors=false, searchDeleted=false, CEF)
+ * (NeighborhoodGraph.h:534-545) for nodes [first_node, first_node+num_nodes) against the index's CURRENT graph:
+ * RefineSearchIndex (BKTIndex.cpp:698-711 / KDTIndex.cpp: Reset(MaxCheckForRefineGraph, CEF+1), searchDuplicated =
+ * false) with the node's own row as the query, then RebuildNeighbors into out_graph[i*neighborhood ..].
+ * The reference refines IN PLACE under OpenMP, so its pass result depends on thread timing; refining every node
+ * against the frozen graph is the deterministic form both the oracle and the device implement.
+ * res_ids / res_dists: NULL or [num_nodes*(cef+1)] -- the refine-search result lists. */
+int ora_refine_nodes(const ora_index* idx, int32_t first_node, int32_t num_nodes, int32_t cef, int32_t neighborhood,
+                     float rng_factor, int32_t* out_graph, int32_t* res_ids, float* res_dists, int32_t threads)
+{
+    static const size_t elem[4] = {1, 1, 2, 4};
+    const size_t row_bytes = elem[idx->value_type] * (size_t)idx->dim;
+    if (idx->quantizer || idx->filter) return 1; /* quantized refine (reconstruct + re-quantize) is not restated */
+    if (first_node < 0 || num_nodes < 0 || first_node + num_nodes > idx->n || cef < 1 || neighborhood < 1) return 1;
+    const int k = cef + 1;
+    const int alloc_check = idx->max_check > idx->max_check_refine ? idx->max_check : idx->max_check_refine;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#else
+    (void)threads;
+#endif
+#pragma omp parallel
+    {
+        ws_t ws;
+        ws_init(&ws, idx->n, alloc_check);
+        res_t* res = (res_t*)malloc(sizeof(res_t) * (size_t)k);
+#pragma omp for schedule(dynamic, 10)
+        for (int32_t i = 0; i < num_nodes; i++) {
+            const int32_t node = first_node + i;
+            qctx_t c = {idx, (const char*)idx->vectors + (size_t)node * row_bytes, row_bytes, idx->metric != ORA_L2};
+            for (int j = 0; j < k; j++) {
+                res[j].vid = -1;
+                res[j].dist = kMaxDist();
+            }
+            ws_reset(&ws, idx->max_check_refine, k);
+            if (idx->tree_kind == ORA_BKT)
+                bkt_search(&c, &ws, res, k, 1);
+            else
+                kdt_search(&c, &ws, res, k);
+            rebuild_neighbors(idx, node, out_graph + (size_t)i * neighborhood, res, k, neighborhood, rng_factor);
+            if (res_ids)
+                for (int j = 0; j < k; j++) res_ids[(size_t)i * k + j] = res[j].vid;
+            if (res_dists)
+                for (int j = 0; j < k; j++) res_dists[(size_t)i * k + j] = res[j].dist;
+        }
+        free(res);
         ws_free(&ws);
     }
     return 0;

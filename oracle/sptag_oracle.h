@@ -101,6 +101,12 @@ float ora_quantizer_l2(const ora_quantizer* q, const uint8_t* x, const uint8_t* 
 int ora_search_batch(const ora_index* idx, const void* queries, int32_t nq, int32_t k,
                      int32_t* ids, float* dists, int32_t* stats, int32_t threads);
 
+/* Restatement of one NeighborhoodGraph::RefineNode pass (NeighborhoodGraph.h:534-545 + BKTIndex.cpp:698-711 +
+ * RelativeNeighborhoodGraph.h:20-38) over nodes [first_node, first_node+num_nodes) against the index's current
+ * graph; out_graph is [num_nodes*neighborhood]; res_ids/res_dists are NULL or [num_nodes*(cef+1)]. */
+int ora_refine_nodes(const ora_index* idx, int32_t first_node, int32_t num_nodes, int32_t cef, int32_t neighborhood,
+                     float rng_factor, int32_t* out_graph, int32_t* res_ids, float* res_dists, int32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,8 @@ EXPORTS = [
     "sptag_b200_get_param", "sptag_b200_search", "sptag_b200_search_device", "sptag_b200_distance_batch",
     "sptag_b200_merge_topk", "sptag_b200_last_kernel_ms", "sptag_b200_launch_count",
     "sptag_b200_num_vectors", "sptag_b200_dim", "sptag_b200_value_type", "sptag_b200_metric",
-    "sptag_b200_algo", "sptag_b200_last_error",
+    "sptag_b200_algo", "sptag_b200_last_error", "sptag_b200_refine_graph", "sptag_b200_get_graph",
+    "sptag_b200_graph_degree",
 ]
 
 
@@ -71,6 +72,10 @@ def lib():
         L.sptag_b200_distance_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         L.sptag_b200_merge_topk.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sptag_b200_refine_graph.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        L.sptag_b200_get_graph.argtypes = [C.c_void_p, C.c_void_p]
+        L.sptag_b200_graph_degree.argtypes = [C.c_void_p]
         L.sptag_b200_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.sptag_b200_launch_count.restype = C.c_int64
         for f in ("num_vectors", "dim", "value_type", "metric", "algo"):
@@ -201,6 +206,30 @@ class B200Index:
         """Same call with device pointers (e.g. torch tensor .data_ptr()), stream-ordered, no sync."""
         _check(lib().sptag_b200_search_device(self._h, d_queries_ptr, nq, k, d_ids_ptr, d_dists_ptr,
                                               d_stats_ptr or None, stream or None))
+
+    def refine_graph(self, cef, first=0, num=None, neighborhood=None, rng_factor=1.0, install=False,
+                     want_rows=True, want_results=False):
+        """One NeighborhoodGraph::RefineNode pass (RefineSearchIndex + RebuildNeighbors) on the device.
+        -> rows [num, neighborhood] (or None), and with want_results also the (ids, dists) refine-search lists."""
+        num = self.num_vectors - first if num is None else num
+        neighborhood = self.graph_degree if neighborhood is None else neighborhood
+        rows = np.empty((num, neighborhood), np.int32) if want_rows else None
+        ids = np.empty((num, cef + 1), np.int32) if want_results else None
+        dists = np.empty((num, cef + 1), np.float32) if want_results else None
+        _check(lib().sptag_b200_refine_graph(self._h, first, num, cef, neighborhood, rng_factor,
+                                             rows.ctypes.data if want_rows else None,
+                                             ids.ctypes.data if want_results else None,
+                                             dists.ctypes.data if want_results else None, 1 if install else 0))
+        return (rows, ids, dists) if want_results else rows
+
+    @property
+    def graph_degree(self):
+        return lib().sptag_b200_graph_degree(self._h)
+
+    def get_graph(self):
+        g = np.empty((self.num_vectors, self.graph_degree), np.int32)
+        _check(lib().sptag_b200_get_graph(self._h, g.ctypes.data))
+        return g
 
     def distance_batch(self, queries, ids):
         queries = np.ascontiguousarray(queries, dtype=np.float32)

@@ -92,6 +92,9 @@ struct SearchParams {
     int direct_load;
     // K > 32: the result set is the reference's own max-heap (QueryResultSet.h:77-120) in a per-slot HBM arena
     int2* topk;                            // per slot, k entries (id, distance bits); nullptr when k <= 32
+    // 1: RefineSearchIndex flavour (searchDuplicated = false -> StaticDispatch::NeverDup, BKTIndex.cpp:447-452, :698-711):
+    // a duplicate group contributes its first live member only
+    int never_dup;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -875,7 +878,7 @@ struct WarpSearch {
                     do {
                         if (not_deleted(tmpNode)) {
                             if (check_filter(tmpNode)) {
-                                if (!add_point(tmpNode, gdist)) break;
+                                if (!add_point(tmpNode, gdist) || p.never_dup) break;
                             }
                         }
                         if (i <= 0) break;
@@ -1224,6 +1227,69 @@ __global__ void distance_batch_kernel(const unsigned char* vectors, unsigned lon
         d = half_warp_distance_int<COSINE, ELEM == 2>(vectors + (size_t)(ok ? id : 0) * row_stride_bytes, qv, dim, j);
     }
     if (valid && j == 0) out[item] = ok ? d : SPTAG_B200_MAXDIST;
+}
+
+// ------------------------------------------------------------------------------------------
+// RelativeNeighborhoodGraph::RebuildNeighbors (RelativeNeighborhoodGraph.h:20-38), one warp per node: walk the node's
+// ascending refine-search list, keep a candidate unless an already kept neighbour is closer to it than the node is
+// (rng_factor * d(kept, cand) < d(node, cand)).  The reference tests the kept neighbours one by one and stops at the
+// first that rejects; the verdict is an AND over all of them, so testing two per step (one per half-warp) with an
+// early exit is the same function.  Distances are the index's ComputeDistance, i.e. the same summation trees.
+// ------------------------------------------------------------------------------------------
+template <bool COSINE, int ELEM>
+__global__ void __launch_bounds__(128) rebuild_neighbors_kernel(const unsigned char* __restrict__ vectors,
+                                                                unsigned long long row_stride_bytes, int dim,
+                                                                int first_node, int num_nodes,
+                                                                const int* __restrict__ res_ids,
+                                                                const float* __restrict__ res_dists, int num_results,
+                                                                int neighborhood, float rng_factor,
+                                                                int* __restrict__ out_graph) {
+    extern __shared__ int kept_sm[];  // neighborhood ints per warp
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j = lane & 15, half = lane >> 4;
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (w >= num_nodes) return;
+    int* kept = kept_sm + warp * neighborhood;
+    const int node = first_node + (int)w;
+    const int* ids = res_ids + (size_t)w * num_results;
+    const float* ds = res_dists + (size_t)w * num_results;
+    int count = 0;
+    for (int r = 0; r < num_results && count < neighborhood; ++r) {
+        const int vid = ids[r];
+        if (vid < 0) break;
+        if (vid == node) continue;
+        const float dist = ds[r];
+        const unsigned char* cand = vectors + (size_t)vid * row_stride_bytes;
+        bool good = true;
+        for (int k0 = 0; k0 < count && good; k0 += 2) {
+            const int k = min(k0 + half, count - 1);
+            const unsigned char* row = vectors + (size_t)kept[k] * row_stride_bytes;
+            float d;
+            if (ELEM == 0) {
+                QueryRegs<0> qr;
+                d = half_warp_distance<0, COSINE>(reinterpret_cast<const float*>(row), qr,
+                                                  reinterpret_cast<const float*>(cand), dim, j);
+            } else {
+                d = half_warp_distance_int<COSINE, ELEM == 2>(row, cand, dim, j);
+            }
+            const bool reject = (j == 0) && (__fmul_rn(rng_factor, d) < dist);
+            if (__any_sync(kFull, reject)) good = false;
+        }
+        if (good) {
+            if (lane == 0) kept[count] = vid;
+            ++count;
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    for (int t = lane; t < neighborhood; t += 32) out_graph[(size_t)w * neighborhood + t] = (t < count) ? kept[t] : -1;
+}
+
+// Installing a refined graph: rows whose last slot named a duplicate group keep naming it (NeighborhoodGraph.h:395-401)
+__global__ void carry_backpointers_kernel(const int* __restrict__ old_graph, int* __restrict__ new_graph, int n, int degree) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int last = old_graph[(size_t)i * degree + degree - 1];
+    if (last < -1) new_graph[(size_t)i * degree + degree - 1] = last;
 }
 
 // ------------------------------------------------------------------------------------------

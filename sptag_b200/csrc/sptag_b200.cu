@@ -113,6 +113,7 @@ struct sptag_b200_index {
     // scratch
     DeviceBuffer d_visited, d_ng_spill, d_spt_spill, d_counter, d_vlog, d_topk;
     DeviceBuffer d_queries, d_ids, d_dists, d_stats;  // staging for the host-buffer entry point
+    DeviceBuffer d_graph_new;                         // sptag_b200_refine_graph: the pass's output rows
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool timed = false;
     int num_sms = 0;
@@ -389,8 +390,11 @@ int quantize_device(sptag_b200_index* h, const void* d_raw, int n, unsigned char
     return 0;
 }
 
+// refine = true: the RefineSearchIndex flavour (BKTIndex.cpp:698-711) -- queries are base rows of the index itself
+// (stride = the padded row stride), duplicate groups are not expanded, ids come back local (no shard offset); the
+// caller has already put MaxCheckForRefineGraph in h->max_check.
 int search_device_impl(sptag_b200_index* h, const void* d_queries, int nq, int k, int* d_ids, float* d_dists,
-                       int* d_stats, cudaStream_t stream) {
+                       int* d_stats, cudaStream_t stream, bool refine = false) {
     if (nq <= 0) return SPTAG_B200_SUCCESS;
     SearchParams p;
     int grid = 0;
@@ -413,6 +417,11 @@ int search_device_impl(sptag_b200_index* h, const void* d_queries, int nq, int k
             p.queries = (const unsigned char*)h->d_codes.ptr;
             p.query_stride_bytes = (size_t)h->q_m;
         }
+    }
+    if (refine) {
+        p.query_stride_bytes = h->row_stride;
+        p.never_dup = 1;
+        p.id_offset = 0;
     }
     p.nq = nq;
     p.out_ids = d_ids;
@@ -546,6 +555,7 @@ void sptag_b200_destroy(sptag_b200_handle h) {
     h->d_tree_starts.release();
     h->d_deleted.release();
     h->d_filter.release();
+    h->d_graph_new.release();
     h->d_codebooks.release();
     h->d_rotation_t.release();
     h->d_sdc.release();
@@ -859,6 +869,93 @@ int sptag_b200_search_filtered(sptag_b200_handle h, const void* queries, int32_t
     }
     return rc;
 }
+
+int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num_nodes, int32_t cef,
+                            int32_t neighborhood_size, float rng_factor, int32_t* out_graph, int32_t* out_res_ids,
+                            float* out_res_dists, int32_t install) {
+    if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
+    if (h->q_type != 0)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "refine on a quantized index (reconstruct + re-quantize) is not built");
+    if (first_node < 0 || num_nodes < 0 || (long long)first_node + num_nodes > h->n)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "node range [%d, %d) outside the index", first_node, first_node + num_nodes);
+    if (cef < 1 || cef + 1 > 1024) return fail(SPTAG_B200_LACK_OF_INPUTS, "CEF = %d outside [1, 1023]", cef);
+    if (neighborhood_size < 1 || neighborhood_size > 1024)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "neighbourhood size %d outside [1, 1024]", neighborhood_size);
+    if (install && (first_node != 0 || num_nodes != h->n || neighborhood_size != h->degree))
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "install needs a full pass with the index's own neighbourhood size");
+    if (num_nodes == 0) return SPTAG_B200_SUCCESS;
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceGuard guard(h->device);
+    const int k = cef + 1;
+    const int batch = std::min(num_nodes, 32768);  // 32768 x 1001 result pairs = 262 MB of scratch
+    if (int rc = h->d_ids.ensure((size_t)batch * k * 4)) return rc;
+    if (int rc = h->d_dists.ensure((size_t)batch * k * 4)) return rc;
+    if (int rc = h->d_graph_new.ensure((size_t)num_nodes * neighborhood_size * 4)) return rc;
+    cudaStream_t stream = nullptr;
+    const int saved_check = h->max_check;
+    h->max_check = h->max_check_refine;  // workSpace->Reset(m_pGraph.m_iMaxCheckForRefineGraph, CEF + 1)
+    int rc = SPTAG_B200_SUCCESS;
+    const unsigned char* dv = (const unsigned char*)h->d_vectors.ptr;
+    const bool l2 = (h->metric == SPTAG_B200_METRIC_L2);
+    for (int done = 0; done < num_nodes && rc == SPTAG_B200_SUCCESS; done += batch) {
+        const int nb = std::min(batch, num_nodes - done);
+        const int first = first_node + done;
+        rc = search_device_impl(h, dv + (size_t)first * h->row_stride, nb, k, (int*)h->d_ids.ptr, (float*)h->d_dists.ptr,
+                                nullptr, stream, /*refine=*/true);
+        if (rc) break;
+        const int warps_per_block = 4;
+        const unsigned blocks = (unsigned)((nb + warps_per_block - 1) / warps_per_block);
+        const size_t smem = (size_t)warps_per_block * neighborhood_size * 4;
+        int* rows = (int*)h->d_graph_new.ptr + (size_t)done * neighborhood_size;
+#define SPTAG_B200_RB(COS, EL)                                                                                          \
+    rebuild_neighbors_kernel<COS, EL><<<blocks, warps_per_block * 32, smem, stream>>>(                                   \
+        dv, h->row_stride, h->dim, first, nb, (const int*)h->d_ids.ptr, (const float*)h->d_dists.ptr, k,                 \
+        neighborhood_size, rng_factor, rows)
+        if (h->value_type == SPTAG_B200_VT_FLOAT) {
+            if (l2) SPTAG_B200_RB(false, 0); else SPTAG_B200_RB(true, 0);
+        } else if (h->value_type == SPTAG_B200_VT_INT8) {
+            if (l2) SPTAG_B200_RB(false, 1); else SPTAG_B200_RB(true, 1);
+        } else {
+            if (l2) SPTAG_B200_RB(false, 2); else SPTAG_B200_RB(true, 2);
+        }
+#undef SPTAG_B200_RB
+        g_launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess && out_res_ids)
+            e = cudaMemcpyAsync(out_res_ids + (size_t)done * k, h->d_ids.ptr, (size_t)nb * k * 4, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess && out_res_dists)
+            e = cudaMemcpyAsync(out_res_dists + (size_t)done * k, h->d_dists.ptr, (size_t)nb * k * 4, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) rc = fail(SPTAG_B200_FAIL, "refine pass failed: %s", cudaGetErrorString(e));
+    }
+    h->max_check = saved_check;
+    if (rc) return rc;
+    if (out_graph)
+        CUDA_OK(cudaMemcpy(out_graph, h->d_graph_new.ptr, (size_t)num_nodes * neighborhood_size * 4, cudaMemcpyDeviceToHost));
+    if (install) {
+        // BuildGraph re-attaches the duplicate-group back-pointers after its refine passes (NeighborhoodGraph.h:395-401)
+        const long long n = h->n;
+        carry_backpointers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const int*)h->d_graph.ptr,
+                                                                                   (int*)h->d_graph_new.ptr, h->n, h->degree);
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaStreamSynchronize(stream));
+        std::swap(h->d_graph.ptr, h->d_graph_new.ptr);
+        std::swap(h->d_graph.bytes, h->d_graph_new.bytes);
+    }
+    return SPTAG_B200_SUCCESS;
+}
+
+int sptag_b200_get_graph(sptag_b200_handle h, int32_t* out_graph) {
+    if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
+    if (!out_graph) return fail(SPTAG_B200_LACK_OF_INPUTS, "null buffer");
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceGuard guard(h->device);
+    CUDA_OK(cudaMemcpy(out_graph, h->d_graph.ptr, (size_t)h->n * h->degree * 4, cudaMemcpyDeviceToHost));
+    return SPTAG_B200_SUCCESS;
+}
+
+int32_t sptag_b200_graph_degree(sptag_b200_handle h) { return h ? h->degree : 0; }
 
 int sptag_b200_distance_batch(sptag_b200_handle h, const void* queries, int32_t num_queries, const int32_t* ids,
                               int32_t ids_per_query, float* out) {

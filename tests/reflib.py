@@ -79,6 +79,8 @@ def ref():
                                           C.c_int, C.c_void_p, C.c_void_p]
         L.ref_search_each.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_refine_nodes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_quiet(3)  # warnings and errors only
         _ref = L
     return _ref
@@ -159,6 +161,18 @@ class RefIndex:
         ref().ref_search_each(self.h, queries.ctypes.data, nq, queries.strides[0], k, threads, ids.ctypes.data,
                               dists.ctypes.data, C.byref(sec))
         return ids, dists, sec.value
+
+    def refine_nodes(self, first, num, cef, neighborhood=32, rng_factor=1.0, threads=0):
+        """NeighborhoodGraph::RefineNode per node against the loaded graph (graph not modified):
+        RefineSearchIndex + RelativeNeighborhoodGraph::RebuildNeighbors.  -> (rows, result ids, result dists)."""
+        rows = np.empty((num, neighborhood), np.int32)
+        ids = np.empty((num, cef + 1), np.int32)
+        dists = np.empty((num, cef + 1), np.float32)
+        rc = ref().ref_refine_nodes(self.h, first, num, cef, neighborhood, rng_factor, threads, rows.ctypes.data,
+                                    ids.ctypes.data, dists.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("reference refine failed: %d" % rc)
+        return rows, ids, dists
 
     def enable_stats(self):
         return ref().ref_enable_stats(self.h)
@@ -399,6 +413,8 @@ def ora():
                                             C.c_int32, C.c_void_p]
         L.ora_search_batch.argtypes = [C.POINTER(_OraIndex), C.c_void_p, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        L.ora_refine_nodes.argtypes = [C.POINTER(_OraIndex), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.ora_quantizer_init.argtypes = [C.POINTER(_OraQuantizer)]
         L.ora_quantizer_encode.argtypes = [C.POINTER(_OraQuantizer), C.c_void_p, C.c_int32, C.c_void_p]
         L.ora_quantizer_l2.restype = C.c_float
@@ -459,6 +475,17 @@ class OracleIndex:
                                     dists.ctypes.data, stats.ctypes.data if want_stats else None, threads)
         assert rc == 0
         return ids, dists, stats
+
+    def refine_nodes(self, first, num, cef, neighborhood=32, rng_factor=1.0, threads=0):
+        """One RefineNode pass over [first, first+num) against the current graph (ora_refine_nodes)."""
+        rows = np.empty((num, neighborhood), np.int32)
+        ids = np.empty((num, cef + 1), np.int32)
+        dists = np.empty((num, cef + 1), np.float32)
+        s = self._struct()
+        rc = ora().ora_refine_nodes(C.byref(s), first, num, cef, neighborhood, rng_factor, rows.ctypes.data,
+                                    ids.ctypes.data, dists.ctypes.data, threads)
+        assert rc == 0
+        return rows, ids, dists
 
 
 # ------------------------------------------------------------------------------------------------

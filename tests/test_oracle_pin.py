@@ -115,6 +115,27 @@ def test_oracle_matches_golden_reference_outputs(oracle_lib, name):
         assert np.array_equal(stats[:, reflib.ST_SPT_LEFT], g["ref_stats"][i][:, 3]), (name, mc)
 
 
+def refine_golden_cases():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "refine", "*.npz")))
+
+
+@pytest.mark.parametrize("name", refine_golden_cases())
+def test_oracle_refine_matches_golden_reference_outputs(oracle_lib, name):
+    """the reference's RefineSearchIndex lists + RebuildNeighbors rows on the committed indexes
+    (tests/golden/make_golden_refine.py) against ora_refine_nodes."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    r = np.load(os.path.join(GOLDEN, "refine", name + ".npz"))
+    files = reflib.IndexFiles.__new__(reflib.IndexFiles)
+    _files_from_npz(files, g)
+    o = reflib.OracleIndex(files)
+    o.max_check_refine = int(r["max_check_refine"])
+    num = r["rows"].shape[0]
+    rows, ids, dists = o.refine_nodes(0, num, int(r["cef"]), int(r["neighborhood"]), float(r["rng_factor"]))
+    assert np.array_equal(ids, r["res_ids"]), name
+    assert np.array_equal(dists.view(np.int32), r["res_dists"].view(np.int32)), name
+    assert np.array_equal(rows, r["rows"]), name
+
+
 # ---------------------------------------------------------------------------------------------
 # the reference itself
 # ---------------------------------------------------------------------------------------------
@@ -306,3 +327,27 @@ def test_filtered_search_bit_exact_vs_reference(oracle_lib, name):
         assert np.array_equal(ids_r, ids_o), (name, mc)
         assert np.array_equal(d_r.view(np.int32), d_o.view(np.int32)), (name, mc)
         assert allowed[ids_r[ids_r >= 0]].all()
+
+
+@needs_ref
+@pytest.mark.parametrize("name,cef,mcr", [("bkt_l2_dups", 20, 256), ("bkt_l2_20k_32", 100, 2048),
+                                          ("bkt_cos_3k_768", 1000, 8192), ("kdt_l2_10k_64", 64, 1024),
+                                          ("bkt_i8_cos_6k_64", 50, 512), ("bkt_u8_l2_6k_128", 50, 512),
+                                          ("bkt_l2_3k_30", 64, 1024)])
+def test_refine_bit_exact_vs_reference(oracle_lib, name, cef, mcr):
+    """NeighborhoodGraph::RefineNode per node on the loaded index (RefineSearchIndex + RebuildNeighbors run by the
+    reference itself) against the oracle's restatement."""
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    r = reflib.RefIndex.load(folder)
+    r.set_param("MaxCheckForRefineGraph", mcr)
+    o = reflib.OracleIndex(files)
+    o.max_check_refine = mcr
+    num = min(files.n, 300)
+    first = files.n // 3
+    for nbh, factor in [(files.degree, 1.0), (12, 1.3)]:
+        rows_r, ids_r, d_r = r.refine_nodes(first, num, cef, nbh, factor, threads=4)
+        rows_o, ids_o, d_o = o.refine_nodes(first, num, cef, nbh, factor, threads=4)
+        assert np.array_equal(ids_r, ids_o), name
+        assert np.array_equal(d_r.view(np.int32), d_o.view(np.int32)), name
+        assert np.array_equal(rows_r, rows_o), name
