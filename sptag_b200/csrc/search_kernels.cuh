@@ -91,7 +91,8 @@ struct SearchParams {
     // 1: small float rows are loaded straight from HBM into registers (no TMA ring) in the static-DIM kernels
     int direct_load;
     // K > 32: the result set is the reference's own max-heap (QueryResultSet.h:77-120) in a per-slot HBM arena
-    int2* topk;                            // per slot, k entries (id, distance bits); nullptr when k <= 32
+    int2* topk;                            // per slot, topk_pad entries (id, distance bits); nullptr when k <= 32
+    int topk_pad;                          // k rounded up to a power of two (the final sort is bitonic)
     // 1: RefineSearchIndex flavour (searchDuplicated = false -> StaticDispatch::NeverDup, BKTIndex.cpp:447-452, :698-711):
     // a duplicate group contributes its first live member only
     int never_dup;
@@ -522,12 +523,13 @@ struct WarpSearch {
     // queues
     WarpHeap ng, spt;
     MResults<RPL> mres;
-    // top-K: lane i holds the i-th best (dist, id) (k <= 32); larger k: heap in HBM
+    // top-K: lane i holds the i-th best (dist, id) (k <= 32); larger k: unordered set in the slot's HBM arena
     int2* tk;
     float tk_d;
     int tk_id;
     float worst_d;
     int worst_id;
+    int tk_count, worst_pos;  // K > 32: entries kept so far / where the worst one sits (valid once K are kept)
     // query slice
     QueryRegs<DIM> qr;
     // counters
@@ -558,53 +560,64 @@ struct WarpSearch {
         return was;
     }
 
-    // ---- K > 32: QueryResultSet as the reference keeps it, a max-heap on (Dist, VID) in the slot's arena ----
+    // ---- K > 32: QueryResultSet in the slot's HBM arena ----
     static __device__ __forceinline__ bool res_less(int2 a, int2 b) {  // QueryResultSet.h:17-20
         const float da = __int_as_float(a.y), db = __int_as_float(b.y);
         return (da < db) || ((da == db) && (a.x < b.x));
     }
-    // QueryResultSet::Heapify(count) with `cur` being the value sitting at the root (QueryResultSet.h:101-116);
-    // executed redundantly by all lanes (uniform loads), lane 0 stores
-    __device__ __forceinline__ void res_heapify(int2 cur, int count) {
-        int parent = 0, next = 1;
-        const int maxidx = count - 1;
-        while (next < maxidx) {
-            int2 a = tk[next];
-            const int2 b = tk[next + 1];
-            if (res_less(a, b)) {
-                next++;
-                a = b;
-            }
-            if (res_less(cur, a)) {
-                if (lane == 0) tk[parent] = a;
-                parent = next;
-                next = (parent << 1) + 1;
-            } else
-                break;
-        }
-        if (next == maxidx) {
-            const int2 a = tk[next];
-            if (res_less(cur, a)) {
-                if (lane == 0) tk[parent] = a;
-                parent = next;
+    // K > 32: the reference keeps the K best in a max-heap on (Dist, VID) (QueryResultSet.h:77-120).  What a caller can
+    // observe of it is (a) the root = the worst kept entry, which gates AddPoint, and (b) the ascending list after
+    // SortResult; both are functions of the SET of kept entries, not of the heap layout.  So the arena holds the set
+    // unordered: an accepted point is appended while fewer than K are kept (the root is then still a (-1, MaxDist)
+    // filler) and otherwise overwrites the worst entry, whose successor is found by one coalesced warp scan; the final
+    // order comes from a warp-wide bitonic sort.  (A heap emulation costs ~log2 K dependent HBM round trips per AddPoint
+    // and K log2 K for the sort -- 7 ms per query at K = 1001.)
+    __device__ __forceinline__ void res_rescan_worst() {
+        int2 best = make_pair(-1, -INFINITY);
+        int bpos = 0;
+        for (int i = lane; i < p.k; i += 32) {
+            const int2 e = tk[i];
+            if (res_less(best, e)) {
+                best = e;
+                bpos = i;
             }
         }
-        if (lane == 0 && count > 0) tk[parent] = cur;
-        __syncwarp();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            int2 oth;
+            oth.x = __shfl_xor_sync(kFull, best.x, o);
+            oth.y = __shfl_xor_sync(kFull, best.y, o);
+            const int op = __shfl_xor_sync(kFull, bpos, o);
+            if (res_less(best, oth)) {
+                best = oth;
+                bpos = op;
+            }
+        }
+        worst_d = __int_as_float(best.y);
+        worst_id = best.x;
+        worst_pos = bpos;
     }
-    __device__ __forceinline__ void res_reset() {
-        for (int i = lane; i < p.k; i += 32) tk[i] = make_pair(-1, SPTAG_B200_MAXDIST);
-        __syncwarp();
-    }
-    // QueryResultSet::SortResult (QueryResultSet.h:89-96): heap-sort ascending in place
+    __device__ __forceinline__ void res_reset() { tk_count = 0; }
+    // QueryResultSet::SortResult (QueryResultSet.h:89-96): ascending by (Dist, VID); unfilled slots are (-1, MaxDist)
     __device__ __forceinline__ void res_sort() {
-        for (int i = p.k - 1; i >= 0; i--) {
-            const int2 root = tk[0];
-            const int2 last = tk[i];
-            __syncwarp();
-            if (lane == 0) tk[i] = root;
-            __syncwarp();
-            res_heapify(last, i);
+        const int n = p.topk_pad;  // power of two >= K
+        for (int i = tk_count + lane; i < n; i += 32)
+            tk[i] = (i < p.k) ? make_pair(-1, SPTAG_B200_MAXDIST) : make_pair(0x7fffffff, INFINITY);
+        __syncwarp();
+        for (int size = 2; size <= n; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = lane; t < (n >> 1); t += 32) {
+                    const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));  // bit `stride` clear
+                    const int j = i | stride;
+                    const bool ascending = (i & size) == 0;
+                    const int2 a = tk[i], b = tk[j];
+                    if (res_less(b, a) == ascending) {
+                        tk[i] = b;
+                        tk[j] = a;
+                    }
+                }
+                __syncwarp();
+            }
         }
     }
 
@@ -612,10 +625,18 @@ struct WarpSearch {
     __device__ __forceinline__ bool add_point(int id, float d) {
         if (!(d < worst_d || (d == worst_d && id < worst_id))) return false;
         if (tk != nullptr) {
-            res_heapify(make_pair(id, d), p.k);
-            const int2 root = tk[0];
-            worst_d = __int_as_float(root.y);
-            worst_id = root.x;
+            if (tk_count < p.k) {
+                if (lane == 0) tk[tk_count] = make_pair(id, d);
+                ++tk_count;
+                if (tk_count == p.k) {
+                    __syncwarp();
+                    res_rescan_worst();
+                }
+            } else {
+                if (lane == 0) tk[worst_pos] = make_pair(id, d);
+                __syncwarp();
+                res_rescan_worst();
+            }
             return true;
         }
         const bool less = (lane < p.k) && ((tk_d < d) || (tk_d == d && tk_id < id));
@@ -1066,7 +1087,7 @@ __global__ void __launch_bounds__(32, MINB) search_kernel(const SearchParams p) 
     w.qs = reinterpret_cast<float*>(smem + p.off_query);
     w.visited = p.visited + (size_t)blockIdx.x * p.visited_words;
     w.vlog = p.vlog ? p.vlog + (size_t)blockIdx.x * p.vlog_entries : nullptr;
-    w.tk = p.topk ? p.topk + (size_t)blockIdx.x * p.k : nullptr;
+    w.tk = p.topk ? p.topk + (size_t)blockIdx.x * p.topk_pad : nullptr;
     w.ng.s = reinterpret_cast<int2*>(smem + p.off_ng);
     w.ng.g = p.ng_spill + (size_t)blockIdx.x * p.ng_spill_entries;
     w.ng.H = p.h_ng;

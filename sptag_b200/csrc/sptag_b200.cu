@@ -114,7 +114,8 @@ struct sptag_b200_index {
     DeviceBuffer d_visited, d_ng_spill, d_spt_spill, d_counter, d_vlog, d_topk;
     DeviceBuffer d_queries, d_ids, d_dists, d_stats;  // staging for the host-buffer entry point
     DeviceBuffer d_graph_new;                         // sptag_b200_refine_graph: the pass's output rows
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_aux = nullptr;
+    double refine_search_ms = 0.0, refine_rebuild_ms = 0.0;  // device time of the last sptag_b200_refine_graph call
     bool timed = false;
     int num_sms = 0;
     size_t smem_optin = 0;
@@ -133,8 +134,10 @@ typedef void (*SearchKernelFn)(const SearchParams);
 template <int DIM, bool COSINE>
 SearchKernelFn pick_rpl(int mres_cap, bool kdt) {
     if (kdt) return search_kernel<DIM, COSINE, 16, true>;  // KDT has no m_Results gate
-    if (mres_cap <= 32 * 16) return search_kernel<DIM, COSINE, 16, false>;
-    if (mres_cap <= 32 * 32) return search_kernel<DIM, COSINE, 32, false>;
+    // register caps (MINB resident single-warp CTAs per SM): 12 -> 168 registers; the kernel is latency-bound per
+    // warp, so residency beats a few spilled values (refine passes run the 32-register m_Results file, K = CEF+1)
+    if (mres_cap <= 32 * 16) return search_kernel<DIM, COSINE, 16, false, false, 0, 12>;
+    if (mres_cap <= 32 * 32) return search_kernel<DIM, COSINE, 32, false, false, 0, 14>;
     return nullptr;
 }
 
@@ -158,7 +161,7 @@ template <bool COSINE, int ELEM>
 SearchKernelFn pick_int(int mres_cap, bool kdt) {
     if (kdt) return search_kernel<0, COSINE, 16, true, false, ELEM>;
     if (mres_cap <= 32 * 16) return search_kernel<0, COSINE, 16, false, false, ELEM>;
-    if (mres_cap <= 32 * 32) return search_kernel<0, COSINE, 32, false, false, ELEM>;
+    if (mres_cap <= 32 * 32) return search_kernel<0, COSINE, 32, false, false, ELEM, 12>;
     return nullptr;
 }
 
@@ -360,7 +363,10 @@ relayout:
     }
     p.topk = nullptr;
     if (k > 32) {  // result heap of the reference in HBM, one arena per slot
-        if (int rc = h->d_topk.ensure(alloc_slots * (size_t)k * 8)) return rc;
+        int pad = 64;
+        while (pad < k) pad <<= 1;
+        p.topk_pad = pad;
+        if (int rc = h->d_topk.ensure(alloc_slots * (size_t)pad * 8)) return rc;
         p.topk = (int2*)h->d_topk.ptr;
     }
     p.visited = (unsigned int*)h->d_visited.ptr;
@@ -537,7 +543,8 @@ int sptag_b200_create(const sptag_b200_index_desc* desc, sptag_b200_handle* out)
         if (int rc = h->d_deleted.ensure((size_t)h->n)) return destroy_on_fail(rc);
         cudaMemcpy(h->d_deleted.ptr, desc->deleted, (size_t)h->n, cudaMemcpyHostToDevice);
     }
-    if (cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess)
+    if (cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess ||
+        cudaEventCreate(&h->ev_aux) != cudaSuccess)
         return destroy_on_fail(fail(SPTAG_B200_FAIL, "cudaEventCreate failed"));
     if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess)
         return destroy_on_fail(fail(SPTAG_B200_FAIL, "index upload failed"));
@@ -574,6 +581,7 @@ void sptag_b200_destroy(sptag_b200_handle h) {
     h->d_stats.release();
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+    if (h->ev_aux) cudaEventDestroy(h->ev_aux);
     delete h;
 }
 
@@ -800,6 +808,8 @@ int sptag_b200_get_param(sptag_b200_handle h, const char* name, char* value_out,
     else if (n == "B200.SlotScheme") v = h->slot_scheme;
     else if (n == "B200.DirectLoad") v = h->direct_load;
     else if (n == "EnableADC") v = h->q_adc;
+    else if (n == "B200.LastRefineSearchUs") v = (long)(h->refine_search_ms * 1000.0);    // read-only: device time
+    else if (n == "B200.LastRefineRebuildUs") v = (long)(h->refine_rebuild_ms * 1000.0);  // of the last refine pass
     else return fail(SPTAG_B200_PARAM_NOT_FOUND, "unknown parameter %s", name);
     snprintf(value_out, (size_t)capacity, "%ld", v);
     return SPTAG_B200_SUCCESS;
@@ -895,6 +905,7 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
     const int saved_check = h->max_check;
     h->max_check = h->max_check_refine;  // workSpace->Reset(m_pGraph.m_iMaxCheckForRefineGraph, CEF + 1)
     int rc = SPTAG_B200_SUCCESS;
+    h->refine_search_ms = h->refine_rebuild_ms = 0.0;
     const unsigned char* dv = (const unsigned char*)h->d_vectors.ptr;
     const bool l2 = (h->metric == SPTAG_B200_METRIC_L2);
     for (int done = 0; done < num_nodes && rc == SPTAG_B200_SUCCESS; done += batch) {
@@ -921,11 +932,19 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
 #undef SPTAG_B200_RB
         g_launches++;
         cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaEventRecord(h->ev_aux, stream);
         if (e == cudaSuccess && out_res_ids)
             e = cudaMemcpyAsync(out_res_ids + (size_t)done * k, h->d_ids.ptr, (size_t)nb * k * 4, cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess && out_res_dists)
             e = cudaMemcpyAsync(out_res_dists + (size_t)done * k, h->d_dists.ptr, (size_t)nb * k * 4, cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess) {
+            float ms_s = 0.f, ms_r = 0.f;
+            cudaEventElapsedTime(&ms_s, h->ev_start, h->ev_stop);
+            cudaEventElapsedTime(&ms_r, h->ev_stop, h->ev_aux);
+            h->refine_search_ms += ms_s;
+            h->refine_rebuild_ms += ms_r;
+        }
         if (e != cudaSuccess) rc = fail(SPTAG_B200_FAIL, "refine pass failed: %s", cudaGetErrorString(e));
     }
     h->max_check = saved_check;

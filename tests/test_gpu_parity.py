@@ -116,6 +116,23 @@ def test_result_counts(k):
         idx.close()
 
 
+@pytest.mark.parametrize("name", ["bkt_l2_10k_128", "kdt_l2_10k_64", "bkt_l2_dups", "bkt_i8_l2_5k_100"])
+def test_large_k_result_set(name):
+    """K > 32 keeps the result set unordered in HBM (append, then overwrite-the-worst + rescan) and sorts it with a
+    bitonic network: small K at a large budget exercises the overwrite path on nearly every accepted point, K = 1024
+    the padded sort; both must reproduce QueryResultSet's heap (QueryResultSet.h:77-120) exactly."""
+    from sptag_b200 import B200Index
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:100]
+    idx = B200Index.load(folder)
+    try:
+        for k, mc in [(40, 8192), (64, 2048), (333, 8192), (1024, 8192)]:
+            _compare(idx, files, q, k, mc, "%s k=%d" % (name, k))
+    finally:
+        idx.close()
+
+
 def test_full_heap_replacement_path():
     # tiny MaxCheck AND tiny MaxCheckForRefineGraph make Heap::insert hit its count == length branch (Heap.h:43-49)
     from sptag_b200 import B200Index
