@@ -144,6 +144,35 @@ public:
         return ErrorCode::Success;
     }
 
+    // VectorIndex::RefineSearchIndex (VectorIndex.h:53, BKTIndex.cpp:698-711) for a base vector of the index: the
+    // refine-flavoured search (MaxCheckForRefineGraph, searchDuplicated = false) with sample `p_node` as the query.
+    // The result buffer of p_query receives the K = GetResultNum() nearest, like the reference's call in
+    // NeighborhoodGraph::RefineNode (NeighborhoodGraph.h:534-545).
+    ErrorCode RefineSearchIndex(SizeType p_node, QueryResult& p_query) const {
+        if (!m_handle) return ErrorCode::EmptyIndex;
+        const int k = p_query.GetResultNum();
+        if (k < 2) return ErrorCode::LackOfInputs;
+        std::vector<std::int32_t> ids((size_t)k);
+        std::vector<float> dists((size_t)k);
+        int rc = sptag_b200_refine_graph(m_handle, p_node, 1, k - 1, sptag_b200_graph_degree(m_handle), 1.0f, nullptr,
+                                         ids.data(), dists.data(), 0);
+        if (rc != 0) return static_cast<ErrorCode>(rc);
+        for (int i = 0; i < k; ++i) {
+            p_query.GetResult(i)->VID = ids[(size_t)i];
+            p_query.GetResult(i)->Dist = dists[(size_t)i];
+        }
+        return ErrorCode::Success;
+    }
+
+    // One NeighborhoodGraph::RefineGraph pass (NeighborhoodGraph.h:459-488: RefineNode for every node) on the device;
+    // p_newGraph (nullable) receives GetNumSamples() x neighbourhood-size rows; p_install replaces the index's graph.
+    ErrorCode RefineGraphPass(int p_cef, float p_rngFactor = 1.0f, std::int32_t* p_newGraph = nullptr, bool p_install = true) {
+        if (!m_handle) return ErrorCode::EmptyIndex;
+        return static_cast<ErrorCode>(sptag_b200_refine_graph(m_handle, 0, sptag_b200_num_vectors(m_handle), p_cef,
+                                                              sptag_b200_graph_degree(m_handle), p_rngFactor, p_newGraph,
+                                                              nullptr, nullptr, p_install ? 1 : 0));
+    }
+
     // VectorIndex::SetParameter / GetParameter (BKTIndex.cpp:980-1025)
     ErrorCode SetParameter(const char* p_param, const char* p_value, const char* /*p_section*/ = nullptr) {
         return static_cast<ErrorCode>(sptag_b200_set_param(m_handle, p_param, p_value));

@@ -1,6 +1,8 @@
 // Drives the C++ adapter (sptag_b200/csrc/vector_index_adapter.hpp) exactly like the reference's own
 // callers drive VectorIndex: LoadIndex -> SetParameter -> SearchIndex(batch) -> read BasicResult.
-// usage: adapter_search <index folder> <queries.f32> <nq> <dim> <k> <maxcheck> <out.bin>
+// usage: adapter_search <index folder> <queries.f32> <nq> <dim> <k> <maxcheck> <out.bin> [<refine.bin> <cef> <nodes>]
+// With the optional arguments it also runs the builder-side calls: RefineSearchIndex on node 0 and one
+// RefineGraphPass (not installed), and writes [nodes x degree] new rows followed by node 0's CEF+1 (VID, Dist) pairs.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -10,7 +12,7 @@
 using namespace SPTAG_B200;
 
 int main(int argc, char** argv) {
-    if (argc != 8) {
+    if (argc != 8 && argc != 11) {
         std::fprintf(stderr, "usage: %s folder queries.f32 nq dim k maxcheck out.bin\n", argv[0]);
         return 2;
     }
@@ -46,5 +48,21 @@ int main(int argc, char** argv) {
         std::fwrite(&r.Dist, 4, 1, f);
     }
     std::fclose(f);
+
+    if (argc == 11) {
+        const int cef = std::atoi(argv[9]), nodes = std::atoi(argv[10]);
+        const int degree = sptag_b200_graph_degree(index->Handle());
+        std::vector<std::int32_t> rows((size_t)index->GetNumSamples() * degree);
+        if (index->RefineGraphPass(cef, 1.0f, rows.data(), /*install=*/false) != ErrorCode::Success) return 9;
+        QueryResult rq(nullptr, cef + 1, false);
+        if (index->RefineSearchIndex(0, rq) != ErrorCode::Success) return 10;
+        f = std::fopen(argv[8], "wb");
+        std::fwrite(rows.data(), 4, (size_t)nodes * degree, f);
+        for (int i = 0; i <= cef; ++i) {
+            std::fwrite(&rq.GetResult(i)->VID, 4, 1, f);
+            std::fwrite(&rq.GetResult(i)->Dist, 4, 1, f);
+        }
+        std::fclose(f);
+    }
     return 0;
 }

@@ -33,3 +33,26 @@ def test_cpp_adapter_matches_oracle():
     ids_o, d_o, _ = o.search(q, k)
     assert np.array_equal(ids, ids_o)
     assert np.array_equal(dist_bits, d_o.view(np.int32))
+
+
+def test_cpp_adapter_refine_calls_match_oracle():
+    """RefineSearchIndex / one RefineGraph pass through the C++ mirror (row f2) against the oracle."""
+    import __graft_entry__
+    exe = __graft_entry__.build_adapter_test()
+    folder = data_folder("bkt_l2_3k_30")
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:8]
+    cef, nodes = 40, 500
+    with tempfile.TemporaryDirectory() as tmp:
+        qf, of, rf = os.path.join(tmp, "q.f32"), os.path.join(tmp, "out.bin"), os.path.join(tmp, "refine.bin")
+        q.astype(np.float32).tofile(qf)
+        subprocess.check_call([exe, folder, qf, str(q.shape[0]), str(q.shape[1]), "10", "1024", of, rf, str(cef),
+                               str(nodes)])
+        raw = np.fromfile(rf, dtype=np.int32)
+    rows = raw[:nodes * files.degree].reshape(nodes, files.degree)
+    pairs = raw[nodes * files.degree:].reshape(cef + 1, 2)
+    o = reflib.OracleIndex(files)   # MaxCheckForRefineGraph from the index's ini, like the adapter's loader
+    rows_o, ids_o, d_o = o.refine_nodes(0, nodes, cef, files.degree, 1.0)
+    assert np.array_equal(rows, rows_o)
+    assert np.array_equal(pairs[:, 0], ids_o[0])
+    assert np.array_equal(pairs[:, 1], d_o[0].view(np.int32))
