@@ -306,6 +306,7 @@ int ref_refine_nodes(void* h, int first, int num, int cef, int neighborhood, flo
     case VectorValueType::Float: return refine_nodes_t<float>(idx.get(), first, num, cef, neighborhood, rng_factor, out_graph, res_ids, res_dists);
     case VectorValueType::Int8: return refine_nodes_t<std::int8_t>(idx.get(), first, num, cef, neighborhood, rng_factor, out_graph, res_ids, res_dists);
     case VectorValueType::UInt8: return refine_nodes_t<std::uint8_t>(idx.get(), first, num, cef, neighborhood, rng_factor, out_graph, res_ids, res_dists);
+    case VectorValueType::Int16: return refine_nodes_t<std::int16_t>(idx.get(), first, num, cef, neighborhood, rng_factor, out_graph, res_ids, res_dists);
     default: return 1;
     }
 }

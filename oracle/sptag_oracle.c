@@ -177,6 +177,60 @@ static float dist_i8u8(int cosine, int width, int is_unsigned, const void* x, co
     return cosine ? (float)(is_unsigned ? 65025 : 16129) - diff : diff;
 }
 
+/* int16 variants, AVX-512 build only (DistanceUtils.cpp:559-596 L2, :930-967 cosine; helpers :263-289).
+ * One 512-bit step covers 32 elements and yields 16 float lanes, t = 4L + p (128-bit lane L, position p):
+ *   cosine: _mm512_mul_epi16 = cvtepi32_ps(madd_epi16): lane t = (float)(int32)(x[2t]*y[2t] + x[2t+1]*y[2t+1]);
+ *   L2:     _mm512_sqdf_epi16: unpacklo/hi_epi16 sign-extend, dlo = (float)(x[8L+p]-y[8L+p]),
+ *           dhi = (float)(x[8L+4+p]-y[8L+4+p]); g++ -O3 contracts add_ps(mul_ps(dlo,dlo), mul_ps(dhi,dhi)) into
+ *           fma(dhi, dhi, dlo*dlo) (vmulps + vfmadd132ps in the compiled reference), the accumulation stays a vaddps.
+ * 256-/128-bit steps do the same on 8 / 4 lanes.  Plain-C tails: the 4-unrolled statements are FMA-contracted
+ * (vfmadd*ss), the single-element remainder loops are NOT (vmulss + vaddss); all checked against the compiled
+ * reference in tests/test_oracle_pin.py -- squares of int16 differences exceed 2^24, so every rounding shows. */
+static inline float lane_term_i16(int cosine, const int16_t* x, const int16_t* y, int base, int t)
+{
+    if (cosine) {
+        int32_t s = (int32_t)((uint32_t)((int32_t)x[base + 2 * t] * y[base + 2 * t]) +
+                              (uint32_t)((int32_t)x[base + 2 * t + 1] * y[base + 2 * t + 1]));
+        return (float)s;
+    }
+    const int off = base + 8 * (t / 4) + (t % 4);
+    const float dlo = (float)((int32_t)x[off] - (int32_t)y[off]);
+    const float dhi = (float)((int32_t)x[off + 4] - (int32_t)y[off + 4]);
+    return fmaf(dhi, dhi, dlo * dlo);
+}
+
+static float dist_i16(int cosine, int width, const int16_t* x, const int16_t* y, int len)
+{
+    int i = 0, j;
+    float diff;
+    float a16[16], a8[8], a4[4];
+    if (width != 16) return NAN; /* the AVX / SSE int16 variants are not restated */
+    for (j = 0; j < 16; j++) a16[j] = 0.0f;
+    for (; i + 32 <= len; i += 32)
+        for (j = 0; j < 16; j++) a16[j] = a16[j] + lane_term_i16(cosine, x, y, i, j);
+    for (j = 0; j < 8; j++) a8[j] = a16[j] + a16[j + 8];
+    for (; i + 16 <= len; i += 16)
+        for (j = 0; j < 8; j++) a8[j] = a8[j] + lane_term_i16(cosine, x, y, i, j);
+    for (j = 0; j < 4; j++) a4[j] = a8[j] + a8[j + 4];
+    for (; i + 8 <= len; i += 8)
+        for (j = 0; j < 4; j++) a4[j] = a4[j] + lane_term_i16(cosine, x, y, i, j);
+    diff = a4[0] + a4[1] + a4[2] + a4[3];
+    for (; i + 4 <= len; i += 4)
+        for (j = 0; j < 4; j++) diff = tail_f32(cosine, (float)x[i + j], (float)y[i + j], diff);
+    for (; i < len; i++) {
+        if (cosine) {
+            float c = (float)x[i] * (float)y[i];
+            diff = diff + c;
+        } else {
+            float c = (float)x[i] - (float)y[i];
+            c = c * c;
+            diff = diff + c;
+        }
+    }
+    /* base^2 - dot with the INTEGER literal 1073676289 = 32767^2 converted to float (DistanceUtils.cpp:966) */
+    return cosine ? (float)1073676289 - diff : diff;
+}
+
 float ora_distance(int32_t metric, int32_t value_type, int32_t simd_width,
                    const void* x, const void* y, int32_t dim)
 {
@@ -185,7 +239,8 @@ float ora_distance(int32_t metric, int32_t value_type, int32_t simd_width,
         return dist_f32(cosine, simd_width, (const float*)x, (const float*)y, dim);
     if (value_type == ORA_INT8 || value_type == ORA_UINT8)
         return dist_i8u8(cosine, simd_width, value_type == ORA_UINT8, x, y, dim);
-    return NAN; /* int16: not restated */
+    if (value_type == ORA_INT16) return dist_i16(cosine, simd_width, (const int16_t*)x, (const int16_t*)y, dim);
+    return NAN;
 }
 
 void ora_distance_f32_many(int32_t metric, int32_t simd_width, const float* a, const float* b,

@@ -23,7 +23,7 @@
 // search_kernel<DIM, COSINE, RPL, KDT, PQ, ELEM, MINB, DIRECT>:
 //   DIM    768 / 128: query slice in registers, fully unrolled; 0: any dimension (query in shared memory)
 //   RPL    registers per lane of the m_Results multiset (16: cap <= 512, 32: cap <= 1024)
-//   KDT    KD-tree flavour of the search loop;  PQ: rows are PQ codes;  ELEM 0 float, 1 int8, 2 uint8
+//   KDT    KD-tree flavour of the search loop;  PQ: rows are PQ codes;  ELEM 0 float, 1 int8, 2 uint8, 3 int16
 //   MINB   __launch_bounds__ minimum resident CTAs per SM (register cap);  DIRECT: experimental no-TMA row loads
 #pragma once
 
@@ -319,6 +319,80 @@ __device__ __forceinline__ float half_warp_distance_int(const unsigned char* __r
     }
     for (; i < dim; ++i) s = dist_tail<COSINE>((float)byte_val<UNSIGNED>(x[i]), (float)byte_val<UNSIGNED>(row[i]), s);
     return COSINE ? __fsub_rn(UNSIGNED ? 65025.0f : 16129.0f, s) : s;
+}
+
+// ------------------------------------------------------------------------------------------
+// int16 rows, AVX-512 variants (DistanceUtils.cpp:559-596 L2, :930-967 cosine; helpers :263-289).  One 512-bit step
+// covers 32 elements and yields 16 float lanes, t = 4L + p (128-bit lane L, position p):
+//   cosine: cvtepi32_ps(madd_epi16): lane t = (float)(int32)(x[2t]*y[2t] + x[2t+1]*y[2t+1]);
+//   L2: unpacklo/hi_epi16 sign-extension: dlo = x[8L+p] - y[8L+p], dhi = x[8L+4+p] - y[8L+4+p]; the compiled reference
+//       (g++ -O3) evaluates the lane as fma(dhi, dhi, dlo*dlo) and accumulates with a separate add.
+// 256-/128-bit steps: same on 8 / 4 lanes.  Plain-C tails: the 4-unrolled statements are FMA-contracted, the
+// single-element remainder loops are not (oracle/sptag_oracle.c dist_i16, pinned to the compiled reference).
+// ------------------------------------------------------------------------------------------
+template <bool COSINE>
+__device__ __forceinline__ float i16_lane_term(const short* __restrict__ x, const short* __restrict__ y, int base, int t) {
+    if (COSINE) {
+        const int x2 = *reinterpret_cast<const int*>(x + base + 2 * t);  // rows and queries are 4-byte aligned
+        const int y2 = *reinterpret_cast<const int*>(y + base + 2 * t);
+        const unsigned lo = (unsigned)((int)(short)(x2 & 0xffff) * (int)(short)(y2 & 0xffff));
+        const unsigned hi = (unsigned)((x2 >> 16) * (y2 >> 16));
+        return __int2float_rn((int)(lo + hi));
+    }
+    const int off = base + 8 * (t >> 2) + (t & 3);
+    const float dlo = __int2float_rn((int)x[off] - (int)y[off]);
+    const float dhi = __int2float_rn((int)x[off + 4] - (int)y[off + 4]);
+    return __fmaf_rn(dhi, dhi, __fmul_rn(dlo, dlo));
+}
+
+// x = query, row = vector (both 4-byte aligned int16 arrays); result valid in lane j == 0 of the half-warp
+template <bool COSINE>
+__device__ __forceinline__ float half_warp_distance_i16(const short* __restrict__ row, const short* __restrict__ x,
+                                                        int dim, int j) {
+    float acc = 0.0f;
+    int i = 0;
+    for (; i + 32 <= dim; i += 32) acc = __fadd_rn(acc, i16_lane_term<COSINE>(x, row, i, j));
+    float a8 = __fadd_rn(acc, __shfl_down_sync(kFull, acc, 8, 16));
+    if (dim & 16) {
+        if (j < 8) a8 = __fadd_rn(a8, i16_lane_term<COSINE>(x, row, i, j));
+        i += 16;
+    }
+    float a4 = __fadd_rn(a8, __shfl_down_sync(kFull, a8, 4, 16));
+    if (dim & 8) {
+        if (j < 4) a4 = __fadd_rn(a4, i16_lane_term<COSINE>(x, row, i, j));
+        i += 8;
+    }
+    const float a1 = __shfl_sync(kFull, a4, 1, 16);
+    const float a2 = __shfl_sync(kFull, a4, 2, 16);
+    const float a3 = __shfl_sync(kFull, a4, 3, 16);
+    float s = __fadd_rn(__fadd_rn(__fadd_rn(a4, a1), a2), a3);
+    if (dim & 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s = dist_tail<COSINE>((float)x[i + k], (float)row[i + k], s);
+        i += 4;
+    }
+    for (; i < dim; ++i) {
+        const float fx = (float)x[i], fy = (float)row[i];
+        const float c = COSINE ? __fmul_rn(fx, fy) : __fmul_rn(__fsub_rn(fx, fy), __fsub_rn(fx, fy));
+        s = __fadd_rn(s, c);
+    }
+    // base^2 - dot with the integer literal 1073676289 = 32767^2 converted to float (DistanceUtils.cpp:966)
+    return COSINE ? __fsub_rn(1073676288.0f, s) : s;
+}
+
+// integer rows by element type: ELEM 1 int8, 2 uint8, 3 int16
+template <bool COSINE, int ELEM>
+__device__ __forceinline__ float half_warp_distance_elem(const unsigned char* __restrict__ row,
+                                                         const unsigned char* __restrict__ x, int dim, int j) {
+    if (ELEM == 3)
+        return half_warp_distance_i16<COSINE>(reinterpret_cast<const short*>(row), reinterpret_cast<const short*>(x), dim, j);
+    return half_warp_distance_int<COSINE, ELEM == 2>(row, x, dim, j);
+}
+// the query element the KD split test reads (KDTree.h:255)
+template <int ELEM>
+__device__ __forceinline__ float int_query_elem(const void* q, int i) {
+    if (ELEM == 3) return (float)reinterpret_cast<const short*>(q)[i];
+    return (float)byte_val<ELEM == 2>(reinterpret_cast<const unsigned char*>(q)[i]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -813,8 +887,8 @@ struct WarpSearch {
                     const float* row = reinterpret_cast<const float*>(slot_ptr(st * p.stage_rows + r));
                     d = half_warp_distance<DIM, COSINE>(row, qr, qs, p.dim, j);
                 } else {
-                    d = half_warp_distance_int<COSINE, ELEM == 2>(slot_ptr(st * p.stage_rows + r),
-                                                                  reinterpret_cast<const unsigned char*>(qs), p.dim, j);
+                    d = half_warp_distance_elem<COSINE, ELEM>(slot_ptr(st * p.stage_rows + r),
+                                                              reinterpret_cast<const unsigned char*>(qs), p.dim, j);
                 }
                 if (j == 0 && r < rows) cand_dist[base + r] = d;
             }
@@ -985,7 +1059,7 @@ struct WarpSearch {
             if (ELEM == 0)
                 qv = qs[tn.z];
             else
-                qv = (float)byte_val<ELEM == 2>(reinterpret_cast<const unsigned char*>(qs)[tn.z]);
+                qv = int_query_elem<ELEM>(qs, tn.z);
             const float diff = __fsub_rn(qv, __int_as_float(tn.w));
             const float distanceBound = __fmaf_rn(diff, diff, distBound);
             int otherChild, bestChild;
@@ -1154,7 +1228,8 @@ __global__ void __launch_bounds__(32, MINB) search_kernel(const SearchParams p) 
         } else if (ELEM != 0) {
             const unsigned char* qb = p.queries + (size_t)q * p.query_stride_bytes;
             unsigned char* qd = reinterpret_cast<unsigned char*>(w.qs);
-            for (int i = lane; i < p.dim; i += 32) qd[i] = qb[i];
+            const int qbytes = p.dim * (ELEM == 3 ? 2 : 1);
+            for (int i = lane; i < qbytes; i += 32) qd[i] = qb[i];
         } else {
             const float* qg = reinterpret_cast<const float*>(p.queries + (size_t)q * p.query_stride_bytes);
             // static dims that are multiples of 16 never read the shared copy in the BKT flavour (no tails, no
@@ -1243,9 +1318,10 @@ __global__ void distance_batch_kernel(const unsigned char* vectors, unsigned lon
         QueryRegs<0> qr;
         d = half_warp_distance<0, COSINE>(row, qr, qv, dim, j);
     } else {
-        // odd dims would make the second query of a pair 1-byte aligned; the host pads the query stride to even
-        const unsigned char* qv = reinterpret_cast<const unsigned char*>(queries_v) + (size_t)q * ((dim + 1) & ~1);
-        d = half_warp_distance_int<COSINE, ELEM == 2>(vectors + (size_t)(ok ? id : 0) * row_stride_bytes, qv, dim, j);
+        // the host pads the query stride to a multiple of 4 bytes (2-/4-byte loads in the lane terms)
+        const unsigned char* qv = reinterpret_cast<const unsigned char*>(queries_v) +
+                                  (size_t)q * (((size_t)dim * (ELEM == 3 ? 2 : 1) + 3) & ~(size_t)3);
+        d = half_warp_distance_elem<COSINE, ELEM>(vectors + (size_t)(ok ? id : 0) * row_stride_bytes, qv, dim, j);
     }
     if (valid && j == 0) out[item] = ok ? d : SPTAG_B200_MAXDIST;
 }
@@ -1290,7 +1366,7 @@ __global__ void __launch_bounds__(128) rebuild_neighbors_kernel(const unsigned c
                 d = half_warp_distance<0, COSINE>(reinterpret_cast<const float*>(row), qr,
                                                   reinterpret_cast<const float*>(cand), dim, j);
             } else {
-                d = half_warp_distance_int<COSINE, ELEM == 2>(row, cand, dim, j);
+                d = half_warp_distance_elem<COSINE, ELEM>(row, cand, dim, j);
             }
             const bool reject = (j == 0) && (__fmul_rn(rng_factor, d) < dist);
             if (__any_sync(kFull, reject)) good = false;

@@ -175,6 +175,7 @@ SearchKernelFn pick_kernel(const sptag_b200_index* h, int mres_cap) {
     const bool l2 = (h->metric == SPTAG_B200_METRIC_L2);
     if (h->value_type == SPTAG_B200_VT_INT8) return l2 ? pick_int<false, 1>(mres_cap, kdt) : pick_int<true, 1>(mres_cap, kdt);
     if (h->value_type == SPTAG_B200_VT_UINT8) return l2 ? pick_int<false, 2>(mres_cap, kdt) : pick_int<true, 2>(mres_cap, kdt);
+    if (h->value_type == SPTAG_B200_VT_INT16) return l2 ? pick_int<false, 3>(mres_cap, kdt) : pick_int<true, 3>(mres_cap, kdt);
     const bool direct = (h->direct_load != 0);
     return l2 ? pick_dim<false>(h->dim, mres_cap, kdt, direct) : pick_dim<true>(h->dim, mres_cap, kdt, direct);
 }
@@ -191,7 +192,7 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
         if (h->algo != SPTAG_B200_ALGO_BKT || h->metric != SPTAG_B200_METRIC_L2)
             return fail(SPTAG_B200_LACK_OF_INPUTS, "quantized indexes are searchable as BKT + L2 only");
     } else if (h->value_type == SPTAG_B200_VT_INT16) {
-        return fail(SPTAG_B200_LACK_OF_INPUTS, "int16 vectors are not supported (DistanceUtils int16 variants are not built)");
+        // int16: every rounding step of the AVX-512 variants is reproduced (no exact-integer argument needed)
     } else if (h->value_type != SPTAG_B200_VT_FLOAT) {
         // int8 / uint8: every partial sum must stay an exactly representable integer for the kernel's and the
         // reference's summation orders to be interchangeable in the scalar tails; true for the supported range
@@ -926,8 +927,10 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
             if (l2) SPTAG_B200_RB(false, 0); else SPTAG_B200_RB(true, 0);
         } else if (h->value_type == SPTAG_B200_VT_INT8) {
             if (l2) SPTAG_B200_RB(false, 1); else SPTAG_B200_RB(true, 1);
-        } else {
+        } else if (h->value_type == SPTAG_B200_VT_UINT8) {
             if (l2) SPTAG_B200_RB(false, 2); else SPTAG_B200_RB(true, 2);
+        } else {
+            if (l2) SPTAG_B200_RB(false, 3); else SPTAG_B200_RB(true, 3);
         }
 #undef SPTAG_B200_RB
         g_launches++;
@@ -981,12 +984,12 @@ int sptag_b200_distance_batch(sptag_b200_handle h, const void* queries, int32_t 
     if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
     if (!queries || !ids || !out || num_queries <= 0 || ids_per_query <= 0)
         return fail(SPTAG_B200_LACK_OF_INPUTS, "null buffer");
-    if (h->q_type != 0 || h->value_type == SPTAG_B200_VT_INT16)
-        return fail(SPTAG_B200_LACK_OF_INPUTS, "distance_batch handles float / int8 / uint8 vectors without a quantizer");
+    if (h->q_type != 0)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "distance_batch handles raw (un-quantized) vectors only");
     std::lock_guard<std::mutex> lock(h->mu);
     DeviceGuard guard(h->device);
-    const bool is_float = (h->value_type == SPTAG_B200_VT_FLOAT);
-    const size_t qstride = is_float ? (size_t)h->dim * 4 : (size_t)((h->dim + 1) & ~1);  // integer rows: even stride
+    const size_t qrow = (size_t)h->dim * value_size(h->value_type);
+    const size_t qstride = (qrow + 3) & ~(size_t)3;  // integer rows: 4-byte aligned queries (2-/4-byte loads per lane)
     const size_t qbytes = (size_t)num_queries * qstride;
     const size_t total = (size_t)num_queries * ids_per_query;
     DeviceBuffer dq, di, dout;
@@ -995,10 +998,10 @@ int sptag_b200_distance_batch(sptag_b200_handle h, const void* queries, int32_t 
         dq.release(); di.release(); dout.release();
         return rc;
     }
-    if (is_float || (h->dim & 1) == 0)
+    if (qrow == qstride)
         cudaMemcpy(dq.ptr, queries, qbytes, cudaMemcpyHostToDevice);
     else
-        cudaMemcpy2D(dq.ptr, qstride, queries, (size_t)h->dim, (size_t)h->dim, (size_t)num_queries, cudaMemcpyHostToDevice);
+        cudaMemcpy2D(dq.ptr, qstride, queries, qrow, qrow, (size_t)num_queries, cudaMemcpyHostToDevice);
     cudaMemcpy(di.ptr, ids, total * 4, cudaMemcpyHostToDevice);
     const long long halfwarps = (long long)((total + 1) / 2) * 2;
     const int threads = 256;
@@ -1013,8 +1016,10 @@ int sptag_b200_distance_batch(sptag_b200_handle h, const void* queries, int32_t 
             if (l2) SPTAG_B200_DB(false, 0); else SPTAG_B200_DB(true, 0);
         } else if (h->value_type == SPTAG_B200_VT_INT8) {
             if (l2) SPTAG_B200_DB(false, 1); else SPTAG_B200_DB(true, 1);
-        } else {
+        } else if (h->value_type == SPTAG_B200_VT_UINT8) {
             if (l2) SPTAG_B200_DB(false, 2); else SPTAG_B200_DB(true, 2);
+        } else {
+            if (l2) SPTAG_B200_DB(false, 3); else SPTAG_B200_DB(true, 3);
         }
 #undef SPTAG_B200_DB
     }

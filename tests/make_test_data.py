@@ -46,6 +46,11 @@ SPECS = {
     "bkt_u8_l2_6k_128": ("BKT", "L2", lambda: _uint8_lowrank(6000, 128, 12, 63), lambda: _uint8_lowrank(200, 128, 12, 64), ""),
     "bkt_i8_l2_5k_100": ("BKT", "L2", lambda: _int8_lowrank(5000, 100, 12, 65), lambda: _int8_lowrank(200, 100, 12, 66), ""),
     "kdt_i8_l2_6k_32": ("KDT", "L2", lambda: _int8_lowrank(6000, 32, 8, 67), lambda: _int8_lowrank(200, 32, 8, 68), ""),
+    # int16 rows (DistanceUtils int16 variants; squares of differences exceed 2^24, every rounding step shows)
+    "bkt_i16_l2_5k_64": ("BKT", "L2", lambda: _int16_lowrank(5000, 64, 10, 81), lambda: _int16_lowrank(200, 64, 10, 82), ""),
+    "bkt_i16_cos_5k_40": ("BKT", "Cosine", lambda: _int16_lowrank(5000, 40, 8, 83), lambda: _norm_i16(_int16_lowrank(200, 40, 8, 84)), ""),
+    "bkt_i16_l2_4k_27": ("BKT", "L2", lambda: _int16_lowrank(4000, 27, 8, 85), lambda: _int16_lowrank(200, 27, 8, 86), ""),
+    "kdt_i16_l2_5k_32": ("KDT", "L2", lambda: _int16_lowrank(5000, 32, 8, 87), lambda: _int16_lowrank(200, 32, 8, 88), ""),
     # more than one space-partition tree (BKTNumber / KDTNumber; the reference's ReconstructIndexSimilarityTest uses KDTNumber=2)
     "bkt2_l2_6k_32": ("BKT", "L2", lambda: reflib.gen_iid(6000, 32, 71), lambda: reflib.gen_iid(200, 32, 72), "BKTNumber=2"),
     "kdt2_l2_6k_32": ("KDT", "L2", lambda: reflib.gen_iid(6000, 32, 73), lambda: reflib.gen_iid(200, 32, 74), "KDTNumber=2"),
@@ -63,6 +68,17 @@ def _norm_i8(x):
     v = x.astype(np.float64)
     n = np.sqrt((v * v).sum(1, keepdims=True))
     return np.trunc(v / n * 127).astype(np.int8)
+
+
+def _int16_lowrank(n, dim, rank, seed):
+    return np.clip(np.round(6000.0 * reflib.gen_lowrank(n, dim, rank, seed)), -32767, 32767).astype(np.int16)
+
+
+def _norm_i16(x):
+    # Utils::Normalize for int16 (CommonUtils.h:62-76): base = 32767, truncation toward zero
+    v = x.astype(np.float64)
+    n = np.sqrt((v * v).sum(1, keepdims=True))
+    return np.trunc(v / n * 32767).astype(np.int16)
 
 
 def _int8_lowrank(n, dim, rank, seed):

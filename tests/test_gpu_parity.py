@@ -327,7 +327,8 @@ def test_gpu_matches_reference_golden_outputs(name):
 # ---------------------------------------------------------------------------------------------
 # int8 / uint8 element types (DistanceUtils integer variants)
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["bkt_i8_cos_6k_64", "bkt_u8_l2_6k_128", "bkt_i8_l2_5k_100", "kdt_i8_l2_6k_32"])
+@pytest.mark.parametrize("name", ["bkt_i8_cos_6k_64", "bkt_u8_l2_6k_128", "bkt_i8_l2_5k_100", "kdt_i8_l2_6k_32",
+                                  "bkt_i16_l2_5k_64", "bkt_i16_cos_5k_40", "bkt_i16_l2_4k_27", "kdt_i16_l2_5k_32"])
 def test_integer_index_search_bit_exact(name):
     from sptag_b200 import B200Index
     folder = data_folder(name)
@@ -341,13 +342,15 @@ def test_integer_index_search_bit_exact(name):
         idx.close()
 
 
-@pytest.mark.parametrize("vt,dt,lo,hi", [(0, np.int8, -127, 128), (1, np.uint8, 0, 256)])
+@pytest.mark.parametrize("vt,dt,lo,hi", [(0, np.int8, -127, 128), (1, np.uint8, 0, 256), (2, np.int16, -32768, 32768),
+                                         (2, np.int16, -2000, 2000)])
 @pytest.mark.parametrize("metric", [0, 1])
 def test_integer_distance_kernel_bit_exact_all_dims(vt, dt, lo, hi, metric):
     from sptag_b200 import B200Index, capi
     rng = np.random.default_rng(13)
     L = reflib.ora()
-    for dim in [1, 3, 4, 5, 15, 16, 17, 31, 32, 33, 48, 63, 64, 65, 80, 96, 100, 127, 128, 131, 200, 256, 258]:
+    for dim in [1, 2, 3, 4, 5, 7, 8, 9, 12, 15, 16, 17, 24, 27, 31, 32, 33, 40, 48, 63, 64, 65, 80, 96, 100, 127, 128, 131,
+                200, 256, 258]:
         n, nq, per = 129, 7, 21
         x = rng.integers(lo, hi, (n, dim)).astype(dt)
         q = rng.integers(lo, hi, (nq, dim)).astype(dt)

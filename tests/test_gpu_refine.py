@@ -24,6 +24,9 @@ CASES = [
     ("bkt_i8_cos_6k_64", 50, 512, 400),
     ("bkt_u8_l2_6k_128", 50, 512, 400),
     ("bkt_i8_l2_5k_100", 31, 300, 400),
+    ("bkt_i16_l2_4k_27", 40, 512, 400),
+    ("bkt_i16_cos_5k_40", 40, 512, 400),
+    ("kdt_i16_l2_5k_32", 40, 512, 400),
 ]
 
 

@@ -238,10 +238,14 @@ def test_quantized_search_bit_exact_vs_reference(oracle_lib, name):
 # int8 / uint8 element types (DistanceUtils.cpp:305-558, :684-874)
 # ---------------------------------------------------------------------------------------------
 @needs_ref
-@pytest.mark.parametrize("vt,dt,lo,hi", [(reflib.VT_INT8, np.int8, -127, 128), (reflib.VT_UINT8, np.uint8, 0, 256)])
+@pytest.mark.parametrize("vt,dt,lo,hi", [(reflib.VT_INT8, np.int8, -127, 128), (reflib.VT_UINT8, np.uint8, 0, 256),
+                                         (reflib.VT_INT16, np.int16, -32768, 32768),
+                                         (reflib.VT_INT16, np.int16, -3000, 3000)])
 def test_integer_distance_bit_exact_vs_reference(oracle_lib, vt, dt, lo, hi):
     rng = np.random.default_rng(9)
     width = {512: 16, 256: 8, 128: 4, 0: 1}[reflib.ref().ref_isa()]
+    if vt == reflib.VT_INT16 and width != 16:
+        pytest.skip("the int16 restatement covers the AVX-512 variants only")
     for metric in (0, 1):
         for dim in [1, 3, 4, 5, 15, 16, 17, 31, 32, 33, 47, 48, 63, 64, 65, 79, 80, 95, 96, 100, 127, 128, 131, 192,
                     200, 256, 258]:
@@ -254,7 +258,8 @@ def test_integer_distance_bit_exact_vs_reference(oracle_lib, vt, dt, lo, hi):
 
 
 @needs_ref
-@pytest.mark.parametrize("name", ["bkt_i8_cos_6k_64", "bkt_u8_l2_6k_128", "bkt_i8_l2_5k_100", "kdt_i8_l2_6k_32"])
+@pytest.mark.parametrize("name", ["bkt_i8_cos_6k_64", "bkt_u8_l2_6k_128", "bkt_i8_l2_5k_100", "kdt_i8_l2_6k_32",
+                                  "bkt_i16_l2_5k_64", "bkt_i16_cos_5k_40", "bkt_i16_l2_4k_27", "kdt_i16_l2_5k_32"])
 def test_integer_index_search_bit_exact_vs_reference(oracle_lib, name):
     folder = data_folder(name)
     files = reflib.IndexFiles(folder)
@@ -333,7 +338,8 @@ def test_filtered_search_bit_exact_vs_reference(oracle_lib, name):
 @pytest.mark.parametrize("name,cef,mcr", [("bkt_l2_dups", 20, 256), ("bkt_l2_20k_32", 100, 2048),
                                           ("bkt_cos_3k_768", 1000, 8192), ("kdt_l2_10k_64", 64, 1024),
                                           ("bkt_i8_cos_6k_64", 50, 512), ("bkt_u8_l2_6k_128", 50, 512),
-                                          ("bkt_l2_3k_30", 64, 1024)])
+                                          ("bkt_l2_3k_30", 64, 1024), ("bkt_i16_l2_4k_27", 40, 512),
+                                          ("bkt_i16_cos_5k_40", 40, 512)])
 def test_refine_bit_exact_vs_reference(oracle_lib, name, cef, mcr):
     """NeighborhoodGraph::RefineNode per node on the loaded index (RefineSearchIndex + RebuildNeighbors run by the
     reference itself) against the oracle's restatement."""
