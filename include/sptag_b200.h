@@ -177,6 +177,24 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
 int sptag_b200_get_graph(sptag_b200_handle h, int32_t* out_graph);
 int32_t sptag_b200_graph_degree(sptag_b200_handle h);
 
+/* Replaces: VectorIndex::GetIterator + ResultIterator::Next / Close (VectorIndex.h:43-49, ResultIterator.cpp,
+ * BKTIndex.cpp:354-427 SearchIterative, :650-696) for a BATCH of queries -- one resumable search per query.
+ *   open:  rents one WorkSpace per query in HBM (visited set, NGQueue, SPTQueue; about N/8 + 8*min(30*MaxCheck, N)
+ *          + 8*min(10*MaxCheck, nodes) bytes each) and copies the queries (they need not outlive the call).
+ *          MaxCheck / MaxCheckForRefineGraph are sampled here, like the reference's RentWorkSpace.
+ *   next:  ResultIterator::Next(batch) for every query: up to `batch` further results per query in pop order, sorted
+ *          ascending within the call; out_ids / out_dists are [num_queries x batch] with unfilled slots (-1, MaxDist),
+ *          out_counts[q] = resultCount (nullable), out_relaxed_mono[q] = RelaxedMono (nullable).  As in the reference,
+ *          the effective batch of a query is capped by the result count of its previous call (ResultIterator.cpp:36-41,
+ *          :52), so a batch never grows and an exhausted iterator stays exhausted.  batch <= 1024.
+ *   close: returns the work spaces.  The handle must outlive its iterators.
+ * BKT without quantizer only; KDT returns Fail like the reference ("ITERATIVE NOT SUPPORT FOR KDT"). */
+typedef struct sptag_b200_iterator* sptag_b200_iter;
+int sptag_b200_iterator_open(sptag_b200_handle h, const void* queries, int32_t num_queries, sptag_b200_iter* out);
+int sptag_b200_iterator_next(sptag_b200_iter it, int32_t batch, int32_t* out_ids, float* out_dists,
+                             int32_t* out_counts, uint8_t* out_relaxed_mono);
+void sptag_b200_iterator_close(sptag_b200_iter it);
+
 /* Vector-partition sharding: merges `num_lists` per-shard result lists of a query
  * batch, each [num_queries x k] ascending by (dist,id), into the global top-k with the comparator
  * of QueryResultSet.h:17-26.  All pointers are DEVICE pointers on `device`; lists are laid out

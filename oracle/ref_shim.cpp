@@ -18,6 +18,7 @@
 #include "inc/Core/Common/IQuantizer.h"
 #include "inc/Core/MetadataSet.h"
 #include "inc/Core/Common/QueryResultSet.h"
+#include "inc/Core/ResultIterator.h"
 #include "inc/Core/Common/RelativeNeighborhoodGraph.h"
 #include "inc/Helper/Logging.h"
 
@@ -309,6 +310,33 @@ int ref_refine_nodes(void* h, int first, int num, int cef, int neighborhood, flo
     case VectorValueType::Int16: return refine_nodes_t<std::int16_t>(idx.get(), first, num, cef, neighborhood, rng_factor, out_graph, res_ids, res_dists);
     default: return 1;
     }
+}
+
+// VectorIndex::GetIterator / ResultIterator::Next / Close (ResultIterator.cpp) -- the reference's own iterator object.
+void* ref_iter_open(void* h, const void* query) {
+    auto& idx = ((RefHandle*)h)->index;
+    std::shared_ptr<ResultIterator> it = idx->GetIterator(query);
+    if (!it) return nullptr;
+    return new std::shared_ptr<ResultIterator>(it);
+}
+
+// -> resultCount; ids/dists get `batch` entries (the QueryResult buffer after Next), *relaxed = GetRelaxedMono()
+int ref_iter_next(void* itp, int batch, int* ids, float* dists, int* relaxed) {
+    auto& it = *(std::shared_ptr<ResultIterator>*)itp;
+    std::shared_ptr<QueryResult> res = it->Next(batch);
+    const int count = res->GetResultNum();
+    for (int j = 0; j < batch; ++j) {
+        ids[j] = j < count ? res->GetResult(j)->VID : -1;
+        dists[j] = j < count ? res->GetResult(j)->Dist : MaxDist;
+    }
+    if (relaxed) *relaxed = it->GetRelaxedMono() ? 1 : 0;
+    return count;
+}
+
+void ref_iter_close(void* itp) {
+    auto* p = (std::shared_ptr<ResultIterator>*)itp;
+    (*p)->Close();
+    delete p;
 }
 
 // Install the counter-reading factory (single-query stats below need it). Irreversible for h.

@@ -1009,3 +1009,137 @@ int ora_refine_nodes(const ora_index* idx, int32_t first_node, int32_t num_nodes
     }
     return 0;
 }
+
+
+/* ------------------------------------------------------------------------------------------ */
+/* ResultIterator (ResultIterator.cpp, BKTIndex.cpp:354-427, :650-696): resumable search       */
+/* ------------------------------------------------------------------------------------------ */
+
+struct ora_iterator {
+    ora_index idx; /* shallow copy: the arrays stay the caller's */
+    ws_t ws;
+    void* query;
+    int is_first, relaxed_mono, max_batch;
+    res_t* res;
+};
+
+/* VectorIndex::GetIterator (BKTIndex.cpp:650-657): RentWorkSpace(1) = a fresh work space after
+ * Initialize(max(MaxCheck, MaxCheckForRefineGraph)) + Reset(MaxCheck, 1) (:686-696).  BKT, no quantizer. */
+ora_iterator* ora_iter_open(const ora_index* idx, const void* query)
+{
+    static const size_t elem[4] = {1, 1, 2, 4};
+    if (idx->tree_kind != ORA_BKT || idx->quantizer || idx->filter) return NULL; /* "ITERATIVE NOT SUPPORT FOR KDT" */
+    ora_iterator* it = (ora_iterator*)calloc(1, sizeof(*it));
+    it->idx = *idx;
+    const size_t qb = elem[idx->value_type] * (size_t)idx->dim;
+    it->query = malloc(qb);
+    memcpy(it->query, query, qb);
+    const int alloc_check = idx->max_check > idx->max_check_refine ? idx->max_check : idx->max_check_refine;
+    ws_init(&it->ws, idx->n, alloc_check);
+    ws_reset(&it->ws, idx->max_check, 1);
+    it->is_first = 1;
+    it->relaxed_mono = 0;
+    it->max_batch = 0;
+    it->res = NULL;
+    return it;
+}
+
+/* ResultIterator::Next(batch) -> SearchIndexIterativeNext (BKTIndex.cpp:659-675) -> SearchIterative<notDeleted, isDup>
+ * (:354-427).  ids/dists: [batch], ascending over the returned entries, unfilled (-1, MaxDist); returns resultCount;
+ * *relaxed_mono = WorkSpace::m_relaxedMono after the call. */
+int ora_iter_next(ora_iterator* it, int32_t batch, int32_t* ids, float* dists, int32_t* relaxed_mono)
+{
+    const ora_index* idx = &it->idx;
+    const ora_bkt_node* nodes = (const ora_bkt_node*)idx->nodes;
+    static const size_t elem[4] = {1, 1, 2, 4};
+    ws_t* ws = &it->ws;
+    /* ResultIterator::Next (ResultIterator.cpp:31-42, :52): the first call creates the QueryResult with `batch` slots;
+     * afterwards the batch is capped by QueryResult::GetResultNum(), which the previous call left at ITS resultCount
+     * (SetResultNum(resultCount)) -- an iterator's batch can only shrink */
+    const int requested = batch;
+    if (it->res == NULL) {
+        it->res = (res_t*)malloc(sizeof(res_t) * (size_t)(batch > 0 ? batch : 1));
+    } else if (batch > it->max_batch) {
+        batch = it->max_batch;
+    }
+    for (int i = batch; i < requested; i++) {
+        ids[i] = -1;
+        dists[i] = kMaxDist();
+    }
+    res_t* res = it->res;
+    for (int i = 0; i < batch; i++) { /* QueryResult::Reset */
+        res[i].vid = -1;
+        res[i].dist = kMaxDist();
+    }
+    /* WorkSpace::ResetResult(m_iMaxCheck, batch) (WorkSpace.h:280-286) */
+    dpq_clear(&ws->results, idx->max_check / 16 > batch ? idx->max_check / 16 : batch);
+    ws->no_better = 0;
+    ws->tree_checked = 0;
+    ws->checked = 0;
+
+    qctx_t c = {idx, it->query, elem[idx->value_type] * (size_t)idx->dim, idx->metric != ORA_L2};
+    if (it->is_first) {
+        bkt_init_search_trees(&c, ws);
+        bkt_search_trees(&c, ws, idx->initial_pivots);
+    }
+    it->is_first = 0;
+    int count = 0;
+    const int checkPos = idx->degree - 1;
+    while (ws->ng.count != 0) {
+        pair_t gnode = heap_pop(&ws->ng);
+        int32_t tmpNode = gnode.node;
+        const int32_t* node = idx->graph + (size_t)tmpNode * idx->degree;
+        ws->nexpand++;
+        if (not_deleted(idx, tmpNode)) {
+            res_add_point(res, batch, tmpNode, gnode.distance);
+            count++;
+            if (gnode.distance > dpq_worst(&ws->results) || ws->checked > ws->max_check) it->relaxed_mono = 1;
+        }
+        int32_t checkNode = node[checkPos];
+        if (checkNode < -1) {
+            const ora_bkt_node* tnode = &nodes[-2 - checkNode];
+            int32_t i = -tnode->childStart;
+            while (i < tnode->childEnd) {
+                tmpNode = nodes[i].centerid;
+                if (not_deleted(idx, tmpNode)) {
+                    float d = qdist(&c, ws, tmpNode);
+                    if (!ws_check_and_set(ws, tmpNode)) {
+                        pair_t p = {tmpNode, d};
+                        heap_insert(&ws->ng, p);
+                    }
+                }
+                i++;
+            }
+        }
+        for (int i = 0; i <= checkPos; i++) {
+            int32_t nn_index = node[i];
+            if (nn_index < 0) break;
+            if (ws_check_and_set(ws, nn_index)) continue;
+            float d = qdist(&c, ws, nn_index);
+            ws->checked++;
+            pair_t p = {nn_index, d};
+            heap_insert(&ws->ng, p);
+            dpq_insert(&ws->results, d);
+        }
+        if (heap_top(&ws->ng)->distance > heap_top(&ws->spt)->distance)
+            bkt_search_trees(&c, ws, idx->other_pivots + ws->checked);
+        if (count >= batch) break;
+    }
+    res_sort(res, batch);
+    for (int i = 0; i < batch; i++) {
+        ids[i] = res[i].vid;
+        dists[i] = res[i].dist;
+    }
+    if (relaxed_mono) *relaxed_mono = it->relaxed_mono;
+    it->max_batch = count; /* m_queryResult->SetResultNum(resultCount) */
+    return count;
+}
+
+void ora_iter_close(ora_iterator* it)
+{
+    if (!it) return;
+    ws_free(&it->ws);
+    free(it->query);
+    free(it->res);
+    free(it);
+}

@@ -107,6 +107,13 @@ int ora_search_batch(const ora_index* idx, const void* queries, int32_t nq, int3
 int ora_refine_nodes(const ora_index* idx, int32_t first_node, int32_t num_nodes, int32_t cef, int32_t neighborhood,
                      float rng_factor, int32_t* out_graph, int32_t* res_ids, float* res_dists, int32_t threads);
 
+/* Restatement of VectorIndex::GetIterator / ResultIterator::Next / Close (ResultIterator.cpp; BKTIndex.cpp:354-427,
+ * :650-696): one resumable search.  BKT without quantizer only (the reference's KDT has no iterator). */
+typedef struct ora_iterator ora_iterator;
+ora_iterator* ora_iter_open(const ora_index* idx, const void* query);
+int ora_iter_next(ora_iterator* it, int32_t batch, int32_t* ids, float* dists, int32_t* relaxed_mono);
+void ora_iter_close(ora_iterator* it);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,7 @@ EXPORTS = [
     "sptag_b200_merge_topk", "sptag_b200_last_kernel_ms", "sptag_b200_launch_count",
     "sptag_b200_num_vectors", "sptag_b200_dim", "sptag_b200_value_type", "sptag_b200_metric",
     "sptag_b200_algo", "sptag_b200_last_error", "sptag_b200_refine_graph", "sptag_b200_get_graph",
-    "sptag_b200_graph_degree",
+    "sptag_b200_graph_degree", "sptag_b200_iterator_open", "sptag_b200_iterator_next", "sptag_b200_iterator_close",
 ]
 
 
@@ -76,6 +76,10 @@ def lib():
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.sptag_b200_get_graph.argtypes = [C.c_void_p, C.c_void_p]
         L.sptag_b200_graph_degree.argtypes = [C.c_void_p]
+        L.sptag_b200_iterator_open.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+        L.sptag_b200_iterator_next.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sptag_b200_iterator_close.argtypes = [C.c_void_p]
+        L.sptag_b200_iterator_close.restype = None
         L.sptag_b200_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.sptag_b200_launch_count.restype = C.c_int64
         for f in ("num_vectors", "dim", "value_type", "metric", "algo"):
@@ -231,6 +235,10 @@ class B200Index:
         _check(lib().sptag_b200_get_graph(self._h, g.ctypes.data))
         return g
 
+    def iterators(self, queries):
+        """VectorIndex::GetIterator for every query of a batch -> B200Iterators (next(batch) / close())."""
+        return B200Iterators(self, queries)
+
     def distance_batch(self, queries, ids):
         queries = np.ascontiguousarray(queries, dtype=np.float32)
         ids = np.ascontiguousarray(ids, dtype=np.int32)
@@ -243,6 +251,39 @@ class B200Index:
         ms = C.c_float()
         _check(lib().sptag_b200_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+
+class B200Iterators:
+    """A batch of ResultIterators (ResultIterator.cpp): one resumable search per query, state resident in HBM."""
+
+    def __init__(self, index, queries):
+        queries = np.ascontiguousarray(queries)
+        self.index = index           # the handle must outlive the iterators
+        self.nq = queries.shape[0]
+        h = C.c_void_p()
+        _check(lib().sptag_b200_iterator_open(index._h, queries.ctypes.data, self.nq, C.byref(h)))
+        self._it = h
+
+    def next(self, batch):
+        """ResultIterator::Next(batch) for every query -> (counts [nq], ids [nq, batch], dists [nq, batch], relaxed [nq])."""
+        ids = np.empty((self.nq, batch), np.int32)
+        dists = np.empty((self.nq, batch), np.float32)
+        counts = np.empty(self.nq, np.int32)
+        relaxed = np.empty(self.nq, np.uint8)
+        _check(lib().sptag_b200_iterator_next(self._it, batch, ids.ctypes.data, dists.ctypes.data, counts.ctypes.data,
+                                              relaxed.ctypes.data))
+        return counts, ids, dists, relaxed.astype(bool)
+
+    def close(self):
+        if self._it:
+            lib().sptag_b200_iterator_close(self._it)
+            self._it = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def merge_topk(device, d_ids_ptr, d_dists_ptr, num_lists, nq, k, d_out_ids_ptr, d_out_dists_ptr, stream=0):

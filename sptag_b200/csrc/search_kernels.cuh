@@ -1034,6 +1034,89 @@ struct WarpSearch {
     }
 
     // ------------------------------------------------------------------------------------
+    // BKT::Index<T>::SearchIterative<notDeleted, isDup> (BKTIndex.cpp:354-427): the resumable loop behind
+    // ResultIterator::Next.  Differences from Search: every popped live node is a result (at most `batch` per call),
+    // neighbours enter NGQueue unconditionally (m_Results only feeds the relaxed-monotonicity flag), duplicate-group
+    // members get their own distance and enter NGQueue, and there is no stop rule besides `count >= batch`.
+    // Results are appended to this query's arena `tk` (sorted afterwards); returns resultCount.
+    // ------------------------------------------------------------------------------------
+    __device__ __forceinline__ int bkt_search_iterative(bool is_first, int batch, int& relaxed) {
+        if (is_first) {
+            init_search_trees();
+            search_trees(p.initial_pivots);
+        }
+        int count = 0;
+        const int checkPos = p.degree - 1;
+        while (ng.count != 0) {
+            const int2 gnode = heap_pop(ng, lane);
+            const int popped = gnode.x;
+            const float gdist = pair_dist(gnode);
+            const int* node = p.graph + (size_t)popped * p.degree;
+            nexpand++;
+            int nn = (lane <= checkPos) ? node[lane] : -1;
+            if (not_deleted(popped)) {
+                if (lane == 0) tk[tk_count] = make_pair(popped, gdist);
+                ++tk_count;
+                ++count;
+                if (gdist > mres.worst || checked > p.max_check) relaxed = 1;
+            }
+            const int checkNode = node[checkPos];
+            if (checkNode < -1) {
+                const int tn = -2 - checkNode;
+                const int tcs = p.nodes[3 * tn + 1], tce = p.nodes[3 * tn + 2];
+                for (int base = -tcs; base < tce; base += 32) {
+                    const int i = base + lane;
+                    const int id = (i < tce) ? p.nodes[3 * i] : -1;
+                    const bool live = (i < tce) && not_deleted(id);
+                    const unsigned livemask = __ballot_sync(kFull, live);
+                    const int cnt = __popc(livemask);
+                    __syncwarp();
+                    if (live) cand_id[__popc(livemask & ((1u << lane) - 1u))] = id;
+                    compute_dists(cnt);
+                    for (int r = 0; r < cnt; ++r) {  // the distance is taken first, CheckAndSet second (:394-401)
+                        const int mid = cand_id[r];
+                        const float md = cand_dist[r];
+                        if (!check_and_set_uniform(mid)) heap_insert(ng, mid, md, lane);
+                    }
+                    __syncwarp();
+                }
+            }
+            for (int cbase = 0; cbase <= checkPos; cbase += 32) {
+                if (cbase > 0) nn = (cbase + lane <= checkPos) ? node[cbase + lane] : -1;
+                const bool in_row = (cbase + lane <= checkPos);
+                const unsigned negmask = __ballot_sync(kFull, in_row && nn < 0) | ~__ballot_sync(kFull, in_row);
+                const int first_neg = negmask ? (__ffs(negmask) - 1) : 32;
+                const bool active = lane < first_neg;
+                const unsigned same = __match_any_sync(kFull, active ? nn : (-1 - lane));
+                const bool leader = active && ((__ffs(same) - 1) == lane);
+                bool fresh = false;
+                if (leader) {
+                    const unsigned bit = 1u << (nn & 31);
+                    const unsigned old = atomicOr(&visited[nn >> 5], bit);
+                    fresh = (old & bit) == 0;
+                }
+                const unsigned freshmask = __ballot_sync(kFull, fresh);
+                const int cnt = __popc(freshmask);
+                __syncwarp();
+                if (fresh) cand_id[__popc(freshmask & ((1u << lane) - 1u))] = nn;
+                compute_dists(cnt);
+                checked += cnt;
+                for (int r = 0; r < cnt; ++r) {
+                    const int id = cand_id[r];
+                    const float d = cand_dist[r];
+                    heap_insert(ng, id, d, lane);
+                    mres.insert(d, lane);
+                }
+                __syncwarp();
+                if (first_neg < 32) break;
+            }
+            if (heap_top_dist(ng) > heap_top_dist(spt)) search_trees(p.other_pivots + checked);
+            if (count >= batch) break;
+        }
+        return count;
+    }
+
+    // ------------------------------------------------------------------------------------
     // KDT flavour: KDTree::KDTSearch (KDTree.h:233-271, tail recursion as a loop),
     // InitSearchTrees/SearchTrees (KDTree.h:213-231), KDT::Index<T>::Search (KDTIndex.cpp:182-241)
     // ------------------------------------------------------------------------------------
@@ -1286,6 +1369,105 @@ __global__ void __launch_bounds__(32, MINB) search_kernel(const SearchParams p) 
             s[5] = w.nexpand;
             s[6] = w.ntree;
             s[7] = 0;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// ResultIterator::Next for a batch of open iterators (ResultIterator.cpp:31-55 -> SearchIndexIterativeNext,
+// BKTIndex.cpp:659-675).  Every query owns persistent arenas in HBM -- visited bitmap, NGQueue, SPTQueue (the
+// reference's rented WorkSpace) -- indexed by query, not by slot; the shared-memory queue heads are restored from and
+// flushed to those arenas around each call.  state[q] = {ng count, spt count, first call, relaxedMono, result slots}.
+// p.k = the batch the caller asked for; the effective batch of a query is capped by the result count of its previous
+// call (QueryResult::SetResultNum(resultCount), ResultIterator.cpp:36-41, :52).
+// ------------------------------------------------------------------------------------------
+constexpr int kIterStateInts = 8;
+
+template <bool COSINE, int RPL, int ELEM>
+__global__ void __launch_bounds__(32, 12) iterate_kernel(const SearchParams p, int* __restrict__ state,
+                                                         int* __restrict__ out_counts,
+                                                         unsigned char* __restrict__ out_relaxed) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x;
+    WarpSearch<0, COSINE, RPL, false, ELEM, false> w(p, lane);
+    w.ring = smem;
+    w.cand_id = reinterpret_cast<int*>(smem + p.off_cand);
+    w.cand_dist = reinterpret_cast<float*>(smem + p.off_cand + 128);
+    w.bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+    w.qs = reinterpret_cast<float*>(smem + p.off_query);
+    w.vlog = nullptr;  // the bitmap belongs to the iterator and is never cleared between calls
+    w.ng.s = reinterpret_cast<int2*>(smem + p.off_ng);
+    w.ng.H = p.h_ng;
+    w.ng.length = p.ng_length;
+    w.ng.lastlevel = p.ng_lastlevel;
+    w.spt.s = reinterpret_cast<int2*>(smem + p.off_spt);
+    w.spt.H = p.h_spt;
+    w.spt.length = p.spt_length;
+    w.spt.lastlevel = p.spt_lastlevel;
+    w.phase_bits = 0;
+    if (lane == 0) {
+        for (int s = 0; s < p.stages; ++s) mbar_init(&w.bars[s], 1);
+        mbar_fence_init();
+        w.ng.s[0] = make_pair(-1, SPTAG_B200_MAXDIST);
+        w.spt.s[0] = make_pair(-1, SPTAG_B200_MAXDIST);
+    }
+    __syncwarp();
+
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = (int)atomicAdd(p.work_counter, 1u);
+        q = __shfl_sync(kFull, q, 0);
+        if (q >= p.nq) break;
+        int* st = state + (size_t)q * kIterStateInts;
+        w.visited = p.visited + (size_t)q * p.visited_words;
+        w.ng.g = p.ng_spill + (size_t)q * p.ng_spill_entries;
+        w.spt.g = p.spt_spill + (size_t)q * p.spt_spill_entries;
+        w.tk = p.topk + (size_t)q * p.topk_pad;
+        w.ng.count = st[0];
+        w.spt.count = st[1];
+        const bool is_first = st[2] != 0;
+        int relaxed = st[3];
+        const int slots = st[4];
+        const int batch = (slots < 0) ? p.k : min(p.k, slots);
+        // queue heads back into shared memory
+        for (int i = 1 + lane; i <= min(w.ng.count, w.ng.H); i += 32) w.ng.s[i] = w.ng.g[i];
+        for (int i = 1 + lane; i <= min(w.spt.count, w.spt.H); i += 32) w.spt.s[i] = w.spt.g[i];
+        // WorkSpace::ResetResult(m_iMaxCheck, batch) (WorkSpace.h:280-286)
+        w.mres.reset(max(p.max_check / 16, batch), lane);
+        w.checked = w.ndist = w.nexpand = w.ntree = 0;
+        w.tree_checked = w.no_better = 0;
+        w.vlog_count = 0;
+        w.tk_count = 0;
+        {   // the query (element type of the index) -> shared memory
+            const unsigned char* qb = p.queries + (size_t)q * p.query_stride_bytes;
+            unsigned char* qd = reinterpret_cast<unsigned char*>(w.qs);
+            const int qbytes = p.dim * (ELEM == 0 ? 4 : (ELEM == 3 ? 2 : 1));
+            for (int i = lane; i < qbytes; i += 32) qd[i] = qb[i];
+        }
+        __syncwarp();
+
+        const int count = w.bkt_search_iterative(is_first, batch, relaxed);
+
+        // QueryResultSet::SortResult over the `count` returned entries; the rest of the caller's row is (-1, MaxDist)
+        __syncwarp();
+        w.res_sort();
+        for (int i = lane; i < p.k; i += 32) {
+            const int2 e = (i < count) ? w.tk[i] : make_pair(-1, SPTAG_B200_MAXDIST);
+            p.out_ids[(size_t)q * p.k + i] = (e.x >= 0) ? e.x + p.id_offset : e.x;
+            p.out_dists[(size_t)q * p.k + i] = __int_as_float(e.y);
+        }
+        // flush the queue heads and the scalars
+        for (int i = 1 + lane; i <= min(w.ng.count, w.ng.H); i += 32) w.ng.g[i] = w.ng.s[i];
+        for (int i = 1 + lane; i <= min(w.spt.count, w.spt.H); i += 32) w.spt.g[i] = w.spt.s[i];
+        if (lane == 0) {
+            st[0] = w.ng.count;
+            st[1] = w.spt.count;
+            st[2] = 0;
+            st[3] = relaxed;
+            st[4] = count;  // m_queryResult->SetResultNum(resultCount)
+            out_counts[q] = count;
+            out_relaxed[q] = (unsigned char)relaxed;
         }
         __syncwarp();
     }

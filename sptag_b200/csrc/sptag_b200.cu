@@ -122,6 +122,22 @@ struct sptag_b200_index {
     std::mutex mu;
 };
 
+// One ResultIterator per query of a batch (VectorIndex::GetIterator, BKTIndex.cpp:650-657): the rented WorkSpace of
+// each query lives in HBM for the iterator's lifetime.
+struct sptag_b200_iterator {
+    sptag_b200_index* h = nullptr;
+    int nq = 0;
+    // sampled at open, like the reference's WorkSpace::Initialize + Reset at RentWorkSpace (BKTIndex.cpp:686-696)
+    int max_check = 0, ng_length = 0, ng_lastlevel = 0, spt_length = 0, spt_lastlevel = 0;
+    size_t visited_words = 0, ng_entries = 0, spt_entries = 0;
+    int topk_pad = 0;
+    DeviceBuffer d_queries, d_visited, d_ng, d_spt, d_state, d_topk, d_ids, d_dists, d_counts, d_relaxed;
+    void release() {
+        d_queries.release(); d_visited.release(); d_ng.release(); d_spt.release(); d_state.release();
+        d_topk.release(); d_ids.release(); d_dists.release(); d_counts.release(); d_relaxed.release();
+    }
+};
+
 namespace {
 
 int heap_lastlevel(int size) {
@@ -163,6 +179,26 @@ SearchKernelFn pick_int(int mres_cap, bool kdt) {
     if (mres_cap <= 32 * 16) return search_kernel<0, COSINE, 16, false, false, ELEM>;
     if (mres_cap <= 32 * 32) return search_kernel<0, COSINE, 32, false, false, ELEM, 12>;
     return nullptr;
+}
+
+typedef void (*IterateKernelFn)(const SearchParams, int*, int*, unsigned char*);
+
+template <bool COSINE, int ELEM>
+IterateKernelFn pick_iter_rpl(int mres_cap) {
+    if (mres_cap <= 32 * 16) return iterate_kernel<COSINE, 16, ELEM>;
+    if (mres_cap <= 32 * 32) return iterate_kernel<COSINE, 32, ELEM>;
+    return nullptr;
+}
+
+IterateKernelFn pick_iterate_kernel(const sptag_b200_index* h, int mres_cap) {
+    const bool l2 = (h->metric == SPTAG_B200_METRIC_L2);
+    switch (h->value_type) {
+    case SPTAG_B200_VT_FLOAT: return l2 ? pick_iter_rpl<false, 0>(mres_cap) : pick_iter_rpl<true, 0>(mres_cap);
+    case SPTAG_B200_VT_INT8: return l2 ? pick_iter_rpl<false, 1>(mres_cap) : pick_iter_rpl<true, 1>(mres_cap);
+    case SPTAG_B200_VT_UINT8: return l2 ? pick_iter_rpl<false, 2>(mres_cap) : pick_iter_rpl<true, 2>(mres_cap);
+    case SPTAG_B200_VT_INT16: return l2 ? pick_iter_rpl<false, 3>(mres_cap) : pick_iter_rpl<true, 3>(mres_cap);
+    default: return nullptr;
+    }
 }
 
 SearchKernelFn pick_kernel(const sptag_b200_index* h, int mres_cap) {
@@ -978,6 +1014,140 @@ int sptag_b200_get_graph(sptag_b200_handle h, int32_t* out_graph) {
 }
 
 int32_t sptag_b200_graph_degree(sptag_b200_handle h) { return h ? h->degree : 0; }
+
+int sptag_b200_iterator_open(sptag_b200_handle h, const void* queries, int32_t num_queries, sptag_b200_iter* out) {
+    if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
+    if (!out || !queries || num_queries <= 0) return fail(SPTAG_B200_LACK_OF_INPUTS, "null buffer");
+    *out = nullptr;
+    if (h->algo != SPTAG_B200_ALGO_BKT) return fail(SPTAG_B200_FAIL, "ITERATIVE NOT SUPPORT FOR KDT");
+    if (h->q_type != 0) return fail(SPTAG_B200_LACK_OF_INPUTS, "iterators on quantized indexes are not built");
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceGuard guard(h->device);
+    SearchParams p;
+    int grid = 0;
+    size_t smem = 0;
+    SearchKernelFn kern = nullptr;
+    if (int rc = configure(h, 1, p, grid, smem, num_queries, kern)) return rc;  // queue lengths, arena sizes
+    auto* it = new sptag_b200_iterator();
+    it->h = h;
+    it->nq = num_queries;
+    it->max_check = h->max_check;
+    it->ng_length = p.ng_length;
+    it->ng_lastlevel = p.ng_lastlevel;
+    it->spt_length = p.spt_length;
+    it->spt_lastlevel = p.spt_lastlevel;
+    it->visited_words = p.visited_words;
+    it->ng_entries = p.ng_spill_entries;
+    it->spt_entries = p.spt_spill_entries;
+    const size_t qbytes = (size_t)num_queries * query_bytes(h);
+    int rc = 0;
+    if ((rc = it->d_queries.ensure(qbytes)) || (rc = it->d_visited.ensure((size_t)num_queries * it->visited_words * 4)) ||
+        (rc = it->d_ng.ensure((size_t)num_queries * it->ng_entries * 8)) ||
+        (rc = it->d_spt.ensure((size_t)num_queries * it->spt_entries * 8)) ||
+        (rc = it->d_state.ensure((size_t)num_queries * kIterStateInts * 4)) ||
+        (rc = it->d_counts.ensure((size_t)num_queries * 4)) || (rc = it->d_relaxed.ensure((size_t)num_queries))) {
+        it->release();
+        delete it;
+        return rc;
+    }
+    std::vector<int> st((size_t)num_queries * kIterStateInts, 0);
+    for (int q = 0; q < num_queries; ++q) {
+        st[(size_t)q * kIterStateInts + 2] = 1;   // first call: InitSearchTrees + SearchTrees
+        st[(size_t)q * kIterStateInts + 4] = -1;  // no QueryResult yet: the first Next sets the slot count
+    }
+    cudaError_t e = cudaMemcpy(it->d_queries.ptr, queries, qbytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(it->d_visited.ptr, 0, it->d_visited.bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(it->d_state.ptr, st.data(), st.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        it->release();
+        delete it;
+        return fail(SPTAG_B200_FAIL, "iterator set-up failed: %s", cudaGetErrorString(e));
+    }
+    *out = it;
+    return SPTAG_B200_SUCCESS;
+}
+
+int sptag_b200_iterator_next(sptag_b200_iter it, int32_t batch, int32_t* out_ids, float* out_dists, int32_t* out_counts,
+                             uint8_t* out_relaxed_mono) {
+    if (!it || !it->h) return fail(SPTAG_B200_EMPTY_INDEX, "null iterator");
+    if (!out_ids || !out_dists) return fail(SPTAG_B200_LACK_OF_INPUTS, "null buffer");
+    if (batch < 1 || batch > 1024) return fail(SPTAG_B200_LACK_OF_INPUTS, "batch = %d outside [1, 1024]", batch);
+    sptag_b200_index* h = it->h;
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceGuard guard(h->device);
+    SearchParams p;
+    int grid = 0;
+    size_t smem = 0;
+    SearchKernelFn skern = nullptr;
+    const int saved_check = h->max_check;
+    h->max_check = it->max_check;  // the rented WorkSpace keeps the budget it was reset with
+    const int rc0 = configure(h, batch, p, grid, smem, it->nq, skern);
+    h->max_check = saved_check;
+    if (rc0) return rc0;
+    IterateKernelFn kern = pick_iterate_kernel(h, p.mres_cap);
+    if (!kern) return fail(SPTAG_B200_LACK_OF_INPUTS, "max(MaxCheck/16, batch) = %d exceeds the supported 1024", p.mres_cap);
+    if (it->topk_pad == 0) {  // the first Next creates the QueryResult: its size bounds every later batch
+        int pad = 64;
+        while (pad < batch) pad <<= 1;
+        it->topk_pad = pad;
+        if (int rc = it->d_topk.ensure((size_t)it->nq * pad * 8)) return rc;
+    }
+    const size_t rn = (size_t)it->nq * batch;
+    if (int rc = it->d_ids.ensure(rn * 4)) return rc;
+    if (int rc = it->d_dists.ensure(rn * 4)) return rc;
+    // generic-DIM kernel: the query is read from shared memory (configure() sized the slot for the static variants)
+    p.off_query = (int)round_up((size_t)p.off_bar + round_up((size_t)p.stages * 8, 16), 16);
+    smem = round_up((size_t)p.off_query + round_up((size_t)h->dim * 4 + 16, 16), 128);
+    p.queries = (const unsigned char*)it->d_queries.ptr;
+    p.query_stride_bytes = query_bytes(h);
+    p.nq = it->nq;
+    p.k = batch;
+    p.max_check = it->max_check;
+    p.ng_length = it->ng_length;
+    p.ng_lastlevel = it->ng_lastlevel;
+    p.spt_length = it->spt_length;
+    p.spt_lastlevel = it->spt_lastlevel;
+    p.visited = (unsigned int*)it->d_visited.ptr;
+    p.visited_words = it->visited_words;
+    p.vlog = nullptr;
+    p.ng_spill = (int2*)it->d_ng.ptr;
+    p.ng_spill_entries = it->ng_entries;
+    p.spt_spill = (int2*)it->d_spt.ptr;
+    p.spt_spill_entries = it->spt_entries;
+    p.topk = (int2*)it->d_topk.ptr;
+    p.topk_pad = it->topk_pad;
+    p.out_ids = (int*)it->d_ids.ptr;
+    p.out_dists = (float*)it->d_dists.ptr;
+    p.out_stats = nullptr;
+    p.filter = nullptr;
+    if (smem > h->smem_optin) return fail(SPTAG_B200_MEMORY_OVERFLOW, "shared memory per query slot %zu exceeds %zu", smem, h->smem_optin);
+    CUDA_OK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaStream_t stream = nullptr;
+    CUDA_OK(cudaMemsetAsync(p.work_counter, 0, 4, stream));
+    CUDA_OK(cudaEventRecord(h->ev_start, stream));
+    kern<<<grid, 32, smem, stream>>>(p, (int*)it->d_state.ptr, (int*)it->d_counts.ptr, (unsigned char*)it->d_relaxed.ptr);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(h->ev_stop, stream));
+    h->timed = true;
+    CUDA_OK(cudaMemcpyAsync(out_ids, it->d_ids.ptr, rn * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemcpyAsync(out_dists, it->d_dists.ptr, rn * 4, cudaMemcpyDeviceToHost, stream));
+    if (out_counts) CUDA_OK(cudaMemcpyAsync(out_counts, it->d_counts.ptr, (size_t)it->nq * 4, cudaMemcpyDeviceToHost, stream));
+    if (out_relaxed_mono)
+        CUDA_OK(cudaMemcpyAsync(out_relaxed_mono, it->d_relaxed.ptr, (size_t)it->nq, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    return SPTAG_B200_SUCCESS;
+}
+
+void sptag_b200_iterator_close(sptag_b200_iter it) {
+    if (!it) return;
+    if (it->h) {
+        std::lock_guard<std::mutex> lock(it->h->mu);
+        DeviceGuard guard(it->h->device);
+        it->release();
+    }
+    delete it;
+}
 
 int sptag_b200_distance_batch(sptag_b200_handle h, const void* queries, int32_t num_queries, const int32_t* ids,
                               int32_t ids_per_query, float* out) {

@@ -81,6 +81,10 @@ def ref():
                                       C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_refine_nodes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_iter_open.restype = C.c_void_p
+        L.ref_iter_open.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_iter_next.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.ref_iter_close.argtypes = [C.c_void_p]
         L.ref_quiet(3)  # warnings and errors only
         _ref = L
     return _ref
@@ -174,6 +178,10 @@ class RefIndex:
             raise RuntimeError("reference refine failed: %d" % rc)
         return rows, ids, dists
 
+    def iterator(self, query):
+        """VectorIndex::GetIterator: the reference's own ResultIterator for one query."""
+        return _RefIterator(self, np.ascontiguousarray(query))
+
     def enable_stats(self):
         return ref().ref_enable_stats(self.h)
 
@@ -185,6 +193,27 @@ class RefIndex:
         ref().ref_search_one_stats(self.h, query.ctypes.data, k, ids.ctypes.data, dists.ctypes.data,
                                    stats.ctypes.data)
         return ids, dists, stats
+
+
+class _RefIterator:
+    def __init__(self, index, query):
+        self.query = query            # the iterator borrows the target buffer
+        self.index = index
+        self.h = ref().ref_iter_open(index.h, query.ctypes.data)
+        if not self.h:
+            raise RuntimeError("GetIterator returned null")
+
+    def next(self, batch):
+        ids = np.empty(batch, np.int32)
+        dists = np.empty(batch, np.float32)
+        relaxed = C.c_int()
+        count = ref().ref_iter_next(self.h, batch, ids.ctypes.data, dists.ctypes.data, C.byref(relaxed))
+        return count, ids, dists, bool(relaxed.value)
+
+    def close(self):
+        if self.h:
+            ref().ref_iter_close(self.h)
+            self.h = None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -415,6 +444,10 @@ def ora():
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.ora_refine_nodes.argtypes = [C.POINTER(_OraIndex), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        L.ora_iter_open.restype = C.c_void_p
+        L.ora_iter_open.argtypes = [C.POINTER(_OraIndex), C.c_void_p]
+        L.ora_iter_next.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        L.ora_iter_close.argtypes = [C.c_void_p]
         L.ora_quantizer_init.argtypes = [C.POINTER(_OraQuantizer)]
         L.ora_quantizer_encode.argtypes = [C.POINTER(_OraQuantizer), C.c_void_p, C.c_int32, C.c_void_p]
         L.ora_quantizer_l2.restype = C.c_float
@@ -476,6 +509,9 @@ class OracleIndex:
         assert rc == 0
         return ids, dists, stats
 
+    def iterator(self, query):
+        return _OraIterator(self, np.ascontiguousarray(query))
+
     def refine_nodes(self, first, num, cef, neighborhood=32, rng_factor=1.0, threads=0):
         """One RefineNode pass over [first, first+num) against the current graph (ora_refine_nodes)."""
         rows = np.empty((num, neighborhood), np.int32)
@@ -486,6 +522,27 @@ class OracleIndex:
                                     ids.ctypes.data, dists.ctypes.data, threads)
         assert rc == 0
         return rows, ids, dists
+
+
+class _OraIterator:
+    def __init__(self, oindex, query):
+        self.oindex = oindex
+        self.struct = oindex._struct()     # keeps the arrays alive through oindex.files
+        self.h = ora().ora_iter_open(C.byref(self.struct), query.ctypes.data)
+        if not self.h:
+            raise RuntimeError("ora_iter_open: unsupported index kind")
+
+    def next(self, batch):
+        ids = np.empty(batch, np.int32)
+        dists = np.empty(batch, np.float32)
+        relaxed = C.c_int32()
+        count = ora().ora_iter_next(self.h, batch, ids.ctypes.data, dists.ctypes.data, C.byref(relaxed))
+        return count, ids, dists, bool(relaxed.value)
+
+    def close(self):
+        if self.h:
+            ora().ora_iter_close(self.h)
+            self.h = None
 
 
 # ------------------------------------------------------------------------------------------------

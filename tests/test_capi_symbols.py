@@ -43,3 +43,36 @@ def test_null_handle_is_rejected_without_a_gpu():
     assert L.sptag_b200_search(None, None, 1, 1, None, None, None) == 0x15  # EmptyIndex
     assert b"null handle" in L.sptag_b200_last_error()
     assert L.sptag_b200_num_vectors(None) == 0
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    """The product path must fail loudly where there is no B200: creating an index on a box without a GPU returns an
+    error code through the C ABI (and the binding raises) -- it never computes anything on the host."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for GPU-less boxes")
+    from sptag_b200 import B200Index, capi
+    x = np.zeros((10, 4), np.float32)
+    with pytest.raises(capi.SptagB200Error) as e:
+        B200Index.create(algo=capi.ALGO_BKT, value_type=capi.VT_FLOAT, metric=capi.METRIC_L2, vectors=x,
+                         graph=np.full((10, 4), -1, np.int32), tree_starts=np.array([0], np.int32),
+                         tree_nodes=np.array([[10, 1, 2], [0, -1, -1], [-1, -1, -1]], np.int32))
+    assert e.value.code != 0
+
+
+def test_load_of_a_missing_folder_is_an_error():
+    from sptag_b200 import B200Index, capi
+    with pytest.raises(capi.SptagB200Error) as e:
+        B200Index.load("/nonexistent/index/folder")
+    assert e.value.code == 0x02  # FailedOpenFile (DefinitionList.h:54-68)
+    assert b"indexloader.ini" in capi.lib().sptag_b200_last_error()
+
+
+def test_missing_library_is_reported_not_papered_over(monkeypatch):
+    from sptag_b200 import capi
+    monkeypatch.setattr(capi, "_lib", None)
+    monkeypatch.setattr(capi, "LIB_PATH", "/nonexistent/libsptag_b200.so")
+    with pytest.raises(capi.SptagB200Error) as e:
+        capi.lib()
+    assert "no CPU fallback" in str(e.value)

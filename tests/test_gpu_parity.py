@@ -499,3 +499,42 @@ def test_filter_rejected_on_kdt():
     with pytest.raises(capi.SptagB200Error):     # "Not Support Filter on KDT Index!" (KDTIndex.cpp:361-365)
         idx.search_filtered(q, 10, np.ones(idx.num_vectors, np.uint8))
     idx.close()
+
+
+def test_concurrent_callers_on_one_handle():
+    """SearchIndex is const and re-entrant in the reference (OpenMP callers, thread pools); the C ABI serialises
+    callers of one handle on its mutex.  Four host threads with different batches, K and budgets must each get
+    exactly what a lone caller gets."""
+    import threading
+    from sptag_b200 import B200Index
+    folder = data_folder("bkt_l2_10k_128")
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))
+    idx = B200Index.load(folder)
+    idx.set_param("MaxCheck", 1024)
+    o = reflib.OracleIndex(files)
+    o.max_check = 1024
+    jobs = [(q[0:80], 10), (q[80:150], 5), (q[150:260], 40), (q[260:300], 1)]
+    expect = [o.search(b, k)[:2] for b, k in jobs]
+    out = [None] * len(jobs)
+    errs = []
+
+    def run(i):
+        try:
+            for _ in range(5):
+                out[i] = idx.search(jobs[i][0], jobs[i][1])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=run, args=(i,)) for i in range(len(jobs))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    try:
+        assert not errs, errs
+        for (ids, dists), (ids_o, d_o) in zip(out, expect):
+            assert np.array_equal(ids, ids_o)
+            assert np.array_equal(dists.view(np.int32), d_o.view(np.int32))
+    finally:
+        idx.close()

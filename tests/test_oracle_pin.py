@@ -357,3 +357,56 @@ def test_refine_bit_exact_vs_reference(oracle_lib, name, cef, mcr):
         assert np.array_equal(ids_r, ids_o), name
         assert np.array_equal(d_r.view(np.int32), d_o.view(np.int32)), name
         assert np.array_equal(rows_r, rows_o), name
+
+
+@needs_ref
+def test_iterator_known_answer_of_the_reference(oracle_lib):
+    """Test/src/IterativeScanTest.cpp: line data, MaxCheck 5, query (0,...): two Next(5) calls return ids 0..9 in order
+    with RelaxedMono set -- run on the reference itself and on the oracle."""
+    folder = data_folder("algo_line_bkt")
+    files = reflib.IndexFiles(folder)
+    q = np.zeros(10, np.float32)
+    r = reflib.RefIndex.load(folder)
+    r.set_param("MaxCheck", 5)
+    o = reflib.OracleIndex(files)
+    o.max_check = 5
+    for make in (r.iterator, o.iterator):
+        it = make(q)
+        got = []
+        for _ in range(2):
+            count, ids, dists, relaxed = it.next(5)
+            assert count == 5 and relaxed
+            got += ids.tolist()
+        it.close()
+        assert got == list(range(10))
+
+
+@needs_ref
+@pytest.mark.parametrize("name,mc", [("bkt_l2_20k_32", 8192), ("bkt_l2_20k_32", 64), ("bkt_cos_10k_128", 1024),
+                                     ("bkt_l2_dups", 256), ("bkt_l2_3k_30", 512), ("bkt_i8_cos_6k_64", 512),
+                                     ("bkt2_l2_6k_32", 256), ("bkt_i16_l2_4k_27", 300)])
+def test_iterator_bit_exact_vs_reference(oracle_lib, name, mc):
+    """ResultIterator::Next sequences (growing/shrinking batches, long scans, exhaustion) on the reference itself
+    against ora_iter_*: count, ids, distances and RelaxedMono per call."""
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    qs = np.load(os.path.join(folder, "queries.npy"))[:10]
+    r = reflib.RefIndex.load(folder)
+    r.set_param("MaxCheck", mc)
+    o = reflib.OracleIndex(files)
+    o.max_check = mc
+    for qi, q in enumerate(qs):
+        ir, io = r.iterator(q), o.iterator(q)
+        batches = [10, 10, 5, 7, 10, 3, 10, 1, 4] if qi % 2 == 0 else [32, 32, 16, 32, 8]
+        if qi == 5:
+            batches = [50] * 40
+        if qi == 7:
+            batches = [1000] * 6
+        for b in batches:
+            a, c = ir.next(b), io.next(b)
+            assert a[0] == c[0], (name, qi, b)
+            assert np.array_equal(a[1], c[1]), (name, qi, b)
+            assert np.array_equal(a[2].view(np.int32), c[2].view(np.int32)), (name, qi, b)
+            assert a[3] == c[3], (name, qi, b)
+        ir.close()
+        io.close()
