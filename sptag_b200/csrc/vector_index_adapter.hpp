@@ -46,8 +46,9 @@ enum class ErrorCode : std::uint16_t {
 struct BasicResult {
     SizeType VID;
     float Dist;
-    BasicResult() : VID(-1), Dist(MaxDist) {}
-    BasicResult(SizeType p_vid, float p_dist) : VID(p_vid), Dist(p_dist) {}
+    bool RelaxedMono;  // SearchResult.h: set by ResultIterator::Next (ResultIterator.cpp:47-50)
+    BasicResult() : VID(-1), Dist(MaxDist), RelaxedMono(false) {}
+    BasicResult(SizeType p_vid, float p_dist) : VID(p_vid), Dist(p_dist), RelaxedMono(false) {}
 };
 
 // SearchQuery.h:15-254: a target plus K result slots (owning or viewing a caller buffer)
@@ -60,6 +61,7 @@ public:
     const void* GetTarget() const { return m_target; }
     void SetTarget(const void* p_target) { m_target = p_target; }
     int GetResultNum() const { return m_resultNum; }
+    void SetResultNum(int p_resultNum) { m_resultNum = p_resultNum; }  // SearchQuery.h:114-117
     BasicResult* GetResult(int i) const { return i < m_resultNum ? m_results + i : nullptr; }
     BasicResult* GetResults() const { return m_results; }
     void Reset() {
@@ -71,6 +73,60 @@ private:
     int m_resultNum;
     std::vector<BasicResult> m_own;
     BasicResult* m_results;
+};
+
+// ResultIterator.h / ResultIterator.cpp: a resumable search for one target, over sptag_b200_iterator_*.
+class ResultIterator {
+public:
+    ResultIterator(sptag_b200_handle p_index, const void* p_target) : m_target(p_target) {
+        if (sptag_b200_iterator_open(p_index, p_target, 1, &m_it) != 0) m_it = nullptr;
+    }
+    ~ResultIterator() { Close(); }
+    ResultIterator(const ResultIterator&) = delete;
+    ResultIterator& operator=(const ResultIterator&) = delete;
+    bool IsOpen() const { return m_it != nullptr; }
+
+    // ResultIterator::Next (ResultIterator.cpp:31-55): the first call sizes the QueryResult; later batches are capped
+    // by the previous result count
+    std::shared_ptr<QueryResult> Next(int batch) {
+        if (m_queryResult == nullptr)
+            m_queryResult = std::make_shared<QueryResult>(m_target, batch, true);
+        else if (batch <= m_queryResult->GetResultNum())
+            m_queryResult->SetResultNum(batch);
+        else
+            batch = m_queryResult->GetResultNum();
+        m_queryResult->Reset();
+        if (m_it == nullptr || batch < 1) {
+            m_queryResult->SetResultNum(0);
+            return m_queryResult;
+        }
+        std::vector<std::int32_t> ids((size_t)batch);
+        std::vector<float> dists((size_t)batch);
+        std::int32_t count = 0;
+        std::uint8_t relaxed = 0;
+        if (sptag_b200_iterator_next(m_it, batch, ids.data(), dists.data(), &count, &relaxed) != 0) count = 0;
+        m_relaxedMono = relaxed != 0;
+        for (int i = 0; i < count; ++i) {
+            BasicResult* r = m_queryResult->GetResult(i);
+            r->VID = ids[(size_t)i];
+            r->Dist = dists[(size_t)i];
+            r->RelaxedMono = m_relaxedMono;
+        }
+        m_queryResult->SetResultNum(count);
+        return m_queryResult;
+    }
+    bool GetRelaxedMono() const { return m_relaxedMono; }
+    void Close() {
+        if (m_it != nullptr) sptag_b200_iterator_close(m_it);
+        m_it = nullptr;
+    }
+    const void* GetTarget() const { return m_target; }
+
+private:
+    sptag_b200_iter m_it = nullptr;
+    const void* m_target;
+    std::shared_ptr<QueryResult> m_queryResult;
+    bool m_relaxedMono = false;
 };
 
 class VectorIndex {
@@ -171,6 +227,15 @@ public:
         return static_cast<ErrorCode>(sptag_b200_refine_graph(m_handle, 0, sptag_b200_num_vectors(m_handle), p_cef,
                                                               sptag_b200_graph_degree(m_handle), p_rngFactor, p_newGraph,
                                                               nullptr, nullptr, p_install ? 1 : 0));
+    }
+
+    // VectorIndex::GetIterator (VectorIndex.h:43, BKTIndex.cpp:650-657); nullptr where the reference returns nullptr
+    // (index not ready, KDT)
+    std::shared_ptr<ResultIterator> GetIterator(const void* p_target, bool /*p_searchDeleted*/ = false) const {
+        if (!m_handle) return nullptr;
+        auto it = std::make_shared<ResultIterator>(m_handle, p_target);
+        if (!it->IsOpen()) return nullptr;
+        return it;
     }
 
     // VectorIndex::SetParameter / GetParameter (BKTIndex.cpp:980-1025)

@@ -63,6 +63,24 @@ int main(int argc, char** argv) {
             std::fwrite(&rq.GetResult(i)->Dist, 4, 1, f);
         }
         std::fclose(f);
+
+        // ResultIterator driven like Test/src/IterativeScanTest.cpp drives the reference's: GetIterator, Next(batch)
+        // twice, Close; the (VID, Dist, RelaxedMono) triples of the first query are appended to refine.bin
+        std::shared_ptr<ResultIterator> it = index->GetIterator(q.data());
+        if (!it) return 11;
+        f = std::fopen(argv[8], "ab");
+        for (int round = 0; round < 2; ++round) {
+            std::shared_ptr<QueryResult> r = it->Next(5);
+            if (r->GetResultNum() != 5) return 12;
+            for (int i = 0; i < r->GetResultNum(); ++i) {
+                std::int32_t mono = r->GetResult(i)->RelaxedMono ? 1 : 0;
+                std::fwrite(&r->GetResult(i)->VID, 4, 1, f);
+                std::fwrite(&r->GetResult(i)->Dist, 4, 1, f);
+                std::fwrite(&mono, 4, 1, f);
+            }
+        }
+        it->Close();
+        std::fclose(f);
     }
     return 0;
 }

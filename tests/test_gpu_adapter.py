@@ -50,9 +50,20 @@ def test_cpp_adapter_refine_calls_match_oracle():
                                str(nodes)])
         raw = np.fromfile(rf, dtype=np.int32)
     rows = raw[:nodes * files.degree].reshape(nodes, files.degree)
-    pairs = raw[nodes * files.degree:].reshape(cef + 1, 2)
+    pairs = raw[nodes * files.degree:nodes * files.degree + 2 * (cef + 1)].reshape(cef + 1, 2)
+    triples = raw[nodes * files.degree + 2 * (cef + 1):].reshape(10, 3)
     o = reflib.OracleIndex(files)   # MaxCheckForRefineGraph from the index's ini, like the adapter's loader
     rows_o, ids_o, d_o = o.refine_nodes(0, nodes, cef, files.degree, 1.0)
     assert np.array_equal(rows, rows_o)
     assert np.array_equal(pairs[:, 0], ids_o[0])
     assert np.array_equal(pairs[:, 1], d_o[0].view(np.int32))
+    # GetIterator / ResultIterator::Next(5) x 2 on the first query (MaxCheck 1024 as set by the driver)
+    o.max_check = 1024
+    oi = o.iterator(q[0])
+    for rnd in range(2):
+        c, ids_i, d_i, relaxed = oi.next(5)
+        assert c == 5
+        assert np.array_equal(triples[5 * rnd:5 * rnd + 5, 0], ids_i)
+        assert np.array_equal(triples[5 * rnd:5 * rnd + 5, 1], d_i.view(np.int32))
+        assert (triples[5 * rnd:5 * rnd + 5, 2] != 0).all() == relaxed
+    oi.close()
