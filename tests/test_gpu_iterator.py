@@ -94,3 +94,32 @@ def test_iterator_rejected_where_the_reference_rejects():
             idx.iterators(np.zeros((1, 64), np.float32))     # "ITERATIVE NOT SUPPORT FOR KDT"
     finally:
         idx.close()
+
+
+class _DeviceIteratorBatch:
+    def __init__(self, files, q, max_check):
+        from sptag_b200 import B200Index, capi
+        self.idx = B200Index.create(algo=capi.ALGO_BKT, value_type=files.value_type, metric=files.metric,
+                                    vectors=files.vectors, graph=files.graph, tree_starts=files.tree_starts,
+                                    tree_nodes=files.nodes)
+        self.idx.set_param("MaxCheck", max_check)
+        self.its = self.idx.iterators(q)
+
+    def next(self, b):
+        return self.its.next(b)
+
+    def close(self):
+        self.its.close()
+        self.idx.close()
+
+
+def _golden_cases():
+    import test_oracle_pin as pin
+    return pin.iterator_golden_cases()
+
+
+@pytest.mark.parametrize("name", _golden_cases())
+def test_iterator_matches_reference_golden_outputs(name):
+    """The device against the committed outputs of the reference's own ResultIterator (no oracle in between)."""
+    import test_oracle_pin as pin
+    pin.check_iterator_golden(name, _DeviceIteratorBatch)

@@ -136,6 +136,53 @@ def test_oracle_refine_matches_golden_reference_outputs(oracle_lib, name):
     assert np.array_equal(rows, r["rows"]), name
 
 
+def iterator_golden_cases():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "iterator", "*.npz")))
+
+
+def check_iterator_golden(name, make_iterators):
+    """make_iterators(files, queries, max_check) -> object with next(batch) -> (counts, ids, dists, relaxed) over all
+    queries; shared by the oracle (here) and the device (tests/test_gpu_iterator.py)."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    r = np.load(os.path.join(GOLDEN, "iterator", name + ".npz"))
+    files = reflib.IndexFiles.__new__(reflib.IndexFiles)
+    _files_from_npz(files, g)
+    nq = int(r["nq"])
+    q = np.ascontiguousarray(g["queries"][:nq])
+    its = make_iterators(files, q, int(r["max_check"]))
+    for s, b in enumerate(r["schedule"].tolist()):
+        counts, ids, dists, relaxed = its.next(b)
+        assert np.array_equal(counts, r["counts"][:, s]), (name, s)
+        assert np.array_equal(ids, r["ids"][:, s, :b]), (name, s)
+        assert np.array_equal(np.ascontiguousarray(dists).view(np.int32),
+                              np.ascontiguousarray(r["dists"][:, s, :b]).view(np.int32)), (name, s)
+        assert np.array_equal(np.asarray(relaxed, bool), r["relaxed"][:, s] != 0), (name, s)
+    its.close()
+
+
+class _OracleIteratorBatch:
+    def __init__(self, files, q, max_check):
+        o = reflib.OracleIndex(files)
+        o.max_check = max_check
+        self.its = [o.iterator(qq) for qq in q]
+
+    def next(self, b):
+        out = [it.next(b) for it in self.its]
+        return (np.array([x[0] for x in out], np.int32), np.stack([x[1] for x in out]),
+                np.stack([x[2] for x in out]), np.array([x[3] for x in out]))
+
+    def close(self):
+        for it in self.its:
+            it.close()
+
+
+@pytest.mark.parametrize("name", iterator_golden_cases())
+def test_oracle_iterator_matches_golden_reference_outputs(oracle_lib, name):
+    """the reference's ResultIterator outputs on the committed indexes
+    (tests/golden/make_golden_iterator.py) against ora_iter_*."""
+    check_iterator_golden(name, _OracleIteratorBatch)
+
+
 # ---------------------------------------------------------------------------------------------
 # the reference itself
 # ---------------------------------------------------------------------------------------------
