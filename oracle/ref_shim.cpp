@@ -339,6 +339,26 @@ void ref_iter_close(void* itp) {
     delete p;
 }
 
+// CPU baseline for iterator scans: one ResultIterator per query, `rounds` x Next(batch), OpenMP over queries.
+// Returns the total number of results; *seconds = wall time of the parallel region.
+long long ref_iter_scan(void* h, const void* queries, int nq, long long stride_bytes, int batch, int rounds, int threads,
+                        double* seconds) {
+    auto& idx = ((RefHandle*)h)->index;
+    if (threads > 0) omp_set_num_threads(threads);
+    long long total = 0;
+    auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : total)
+    for (int i = 0; i < nq; ++i) {
+        std::shared_ptr<ResultIterator> it = idx->GetIterator((const char*)queries + (size_t)i * stride_bytes);
+        if (!it) continue;
+        for (int r = 0; r < rounds; ++r) total += it->Next(batch)->GetResultNum();
+        it->Close();
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    return total;
+}
+
 // Install the counter-reading factory (single-query stats below need it). Irreversible for h.
 int ref_enable_stats(void* h) {
     auto& idx = ((RefHandle*)h)->index;

@@ -85,6 +85,9 @@ def ref():
         L.ref_iter_open.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_iter_next.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         L.ref_iter_close.argtypes = [C.c_void_p]
+        L.ref_iter_scan.restype = C.c_longlong
+        L.ref_iter_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                    C.POINTER(C.c_double)]
         L.ref_quiet(3)  # warnings and errors only
         _ref = L
     return _ref
@@ -177,6 +180,14 @@ class RefIndex:
         if rc != 0:
             raise RuntimeError("reference refine failed: %d" % rc)
         return rows, ids, dists
+
+    def iterator_scan(self, queries, batch, rounds, threads=0):
+        """All-cores CPU baseline: one ResultIterator per query, rounds x Next(batch) -> (results, seconds)."""
+        queries = np.ascontiguousarray(queries)
+        sec = C.c_double()
+        n = ref().ref_iter_scan(self.h, queries.ctypes.data, queries.shape[0], queries.strides[0], batch, rounds, threads,
+                                C.byref(sec))
+        return int(n), sec.value
 
     def iterator(self, query):
         """VectorIndex::GetIterator: the reference's own ResultIterator for one query."""
