@@ -359,6 +359,15 @@ long long ref_iter_scan(void* h, const void* queries, int nq, long long stride_b
     return total;
 }
 
+// VectorIndex::DeleteIndex(const SizeType&) for a list of ids (tombstones, Labelset.h:43-83) -> number of failures
+int ref_delete(void* h, const int* ids, int n) {
+    auto& idx = ((RefHandle*)h)->index;
+    int bad = 0;
+    for (int i = 0; i < n; ++i)
+        if (idx->DeleteIndex((SizeType)ids[i]) != ErrorCode::Success) bad++;
+    return bad;
+}
+
 // Install the counter-reading factory (single-query stats below need it). Irreversible for h.
 int ref_enable_stats(void* h) {
     auto& idx = ((RefHandle*)h)->index;

@@ -119,9 +119,45 @@ def make_quantized(name, force=False):
     return folder
 
 
+# indexes with tombstones: name -> (base spec name of SPECS-like tuple, fraction deleted, seed).  Built by the
+# reference, then VectorIndex::DeleteIndex(id) on a random subset plus the exact nearest neighbours of some queries
+# (so that deleted vectors are popped, skipped as results and still expanded), then SaveIndex -> deletes.bin
+DSPECS = {
+    "bkt_l2_deleted_6k_32": ("BKT", "L2", lambda: reflib.gen_lowrank(6000, 32, 8, 91), lambda: reflib.gen_lowrank(200, 32, 8, 92), 0.25, 93),
+    "bkt_cos_deleted_5k_64": ("BKT", "Cosine", lambda: reflib.gen_lowrank(5000, 64, 10, 94),
+                              lambda: reflib.normalize_rows(reflib.gen_lowrank(200, 64, 10, 95)), 0.3, 96),
+}
+
+
+def make_deleted(name, force=False):
+    folder = os.path.join(reflib.DATA_DIR, name)
+    if os.path.exists(os.path.join(folder, "indexloader.ini")) and os.path.exists(
+            os.path.join(folder, "queries.npy")) and not force:
+        return folder
+    if not reflib.have_ref():
+        raise RuntimeError("oracle/_ref/libsptag_ref.so missing")
+    algo, metric, gen_data, gen_q, frac, seed = DSPECS[name]
+    data = np.ascontiguousarray(gen_data())
+    q = np.ascontiguousarray(gen_q())
+    t = time.time()
+    idx = reflib.RefIndex.build(algo, data, metric, threads=os.cpu_count() or 8)
+    rng = np.random.default_rng(seed)
+    dele = set(np.nonzero(rng.random(data.shape[0]) < frac)[0].tolist())
+    ids, _, _ = idx.search(q[:60], 3, threads=4)          # the top-3 of the first 60 queries go too
+    dele.update(int(v) for v in ids.ravel() if v >= 0)
+    idx.delete(np.array(sorted(dele), np.int32))
+    idx.save(folder)
+    np.save(os.path.join(folder, "queries.npy"), q)
+    print("built %-18s n=%d dim=%d deleted=%d in %.1fs" % (name, data.shape[0], data.shape[1], len(dele), time.time() - t),
+          flush=True)
+    return folder
+
+
 def make(name, force=False):
     if name in QSPECS:
         return make_quantized(name, force)
+    if name in DSPECS:
+        return make_deleted(name, force)
     folder = os.path.join(reflib.DATA_DIR, name)
     if os.path.exists(os.path.join(folder, "indexloader.ini")) and os.path.exists(
             os.path.join(folder, "queries.npy")) and not force:
@@ -139,6 +175,6 @@ def make(name, force=False):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(SPECS) + list(QSPECS))
+    names = sys.argv[1:] or (list(SPECS) + list(QSPECS) + list(DSPECS))
     for nm in names:
         make(nm)

@@ -88,6 +88,7 @@ def ref():
         L.ref_iter_scan.restype = C.c_longlong
         L.ref_iter_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(C.c_double)]
+        L.ref_delete.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ref_quiet(3)  # warnings and errors only
         _ref = L
     return _ref
@@ -180,6 +181,13 @@ class RefIndex:
         if rc != 0:
             raise RuntimeError("reference refine failed: %d" % rc)
         return rows, ids, dists
+
+    def delete(self, ids):
+        """VectorIndex::DeleteIndex(id) for every id (tombstones)."""
+        ids = np.ascontiguousarray(ids, np.int32)
+        bad = ref().ref_delete(self.h, ids.ctypes.data, ids.shape[0])
+        if bad:
+            raise RuntimeError("DeleteIndex failed for %d ids" % bad)
 
     def iterator_scan(self, queries, batch, rounds, threads=0):
         """All-cores CPU baseline: one ResultIterator per query, rounds x Next(batch) -> (results, seconds)."""

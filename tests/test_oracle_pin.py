@@ -457,3 +457,39 @@ def test_iterator_bit_exact_vs_reference(oracle_lib, name, mc):
             assert a[3] == c[3], (name, qi, b)
         ir.close()
         io.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["bkt_l2_deleted_6k_32", "bkt_cos_deleted_5k_64"])
+def test_tombstones_bit_exact_vs_reference(oracle_lib, name):
+    """Row A9 (Labelset::Contains via CheckIfNotDeleted): indexes the reference built, deleted ~30 % of (including the
+    true nearest neighbours of the first queries) with VectorIndex::DeleteIndex and saved with deletes.bin -- search,
+    one refine step and iterator scans on the reference itself against the oracle with the same tombstone map."""
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    assert files.num_deleted > 1000 and int((files.deleted == 1).sum()) == files.num_deleted
+    q = np.load(os.path.join(folder, "queries.npy"))
+    r = reflib.RefIndex.load(folder)
+    o = reflib.OracleIndex(files)
+    for mc in (8192, 512, 64):
+        r.set_param("MaxCheck", mc)
+        o.max_check = mc
+        ids_r, d_r, _ = r.search(q, 10, threads=4)
+        ids_o, d_o, _ = o.search(q, 10, threads=4)
+        assert np.array_equal(ids_r, ids_o), (name, mc)
+        assert np.array_equal(d_r.view(np.int32), d_o.view(np.int32)), (name, mc)
+        assert not (files.deleted[ids_r[ids_r >= 0]] == 1).any()
+    r.set_param("MaxCheckForRefineGraph", 512)
+    o.max_check_refine = 512
+    for a, b in zip(r.refine_nodes(100, 400, 48, files.degree, 1.0), o.refine_nodes(100, 400, 48, files.degree, 1.0)):
+        assert np.array_equal(a.view(np.int32), b.view(np.int32)), name
+    r.set_param("MaxCheck", 256)
+    o.max_check = 256
+    for qi in range(12):
+        ir, io = r.iterator(q[qi]), o.iterator(q[qi])
+        for b in [10, 10, 5, 10, 10, 10]:
+            a, c = ir.next(b), io.next(b)
+            assert a[0] == c[0] and np.array_equal(a[1], c[1]) and a[3] == c[3], (name, qi, b)
+            assert np.array_equal(a[2].view(np.int32), c[2].view(np.int32)), (name, qi, b)
+        ir.close()
+        io.close()
