@@ -239,6 +239,15 @@ class B200Index:
         """VectorIndex::GetIterator for every query of a batch -> B200Iterators (next(batch) / close())."""
         return B200Iterators(self, queries)
 
+    def save_graph(self, path):
+        """NeighborhoodGraph::SaveGraph (NeighborhoodGraph.h:606-615): int32 rows, int32 cols, rows x cols int32 --
+        the index's current (e.g. device-refined) graph as a graph.bin the reference's LoadIndex reads."""
+        g = self.get_graph()
+        with open(path, "wb") as f:
+            np.array([g.shape[0], g.shape[1]], np.int32).tofile(f)
+            g.tofile(f)
+        return g
+
     def distance_batch(self, queries, ids):
         queries = np.ascontiguousarray(queries, dtype=np.float32)
         ids = np.ascontiguousarray(ids, dtype=np.int32)

@@ -17,6 +17,7 @@
 #include <limits>
 #include <cstdint>
 #include <cstring>
+#include <cstdio>
 #include <memory>
 #include <string>
 #include <vector>
@@ -227,6 +228,22 @@ public:
         return static_cast<ErrorCode>(sptag_b200_refine_graph(m_handle, 0, sptag_b200_num_vectors(m_handle), p_cef,
                                                               sptag_b200_graph_degree(m_handle), p_rngFactor, p_newGraph,
                                                               nullptr, nullptr, p_install ? 1 : 0));
+    }
+
+    // NeighborhoodGraph::SaveGraph (NeighborhoodGraph.h:606-615) for the index's current -- e.g. device-refined -- graph:
+    // a graph.bin the reference's LoadIndex reads
+    ErrorCode SaveGraph(const std::string& p_graphFile) const {
+        if (!m_handle) return ErrorCode::EmptyIndex;
+        const std::int32_t rows = sptag_b200_num_vectors(m_handle), cols = sptag_b200_graph_degree(m_handle);
+        std::vector<std::int32_t> g((size_t)rows * cols);
+        int rc = sptag_b200_get_graph(m_handle, g.data());
+        if (rc != 0) return static_cast<ErrorCode>(rc);
+        FILE* f = std::fopen(p_graphFile.c_str(), "wb");
+        if (!f) return ErrorCode::FailedOpenFile;
+        bool ok = std::fwrite(&rows, 4, 1, f) == 1 && std::fwrite(&cols, 4, 1, f) == 1 &&
+                  std::fwrite(g.data(), 4, g.size(), f) == g.size();
+        ok = (std::fclose(f) == 0) && ok;
+        return ok ? ErrorCode::Success : ErrorCode::Fail;
     }
 
     // VectorIndex::GetIterator (VectorIndex.h:43, BKTIndex.cpp:650-657); nullptr where the reference returns nullptr

@@ -82,3 +82,34 @@ def test_iterator_with_tombstones(name):
             oi.close()
     finally:
         idx.close()
+
+
+def test_device_refined_graph_round_trips_through_the_reference(tmp_path):
+    """Builder-side loop closed: refine + install on the device, write graph.bin (NeighborhoodGraph::SaveGraph format)
+    next to the other files of the folder, and let the UNMODIFIED REFERENCE load that folder (oracle/_ref travels to
+    the GPU box): its SearchIndex on the device-built graph must equal the device's own search on it."""
+    import shutil
+    from sptag_b200 import B200Index
+    if not reflib.have_ref():
+        pytest.skip("oracle/_ref not built")
+    folder = data_folder("bkt_l2_5k_100")
+    q = np.load(os.path.join(folder, "queries.npy"))
+    out = str(tmp_path / "refined")
+    shutil.copytree(folder, out)
+    idx = B200Index.load(folder)
+    try:
+        idx.set_param("MaxCheckForRefineGraph", 1024)
+        idx.refine_graph(64, install=True, want_rows=False)
+        g = idx.save_graph(os.path.join(out, "graph.bin"))
+        files = reflib.IndexFiles(out)
+        assert np.array_equal(files.graph, g)
+        r = reflib.RefIndex.load(out)
+        for mc in (2048, 256):
+            idx.set_param("MaxCheck", mc)
+            r.set_param("MaxCheck", mc)
+            ids, dists = idx.search(q, 10)
+            ids_r, d_r, _ = r.search(q, 10, threads=4)
+            assert np.array_equal(ids, ids_r), mc
+            assert np.array_equal(dists.view(np.int32), d_r.view(np.int32)), mc
+    finally:
+        idx.close()
