@@ -76,3 +76,19 @@ def test_missing_library_is_reported_not_papered_over(monkeypatch):
     with pytest.raises(capi.SptagB200Error) as e:
         capi.lib()
     assert "no CPU fallback" in str(e.value)
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/sptag_b200.h must compile as C99 (what cgo / JNI / ctypes generators consume)
+    and as C++14 (what the reference would include)."""
+    import shutil
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "sptag_b200.h"\nint main(void) { sptag_b200_index_desc d; (void)d; return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    if shutil.which("gcc"):
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc,
+                               str(src)])
+    if shutil.which("g++"):
+        subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc,
+                               str(src)])
