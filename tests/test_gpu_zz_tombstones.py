@@ -2,7 +2,7 @@
 reference built, deleted ~30 % of with VectorIndex::DeleteIndex (including true nearest neighbours of the first
 queries) and saved.  Search, one refine step and iterator scans against the oracle, whose tombstone handling is pinned
 to the reference on the same folders (tests/test_oracle_pin.py::test_tombstones_bit_exact_vs_reference).
-This file sorts last on purpose: it was added after the round's last GPU session and has not run on a device yet."""
+Also closes the builder-side loop: a device-refined graph written as graph.bin and searched by the unmodified reference."""
 import os
 
 import numpy as np
