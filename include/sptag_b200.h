@@ -167,7 +167,8 @@ int sptag_b200_distance_batch(sptag_b200_handle h, const void* queries, int32_t 
  * out_res_ids / out_res_dists (host, nullable): [num_nodes x (cef+1)] the refine-search result lists.
  * install != 0 (needs a full pass with neighborhood_size == the index's degree): the new rows replace the index's
  * graph on the device; duplicate-group back-pointers in the last slot are carried over (NeighborhoodGraph.h:395-401).
- * cef <= 1023.  Not available for quantized indexes. */
+ * cef <= 2047 (cef > 1023 and K > 1024 use kernel variants that are compiled but were not yet run on a device when
+ * this header was written -- see DESIGN.md row A7).  Not available for quantized indexes. */
 int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num_nodes, int32_t cef,
                             int32_t neighborhood_size, float rng_factor, int32_t* out_graph, int32_t* out_res_ids,
                             float* out_res_dists, int32_t install);

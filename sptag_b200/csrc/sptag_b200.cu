@@ -154,6 +154,9 @@ SearchKernelFn pick_rpl(int mres_cap, bool kdt) {
     // warp, so residency beats a few spilled values (refine passes run the 32-register m_Results file, K = CEF+1)
     if (mres_cap <= 32 * 16) return search_kernel<DIM, COSINE, 16, false, false, 0, 12>;
     if (mres_cap <= 32 * 32) return search_kernel<DIM, COSINE, 32, false, false, 0, 14>;
+    // 64 registers per lane: K / CEF+1 up to 2048 (the reference's default RefineGraph schedule searches with
+    // CEF x CEFScale + 1 = 2001 results, NeighborhoodGraph.h:459-470)
+    if (mres_cap <= 32 * 64) return search_kernel<DIM, COSINE, 64, false, false, 0, 8>;
     return nullptr;
 }
 
@@ -178,6 +181,7 @@ SearchKernelFn pick_int(int mres_cap, bool kdt) {
     if (kdt) return search_kernel<0, COSINE, 16, true, false, ELEM>;
     if (mres_cap <= 32 * 16) return search_kernel<0, COSINE, 16, false, false, ELEM>;
     if (mres_cap <= 32 * 32) return search_kernel<0, COSINE, 32, false, false, ELEM, 12>;
+    if (mres_cap <= 32 * 64) return search_kernel<0, COSINE, 64, false, false, ELEM, 8>;
     return nullptr;
 }
 
@@ -239,7 +243,7 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     }
     if (h->simd_width != 16)
         return fail(SPTAG_B200_LACK_OF_INPUTS, "B200.SimdWidth %d not built (16 only)", h->simd_width);
-    if (k < 1 || k > 1024) return fail(SPTAG_B200_LACK_OF_INPUTS, "k = %d outside the supported range [1, 1024]", k);
+    if (k < 1 || k > 2048) return fail(SPTAG_B200_LACK_OF_INPUTS, "k = %d outside the supported range [1, 2048]", k);
 
     memset(&p, 0, sizeof(p));
     p.vectors = (const unsigned char*)h->d_vectors.ptr;
@@ -337,7 +341,7 @@ relayout:
 
     kern = pick_kernel(h, p.mres_cap);
     if (!kern)
-        return fail(SPTAG_B200_LACK_OF_INPUTS, "max(MaxCheck/16, K) = %d exceeds the supported 1024", p.mres_cap);
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "max(MaxCheck/16, K) = %d exceeds what this index type supports (2048; quantized: 1024)", p.mres_cap);
     CUDA_OK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // resident single-warp CTAs per SM allowed by registers + shared memory for this instantiation
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, (const void*)kern, 32, smem));
@@ -925,7 +929,7 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
         return fail(SPTAG_B200_LACK_OF_INPUTS, "refine on a quantized index (reconstruct + re-quantize) is not built");
     if (first_node < 0 || num_nodes < 0 || (long long)first_node + num_nodes > h->n)
         return fail(SPTAG_B200_LACK_OF_INPUTS, "node range [%d, %d) outside the index", first_node, first_node + num_nodes);
-    if (cef < 1 || cef + 1 > 1024) return fail(SPTAG_B200_LACK_OF_INPUTS, "CEF = %d outside [1, 1023]", cef);
+    if (cef < 1 || cef + 1 > 2048) return fail(SPTAG_B200_LACK_OF_INPUTS, "CEF = %d outside [1, 2047]", cef);
     if (neighborhood_size < 1 || neighborhood_size > 1024)
         return fail(SPTAG_B200_LACK_OF_INPUTS, "neighbourhood size %d outside [1, 1024]", neighborhood_size);
     if (install && (first_node != 0 || num_nodes != h->n || neighborhood_size != h->degree))
@@ -934,7 +938,7 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
     std::lock_guard<std::mutex> lock(h->mu);
     DeviceGuard guard(h->device);
     const int k = cef + 1;
-    const int batch = std::min(num_nodes, 32768);  // 32768 x 1001 result pairs = 262 MB of scratch
+    const int batch = std::min(num_nodes, 32768);  // 32768 x 1001 result pairs = 262 MB of scratch (524 MB at CEF 2000)
     if (int rc = h->d_ids.ensure((size_t)batch * k * 4)) return rc;
     if (int rc = h->d_dists.ensure((size_t)batch * k * 4)) return rc;
     if (int rc = h->d_graph_new.ensure((size_t)num_nodes * neighborhood_size * 4)) return rc;

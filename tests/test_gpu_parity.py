@@ -420,7 +420,7 @@ def test_empty_and_single_query_batches():
         all_ids, all_d = idx.search(q, 10)
         assert np.array_equal(one_ids[0], all_ids[0]) and np.array_equal(one_d[0], all_d[0])
         with pytest.raises(capi.SptagB200Error):
-            idx.search(q, 1025)          # K > 1024 is rejected loudly, not truncated
+            idx.search(q, 2049)          # K > 2048 is rejected loudly, not truncated
         with pytest.raises(capi.SptagB200Error):
             idx.set_param("NoSuchParameter", 1)
     finally:

@@ -113,7 +113,7 @@ def test_refine_argument_errors():
     idx = B200Index.load(data_folder("bkt_l2_3k_30"))
     try:
         with pytest.raises(capi.SptagB200Error):
-            idx.refine_graph(1024)                       # K = CEF + 1 > 1024
+            idx.refine_graph(2048)                       # K = CEF + 1 > 2048
         with pytest.raises(capi.SptagB200Error):
             idx.refine_graph(10, first=2990, num=100)    # past the end
         with pytest.raises(capi.SptagB200Error):

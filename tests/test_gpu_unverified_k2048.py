@@ -1,0 +1,58 @@
+"""Device paths that compile (and leave the SASS of every validated kernel byte-identical) but have NOT run on a B200
+yet: K and CEF+1 up to 2048 -- the 64-register m_Results variants needed by the reference's default RefineGraph schedule
+(CEF x CEFScale + 1 = 2001 results, NeighborhoodGraph.h:459-470) and by MaxCheck > 16384.  The oracle side of every
+case IS pinned to the reference (tests/test_oracle_pin.py::test_large_k_and_budget_bit_exact_vs_reference).
+Run on a GPU box with:  SPTAG_B200_RUN_UNVERIFIED=1 python -m pytest tests -m gpu_unverified -q"""
+import os
+
+import numpy as np
+import pytest
+
+import reflib
+from conftest import data_folder
+
+pytestmark = pytest.mark.gpu_unverified
+
+
+@pytest.mark.parametrize("name,k,mc", [("bkt_l2_10k_128", 2048, 8192), ("bkt_l2_10k_128", 1500, 2048),
+                                       ("bkt_l2_10k_128", 10, 20000), ("bkt_i8_l2_5k_100", 2048, 8192),
+                                       ("bkt_cos_3k_768", 1100, 8192), ("bkt_i16_l2_5k_64", 1025, 4096)])
+def test_search_k_up_to_2048(name, k, mc):
+    from sptag_b200 import B200Index
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:60]
+    idx = B200Index.load(folder)
+    try:
+        idx.set_param("MaxCheck", mc)
+        if mc > 8192:
+            idx.set_param("MaxCheckForRefineGraph", mc)
+        ids, dists = idx.search(q, k)
+        o = reflib.OracleIndex(files)
+        o.max_check = mc
+        if mc > 8192:
+            o.max_check_refine = mc
+        ids_o, d_o, _ = o.search(q, k)
+        assert np.array_equal(ids, ids_o)
+        assert np.array_equal(dists.view(np.int32), d_o.view(np.int32))
+    finally:
+        idx.close()
+
+
+@pytest.mark.parametrize("name", ["bkt_cos_3k_768", "bkt_l2_20k_32", "bkt_i16_l2_4k_27"])
+def test_refine_with_the_reference_default_first_pass_cef(name):
+    from sptag_b200 import B200Index
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    idx = B200Index.load(folder)
+    try:
+        idx.set_param("MaxCheckForRefineGraph", 8192)
+        rows, ids, dists = idx.refine_graph(2000, first=10, num=200, want_results=True)
+        o = reflib.OracleIndex(files)
+        o.max_check_refine = 8192
+        rows_o, ids_o, d_o = o.refine_nodes(10, 200, 2000, files.degree, 1.0)
+        assert np.array_equal(ids, ids_o)
+        assert np.array_equal(dists.view(np.int32), d_o.view(np.int32))
+        assert np.array_equal(rows, rows_o)
+    finally:
+        idx.close()

@@ -493,3 +493,30 @@ def test_tombstones_bit_exact_vs_reference(oracle_lib, name):
             assert np.array_equal(a[2].view(np.int32), c[2].view(np.int32)), (name, qi, b)
         ir.close()
         io.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("name,k,mc", [("bkt_l2_10k_128", 2048, 8192), ("bkt_l2_10k_128", 10, 20000),
+                                       ("bkt_i8_l2_5k_100", 2048, 8192), ("bkt_cos_3k_768", 1100, 8192)])
+def test_large_k_and_budget_bit_exact_vs_reference(oracle_lib, name, k, mc):
+    """K up to 2048 and MaxCheck beyond 16384 (m_Results capacity > 1024), plus a refine step with the reference's
+    default first-pass CEF x CEFScale = 2000: the reference itself against the oracle."""
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:60]
+    r = reflib.RefIndex.load(folder)
+    r.set_param("MaxCheck", mc)
+    o = reflib.OracleIndex(files)
+    o.max_check = mc
+    if mc > 8192:
+        r.set_param("MaxCheckForRefineGraph", mc)
+        o.max_check_refine = mc
+    ids_r, d_r, _ = r.search(q, k, threads=4)
+    ids_o, d_o, _ = o.search(q, k, threads=4)
+    assert np.array_equal(ids_r, ids_o)
+    assert np.array_equal(d_r.view(np.int32), d_o.view(np.int32))
+    if mc <= 8192:
+        r.set_param("MaxCheckForRefineGraph", 8192)
+        o.max_check_refine = 8192
+        for a, b in zip(r.refine_nodes(10, 100, 2000, files.degree, 1.0), o.refine_nodes(10, 100, 2000, files.degree, 1.0)):
+            assert np.array_equal(a.view(np.int32), b.view(np.int32))
