@@ -113,7 +113,10 @@ void sptag_b200_destroy(sptag_b200_handle h);
  * parameters, same names as the ini file: MaxCheck, MaxCheckForRefineGraph,
  * NumberOfInitialDynamicPivots, NumberOfOtherDynamicPivots,
  * ThresholdOfNumberOfContinuousNoBetterPropagation; "EnableADC" = VectorIndex::SetQuantizerADC
- * (VectorIndex.h:136-138) for quantized indexes.  Additional B200 tuning knobs (not in the
+ * (VectorIndex.h:136-138) for quantized indexes; "SearchDeleted" (0/1) = the p_searchDeleted argument of
+ * SearchIndex / SearchIndexWithFilter / GetIterator (VectorIndex.h:41-57; BKTIndex.cpp:473, KDTIndex.cpp:260):
+ * 1 makes tombstoned vectors eligible results; searches read it per call, iterators sample it at open, the refine
+ * pass always runs with 0 like NeighborhoodGraph::RefineNode.  Additional B200 tuning knobs (not in the
  * reference) are prefixed "B200.": B200.QueriesPerSM, B200.StageRows, B200.Stages,
  * B200.NGCacheEntries, B200.SPTCacheEntries, B200.SimdWidth (16/8/4: which DistanceUtils
  * summation tree to reproduce bit-exactly; default 16 = AVX-512), B200.VisitedLog (-1 auto, 0 clear the

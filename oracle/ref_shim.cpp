@@ -368,6 +368,30 @@ int ref_delete(void* h, const int* ids, int n) {
     return bad;
 }
 
+// SearchIndex(QueryResult&, p_searchDeleted) per query (VectorIndex.h:41) and GetIterator(target, p_searchDeleted)
+int ref_search_each_flag(void* h, const void* queries, int nq, long long stride_bytes, int k, int threads,
+                         int search_deleted, int* ids, float* dists) {
+    auto& idx = ((RefHandle*)h)->index;
+    if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(dynamic, 10)
+    for (int i = 0; i < nq; ++i) {
+        QueryResult res((const char*)queries + (size_t)i * stride_bytes, k, false);
+        idx->SearchIndex(res, search_deleted != 0);
+        for (int j = 0; j < k; ++j) {
+            ids[(size_t)i * k + j] = res.GetResult(j)->VID;
+            dists[(size_t)i * k + j] = res.GetResult(j)->Dist;
+        }
+    }
+    return 0;
+}
+
+void* ref_iter_open_flag(void* h, const void* query, int search_deleted) {
+    auto& idx = ((RefHandle*)h)->index;
+    std::shared_ptr<ResultIterator> it = idx->GetIterator(query, search_deleted != 0);
+    if (!it) return nullptr;
+    return new std::shared_ptr<ResultIterator>(it);
+}
+
 // Install the counter-reading factory (single-query stats below need it). Irreversible for h.
 int ref_enable_stats(void* h) {
     auto& idx = ((RefHandle*)h)->index;

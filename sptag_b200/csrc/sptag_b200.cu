@@ -91,6 +91,7 @@ struct sptag_b200_index {
     // device-resident index
     DeviceBuffer d_vectors, d_graph, d_nodes, d_tree_starts, d_deleted, d_filter;
     bool use_filter = false;  // set for the duration of a sptag_b200_search_filtered call
+    int search_deleted = 0;   // p_searchDeleted of SearchIndex / SearchIndexWithFilter / GetIterator (parameter "SearchDeleted")
     // search parameters (reference names)
     int max_check = 8192, max_check_refine = 8192, initial_pivots = 50, other_pivots = 4, no_better_threshold = 3;
     // B200 tuning knobs
@@ -131,6 +132,7 @@ struct sptag_b200_iterator {
     int max_check = 0, ng_length = 0, ng_lastlevel = 0, spt_length = 0, spt_lastlevel = 0;
     size_t visited_words = 0, ng_entries = 0, spt_entries = 0;
     int topk_pad = 0;
+    int search_deleted = 0;  // GetIterator(p_target, p_searchDeleted)
     DeviceBuffer d_queries, d_visited, d_ng, d_spt, d_state, d_topk, d_ids, d_dists, d_counts, d_relaxed;
     void release() {
         d_queries.release(); d_visited.release(); d_ng.release(); d_spt.release(); d_state.release();
@@ -257,7 +259,8 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     p.tree_starts = (const int*)h->d_tree_starts.ptr;
     p.tree_num = h->tree_num;
     p.node_count = h->node_count;
-    p.deleted = (h->num_deleted > 0) ? (const signed char*)h->d_deleted.ptr : nullptr;
+    // flags += (m_deletedID.Count() == 0 || p_searchDeleted) << 2  (BKTIndex.cpp:473, KDTIndex.cpp:260)
+    p.deleted = (h->num_deleted > 0 && !h->search_deleted) ? (const signed char*)h->d_deleted.ptr : nullptr;
     p.filter = h->use_filter ? (const unsigned char*)h->d_filter.ptr : nullptr;
     p.k = k;
     p.id_offset = h->id_offset;
@@ -810,6 +813,7 @@ int sptag_b200_set_param(sptag_b200_handle h, const char* name, const char* valu
     const std::string n(name);
     if (n == "MaxCheck") h->max_check = (int)v;
     else if (n == "MaxCheckForRefineGraph") h->max_check_refine = (int)v;
+    else if (n == "SearchDeleted") h->search_deleted = (v != 0) ? 1 : 0;
     else if (n == "NumberOfInitialDynamicPivots") h->initial_pivots = (int)v;
     else if (n == "NumberOfOtherDynamicPivots") h->other_pivots = (int)v;
     else if (n == "ThresholdOfNumberOfContinuousNoBetterPropagation") h->no_better_threshold = (int)v;
@@ -835,6 +839,7 @@ int sptag_b200_get_param(sptag_b200_handle h, const char* name, char* value_out,
     long v;
     if (n == "MaxCheck") v = h->max_check;
     else if (n == "MaxCheckForRefineGraph") v = h->max_check_refine;
+    else if (n == "SearchDeleted") v = h->search_deleted;
     else if (n == "NumberOfInitialDynamicPivots") v = h->initial_pivots;
     else if (n == "NumberOfOtherDynamicPivots") v = h->other_pivots;
     else if (n == "ThresholdOfNumberOfContinuousNoBetterPropagation") v = h->no_better_threshold;
@@ -943,8 +948,9 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
     if (int rc = h->d_dists.ensure((size_t)batch * k * 4)) return rc;
     if (int rc = h->d_graph_new.ensure((size_t)num_nodes * neighborhood_size * 4)) return rc;
     cudaStream_t stream = nullptr;
-    const int saved_check = h->max_check;
+    const int saved_check = h->max_check, saved_sd = h->search_deleted;
     h->max_check = h->max_check_refine;  // workSpace->Reset(m_pGraph.m_iMaxCheckForRefineGraph, CEF + 1)
+    h->search_deleted = 0;               // RefineNode(index, node, false, searchDeleted = false, CEF)
     int rc = SPTAG_B200_SUCCESS;
     h->refine_search_ms = h->refine_rebuild_ms = 0.0;
     const unsigned char* dv = (const unsigned char*)h->d_vectors.ptr;
@@ -991,6 +997,7 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
         if (e != cudaSuccess) rc = fail(SPTAG_B200_FAIL, "refine pass failed: %s", cudaGetErrorString(e));
     }
     h->max_check = saved_check;
+    h->search_deleted = saved_sd;
     if (rc) return rc;
     if (out_graph)
         CUDA_OK(cudaMemcpy(out_graph, h->d_graph_new.ptr, (size_t)num_nodes * neighborhood_size * 4, cudaMemcpyDeviceToHost));
@@ -1036,6 +1043,7 @@ int sptag_b200_iterator_open(sptag_b200_handle h, const void* queries, int32_t n
     it->h = h;
     it->nq = num_queries;
     it->max_check = h->max_check;
+    it->search_deleted = h->search_deleted;
     it->ng_length = p.ng_length;
     it->ng_lastlevel = p.ng_lastlevel;
     it->spt_length = p.spt_length;
@@ -1083,10 +1091,12 @@ int sptag_b200_iterator_next(sptag_b200_iter it, int32_t batch, int32_t* out_ids
     int grid = 0;
     size_t smem = 0;
     SearchKernelFn skern = nullptr;
-    const int saved_check = h->max_check;
+    const int saved_check = h->max_check, saved_sd = h->search_deleted;
     h->max_check = it->max_check;  // the rented WorkSpace keeps the budget it was reset with
+    h->search_deleted = it->search_deleted;
     const int rc0 = configure(h, batch, p, grid, smem, it->nq, skern);
     h->max_check = saved_check;
+    h->search_deleted = saved_sd;
     if (rc0) return rc0;
     IterateKernelFn kern = pick_iterate_kernel(h, p.mres_cap);
     if (!kern) return fail(SPTAG_B200_LACK_OF_INPUTS, "max(MaxCheck/16, batch) = %d exceeds the supported 1024", p.mres_cap);

@@ -157,7 +157,8 @@ public:
 
     // VectorIndex::SearchIndex(QueryResult&, bool) (VectorIndex.h:41; BKTIndex.cpp:595-620).
     // One query is one tiny batch on the device; prefer the batched overload.
-    ErrorCode SearchIndex(QueryResult& p_query, bool /*p_searchDeleted*/ = false) const {
+    ErrorCode SearchIndex(QueryResult& p_query, bool p_searchDeleted = false) const {
+        SearchDeletedScope scope(m_handle, p_searchDeleted);
         return SearchIndex(p_query.GetTarget(), 1, p_query.GetResultNum(), false, p_query.GetResults());
     }
 
@@ -183,7 +184,8 @@ public:
     // vector's metadata; here the predicate receives the vector id (the caller owns the id -> metadata mapping) and is
     // evaluated once per vector on the host before the batch runs on the device.
     template <typename Pred>
-    ErrorCode SearchIndexWithFilter(QueryResult& p_query, Pred p_allowed, int maxCheck = 0, bool /*p_searchDeleted*/ = false) const {
+    ErrorCode SearchIndexWithFilter(QueryResult& p_query, Pred p_allowed, int maxCheck = 0, bool p_searchDeleted = false) const {
+        SearchDeletedScope scope(m_handle, p_searchDeleted);
         if (!m_handle) return ErrorCode::EmptyIndex;
         const SizeType n = GetNumSamples();
         std::vector<std::uint8_t> allowed((size_t)n);
@@ -248,8 +250,9 @@ public:
 
     // VectorIndex::GetIterator (VectorIndex.h:43, BKTIndex.cpp:650-657); nullptr where the reference returns nullptr
     // (index not ready, KDT)
-    std::shared_ptr<ResultIterator> GetIterator(const void* p_target, bool /*p_searchDeleted*/ = false) const {
+    std::shared_ptr<ResultIterator> GetIterator(const void* p_target, bool p_searchDeleted = false) const {
         if (!m_handle) return nullptr;
+        SearchDeletedScope scope(m_handle, p_searchDeleted);  // the iterator samples the flag when it opens
         auto it = std::make_shared<ResultIterator>(m_handle, p_target);
         if (!it->IsOpen()) return nullptr;
         return it;
@@ -270,6 +273,18 @@ public:
     sptag_b200_handle Handle() const { return m_handle; }
 
 private:
+    // p_searchDeleted travels as the handle parameter "SearchDeleted" for the duration of one call; callers that mix
+    // both settings concurrently on one handle must serialise those calls themselves (the flag is per handle)
+    struct SearchDeletedScope {
+        sptag_b200_handle h;
+        bool on;
+        SearchDeletedScope(sptag_b200_handle p_h, bool p_on) : h(p_h), on(p_on) {
+            if (on) sptag_b200_set_param(h, "SearchDeleted", "1");
+        }
+        ~SearchDeletedScope() {
+            if (on) sptag_b200_set_param(h, "SearchDeleted", "0");
+        }
+    };
     explicit VectorIndex(sptag_b200_handle h) : m_handle(h) {}
     sptag_b200_handle m_handle;
 };

@@ -89,6 +89,10 @@ def ref():
         L.ref_iter_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(C.c_double)]
         L.ref_delete.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_search_each_flag.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p]
+        L.ref_iter_open_flag.restype = C.c_void_p
+        L.ref_iter_open_flag.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ref_quiet(3)  # warnings and errors only
         _ref = L
     return _ref
@@ -182,6 +186,16 @@ class RefIndex:
             raise RuntimeError("reference refine failed: %d" % rc)
         return rows, ids, dists
 
+    def search_flag(self, queries, k, search_deleted, threads=0):
+        """SearchIndex(QueryResult&, p_searchDeleted) per query."""
+        queries = np.ascontiguousarray(queries)
+        nq = queries.shape[0]
+        ids = np.empty((nq, k), np.int32)
+        dists = np.empty((nq, k), np.float32)
+        ref().ref_search_each_flag(self.h, queries.ctypes.data, nq, queries.strides[0], k, threads,
+                                   1 if search_deleted else 0, ids.ctypes.data, dists.ctypes.data)
+        return ids, dists
+
     def delete(self, ids):
         """VectorIndex::DeleteIndex(id) for every id (tombstones)."""
         ids = np.ascontiguousarray(ids, np.int32)
@@ -197,9 +211,9 @@ class RefIndex:
                                 C.byref(sec))
         return int(n), sec.value
 
-    def iterator(self, query):
+    def iterator(self, query, search_deleted=False):
         """VectorIndex::GetIterator: the reference's own ResultIterator for one query."""
-        return _RefIterator(self, np.ascontiguousarray(query))
+        return _RefIterator(self, np.ascontiguousarray(query), search_deleted)
 
     def enable_stats(self):
         return ref().ref_enable_stats(self.h)
@@ -215,10 +229,10 @@ class RefIndex:
 
 
 class _RefIterator:
-    def __init__(self, index, query):
+    def __init__(self, index, query, search_deleted=False):
         self.query = query            # the iterator borrows the target buffer
         self.index = index
-        self.h = ref().ref_iter_open(index.h, query.ctypes.data)
+        self.h = ref().ref_iter_open_flag(index.h, query.ctypes.data, 1 if search_deleted else 0)
         if not self.h:
             raise RuntimeError("GetIterator returned null")
 
@@ -489,6 +503,7 @@ class OracleIndex:
         self.oq = OracleQuantizer(files.quantizer, simd_width) if getattr(files, "quantizer", None) is not None else None
         self.enable_adc = False
         self.filter = None   # numpy uint8 [n]: SearchIndexWithFilter semantics
+        self.search_deleted = False   # p_searchDeleted: tombstones are ignored (dispatch flag, BKTIndex.cpp:473)
 
     def _struct(self):
         f = self.files
@@ -502,8 +517,9 @@ class OracleIndex:
         s.node_count = f.nodes.shape[0]
         s.tree_starts = f.tree_starts.ctypes.data
         s.nodes = f.nodes.ctypes.data
-        s.deleted = f.deleted.ctypes.data if (f.deleted is not None and f.num_deleted > 0) else None
-        s.num_deleted = f.num_deleted
+        use_del = f.deleted is not None and f.num_deleted > 0 and not self.search_deleted
+        s.deleted = f.deleted.ctypes.data if use_del else None
+        s.num_deleted = f.num_deleted if use_del else 0
         s.max_check = self.max_check
         s.max_check_refine = self.max_check_refine
         s.initial_pivots = self.initial_pivots

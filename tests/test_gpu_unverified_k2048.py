@@ -56,3 +56,43 @@ def test_refine_with_the_reference_default_first_pass_cef(name):
         assert np.array_equal(rows, rows_o)
     finally:
         idx.close()
+
+
+@pytest.mark.parametrize("name", ["bkt_l2_deleted_6k_32", "bkt_cos_deleted_5k_64"])
+def test_search_deleted_parameter(name):
+    """Handle parameter "SearchDeleted" = p_searchDeleted of SearchIndex / GetIterator (host-side switch: the kernel
+    simply gets no tombstone map); sticky until reset, refine ignores it."""
+    from sptag_b200 import B200Index
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:100]
+    idx = B200Index.load(folder)
+    try:
+        idx.set_param("MaxCheck", 1024)
+        o = reflib.OracleIndex(files)
+        o.max_check = 1024
+        ids0, d0 = idx.search(q, 10)
+        idx.set_param("SearchDeleted", 1)
+        assert idx.get_param("SearchDeleted") == "1"
+        o.search_deleted = True
+        ids, dists = idx.search(q, 10)
+        ids_o, d_o, _ = o.search(q, 10)
+        assert np.array_equal(ids, ids_o)
+        assert np.array_equal(dists.view(np.int32), d_o.view(np.int32))
+        assert (files.deleted[ids[ids >= 0]] == 1).any()
+        its = idx.iterators(q[:8])                  # sampled at open
+        idx.set_param("SearchDeleted", 0)
+        oits = [o.iterator(qq) for qq in q[:8]]
+        for b in (10, 10, 10):
+            counts, iids, idists, relaxed = its.next(b)
+            for i, oi in enumerate(oits):
+                c, io, do, ro = oi.next(b)
+                assert counts[i] == c and np.array_equal(iids[i], io) and bool(relaxed[i]) == ro
+                assert np.array_equal(idists[i].view(np.int32), do.view(np.int32))
+        its.close()
+        for oi in oits:
+            oi.close()
+        ids1, d1 = idx.search(q, 10)                # back to the default: identical to the first search
+        assert np.array_equal(ids0, ids1) and np.array_equal(d0.view(np.int32), d1.view(np.int32))
+    finally:
+        idx.close()

@@ -520,3 +520,31 @@ def test_large_k_and_budget_bit_exact_vs_reference(oracle_lib, name, k, mc):
         o.max_check_refine = 8192
         for a, b in zip(r.refine_nodes(10, 100, 2000, files.degree, 1.0), o.refine_nodes(10, 100, 2000, files.degree, 1.0)):
             assert np.array_equal(a.view(np.int32), b.view(np.int32))
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["bkt_l2_deleted_6k_32", "bkt_cos_deleted_5k_64"])
+def test_search_deleted_flag_vs_reference(oracle_lib, name):
+    """p_searchDeleted = true (VectorIndex.h:41, dispatch flag BKTIndex.cpp:473): tombstoned vectors are eligible
+    results again -- SearchIndex and GetIterator on the reference itself against the oracle without its tombstone map."""
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))
+    r = reflib.RefIndex.load(folder)
+    r.set_param("MaxCheck", 1024)
+    o = reflib.OracleIndex(files)
+    o.max_check = 1024
+    o.search_deleted = True
+    ids_r, d_r = r.search_flag(q, 10, True, threads=4)
+    ids_o, d_o, _ = o.search(q, 10, threads=4)
+    assert np.array_equal(ids_r, ids_o)
+    assert np.array_equal(d_r.view(np.int32), d_o.view(np.int32))
+    assert (files.deleted[ids_r[ids_r >= 0]] == 1).sum() > 100      # deleted vectors do come back
+    for qi in range(8):
+        a, b = r.iterator(q[qi], True), o.iterator(q[qi])
+        for bt in [10, 10, 10]:
+            x, y = a.next(bt), b.next(bt)
+            assert x[0] == y[0] and np.array_equal(x[1], y[1]) and x[3] == y[3]
+            assert np.array_equal(x[2].view(np.int32), y[2].view(np.int32))
+        a.close()
+        b.close()
