@@ -197,6 +197,15 @@ typedef struct sptag_b200_iterator* sptag_b200_iter;
 int sptag_b200_iterator_open(sptag_b200_handle h, const void* queries, int32_t num_queries, sptag_b200_iter* out);
 int sptag_b200_iterator_next(sptag_b200_iter it, int32_t batch, int32_t* out_ids, float* out_dists,
                              int32_t* out_counts, uint8_t* out_relaxed_mono);
+/* Replaces: VectorIndex::SearchIndexIterativeFromNeareast(QueryResult&, WorkSpace*, p_isFirst) (VectorIndex.h:49,
+ * BKTIndex.cpp:543-595) for every query of an iterator -- the head-index call of SPANN's iterative search
+ * (SPANNIndex.cpp:259-285).  The first call on a freshly opened iterator returns the k nearest by a full search and
+ * re-seeds the scan from their graph neighbours; every later call (same k) returns the next k in pop order, sorted.
+ * out_ids / out_dists: [num_queries x k], unfilled slots (-1, MaxDist); out_found[q] (nullable) = the reference's bool
+ * (first slot holds a vector).  k <= 1024.  Do not mix with sptag_b200_iterator_next on the same iterator before the
+ * first call. */
+int sptag_b200_iterator_next_from_nearest(sptag_b200_iter it, int32_t k, int32_t* out_ids, float* out_dists,
+                                          uint8_t* out_found);
 void sptag_b200_iterator_close(sptag_b200_iter it);
 
 /* Vector-partition sharding: merges `num_lists` per-shard result lists of a query

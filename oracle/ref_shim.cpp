@@ -392,6 +392,32 @@ void* ref_iter_open_flag(void* h, const void* query, int search_deleted) {
     return new std::shared_ptr<ResultIterator>(it);
 }
 
+// VectorIndex::SearchIndexIterativeFromNeareast (VectorIndex.h:49, BKTIndex.cpp:543-595) driven the way SPANN's
+// iterative search drives its head index (SPANNIndex.cpp:259-285): RentWorkSpace(k) once, then one call per batch on a
+// freshly Reset() QueryResult of k slots; SearchIndexIterativeEnd returns the work space.
+void* ref_nearest_open(void* h, int k) {
+    auto& idx = ((RefHandle*)h)->index;
+    std::unique_ptr<COMMON::WorkSpace> ws = idx->RentWorkSpace(k);
+    return ws.release();
+}
+
+int ref_nearest_next(void* h, void* wsp, const void* query, int k, int is_first, int* ids, float* dists) {
+    auto& idx = ((RefHandle*)h)->index;
+    QueryResult res(query, k, false);
+    res.Reset();
+    const bool ok = idx->SearchIndexIterativeFromNeareast(res, (COMMON::WorkSpace*)wsp, is_first != 0);
+    for (int j = 0; j < k; ++j) {
+        ids[j] = res.GetResult(j)->VID;
+        dists[j] = res.GetResult(j)->Dist;
+    }
+    return ok ? 1 : 0;
+}
+
+void ref_nearest_close(void* h, void* wsp) {
+    auto& idx = ((RefHandle*)h)->index;
+    idx->SearchIndexIterativeEnd(std::unique_ptr<COMMON::WorkSpace>((COMMON::WorkSpace*)wsp));
+}
+
 // Install the counter-reading factory (single-query stats below need it). Irreversible for h.
 int ref_enable_stats(void* h) {
     auto& idx = ((RefHandle*)h)->index;

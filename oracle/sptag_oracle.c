@@ -1044,45 +1044,18 @@ ora_iterator* ora_iter_open(const ora_index* idx, const void* query)
     return it;
 }
 
-/* ResultIterator::Next(batch) -> SearchIndexIterativeNext (BKTIndex.cpp:659-675) -> SearchIterative<notDeleted, isDup>
- * (:354-427).  ids/dists: [batch], ascending over the returned entries, unfilled (-1, MaxDist); returns resultCount;
- * *relaxed_mono = WorkSpace::m_relaxedMono after the call. */
-int ora_iter_next(ora_iterator* it, int32_t batch, int32_t* ids, float* dists, int32_t* relaxed_mono)
+/* BKT::Index<T>::SearchIterative<notDeleted, isDup> (BKTIndex.cpp:354-427) on the iterator's work space */
+static int iter_loop(ora_iterator* it, int batch, res_t* res, int is_first)
 {
     const ora_index* idx = &it->idx;
     const ora_bkt_node* nodes = (const ora_bkt_node*)idx->nodes;
     static const size_t elem[4] = {1, 1, 2, 4};
     ws_t* ws = &it->ws;
-    /* ResultIterator::Next (ResultIterator.cpp:31-42, :52): the first call creates the QueryResult with `batch` slots;
-     * afterwards the batch is capped by QueryResult::GetResultNum(), which the previous call left at ITS resultCount
-     * (SetResultNum(resultCount)) -- an iterator's batch can only shrink */
-    const int requested = batch;
-    if (it->res == NULL) {
-        it->res = (res_t*)malloc(sizeof(res_t) * (size_t)(batch > 0 ? batch : 1));
-    } else if (batch > it->max_batch) {
-        batch = it->max_batch;
-    }
-    for (int i = batch; i < requested; i++) {
-        ids[i] = -1;
-        dists[i] = kMaxDist();
-    }
-    res_t* res = it->res;
-    for (int i = 0; i < batch; i++) { /* QueryResult::Reset */
-        res[i].vid = -1;
-        res[i].dist = kMaxDist();
-    }
-    /* WorkSpace::ResetResult(m_iMaxCheck, batch) (WorkSpace.h:280-286) */
-    dpq_clear(&ws->results, idx->max_check / 16 > batch ? idx->max_check / 16 : batch);
-    ws->no_better = 0;
-    ws->tree_checked = 0;
-    ws->checked = 0;
-
     qctx_t c = {idx, it->query, elem[idx->value_type] * (size_t)idx->dim, idx->metric != ORA_L2};
-    if (it->is_first) {
+    if (is_first) {
         bkt_init_search_trees(&c, ws);
         bkt_search_trees(&c, ws, idx->initial_pivots);
     }
-    it->is_first = 0;
     int count = 0;
     const int checkPos = idx->degree - 1;
     while (ws->ng.count != 0) {
@@ -1125,6 +1098,42 @@ int ora_iter_next(ora_iterator* it, int32_t batch, int32_t* ids, float* dists, i
             bkt_search_trees(&c, ws, idx->other_pivots + ws->checked);
         if (count >= batch) break;
     }
+    return count;
+}
+
+/* ResultIterator::Next(batch) -> SearchIndexIterativeNext (BKTIndex.cpp:659-675) -> SearchIterative<notDeleted, isDup>
+ * (:354-427).  ids/dists: [batch], ascending over the returned entries, unfilled (-1, MaxDist); returns resultCount;
+ * *relaxed_mono = WorkSpace::m_relaxedMono after the call. */
+int ora_iter_next(ora_iterator* it, int32_t batch, int32_t* ids, float* dists, int32_t* relaxed_mono)
+{
+    const ora_index* idx = &it->idx;
+    ws_t* ws = &it->ws;
+    /* ResultIterator::Next (ResultIterator.cpp:31-42, :52): the first call creates the QueryResult with `batch` slots;
+     * afterwards the batch is capped by QueryResult::GetResultNum(), which the previous call left at ITS resultCount
+     * (SetResultNum(resultCount)) -- an iterator's batch can only shrink */
+    const int requested = batch;
+    if (it->res == NULL) {
+        it->res = (res_t*)malloc(sizeof(res_t) * (size_t)(batch > 0 ? batch : 1));
+    } else if (batch > it->max_batch) {
+        batch = it->max_batch;
+    }
+    for (int i = batch; i < requested; i++) {
+        ids[i] = -1;
+        dists[i] = kMaxDist();
+    }
+    res_t* res = it->res;
+    for (int i = 0; i < batch; i++) { /* QueryResult::Reset */
+        res[i].vid = -1;
+        res[i].dist = kMaxDist();
+    }
+    /* WorkSpace::ResetResult(m_iMaxCheck, batch) (WorkSpace.h:280-286) */
+    dpq_clear(&ws->results, idx->max_check / 16 > batch ? idx->max_check / 16 : batch);
+    ws->no_better = 0;
+    ws->tree_checked = 0;
+    ws->checked = 0;
+
+    const int count = iter_loop(it, batch, res, it->is_first);
+    it->is_first = 0;
     res_sort(res, batch);
     for (int i = 0; i < batch; i++) {
         ids[i] = res[i].vid;
@@ -1142,4 +1151,60 @@ void ora_iter_close(ora_iterator* it)
     free(it->query);
     free(it->res);
     free(it);
+}
+
+
+/* BKT::Index<T>::SearchIndexIterativeFromNeareast (BKTIndex.cpp:543-595), the head-index call of SPANN's iterative
+ * search (SPANNIndex.cpp:273-285).  First call: a full SearchIndex(query, workspace, searchDeleted = false,
+ * searchDuplicated = true) for the k nearest on the rented work space, then the visited set is cleared (the queues keep
+ * whatever the search left in them), every result is marked visited and its unvisited graph neighbours enter NGQueue
+ * with their distances.  Later calls: ResetResult + SearchIterative(isFirst = false, batch = k).
+ * ids/dists: [k]; returns 1 if the first result slot is a real vector (the reference's bool), else 0. */
+int ora_iter_next_from_nearest(ora_iterator* it, int32_t k, int32_t* ids, float* dists)
+{
+    const ora_index* idx = &it->idx;
+    static const size_t elem[4] = {1, 1, 2, 4};
+    ws_t* ws = &it->ws;
+    if (it->res == NULL) {
+        it->max_batch = k;
+        it->res = (res_t*)malloc(sizeof(res_t) * (size_t)(k > 0 ? k : 1));
+    }
+    if (k != it->max_batch) return -1; /* the caller's QueryResult keeps its size (SPANN passes the same object) */
+    res_t* res = it->res;
+    for (int i = 0; i < k; i++) { /* p_headQueryResults->Reset() */
+        res[i].vid = -1;
+        res[i].dist = kMaxDist();
+    }
+    dpq_clear(&ws->results, idx->max_check / 16 > k ? idx->max_check / 16 : k); /* ResetResult(m_iMaxCheck, k) */
+    ws->no_better = 0;
+    ws->tree_checked = 0;
+    ws->checked = 0;
+    if (it->is_first) {
+        qctx_t c = {idx, it->query, elem[idx->value_type] * (size_t)idx->dim, idx->metric != ORA_L2};
+        bkt_search(&c, ws, res, k, 0);
+        memset(ws->visited, 0, (size_t)ws->n + 1); /* nodeCheckStatus.clear() */
+        const int checkPos = idx->degree - 1;
+        for (int i = 0; i < k; i++) {
+            const int32_t result = res[i].vid;
+            if (result < 0) continue;
+            ws_check_and_set(ws, result);
+            const int32_t* node = idx->graph + (size_t)result * idx->degree;
+            for (int j = 0; j <= checkPos; j++) {
+                const int32_t nn = node[j];
+                if (nn < 0) break;
+                if (ws_check_and_set(ws, nn)) continue;
+                pair_t p = {nn, qdist(&c, ws, nn)};
+                heap_insert(&ws->ng, p);
+            }
+        }
+        it->is_first = 0;
+    } else {
+        iter_loop(it, k, res, 0);
+        res_sort(res, k);
+    }
+    for (int i = 0; i < k; i++) {
+        ids[i] = res[i].vid;
+        dists[i] = res[i].dist;
+    }
+    return res[0].vid >= 0 ? 1 : 0;
 }

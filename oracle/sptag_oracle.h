@@ -113,6 +113,9 @@ typedef struct ora_iterator ora_iterator;
 ora_iterator* ora_iter_open(const ora_index* idx, const void* query);
 int ora_iter_next(ora_iterator* it, int32_t batch, int32_t* ids, float* dists, int32_t* relaxed_mono);
 void ora_iter_close(ora_iterator* it);
+/* BKT::Index<T>::SearchIndexIterativeFromNeareast (BKTIndex.cpp:543-595) on an iterator opened with ora_iter_open:
+ * first call = the k nearest by a full search + re-seeding from their neighbours, later calls = the next k. */
+int ora_iter_next_from_nearest(ora_iterator* it, int32_t k, int32_t* ids, float* dists);
 
 #ifdef __cplusplus
 }

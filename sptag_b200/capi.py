@@ -27,6 +27,7 @@ EXPORTS = [
     "sptag_b200_num_vectors", "sptag_b200_dim", "sptag_b200_value_type", "sptag_b200_metric",
     "sptag_b200_algo", "sptag_b200_last_error", "sptag_b200_refine_graph", "sptag_b200_get_graph",
     "sptag_b200_graph_degree", "sptag_b200_iterator_open", "sptag_b200_iterator_next", "sptag_b200_iterator_close",
+    "sptag_b200_iterator_next_from_nearest",
 ]
 
 
@@ -78,6 +79,7 @@ def lib():
         L.sptag_b200_graph_degree.argtypes = [C.c_void_p]
         L.sptag_b200_iterator_open.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
         L.sptag_b200_iterator_next.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sptag_b200_iterator_next_from_nearest.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sptag_b200_iterator_close.argtypes = [C.c_void_p]
         L.sptag_b200_iterator_close.restype = None
         L.sptag_b200_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -282,6 +284,15 @@ class B200Iterators:
         _check(lib().sptag_b200_iterator_next(self._it, batch, ids.ctypes.data, dists.ctypes.data, counts.ctypes.data,
                                               relaxed.ctypes.data))
         return counts, ids, dists, relaxed.astype(bool)
+
+    def next_from_nearest(self, k):
+        """SearchIndexIterativeFromNeareast for every query -> (found [nq] bool, ids [nq, k], dists [nq, k])."""
+        ids = np.empty((self.nq, k), np.int32)
+        dists = np.empty((self.nq, k), np.float32)
+        found = np.empty(self.nq, np.uint8)
+        _check(lib().sptag_b200_iterator_next_from_nearest(self._it, k, ids.ctypes.data, dists.ctypes.data,
+                                                           found.ctypes.data))
+        return found.astype(bool), ids, dists
 
     def close(self):
         if self._it:

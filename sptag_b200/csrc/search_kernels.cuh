@@ -1116,6 +1116,38 @@ struct WarpSearch {
         return count;
     }
 
+    // SearchIndexIterativeFromNeareast, first call (BKTIndex.cpp:549-572): one result of the finished search is marked
+    // visited and its not-yet-visited graph neighbours enter NGQueue with their distances (no budget accounting, no
+    // m_Results)
+    __device__ __forceinline__ void seed_from_result(int result) {
+        check_and_set_uniform(result);
+        const int checkPos = p.degree - 1;
+        const int* node = p.graph + (size_t)result * p.degree;
+        for (int cbase = 0; cbase <= checkPos; cbase += 32) {
+            const bool in_row = (cbase + lane <= checkPos);
+            const int nn = in_row ? node[cbase + lane] : -1;
+            const unsigned negmask = __ballot_sync(kFull, in_row && nn < 0) | ~__ballot_sync(kFull, in_row);
+            const int first_neg = negmask ? (__ffs(negmask) - 1) : 32;
+            const bool active = lane < first_neg;
+            const unsigned same = __match_any_sync(kFull, active ? nn : (-1 - lane));
+            const bool leader = active && ((__ffs(same) - 1) == lane);
+            bool fresh = false;
+            if (leader) {
+                const unsigned bit = 1u << (nn & 31);
+                const unsigned old = atomicOr(&visited[nn >> 5], bit);
+                fresh = (old & bit) == 0;
+            }
+            const unsigned freshmask = __ballot_sync(kFull, fresh);
+            const int cnt = __popc(freshmask);
+            __syncwarp();
+            if (fresh) cand_id[__popc(freshmask & ((1u << lane) - 1u))] = nn;
+            compute_dists(cnt);
+            for (int r = 0; r < cnt; ++r) heap_insert(ng, cand_id[r], cand_dist[r], lane);
+            __syncwarp();
+            if (first_neg < 32) break;
+        }
+    }
+
     // ------------------------------------------------------------------------------------
     // KDT flavour: KDTree::KDTSearch (KDTree.h:233-271, tail recursion as a loop),
     // InitSearchTrees/SearchTrees (KDTree.h:213-231), KDT::Index<T>::Search (KDTIndex.cpp:182-241)
@@ -1468,6 +1500,114 @@ __global__ void __launch_bounds__(32, 12) iterate_kernel(const SearchParams p, i
             st[4] = count;  // m_queryResult->SetResultNum(resultCount)
             out_counts[q] = count;
             out_relaxed[q] = (unsigned char)relaxed;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// BKT::Index<T>::SearchIndexIterativeFromNeareast, FIRST call (BKTIndex.cpp:543-573), for a batch of freshly opened
+// iterators -- the head-index call of SPANN's iterative search (SPANNIndex.cpp:273): a full Search for the p.k nearest on
+// the query's own work-space arenas, nodeCheckStatus.clear(), then every result re-seeds NGQueue from its graph row.
+// Later calls are iterate_kernel with batch = k (the host resets the result-slot cap: the caller's QueryResult keeps
+// its size there).
+// ------------------------------------------------------------------------------------------
+template <bool COSINE, int RPL, int ELEM>
+__global__ void __launch_bounds__(32, 12) nearest_first_kernel(const SearchParams p, int* __restrict__ state) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x;
+    WarpSearch<0, COSINE, RPL, false, ELEM, false> w(p, lane);
+    w.ring = smem;
+    w.cand_id = reinterpret_cast<int*>(smem + p.off_cand);
+    w.cand_dist = reinterpret_cast<float*>(smem + p.off_cand + 128);
+    w.bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+    w.qs = reinterpret_cast<float*>(smem + p.off_query);
+    w.vlog = nullptr;
+    w.ng.s = reinterpret_cast<int2*>(smem + p.off_ng);
+    w.ng.H = p.h_ng;
+    w.ng.length = p.ng_length;
+    w.ng.lastlevel = p.ng_lastlevel;
+    w.spt.s = reinterpret_cast<int2*>(smem + p.off_spt);
+    w.spt.H = p.h_spt;
+    w.spt.length = p.spt_length;
+    w.spt.lastlevel = p.spt_lastlevel;
+    w.phase_bits = 0;
+    if (lane == 0) {
+        for (int s = 0; s < p.stages; ++s) mbar_init(&w.bars[s], 1);
+        mbar_fence_init();
+        w.ng.s[0] = make_pair(-1, SPTAG_B200_MAXDIST);
+        w.spt.s[0] = make_pair(-1, SPTAG_B200_MAXDIST);
+    }
+    __syncwarp();
+
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = (int)atomicAdd(p.work_counter, 1u);
+        q = __shfl_sync(kFull, q, 0);
+        if (q >= p.nq) break;
+        int* st = state + (size_t)q * kIterStateInts;
+        w.visited = p.visited + (size_t)q * p.visited_words;  // zeroed when the iterator was opened
+        w.ng.g = p.ng_spill + (size_t)q * p.ng_spill_entries;
+        w.spt.g = p.spt_spill + (size_t)q * p.spt_spill_entries;
+        w.tk = (p.k > 32) ? p.topk + (size_t)q * p.topk_pad : nullptr;
+        // the rented WorkSpace after Reset(MaxCheck, k) + ResetResult(MaxCheck, k)
+        w.vlog_count = 0;
+        w.ng.count = 0;
+        w.spt.count = 0;
+        w.mres.reset(max(p.max_check / 16, p.k), lane);
+        w.tk_d = SPTAG_B200_MAXDIST;
+        w.tk_id = -1;
+        w.worst_d = SPTAG_B200_MAXDIST;
+        w.worst_id = -1;
+        if (w.tk != nullptr) w.res_reset();
+        w.checked = w.ndist = w.nexpand = w.ntree = 0;
+        w.tree_checked = w.no_better = 0;
+        {
+            const unsigned char* qb = p.queries + (size_t)q * p.query_stride_bytes;
+            unsigned char* qd = reinterpret_cast<unsigned char*>(w.qs);
+            const int qbytes = p.dim * (ELEM == 0 ? 4 : (ELEM == 3 ? 2 : 1));
+            for (int i = lane; i < qbytes; i += 32) qd[i] = qb[i];
+        }
+        __syncwarp();
+
+        w.bkt_search();  // SearchIndex(query, workspace, p_searchDeleted, searchDuplicated = true)
+
+        __syncwarp();
+        if (w.tk != nullptr) w.res_sort();
+        // p_space->nodeCheckStatus.clear(): other nodes may be traversed again after the top k were found
+        {
+            uint4* v4 = reinterpret_cast<uint4*>(w.visited);
+            const size_t n4 = p.visited_words >> 2;
+            for (size_t i = lane; i < n4; i += 32) v4[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();
+        for (int i = 0; i < p.k; ++i) {
+            int rid;
+            float rd;
+            if (w.tk != nullptr) {
+                const int2 e = w.tk[i];
+                rid = e.x;
+                rd = __int_as_float(e.y);
+            } else {
+                rid = __shfl_sync(kFull, w.tk_id, i);
+                rd = __shfl_sync(kFull, w.tk_d, i);
+            }
+            if (lane == 0) {
+                p.out_ids[(size_t)q * p.k + i] = (rid >= 0) ? rid + p.id_offset : rid;
+                p.out_dists[(size_t)q * p.k + i] = rd;
+            }
+            if (rid < 0) continue;
+            w.seed_from_result(rid);
+        }
+        // flush the queue heads and the scalars
+        __syncwarp();
+        for (int i = 1 + lane; i <= min(w.ng.count, w.ng.H); i += 32) w.ng.g[i] = w.ng.s[i];
+        for (int i = 1 + lane; i <= min(w.spt.count, w.spt.H); i += 32) w.spt.g[i] = w.spt.s[i];
+        if (lane == 0) {
+            st[0] = w.ng.count;
+            st[1] = w.spt.count;
+            st[2] = 0;
+            st[4] = -1;
         }
         __syncwarp();
     }

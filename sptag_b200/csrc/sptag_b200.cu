@@ -133,6 +133,8 @@ struct sptag_b200_iterator {
     size_t visited_words = 0, ng_entries = 0, spt_entries = 0;
     int topk_pad = 0;
     int search_deleted = 0;  // GetIterator(p_target, p_searchDeleted)
+    int nearest_k = 0;       // > 0 once sptag_b200_iterator_next_from_nearest ran: the head QueryResult's size
+    bool stepped = false;    // a Next of either kind has run
     DeviceBuffer d_queries, d_visited, d_ng, d_spt, d_state, d_topk, d_ids, d_dists, d_counts, d_relaxed;
     void release() {
         d_queries.release(); d_visited.release(); d_ng.release(); d_spt.release(); d_state.release();
@@ -194,6 +196,26 @@ IterateKernelFn pick_iter_rpl(int mres_cap) {
     if (mres_cap <= 32 * 16) return iterate_kernel<COSINE, 16, ELEM>;
     if (mres_cap <= 32 * 32) return iterate_kernel<COSINE, 32, ELEM>;
     return nullptr;
+}
+
+typedef void (*NearestFirstKernelFn)(const SearchParams, int*);
+
+template <bool COSINE, int ELEM>
+NearestFirstKernelFn pick_nearest_rpl(int mres_cap) {
+    if (mres_cap <= 32 * 16) return nearest_first_kernel<COSINE, 16, ELEM>;
+    if (mres_cap <= 32 * 32) return nearest_first_kernel<COSINE, 32, ELEM>;
+    return nullptr;
+}
+
+NearestFirstKernelFn pick_nearest_first_kernel(const sptag_b200_index* h, int mres_cap) {
+    const bool l2 = (h->metric == SPTAG_B200_METRIC_L2);
+    switch (h->value_type) {
+    case SPTAG_B200_VT_FLOAT: return l2 ? pick_nearest_rpl<false, 0>(mres_cap) : pick_nearest_rpl<true, 0>(mres_cap);
+    case SPTAG_B200_VT_INT8: return l2 ? pick_nearest_rpl<false, 1>(mres_cap) : pick_nearest_rpl<true, 1>(mres_cap);
+    case SPTAG_B200_VT_UINT8: return l2 ? pick_nearest_rpl<false, 2>(mres_cap) : pick_nearest_rpl<true, 2>(mres_cap);
+    case SPTAG_B200_VT_INT16: return l2 ? pick_nearest_rpl<false, 3>(mres_cap) : pick_nearest_rpl<true, 3>(mres_cap);
+    default: return nullptr;
+    }
 }
 
 IterateKernelFn pick_iterate_kernel(const sptag_b200_index* h, int mres_cap) {
@@ -1150,6 +1172,95 @@ int sptag_b200_iterator_next(sptag_b200_iter it, int32_t batch, int32_t* out_ids
     if (out_relaxed_mono)
         CUDA_OK(cudaMemcpyAsync(out_relaxed_mono, it->d_relaxed.ptr, (size_t)it->nq, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
+    it->stepped = true;
+    return SPTAG_B200_SUCCESS;
+}
+
+int sptag_b200_iterator_next_from_nearest(sptag_b200_iter it, int32_t k, int32_t* out_ids, float* out_dists,
+                                          uint8_t* out_found) {
+    if (!it || !it->h) return fail(SPTAG_B200_EMPTY_INDEX, "null iterator");
+    if (!out_ids || !out_dists) return fail(SPTAG_B200_LACK_OF_INPUTS, "null buffer");
+    if (k < 1 || k > 1024) return fail(SPTAG_B200_LACK_OF_INPUTS, "k = %d outside [1, 1024]", k);
+    const bool first = (it->nearest_k == 0);
+    if (first && it->stepped)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "the first SearchIndexIterativeFromNeareast call needs a freshly opened iterator");
+    if (!first && k != it->nearest_k)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "k = %d differs from the head QueryResult's %d slots", k, it->nearest_k);
+    sptag_b200_index* h = it->h;
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceGuard guard(h->device);
+    SearchParams p;
+    int grid = 0;
+    size_t smem = 0;
+    SearchKernelFn skern = nullptr;
+    const int saved_check = h->max_check, saved_sd = h->search_deleted;
+    h->max_check = it->max_check;
+    h->search_deleted = it->search_deleted;
+    const int rc0 = configure(h, k, p, grid, smem, it->nq, skern);
+    h->max_check = saved_check;
+    h->search_deleted = saved_sd;
+    if (rc0) return rc0;
+    NearestFirstKernelFn kfirst = pick_nearest_first_kernel(h, p.mres_cap);
+    IterateKernelFn knext = pick_iterate_kernel(h, p.mres_cap);
+    if (!kfirst || !knext)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "max(MaxCheck/16, k) = %d exceeds the supported 1024", p.mres_cap);
+    if (it->topk_pad == 0) {
+        int pad = 64;
+        while (pad < k) pad <<= 1;
+        it->topk_pad = pad;
+        if (int rc = it->d_topk.ensure((size_t)it->nq * pad * 8)) return rc;
+    }
+    const size_t rn = (size_t)it->nq * k;
+    if (int rc = it->d_ids.ensure(rn * 4)) return rc;
+    if (int rc = it->d_dists.ensure(rn * 4)) return rc;
+    p.off_query = (int)round_up((size_t)p.off_bar + round_up((size_t)p.stages * 8, 16), 16);
+    smem = round_up((size_t)p.off_query + round_up((size_t)h->dim * 4 + 16, 16), 128);
+    p.queries = (const unsigned char*)it->d_queries.ptr;
+    p.query_stride_bytes = query_bytes(h);
+    p.nq = it->nq;
+    p.k = k;
+    p.max_check = it->max_check;
+    p.ng_length = it->ng_length;
+    p.ng_lastlevel = it->ng_lastlevel;
+    p.spt_length = it->spt_length;
+    p.spt_lastlevel = it->spt_lastlevel;
+    p.visited = (unsigned int*)it->d_visited.ptr;
+    p.visited_words = it->visited_words;
+    p.vlog = nullptr;
+    p.ng_spill = (int2*)it->d_ng.ptr;
+    p.ng_spill_entries = it->ng_entries;
+    p.spt_spill = (int2*)it->d_spt.ptr;
+    p.spt_spill_entries = it->spt_entries;
+    p.topk = (int2*)it->d_topk.ptr;
+    p.topk_pad = it->topk_pad;
+    p.out_ids = (int*)it->d_ids.ptr;
+    p.out_dists = (float*)it->d_dists.ptr;
+    p.out_stats = nullptr;
+    p.filter = nullptr;
+    if (smem > h->smem_optin) return fail(SPTAG_B200_MEMORY_OVERFLOW, "shared memory per query slot %zu exceeds %zu", smem, h->smem_optin);
+    cudaStream_t stream = nullptr;
+    CUDA_OK(cudaMemsetAsync(p.work_counter, 0, 4, stream));
+    CUDA_OK(cudaEventRecord(h->ev_start, stream));
+    if (first) {
+        CUDA_OK(cudaFuncSetAttribute((const void*)kfirst, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kfirst<<<grid, 32, smem, stream>>>(p, (int*)it->d_state.ptr);
+    } else {
+        // the caller Reset()s a QueryResult that keeps its k slots (SPANNIndex.cpp:284): no cap from the previous count
+        CUDA_OK(cudaMemset2DAsync((int*)it->d_state.ptr + 4, (size_t)kIterStateInts * 4, 0xFF, 4, (size_t)it->nq, stream));
+        CUDA_OK(cudaFuncSetAttribute((const void*)knext, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knext<<<grid, 32, smem, stream>>>(p, (int*)it->d_state.ptr, (int*)it->d_counts.ptr, (unsigned char*)it->d_relaxed.ptr);
+    }
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(h->ev_stop, stream));
+    h->timed = true;
+    CUDA_OK(cudaMemcpyAsync(out_ids, it->d_ids.ptr, rn * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemcpyAsync(out_dists, it->d_dists.ptr, rn * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    if (out_found)  // the reference's return value: is the first result slot a real vector
+        for (int q = 0; q < it->nq; ++q) out_found[q] = out_ids[(size_t)q * k] >= 0 ? 1 : 0;
+    it->nearest_k = k;
+    it->stepped = true;
     return SPTAG_B200_SUCCESS;
 }
 

@@ -89,6 +89,10 @@ def ref():
         L.ref_iter_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(C.c_double)]
         L.ref_delete.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_nearest_open.restype = C.c_void_p
+        L.ref_nearest_open.argtypes = [C.c_void_p, C.c_int]
+        L.ref_nearest_next.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_nearest_close.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_search_each_flag.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p]
         L.ref_iter_open_flag.restype = C.c_void_p
@@ -226,6 +230,28 @@ class RefIndex:
         ref().ref_search_one_stats(self.h, query.ctypes.data, k, ids.ctypes.data, dists.ctypes.data,
                                    stats.ctypes.data)
         return ids, dists, stats
+
+
+class RefNearestScan:
+    """SearchIndexIterativeFromNeareast driven like SPANN drives its head index: k results per call."""
+
+    def __init__(self, index, query, k):
+        self.index, self.query, self.k = index, np.ascontiguousarray(query), k
+        self.ws = ref().ref_nearest_open(index.h, k)
+        self.first = True
+
+    def next(self):
+        ids = np.empty(self.k, np.int32)
+        dists = np.empty(self.k, np.float32)
+        ok = ref().ref_nearest_next(self.index.h, self.ws, self.query.ctypes.data, self.k, 1 if self.first else 0,
+                                    ids.ctypes.data, dists.ctypes.data)
+        self.first = False
+        return bool(ok), ids, dists
+
+    def close(self):
+        if self.ws:
+            ref().ref_nearest_close(self.index.h, self.ws)
+            self.ws = None
 
 
 class _RefIterator:
@@ -481,6 +507,7 @@ def ora():
         L.ora_iter_open.argtypes = [C.POINTER(_OraIndex), C.c_void_p]
         L.ora_iter_next.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
         L.ora_iter_close.argtypes = [C.c_void_p]
+        L.ora_iter_next_from_nearest.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.ora_quantizer_init.argtypes = [C.POINTER(_OraQuantizer)]
         L.ora_quantizer_encode.argtypes = [C.POINTER(_OraQuantizer), C.c_void_p, C.c_int32, C.c_void_p]
         L.ora_quantizer_l2.restype = C.c_float
@@ -573,6 +600,14 @@ class _OraIterator:
         relaxed = C.c_int32()
         count = ora().ora_iter_next(self.h, batch, ids.ctypes.data, dists.ctypes.data, C.byref(relaxed))
         return count, ids, dists, bool(relaxed.value)
+
+    def next_from_nearest(self, k):
+        """SearchIndexIterativeFromNeareast: -> (ok, ids [k], dists [k])."""
+        ids = np.empty(k, np.int32)
+        dists = np.empty(k, np.float32)
+        ok = ora().ora_iter_next_from_nearest(self.h, k, ids.ctypes.data, dists.ctypes.data)
+        assert ok >= 0
+        return bool(ok), ids, dists
 
     def close(self):
         if self.h:

@@ -96,3 +96,35 @@ def test_search_deleted_parameter(name):
         assert np.array_equal(ids0, ids1) and np.array_equal(d0.view(np.int32), d1.view(np.int32))
     finally:
         idx.close()
+
+
+@pytest.mark.parametrize("name,mc,k", [("bkt_l2_20k_32", 8192, 10), ("bkt_l2_20k_32", 128, 32), ("bkt_cos_10k_128", 1024, 64),
+                                       ("bkt_l2_dups", 256, 16), ("bkt_l2_3k_30", 512, 8), ("bkt_i8_cos_6k_64", 512, 10),
+                                       ("bkt_l2_deleted_6k_32", 512, 10), ("bkt_i16_l2_4k_27", 300, 5),
+                                       ("bkt_cos_3k_768", 2048, 100)])
+def test_iterative_from_nearest(name, mc, k):
+    """sptag_b200_iterator_next_from_nearest (SearchIndexIterativeFromNeareast, the SPANN head-index call): first call
+    = the k nearest + re-seeding, later calls = the next k -- against the oracle, pinned to the reference on CPU."""
+    from sptag_b200 import B200Index
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:12]
+    idx = B200Index.load(folder)
+    try:
+        idx.set_param("MaxCheck", mc)
+        o = reflib.OracleIndex(files)
+        o.max_check = mc
+        oits = [o.iterator(qq) for qq in q]
+        its = idx.iterators(q)
+        for rd in range(10):
+            found, ids, dists = its.next_from_nearest(k)
+            for i, oi in enumerate(oits):
+                ok, io, do = oi.next_from_nearest(k)
+                assert bool(found[i]) == ok, (name, rd, i)
+                assert np.array_equal(ids[i], io), (name, rd, i)
+                assert np.array_equal(dists[i].view(np.int32), do.view(np.int32)), (name, rd, i)
+        its.close()
+        for oi in oits:
+            oi.close()
+    finally:
+        idx.close()

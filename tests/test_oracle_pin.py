@@ -548,3 +548,30 @@ def test_search_deleted_flag_vs_reference(oracle_lib, name):
             assert np.array_equal(x[2].view(np.int32), y[2].view(np.int32))
         a.close()
         b.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("name,mc,k", [("bkt_l2_20k_32", 8192, 10), ("bkt_l2_20k_32", 128, 32), ("bkt_cos_10k_128", 1024, 64),
+                                       ("bkt_l2_dups", 256, 16), ("bkt_l2_3k_30", 512, 8), ("bkt_i8_cos_6k_64", 512, 10),
+                                       ("bkt_l2_deleted_6k_32", 512, 10), ("bkt_i16_l2_4k_27", 300, 5)])
+def test_iterative_from_nearest_bit_exact_vs_reference(oracle_lib, name, mc, k):
+    """VectorIndex::SearchIndexIterativeFromNeareast driven the way SPANN drives its head index (RentWorkSpace(k), one
+    call per batch on a Reset() QueryResult, SearchIndexIterativeEnd) on the reference itself, against the oracle."""
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    qs = np.load(os.path.join(folder, "queries.npy"))[:8]
+    r = reflib.RefIndex.load(folder)
+    r.set_param("MaxCheck", mc)
+    o = reflib.OracleIndex(files)
+    o.max_check = mc
+    for qi, q in enumerate(qs):
+        a, b = reflib.RefNearestScan(r, q, k), o.iterator(q)
+        for rd in range(12 if qi != 3 else 300):
+            x, y = a.next(), b.next_from_nearest(k)
+            assert x[0] == y[0], (name, qi, rd)
+            assert np.array_equal(x[1], y[1]), (name, qi, rd)
+            assert np.array_equal(x[2].view(np.int32), y[2].view(np.int32)), (name, qi, rd)
+            if not x[0]:
+                break
+        a.close()
+        b.close()
