@@ -92,3 +92,23 @@ def test_header_is_plain_c(tmp_path):
     if shutil.which("g++"):
         subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc,
                                str(src)])
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under sptag_b200/ or include/ may import, link or execute it, and the
+    shipped library must not depend on the oracle's shared objects."""
+    import subprocess
+    pkg = os.path.join(ROOT, "sptag_b200")
+    offenders = []
+    for base, _, names in os.walk(pkg):
+        for n in names:
+            if n.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                text = open(os.path.join(base, n), errors="replace").read()
+                for needle in ("libsptag_oracle", "libsptag_ref", "sptag_oracle.h", "import reflib", "oracle/_ref",
+                               "oracle/_build"):
+                    if needle in text:
+                        offenders.append((os.path.relpath(os.path.join(base, n), ROOT), needle))
+    assert not offenders, offenders
+    if os.path.exists(LIB):
+        out = subprocess.run(["ldd", LIB], capture_output=True, text=True).stdout
+        assert "sptag_oracle" not in out and "sptag_ref" not in out, out
