@@ -118,8 +118,9 @@ void sptag_b200_destroy(sptag_b200_handle h);
  * 1 makes tombstoned vectors eligible results; searches read it per call, iterators sample it at open, the refine
  * pass always runs with 0 like NeighborhoodGraph::RefineNode.  Additional B200 tuning knobs (not in the
  * reference) are prefixed "B200.": B200.QueriesPerSM, B200.StageRows, B200.Stages,
- * B200.NGCacheEntries, B200.SPTCacheEntries, B200.SimdWidth (16/8/4: which DistanceUtils
- * summation tree to reproduce bit-exactly; default 16 = AVX-512), B200.VisitedLog (-1 auto, 0 clear the
+ * B200.NGCacheEntries, B200.SPTCacheEntries, B200.SimdWidth (which DistanceUtils summation tree to
+ * reproduce bit-exactly: 16 = AVX-512, the only one built -- 8 / 4 make the search calls return
+ * LackOfInputs rather than a differently rounded distance), B200.VisitedLog (-1 auto, 0 clear the
  * visited bitmap per query, 1 log the touched words and clear only those: for indexes of tens of millions
  * of vectors), B200.VisitedLogEntries. */
 int sptag_b200_set_param(sptag_b200_handle h, const char* name, const char* value);
