@@ -1613,219 +1613,4 @@ __global__ void __launch_bounds__(32, 12) nearest_first_kernel(const SearchParam
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// stand-alone batched distance kernel (inner-loop parity): one half-warp per (query, id)
-// ------------------------------------------------------------------------------------------
-template <bool COSINE, int ELEM>
-__global__ void distance_batch_kernel(const unsigned char* vectors, unsigned long long row_stride_bytes, int n,
-                                      int dim, const void* queries_v, int nq, const int* ids, int ids_per_query,
-                                      float* out) {
-    const int lane = threadIdx.x & 31;
-    const int j = lane & 15;
-    const long long hw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    const long long total = (long long)nq * ids_per_query;
-    // all 32 lanes of a warp run the same number of iterations (shuffles inside)
-    const long long pair = hw >> 1;
-    const long long npairs = (total + 1) >> 1;
-    if (pair >= npairs) return;
-    const bool valid = hw < total;
-    const long long item = valid ? hw : total - 1;
-    const int q = (int)(item / ids_per_query);
-    const int id = ids[item];
-    const bool ok = (id >= 0 && id < n);
-    float d;
-    if (ELEM == 0) {
-        const float* row = reinterpret_cast<const float*>(vectors + (size_t)(ok ? id : 0) * row_stride_bytes);
-        const float* qv = reinterpret_cast<const float*>(queries_v) + (size_t)q * dim;
-        QueryRegs<0> qr;
-        d = half_warp_distance<0, COSINE>(row, qr, qv, dim, j);
-    } else {
-        // the host pads the query stride to a multiple of 4 bytes (2-/4-byte loads in the lane terms)
-        const unsigned char* qv = reinterpret_cast<const unsigned char*>(queries_v) +
-                                  (size_t)q * (((size_t)dim * (ELEM == 3 ? 2 : 1) + 3) & ~(size_t)3);
-        d = half_warp_distance_elem<COSINE, ELEM>(vectors + (size_t)(ok ? id : 0) * row_stride_bytes, qv, dim, j);
-    }
-    if (valid && j == 0) out[item] = ok ? d : SPTAG_B200_MAXDIST;
-}
-
-// ------------------------------------------------------------------------------------------
-// RelativeNeighborhoodGraph::RebuildNeighbors (RelativeNeighborhoodGraph.h:20-38), one warp per node: walk the node's
-// ascending refine-search list, keep a candidate unless an already kept neighbour is closer to it than the node is
-// (rng_factor * d(kept, cand) < d(node, cand)).  The reference tests the kept neighbours one by one and stops at the
-// first that rejects; the verdict is an AND over all of them, so testing two per step (one per half-warp) with an
-// early exit is the same function.  Distances are the index's ComputeDistance, i.e. the same summation trees.
-// ------------------------------------------------------------------------------------------
-template <bool COSINE, int ELEM>
-__global__ void __launch_bounds__(128) rebuild_neighbors_kernel(const unsigned char* __restrict__ vectors,
-                                                                unsigned long long row_stride_bytes, int dim,
-                                                                int first_node, int num_nodes,
-                                                                const int* __restrict__ res_ids,
-                                                                const float* __restrict__ res_dists, int num_results,
-                                                                int neighborhood, float rng_factor,
-                                                                int* __restrict__ out_graph) {
-    extern __shared__ int kept_sm[];  // neighborhood ints per warp
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j = lane & 15, half = lane >> 4;
-    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (w >= num_nodes) return;
-    int* kept = kept_sm + warp * neighborhood;
-    const int node = first_node + (int)w;
-    const int* ids = res_ids + (size_t)w * num_results;
-    const float* ds = res_dists + (size_t)w * num_results;
-    int count = 0;
-    for (int r = 0; r < num_results && count < neighborhood; ++r) {
-        const int vid = ids[r];
-        if (vid < 0) break;
-        if (vid == node) continue;
-        const float dist = ds[r];
-        const unsigned char* cand = vectors + (size_t)vid * row_stride_bytes;
-        bool good = true;
-        for (int k0 = 0; k0 < count && good; k0 += 2) {
-            const int k = min(k0 + half, count - 1);
-            const unsigned char* row = vectors + (size_t)kept[k] * row_stride_bytes;
-            float d;
-            if (ELEM == 0) {
-                QueryRegs<0> qr;
-                d = half_warp_distance<0, COSINE>(reinterpret_cast<const float*>(row), qr,
-                                                  reinterpret_cast<const float*>(cand), dim, j);
-            } else {
-                d = half_warp_distance_elem<COSINE, ELEM>(row, cand, dim, j);
-            }
-            const bool reject = (j == 0) && (__fmul_rn(rng_factor, d) < dist);
-            if (__any_sync(kFull, reject)) good = false;
-        }
-        if (good) {
-            if (lane == 0) kept[count] = vid;
-            ++count;
-            __syncwarp();
-        }
-    }
-    __syncwarp();
-    for (int t = lane; t < neighborhood; t += 32) out_graph[(size_t)w * neighborhood + t] = (t < count) ? kept[t] : -1;
-}
-
-// Installing a refined graph: rows whose last slot named a duplicate group keep naming it (NeighborhoodGraph.h:395-401)
-__global__ void carry_backpointers_kernel(const int* __restrict__ old_graph, int* __restrict__ new_graph, int n, int degree) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int last = old_graph[(size_t)i * degree + degree - 1];
-    if (last < -1) new_graph[(size_t)i * degree + degree - 1] = last;
-}
-
-// ------------------------------------------------------------------------------------------
-// PQ / OPQ quantizer kernels (query side + tables; PQQuantizer.h:138-180, :333-348, OPQQuantizer.h:96-121)
-// ------------------------------------------------------------------------------------------
-
-// PQQuantizer::InitializeDistanceTables (PQQuantizer.h:333-348): sdc[i][j][k] = L2(codebook[i][j], codebook[i][k])
-__global__ void sdc_table_kernel(const float* __restrict__ codebooks, int m, int ks, int dsub, float* __restrict__ sdc) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)m * ks * ks;
-    if (t >= total) return;
-    const int k = (int)(t % ks);
-    const int j = (int)((t / ks) % ks);
-    const int i = (int)(t / ((long long)ks * ks));
-    const float* base = codebooks + (size_t)i * ks * dsub;
-    sdc[t] = exact_dist_thread<false>(base + (size_t)j * dsub, base + (size_t)k * dsub, dsub);
-}
-
-// IQuantizer::QuantizeVector(raw, codes, ADC=false) for a batch: one CTA per raw vector.
-//   OPQ: rot[i] = m_base - m_fdot(vec, OPQMatrix_T row i) with m_base = 1 and m_fdot = float cosine distance
-//        (OPQQuantizer.h:96-121, :198-206); PQ: rot = vec.
-//   then per sub-vector the first codeword with the strictly smallest L2 distance (PQQuantizer.h:158-179).
-// raw_type: 0 int8, 1 uint8, 2 int16, 3 float (the quantizer's reconstruct type).
-__global__ void pq_quantize_kernel(const unsigned char* __restrict__ raw, int raw_type, long long raw_stride_bytes,
-                                   int nvec, const float* __restrict__ codebooks, const float* __restrict__ rotation_t,
-                                   int m, int ks, int dsub, unsigned char* __restrict__ codes,
-                                   float* __restrict__ rotated_out) {
-    extern __shared__ float qsm[];  // vec[dim] | rot[dim]
-    const int dim = m * dsub;
-    float* vec = qsm;
-    float* rot = qsm + dim;
-    const int v = blockIdx.x;
-    if (v >= nvec) return;
-    const unsigned char* src = raw + (size_t)v * raw_stride_bytes;
-    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
-        float f;
-        switch (raw_type) {
-        case 0: f = (float)reinterpret_cast<const signed char*>(src)[i]; break;
-        case 1: f = (float)src[i]; break;
-        case 2: f = (float)reinterpret_cast<const short*>(src)[i]; break;
-        default: f = reinterpret_cast<const float*>(src)[i]; break;
-        }
-        vec[i] = f;
-    }
-    __syncthreads();
-    const float* q = vec;
-    if (rotation_t != nullptr) {
-        for (int i = threadIdx.x; i < dim; i += blockDim.x)
-            rot[i] = __fsub_rn(1.0f, exact_dist_thread<true>(vec, rotation_t + (size_t)i * dim, dim));
-        __syncthreads();
-        q = rot;
-    }
-    if (rotated_out != nullptr) {  // ADC mode: the search kernel builds the distance table from the rotated vector
-        for (int i = threadIdx.x; i < dim; i += blockDim.x) rotated_out[(size_t)v * dim + i] = q[i];
-        return;
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int i = warp; i < m; i += nwarps) {
-        float best = INFINITY;
-        int bestj = 0x7fffffff;
-        for (int j = lane; j < ks; j += 32) {
-            const float d = exact_dist_thread<false>(q + (size_t)i * dsub, codebooks + ((size_t)i * ks + j) * dsub, dsub);
-            if (d < best) {  // increasing j per lane: strict '<' keeps the first minimum
-                best = d;
-                bestj = j;
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(kFull, best, o);
-            const int oj = __shfl_xor_sync(kFull, bestj, o);
-            if (ob < best || (ob == best && oj < bestj)) {
-                best = ob;
-                bestj = oj;
-            }
-        }
-        if (lane == 0) codes[(size_t)v * m + i] = (unsigned char)bestj;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// k-way merge of per-shard top-k lists (QueryResultSet.h:17-26 comparator): one thread per query
-// ------------------------------------------------------------------------------------------
-__global__ void merge_topk_kernel(const int* __restrict__ ids, const float* __restrict__ dists, int num_lists,
-                                  int nq, int k, int* __restrict__ out_ids, float* __restrict__ out_dists) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    // every list is ascending; keep one cursor per list (num_lists <= 16)
-    int cur[16];
-    for (int l = 0; l < num_lists; ++l) cur[l] = 0;
-    for (int o = 0; o < k; ++o) {
-        int bl = -1, bid = -1;
-        float bd = 0.0f;
-        for (int l = 0; l < num_lists; ++l) {
-            if (cur[l] >= k) continue;
-            const size_t at = ((size_t)l * nq + q) * k + cur[l];
-            const int id = ids[at];
-            const float d = dists[at];
-            if (id < 0) {  // unfilled tail of this list
-                cur[l] = k;
-                continue;
-            }
-            if (bl < 0 || d < bd || (d == bd && id < bid)) {
-                bl = l;
-                bd = d;
-                bid = id;
-            }
-        }
-        if (bl < 0) {
-            out_ids[(size_t)q * k + o] = -1;
-            out_dists[(size_t)q * k + o] = SPTAG_B200_MAXDIST;
-        } else {
-            out_ids[(size_t)q * k + o] = bid;
-            out_dists[(size_t)q * k + o] = bd;
-            cur[bl]++;
-        }
-    }
-}
-
 }  // namespace sptag_b200

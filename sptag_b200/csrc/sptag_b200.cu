@@ -6,7 +6,8 @@
 // (BKT/ParameterDefinitionList.h:44-49), per-slot scratch management and the kernel launches.
 // No torch, no CPU fallback: a search either runs the CUDA kernels or returns an error code.
 #include "../../include/sptag_b200.h"
-#include "search_kernels.cuh"
+#include "aux_kernels.cuh"
+#include "kernel_select.h"
 
 #include <algorithm>
 #include <atomic>
@@ -149,99 +150,25 @@ int heap_lastlevel(int size) {
     return (int)std::pow(2.0, std::floor(std::log2((float)size)));
 }
 
-typedef void (*SearchKernelFn)(const SearchParams);
-
-template <int DIM, bool COSINE>
-SearchKernelFn pick_rpl(int mres_cap, bool kdt) {
-    if (kdt) return search_kernel<DIM, COSINE, 16, true>;  // KDT has no m_Results gate
-    // register caps (MINB resident single-warp CTAs per SM): 12 -> 168 registers; the kernel is latency-bound per
-    // warp, so residency beats a few spilled values (refine passes run the 32-register m_Results file, K = CEF+1)
-    if (mres_cap <= 32 * 16) return search_kernel<DIM, COSINE, 16, false, false, 0, 12>;
-    if (mres_cap <= 32 * 32) return search_kernel<DIM, COSINE, 32, false, false, 0, 14>;
-    // 64 registers per lane: K / CEF+1 up to 2048 (the reference's default RefineGraph schedule searches with
-    // CEF x CEFScale + 1 = 2001 results, NeighborhoodGraph.h:459-470)
-    if (mres_cap <= 32 * 64) return search_kernel<DIM, COSINE, 64, false, false, 0, 8>;
-    return nullptr;
-}
-
-template <bool COSINE>
-SearchKernelFn pick_dim(int dim, int mres_cap, bool kdt, bool direct) {
-    switch (dim) {
-    case 128:
-        if (direct && !kdt && mres_cap <= 32 * 16) return search_kernel<128, COSINE, 16, false, false, 0, 16, true>;
-        if (!kdt && mres_cap <= 32 * 16) return search_kernel<128, COSINE, 16, false, false, 0, 16>;  // 128 regs, 16/SM
-        return pick_rpl<128, COSINE>(mres_cap, kdt);
-    case 768:
-        // 15 resident queries per SM (127 registers, no spills) when the m_Results file is the 16-register one
-        if (!kdt && mres_cap <= 32 * 16) return search_kernel<768, COSINE, 16, false, false, 0, 15>;
-        return pick_rpl<768, COSINE>(mres_cap, kdt);
-    default: return pick_rpl<0, COSINE>(mres_cap, kdt);
-    }
-}
-
-// The kernel instantiation for this index / parameter set (nullptr: unsupported m_Results capacity)
-template <bool COSINE, int ELEM>
-SearchKernelFn pick_int(int mres_cap, bool kdt) {
-    if (kdt) return search_kernel<0, COSINE, 16, true, false, ELEM>;
-    if (mres_cap <= 32 * 16) return search_kernel<0, COSINE, 16, false, false, ELEM>;
-    if (mres_cap <= 32 * 32) return search_kernel<0, COSINE, 32, false, false, ELEM, 12>;
-    if (mres_cap <= 32 * 64) return search_kernel<0, COSINE, 64, false, false, ELEM, 8>;
-    return nullptr;
-}
-
-typedef void (*IterateKernelFn)(const SearchParams, int*, int*, unsigned char*);
-
-template <bool COSINE, int ELEM>
-IterateKernelFn pick_iter_rpl(int mres_cap) {
-    if (mres_cap <= 32 * 16) return iterate_kernel<COSINE, 16, ELEM>;
-    if (mres_cap <= 32 * 32) return iterate_kernel<COSINE, 32, ELEM>;
-    return nullptr;
-}
-
-typedef void (*NearestFirstKernelFn)(const SearchParams, int*);
-
-template <bool COSINE, int ELEM>
-NearestFirstKernelFn pick_nearest_rpl(int mres_cap) {
-    if (mres_cap <= 32 * 16) return nearest_first_kernel<COSINE, 16, ELEM>;
-    if (mres_cap <= 32 * 32) return nearest_first_kernel<COSINE, 32, ELEM>;
-    return nullptr;
-}
-
 NearestFirstKernelFn pick_nearest_first_kernel(const sptag_b200_index* h, int mres_cap) {
-    const bool l2 = (h->metric == SPTAG_B200_METRIC_L2);
-    switch (h->value_type) {
-    case SPTAG_B200_VT_FLOAT: return l2 ? pick_nearest_rpl<false, 0>(mres_cap) : pick_nearest_rpl<true, 0>(mres_cap);
-    case SPTAG_B200_VT_INT8: return l2 ? pick_nearest_rpl<false, 1>(mres_cap) : pick_nearest_rpl<true, 1>(mres_cap);
-    case SPTAG_B200_VT_UINT8: return l2 ? pick_nearest_rpl<false, 2>(mres_cap) : pick_nearest_rpl<true, 2>(mres_cap);
-    case SPTAG_B200_VT_INT16: return l2 ? pick_nearest_rpl<false, 3>(mres_cap) : pick_nearest_rpl<true, 3>(mres_cap);
-    default: return nullptr;
-    }
+    return pick_nearest_first_kernel_for(h->value_type, h->metric != SPTAG_B200_METRIC_L2, mres_cap);
 }
 
 IterateKernelFn pick_iterate_kernel(const sptag_b200_index* h, int mres_cap) {
-    const bool l2 = (h->metric == SPTAG_B200_METRIC_L2);
-    switch (h->value_type) {
-    case SPTAG_B200_VT_FLOAT: return l2 ? pick_iter_rpl<false, 0>(mres_cap) : pick_iter_rpl<true, 0>(mres_cap);
-    case SPTAG_B200_VT_INT8: return l2 ? pick_iter_rpl<false, 1>(mres_cap) : pick_iter_rpl<true, 1>(mres_cap);
-    case SPTAG_B200_VT_UINT8: return l2 ? pick_iter_rpl<false, 2>(mres_cap) : pick_iter_rpl<true, 2>(mres_cap);
-    case SPTAG_B200_VT_INT16: return l2 ? pick_iter_rpl<false, 3>(mres_cap) : pick_iter_rpl<true, 3>(mres_cap);
-    default: return nullptr;
-    }
+    return pick_iterate_kernel_for(h->value_type, h->metric != SPTAG_B200_METRIC_L2, mres_cap);
 }
 
+// The kernel instantiation for this index / parameter set (nullptr: unsupported m_Results capacity); the
+// instantiations live in kern_*.cu (kernel_select.h)
 SearchKernelFn pick_kernel(const sptag_b200_index* h, int mres_cap) {
     const bool kdt = (h->algo == SPTAG_B200_ALGO_KDT);
-    if (h->q_type != 0) {  // quantized: BKT + L2 only (the quantizer has no cosine distance, PQQuantizer.h:130-136)
-        if (mres_cap <= 32 * 16) return search_kernel<0, false, 16, false, true, 0, 24>;
-        if (mres_cap <= 32 * 32) return search_kernel<0, false, 32, false, true, 0, 16>;
-        return nullptr;
-    }
+    if (h->q_type != 0) return pick_pq_kernel(mres_cap);  // quantized: BKT + L2 only (PQQuantizer.h:130-136)
     const bool l2 = (h->metric == SPTAG_B200_METRIC_L2);
-    if (h->value_type == SPTAG_B200_VT_INT8) return l2 ? pick_int<false, 1>(mres_cap, kdt) : pick_int<true, 1>(mres_cap, kdt);
-    if (h->value_type == SPTAG_B200_VT_UINT8) return l2 ? pick_int<false, 2>(mres_cap, kdt) : pick_int<true, 2>(mres_cap, kdt);
-    if (h->value_type == SPTAG_B200_VT_INT16) return l2 ? pick_int<false, 3>(mres_cap, kdt) : pick_int<true, 3>(mres_cap, kdt);
+    if (h->value_type == SPTAG_B200_VT_INT8) return pick_int8_kernel(false, !l2, mres_cap, kdt);
+    if (h->value_type == SPTAG_B200_VT_UINT8) return pick_int8_kernel(true, !l2, mres_cap, kdt);
+    if (h->value_type == SPTAG_B200_VT_INT16) return pick_int16_kernel(!l2, mres_cap, kdt);
     const bool direct = (h->direct_load != 0);
-    return l2 ? pick_dim<false>(h->dim, mres_cap, kdt, direct) : pick_dim<true>(h->dim, mres_cap, kdt, direct);
+    return l2 ? pick_float_kernel_l2(h->dim, mres_cap, kdt, direct) : pick_float_kernel_cosine(h->dim, mres_cap, kdt, direct);
 }
 
 // Fill SearchParams + launch geometry for this handle.  Allocates per-slot scratch.

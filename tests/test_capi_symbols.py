@@ -112,17 +112,3 @@ def test_product_never_touches_the_oracle():
     if os.path.exists(LIB):
         out = subprocess.run(["ldd", LIB], capture_output=True, text=True).stdout
         assert "sptag_oracle" not in out and "sptag_ref" not in out, out
-
-
-def test_validated_kernels_are_unchanged():
-    """every kernel that ran (green) on a B200 must be byte-identical in the library that ships -- code
-    added afterwards may only add kernels.  Refresh profiles/r01_validated_sass_hashes.json with
-    `python tools/sass_diff.py --write ...` after the next validated GPU session."""
-    import shutil
-    import subprocess
-    import sys
-    if not shutil.which("cuobjdump") or not os.path.exists(LIB):
-        pytest.skip("cuobjdump or the built library is missing")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_diff.py"), "--check",
-                        os.path.join(ROOT, "profiles", "r01_validated_sass_hashes.json")], capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout + r.stderr

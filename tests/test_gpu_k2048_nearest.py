@@ -1,8 +1,8 @@
-"""Device paths that compile (and leave the SASS of every validated kernel byte-identical) but have NOT run on a B200
-yet: K and CEF+1 up to 2048 -- the 64-register m_Results variants needed by the reference's default RefineGraph schedule
-(CEF x CEFScale + 1 = 2001 results, NeighborhoodGraph.h:459-470) and by MaxCheck > 16384.  The oracle side of every
-case IS pinned to the reference (tests/test_oracle_pin.py::test_large_k_and_budget_bit_exact_vs_reference).
-Run on a GPU box with:  SPTAG_B200_RUN_UNVERIFIED=1 python -m pytest tests -m gpu_unverified -q"""
+"""K and CEF+1 up to 2048 (the 64-register m_Results variants needed by the reference's default RefineGraph schedule:
+CEF x CEFScale + 1 = 2001 results, NeighborhoodGraph.h:459-470, and by MaxCheck > 16384), p_searchDeleted = true, and
+SearchIndexIterativeFromNeareast (BKTIndex.cpp:543-595).  First run on a B200 in round 2 (20 / 20 green,
+gpurun_out/r02_unverified.log); the oracle side of every case is pinned to the reference
+(tests/test_oracle_pin.py::test_large_k_and_budget_bit_exact_vs_reference)."""
 import os
 
 import numpy as np
@@ -11,7 +11,7 @@ import pytest
 import reflib
 from conftest import data_folder
 
-pytestmark = pytest.mark.gpu_unverified
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name,k,mc", [("bkt_l2_10k_128", 2048, 8192), ("bkt_l2_10k_128", 1500, 2048),
