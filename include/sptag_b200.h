@@ -113,10 +113,9 @@ void sptag_b200_destroy(sptag_b200_handle h);
  * parameters, same names as the ini file: MaxCheck, MaxCheckForRefineGraph,
  * NumberOfInitialDynamicPivots, NumberOfOtherDynamicPivots,
  * ThresholdOfNumberOfContinuousNoBetterPropagation; "EnableADC" = VectorIndex::SetQuantizerADC
- * (VectorIndex.h:136-138) for quantized indexes; "SearchDeleted" (0/1) = the p_searchDeleted argument of
- * SearchIndex / SearchIndexWithFilter / GetIterator (VectorIndex.h:41-57; BKTIndex.cpp:473, KDTIndex.cpp:260):
- * 1 makes tombstoned vectors eligible results; searches read it per call, iterators sample it at open, the refine
- * pass always runs with 0 like NeighborhoodGraph::RefineNode.  Additional B200 tuning knobs (not in the
+ * (VectorIndex.h:136-138) for quantized indexes; "SearchDeleted" (0/1) = the handle-wide DEFAULT of the
+ * p_searchDeleted argument (the per-call value is sptag_b200_search_options.search_deleted /
+ * sptag_b200_iterator_open_ex); the refine pass always runs with 0 like NeighborhoodGraph::RefineNode.  Additional B200 tuning knobs (not in the
  * reference) are prefixed "B200.": B200.QueriesPerSM, B200.StageRows, B200.Stages,
  * B200.NGCacheEntries, B200.SPTCacheEntries, B200.SimdWidth (which DistanceUtils summation tree to
  * reproduce bit-exactly: 16 = AVX-512, the only one built -- 8 / 4 make the search calls return
@@ -135,6 +134,28 @@ int sptag_b200_get_param(sptag_b200_handle h, const char* name, char* value_out,
 int sptag_b200_search(sptag_b200_handle h, const void* queries, int32_t num_queries, int32_t k,
                       int32_t* out_ids, float* out_dists, int32_t* out_stats);
 
+/* Per-call arguments of the reference's search entry points that are not part of the index state:
+ *   search_deleted = p_searchDeleted of SearchIndex(QueryResult&, bool) / SearchIndexWithFilter / GetIterator
+ *                    (VectorIndex.h:41-57; dispatch flag BKTIndex.cpp:473, KDTIndex.cpp:260): 1 makes tombstoned
+ *                    vectors eligible results;
+ *   max_check      = maxCheck of SearchIndexWithFilter (BKTIndex.cpp:622-647): 0 = the index's MaxCheck;
+ *   allowed        = filterFunc evaluated once per vector by the caller: HOST buffer, one byte per vector,
+ *                    0 = never added to the results (filtered vectors are still traversed); NULL = no filter.
+ * They travel with the call, never through the handle, so concurrent callers with different values do not interact. */
+typedef struct {
+    int32_t struct_size;    /* sizeof(sptag_b200_search_options) */
+    int32_t search_deleted;
+    int32_t max_check;
+    const uint8_t* allowed;
+} sptag_b200_search_options;
+
+/* sptag_b200_search with per-call options (NULL = defaults: the handle's "SearchDeleted", the index's MaxCheck, no
+ * filter).  Thread-safe: concurrent callers are served from two internal staging sets, so one caller's H2D / D2H copies
+ * overlap another caller's kernel; kernels of one handle run one after the other (they share the per-slot scratch). */
+int sptag_b200_search_ex(sptag_b200_handle h, const void* queries, int32_t num_queries, int32_t k,
+                         const sptag_b200_search_options* options, int32_t* out_ids, float* out_dists,
+                         int32_t* out_stats);
+
 /* Replaces: VectorIndex::SearchIndexWithFilter(QueryResult&, std::function<bool(const ByteArray&)> filterFunc,
  * int maxCheck, bool) (VectorIndex.h:57, BKTIndex.cpp:622-647) for a batch.  The reference evaluates `filterFunc` on
  * the metadata of every vector it is about to add to the results; a device cannot call back into host code, so the
@@ -147,7 +168,9 @@ int sptag_b200_search_filtered(sptag_b200_handle h, const void* queries, int32_t
                                int32_t* out_stats);
 
 /* Same call with every buffer already resident in HBM on the index's device (device pointers) and
- * stream-ordered on `cuda_stream` (a cudaStream_t; NULL = default stream).  Does not synchronise. */
+ * stream-ordered on `cuda_stream` (a cudaStream_t; NULL = default stream).  Does not synchronise.  Calls on different
+ * streams are safe: all kernels of a handle share its per-slot scratch, so the library orders each launch after the
+ * handle's previous one with an event (they do not overlap each other; copies and other work on the streams do). */
 int sptag_b200_search_device(sptag_b200_handle h, const void* d_queries, int32_t num_queries, int32_t k,
                              int32_t* d_out_ids, float* d_out_dists, int32_t* d_out_stats,
                              void* cuda_stream);
@@ -171,11 +194,18 @@ int sptag_b200_distance_batch(sptag_b200_handle h, const void* queries, int32_t 
  * out_res_ids / out_res_dists (host, nullable): [num_nodes x (cef+1)] the refine-search result lists.
  * install != 0 (needs a full pass with neighborhood_size == the index's degree): the new rows replace the index's
  * graph on the device; duplicate-group back-pointers in the last slot are carried over (NeighborhoodGraph.h:395-401).
- * cef <= 2047 (cef > 1023 and K > 1024 use kernel variants that are compiled but were not yet run on a device when
- * this header was written -- see DESIGN.md row A7).  Not available for quantized indexes. */
+ * cef <= 2047.  Not available for quantized indexes. */
 int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num_nodes, int32_t cef,
                             int32_t neighborhood_size, float rng_factor, int32_t* out_graph, int32_t* out_res_ids,
                             float* out_res_dists, int32_t install);
+
+/* Replaces: VectorIndex::RefineSearchIndex(QueryResult&, bool p_searchDeleted) (VectorIndex.h:53, BKTIndex.cpp:698-711,
+ * KDTIndex.cpp:367-390) for a batch of arbitrary query vectors in HOST memory (element type of the index): the search
+ * with MaxCheckForRefineGraph as the budget and searchDuplicated = false; ids are local (no shard offset).  This is the
+ * call NeighborhoodGraph::RefineNode makes with a base vector as the target; sptag_b200_refine_graph is the batched
+ * form that never leaves the device. */
+int sptag_b200_refine_search(sptag_b200_handle h, const void* queries, int32_t num_queries, int32_t k,
+                             int32_t search_deleted, int32_t* out_ids, float* out_dists);
 
 /* The index's current graph rows (NeighborhoodGraph::SaveGraph payload, NeighborhoodGraph.h:606-615):
  * [num_vectors x graph_degree] int32 to a host buffer. */
@@ -196,6 +226,9 @@ int32_t sptag_b200_graph_degree(sptag_b200_handle h);
  * BKT without quantizer only; KDT returns Fail like the reference ("ITERATIVE NOT SUPPORT FOR KDT"). */
 typedef struct sptag_b200_iterator* sptag_b200_iter;
 int sptag_b200_iterator_open(sptag_b200_handle h, const void* queries, int32_t num_queries, sptag_b200_iter* out);
+/* GetIterator(p_target, p_searchDeleted): search_deleted 0 / 1, or -1 for the handle's "SearchDeleted" default */
+int sptag_b200_iterator_open_ex(sptag_b200_handle h, const void* queries, int32_t num_queries, int32_t search_deleted,
+                                sptag_b200_iter* out);
 int sptag_b200_iterator_next(sptag_b200_iter it, int32_t batch, int32_t* out_ids, float* out_dists,
                              int32_t* out_counts, uint8_t* out_relaxed_mono);
 /* Replaces: VectorIndex::SearchIndexIterativeFromNeareast(QueryResult&, WorkSpace*, p_isFirst) (VectorIndex.h:49,

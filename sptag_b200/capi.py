@@ -27,7 +27,8 @@ EXPORTS = [
     "sptag_b200_num_vectors", "sptag_b200_dim", "sptag_b200_value_type", "sptag_b200_metric",
     "sptag_b200_algo", "sptag_b200_last_error", "sptag_b200_refine_graph", "sptag_b200_get_graph",
     "sptag_b200_graph_degree", "sptag_b200_iterator_open", "sptag_b200_iterator_next", "sptag_b200_iterator_close",
-    "sptag_b200_iterator_next_from_nearest",
+    "sptag_b200_iterator_next_from_nearest", "sptag_b200_search_ex", "sptag_b200_iterator_open_ex",
+    "sptag_b200_refine_search",
 ]
 
 
@@ -38,6 +39,11 @@ class IndexDesc(C.Structure):
                 ("graph", C.c_void_p), ("tree_num", C.c_int32), ("node_count", C.c_int32),
                 ("tree_starts", C.c_void_p), ("tree_nodes", C.c_void_p), ("deleted", C.c_void_p),
                 ("num_deleted", C.c_int32), ("id_offset", C.c_int32)]
+
+
+class SearchOptions(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("search_deleted", C.c_int32), ("max_check", C.c_int32),
+                ("allowed", C.c_void_p)]
 
 
 class SptagB200Error(RuntimeError):
@@ -66,6 +72,10 @@ def lib():
         L.sptag_b200_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.sptag_b200_get_param.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int32]
         L.sptag_b200_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sptag_b200_search_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(SearchOptions), C.c_void_p,
+                                           C.c_void_p, C.c_void_p]
+        L.sptag_b200_iterator_open_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.sptag_b200_refine_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.sptag_b200_search_filtered.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                                  C.c_void_p, C.c_void_p, C.c_void_p]
         L.sptag_b200_search_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
@@ -184,15 +194,25 @@ class B200Index:
         return buf.value.decode()
 
     # -- search ---------------------------------------------------------------------------------
-    def search(self, queries, k, want_stats=False, out_ids=None, out_dists=None):
-        """VectorIndex::SearchIndex(batch) with HOST buffers (numpy or pinned torch memory viewed as numpy)."""
+    def search(self, queries, k, want_stats=False, out_ids=None, out_dists=None, search_deleted=None, max_check=0,
+               allowed=None):
+        """VectorIndex::SearchIndex(batch) with HOST buffers (numpy or pinned torch memory viewed as numpy).
+        search_deleted / max_check / allowed: the per-call arguments (sptag_b200_search_ex); all None/0 = sptag_b200_search."""
         queries = np.ascontiguousarray(queries)
         nq = queries.shape[0]
         ids = out_ids if out_ids is not None else np.empty((nq, k), np.int32)
         dists = out_dists if out_dists is not None else np.empty((nq, k), np.float32)
         stats = np.zeros((nq, STATS_PER_QUERY), np.int32) if want_stats else None
-        _check(lib().sptag_b200_search(self._h, queries.ctypes.data, nq, k, ids.ctypes.data, dists.ctypes.data,
-                                       stats.ctypes.data if want_stats else None))
+        if search_deleted is None and not max_check and allowed is None:
+            _check(lib().sptag_b200_search(self._h, queries.ctypes.data, nq, k, ids.ctypes.data, dists.ctypes.data,
+                                           stats.ctypes.data if want_stats else None))
+        else:
+            if allowed is not None:
+                allowed = np.ascontiguousarray(allowed, dtype=np.uint8)
+            o = SearchOptions(C.sizeof(SearchOptions), 1 if search_deleted else 0, int(max_check),
+                              allowed.ctypes.data if allowed is not None else None)
+            _check(lib().sptag_b200_search_ex(self._h, queries.ctypes.data, nq, k, C.byref(o), ids.ctypes.data,
+                                              dists.ctypes.data, stats.ctypes.data if want_stats else None))
         return (ids, dists, stats) if want_stats else (ids, dists)
 
     def search_filtered(self, queries, k, allowed, max_check=0, want_stats=False):
@@ -207,6 +227,16 @@ class B200Index:
                                                 ids.ctypes.data, dists.ctypes.data,
                                                 stats.ctypes.data if want_stats else None))
         return (ids, dists, stats) if want_stats else (ids, dists)
+
+    def refine_search(self, queries, k, search_deleted=False):
+        """VectorIndex::RefineSearchIndex for a batch of host query vectors (MaxCheckForRefineGraph, searchDuplicated = false)."""
+        queries = np.ascontiguousarray(queries)
+        nq = queries.shape[0]
+        ids = np.empty((nq, k), np.int32)
+        dists = np.empty((nq, k), np.float32)
+        _check(lib().sptag_b200_refine_search(self._h, queries.ctypes.data, nq, k, 1 if search_deleted else 0,
+                                              ids.ctypes.data, dists.ctypes.data))
+        return ids, dists
 
     def search_device(self, d_queries_ptr, nq, k, d_ids_ptr, d_dists_ptr, d_stats_ptr=0, stream=0):
         """Same call with device pointers (e.g. torch tensor .data_ptr()), stream-ordered, no sync."""
@@ -237,9 +267,9 @@ class B200Index:
         _check(lib().sptag_b200_get_graph(self._h, g.ctypes.data))
         return g
 
-    def iterators(self, queries):
+    def iterators(self, queries, search_deleted=None):
         """VectorIndex::GetIterator for every query of a batch -> B200Iterators (next(batch) / close())."""
-        return B200Iterators(self, queries)
+        return B200Iterators(self, queries, search_deleted)
 
     def save_graph(self, path):
         """NeighborhoodGraph::SaveGraph (NeighborhoodGraph.h:606-615): int32 rows, int32 cols, rows x cols int32 --
@@ -267,12 +297,16 @@ class B200Index:
 class B200Iterators:
     """A batch of ResultIterators (ResultIterator.cpp): one resumable search per query, state resident in HBM."""
 
-    def __init__(self, index, queries):
+    def __init__(self, index, queries, search_deleted=None):
         queries = np.ascontiguousarray(queries)
         self.index = index           # the handle must outlive the iterators
         self.nq = queries.shape[0]
         h = C.c_void_p()
-        _check(lib().sptag_b200_iterator_open(index._h, queries.ctypes.data, self.nq, C.byref(h)))
+        if search_deleted is None:
+            _check(lib().sptag_b200_iterator_open(index._h, queries.ctypes.data, self.nq, C.byref(h)))
+        else:
+            _check(lib().sptag_b200_iterator_open_ex(index._h, queries.ctypes.data, self.nq, 1 if search_deleted else 0,
+                                                     C.byref(h)))
         self._it = h
 
     def next(self, batch):

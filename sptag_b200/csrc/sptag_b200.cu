@@ -90,9 +90,8 @@ struct sptag_b200_index {
     int n = 0, dim = 0, degree = 0, tree_num = 0, node_count = 0, num_deleted = 0, id_offset = 0;
     size_t row_stride = 0;  // bytes, multiple of 16
     // device-resident index
-    DeviceBuffer d_vectors, d_graph, d_nodes, d_tree_starts, d_deleted, d_filter;
-    bool use_filter = false;  // set for the duration of a sptag_b200_search_filtered call
-    int search_deleted = 0;   // p_searchDeleted of SearchIndex / SearchIndexWithFilter / GetIterator (parameter "SearchDeleted")
+    DeviceBuffer d_vectors, d_graph, d_nodes, d_tree_starts, d_deleted;
+    int search_deleted = 0;   // handle-wide default of p_searchDeleted (parameter "SearchDeleted"); per-call value: sptag_b200_search_ex
     // search parameters (reference names)
     int max_check = 8192, max_check_refine = 8192, initial_pivots = 50, other_pivots = 4, no_better_threshold = 3;
     // B200 tuning knobs
@@ -114,7 +113,16 @@ struct sptag_b200_index {
     DeviceBuffer d_codebooks, d_rotation_t, d_sdc, d_codes, d_raw, d_adc;
     // scratch
     DeviceBuffer d_visited, d_ng_spill, d_spt_spill, d_counter, d_vlog, d_topk;
-    DeviceBuffer d_queries, d_ids, d_dists, d_stats;  // staging for the host-buffer entry point
+    DeviceBuffer d_ids, d_dists;                      // refine pass: per-batch result lists
+    // Host-buffer entry points: two staging sets, each with its own stream, so that one caller's H2D / D2H overlaps
+    // another caller's kernel (the kernels themselves share the per-slot scratch and are ordered by ev_done)
+    struct Staging {
+        std::mutex mu;
+        cudaStream_t stream = nullptr;
+        DeviceBuffer d_queries, d_ids, d_dists, d_stats, d_filter;
+    } staging[2];
+    std::atomic<unsigned> staging_rr{0};
+    cudaEvent_t ev_done = nullptr;  // recorded after every kernel that uses the handle's scratch; the next launch waits on it
     DeviceBuffer d_graph_new;                         // sptag_b200_refine_graph: the pass's output rows
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_aux = nullptr;
     double refine_search_ms = 0.0, refine_rebuild_ms = 0.0;  // device time of the last sptag_b200_refine_graph call
@@ -171,8 +179,21 @@ SearchKernelFn pick_kernel(const sptag_b200_index* h, int mres_cap) {
     return l2 ? pick_float_kernel_l2(h->dim, mres_cap, kdt, direct) : pick_float_kernel_cosine(h->dim, mres_cap, kdt, direct);
 }
 
-// Fill SearchParams + launch geometry for this handle.  Allocates per-slot scratch.
-int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& smem, int nq, SearchKernelFn& kern) {
+// What one call may override (the reference passes these per call: p_searchDeleted of SearchIndex / GetIterator,
+// maxCheck + filterFunc of SearchIndexWithFilter, MaxCheckForRefineGraph of RefineSearchIndex).  Nothing here is ever
+// written into the handle, so concurrent callers cannot see each other's settings.
+struct CallOpts {
+    int max_check = 0;          // 0 = the index's MaxCheck
+    int search_deleted = -1;    // -1 = the handle's "SearchDeleted" default, else 0 / 1
+    const unsigned char* d_filter = nullptr;  // device byte map (0 = never added to the results) or nullptr
+    size_t refine_query_stride = 0;  // refine flavour: bytes between queries (index rows: the padded row stride)
+};
+
+// Fill SearchParams + launch geometry for this handle.  Allocates per-slot scratch.  Caller holds h->mu.
+int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& smem, int nq, SearchKernelFn& kern,
+              const CallOpts& opts = CallOpts()) {
+    const int eff_max_check = opts.max_check > 0 ? opts.max_check : h->max_check;
+    const int eff_search_deleted = opts.search_deleted >= 0 ? opts.search_deleted : h->search_deleted;
     if (h->algo != SPTAG_B200_ALGO_BKT && h->algo != SPTAG_B200_ALGO_KDT)
         return fail(SPTAG_B200_LACK_OF_INPUTS, "unsupported index algorithm %d", h->algo);
     const bool pq = (h->q_type != 0);
@@ -209,25 +230,25 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     p.tree_num = h->tree_num;
     p.node_count = h->node_count;
     // flags += (m_deletedID.Count() == 0 || p_searchDeleted) << 2  (BKTIndex.cpp:473, KDTIndex.cpp:260)
-    p.deleted = (h->num_deleted > 0 && !h->search_deleted) ? (const signed char*)h->d_deleted.ptr : nullptr;
-    p.filter = h->use_filter ? (const unsigned char*)h->d_filter.ptr : nullptr;
+    p.deleted = (h->num_deleted > 0 && !eff_search_deleted) ? (const signed char*)h->d_deleted.ptr : nullptr;
+    p.filter = opts.d_filter;
     p.k = k;
     p.id_offset = h->id_offset;
-    p.max_check = h->max_check;
+    p.max_check = eff_max_check;
     p.initial_pivots = h->initial_pivots;
     p.other_pivots = h->other_pivots;
     p.no_better_threshold = h->no_better_threshold;
     // a fresh thread's WorkSpace: Initialize(max(MaxCheck, MaxCheckForRefineGraph)) then
     // Reset(MaxCheck, K) (BKTIndex.cpp:600-605, WorkSpace.h:243-278)
-    const int alloc_check = std::max(h->max_check, h->max_check_refine);
+    const int alloc_check = std::max(eff_max_check, h->max_check_refine);
     p.ng_length = alloc_check * 30;
     p.ng_lastlevel = heap_lastlevel(p.ng_length);
     p.spt_length = alloc_check * 10;
     p.spt_lastlevel = heap_lastlevel(p.spt_length);
-    p.mres_cap = std::max(h->max_check / 16, k);
+    p.mres_cap = std::max(eff_max_check / 16, k);
     // must mirror pick_dim: the direct-load instantiation exists for 128-d float BKT with the 16-register m_Results file
     p.direct_load = (h->direct_load != 0 && !pq && h->value_type == SPTAG_B200_VT_FLOAT && h->dim == 128 &&
-                     h->algo == SPTAG_B200_ALGO_BKT && std::max(h->max_check / 16, k) <= 512) ? 1 : 0;
+                     h->algo == SPTAG_B200_ALGO_BKT && p.mres_cap <= 512) ? 1 : 0;
     p.sdc = (const float*)h->d_sdc.ptr;
     p.pq_m = h->q_m;
     p.pq_ks = h->q_ks;
@@ -389,17 +410,30 @@ int quantize_device(sptag_b200_index* h, const void* d_raw, int n, unsigned char
     return 0;
 }
 
+// Every kernel that touches the handle's shared scratch (visited bitmaps, queue arenas, work counter, quantized-query
+// buffer) is ordered after the previous one, whatever stream it was launched on: the caller's stream waits on ev_done
+// before the launch sequence and records it afterwards.  Caller holds h->mu.
+int scratch_acquire(sptag_b200_index* h, cudaStream_t stream) {
+    CUDA_OK(cudaStreamWaitEvent(stream, h->ev_done, 0));
+    return 0;
+}
+int scratch_release(sptag_b200_index* h, cudaStream_t stream) {
+    CUDA_OK(cudaEventRecord(h->ev_done, stream));
+    return 0;
+}
+
 // refine = true: the RefineSearchIndex flavour (BKTIndex.cpp:698-711) -- queries are base rows of the index itself
 // (stride = the padded row stride), duplicate groups are not expanded, ids come back local (no shard offset); the
-// caller has already put MaxCheckForRefineGraph in h->max_check.
+// caller passes MaxCheckForRefineGraph as opts.max_check.  Caller holds h->mu.
 int search_device_impl(sptag_b200_index* h, const void* d_queries, int nq, int k, int* d_ids, float* d_dists,
-                       int* d_stats, cudaStream_t stream, bool refine = false) {
+                       int* d_stats, cudaStream_t stream, bool refine = false, const CallOpts& opts = CallOpts()) {
     if (nq <= 0) return SPTAG_B200_SUCCESS;
     SearchParams p;
     int grid = 0;
     size_t smem = 0;
     SearchKernelFn kern = nullptr;
-    if (int rc = configure(h, k, p, grid, smem, nq, kern)) return rc;
+    if (int rc = configure(h, k, p, grid, smem, nq, kern, opts)) return rc;
+    if (int rc = scratch_acquire(h, stream)) return rc;
     p.queries = (const unsigned char*)d_queries;
     p.query_stride_bytes = (size_t)h->dim * value_size(h->value_type);
     if (h->q_type != 0) {
@@ -418,7 +452,7 @@ int search_device_impl(sptag_b200_index* h, const void* d_queries, int nq, int k
         }
     }
     if (refine) {
-        p.query_stride_bytes = h->row_stride;
+        if (opts.refine_query_stride) p.query_stride_bytes = opts.refine_query_stride;
         p.never_dup = 1;
         p.id_offset = 0;
     }
@@ -433,7 +467,7 @@ int search_device_impl(sptag_b200_index* h, const void* d_queries, int nq, int k
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(h->ev_stop, stream));
     h->timed = true;
-    return SPTAG_B200_SUCCESS;
+    return scratch_release(h, stream);
 }
 
 struct DeviceGuard {
@@ -458,6 +492,191 @@ bool read_file(const std::string& path, std::vector<char>& out) {
     return (bool)f.read(out.data(), sz);
 }
 
+// Shape of an index and where its arrays come from: host arrays (sptag_b200_create) or the reference's files
+// streamed through pinned chunks (sptag_b200_load).  Exactly one of (ptr, file) is set per array.
+struct ArraySource {
+    const void* ptr = nullptr;
+    FILE* file = nullptr;
+    long long offset = 0;  // body offset in the file
+};
+
+// Chunked upload: rows of `row_bytes` from `src` to a device array with `dst_stride` bytes between rows.  Files are
+// read into two pinned buffers alternately, so the read of chunk i+1 overlaps the H2D copy of chunk i and no
+// full-file host copy ever exists (f1: the 10 GB codes / 12.8 GB graph of config C4 used to sit twice in host memory).
+int upload_rows(const ArraySource& src, void* dst, size_t rows, size_t row_bytes, size_t dst_stride, cudaStream_t stream) {
+    if (rows == 0 || row_bytes == 0) return 0;
+    if (src.ptr != nullptr) {
+        if (dst_stride == row_bytes)
+            CUDA_OK(cudaMemcpyAsync(dst, src.ptr, rows * row_bytes, cudaMemcpyHostToDevice, stream));
+        else
+            CUDA_OK(cudaMemcpy2DAsync(dst, dst_stride, src.ptr, row_bytes, row_bytes, rows, cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        return 0;
+    }
+    const size_t chunk_bytes = (size_t)32 << 20;
+    const size_t rows_per_chunk = std::max<size_t>(1, chunk_bytes / row_bytes);
+    void* pinned[2] = {nullptr, nullptr};
+    cudaEvent_t freed[2] = {nullptr, nullptr};
+    int rc = 0;
+    for (int i = 0; i < 2 && rc == 0; ++i) {
+        if (cudaMallocHost(&pinned[i], rows_per_chunk * row_bytes) != cudaSuccess ||
+            cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming) != cudaSuccess)
+            rc = fail(SPTAG_B200_MEMORY_OVERFLOW, "pinned staging buffer (%zu bytes) failed", rows_per_chunk * row_bytes);
+    }
+    if (rc == 0 && fseeko(src.file, (off_t)src.offset, SEEK_SET) != 0) rc = fail(SPTAG_B200_FAIL, "seek failed");
+    size_t done = 0;
+    for (int c = 0; rc == 0 && done < rows; ++c) {
+        const int b = c & 1;
+        const size_t nr = std::min(rows_per_chunk, rows - done);
+        if (c >= 2 && cudaEventSynchronize(freed[b]) != cudaSuccess) rc = fail(SPTAG_B200_FAIL, "upload failed");
+        if (rc == 0 && fread(pinned[b], row_bytes, nr, src.file) != nr) rc = fail(SPTAG_B200_FAIL, "file truncated");
+        if (rc) break;
+        unsigned char* d = (unsigned char*)dst + done * dst_stride;
+        cudaError_t e = (dst_stride == row_bytes)
+                            ? cudaMemcpyAsync(d, pinned[b], nr * row_bytes, cudaMemcpyHostToDevice, stream)
+                            : cudaMemcpy2DAsync(d, dst_stride, pinned[b], row_bytes, row_bytes, nr, cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaEventRecord(freed[b], stream);
+        if (e != cudaSuccess) rc = fail(SPTAG_B200_FAIL, "upload failed: %s", cudaGetErrorString(e));
+        done += nr;
+    }
+    if (cudaStreamSynchronize(stream) != cudaSuccess && rc == 0) rc = fail(SPTAG_B200_FAIL, "upload failed");
+    for (int i = 0; i < 2; ++i) {
+        if (pinned[i]) cudaFreeHost(pinned[i]);
+        if (freed[i]) cudaEventDestroy(freed[i]);
+    }
+    return rc;
+}
+
+// Range checks a kernel relies on: graph ids in [-1, n) (last slot: a duplicate back-pointer -2-node), tree starts and
+// BKT child ranges inside the node array.  Runs on the device copy, so it also covers streamed files.
+__global__ void validate_graph_kernel(const int* __restrict__ graph, long long entries, int degree, int n, int node_count,
+                                      int* __restrict__ bad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= entries) return;
+    const int v = graph[i];
+    const bool last = (int)(i % degree) == degree - 1;
+    bool ok = (v >= -1 && v < n);
+    if (!ok && last && v < -1) ok = (-2 - v) < node_count;
+    if (!ok) atomicAdd(bad, 1);
+}
+__global__ void validate_bkt_kernel(const int* __restrict__ nodes, int node_count, int n, int* __restrict__ bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= node_count) return;
+    const int c = nodes[3 * i], cs = nodes[3 * i + 1], ce = nodes[3 * i + 2];
+    bool ok = (c >= -1 && c <= n);
+    if (cs >= 0) ok = ok && (cs <= ce && ce <= node_count);
+    else if (cs < -1) ok = ok && (-cs <= node_count && ce <= node_count);  // duplicate-group head: members at [-cs, ce)
+    if (!ok) atomicAdd(bad, 1);
+}
+__global__ void validate_kdt_kernel(const int4* __restrict__ nodes, int node_count, int n, int* __restrict__ bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= node_count) return;
+    const int4 t = nodes[i];
+    // children: node index, or -(vector id)-1 (KDTree.h:283,293)
+    const bool ok = (t.x < node_count && t.y < node_count && -t.x - 1 <= n && -t.y - 1 <= n);
+    if (!ok) atomicAdd(bad, 1);
+}
+
+struct IndexShape {
+    int device = -1, algo = 0, value_type = 0, metric = 0, n = 0, dim = 0, degree = 0, tree_num = 0, node_count = 0,
+        num_deleted = 0, id_offset = 0;
+};
+
+int build_handle(const IndexShape& sh, const ArraySource& vectors, const ArraySource& graph, const int32_t* tree_starts,
+                 const ArraySource& nodes, const ArraySource& deleted, sptag_b200_handle* out) {
+    *out = nullptr;
+    if (sh.n <= 0) return fail(SPTAG_B200_EMPTY_INDEX, "empty index");
+    if (sh.dim <= 0 || sh.degree <= 0 || sh.tree_num <= 0 || sh.node_count <= 0)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "bad index shape");
+    const size_t vs = value_size(sh.value_type);
+    if (vs == 0) return fail(SPTAG_B200_LACK_OF_INPUTS, "bad value type %d", sh.value_type);
+    if (sh.algo != SPTAG_B200_ALGO_BKT && sh.algo != SPTAG_B200_ALGO_KDT)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "unsupported index algorithm %d", sh.algo);
+    for (int t = 0; t < sh.tree_num; ++t)
+        if (tree_starts[t] < 0 || tree_starts[t] >= sh.node_count)
+            return fail(SPTAG_B200_FAIL, "tree start %d = %d outside the %d tree nodes", t, tree_starts[t], sh.node_count);
+
+    int device = sh.device;
+    if (device < 0) CUDA_OK(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(SPTAG_B200_FAIL, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+
+    auto* h = new sptag_b200_index();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    h->algo = sh.algo;
+    h->value_type = sh.value_type;
+    h->metric = sh.metric;
+    h->n = sh.n;
+    h->dim = sh.dim;
+    h->degree = sh.degree;
+    h->tree_num = sh.tree_num;
+    h->node_count = sh.node_count;
+    h->num_deleted = (deleted.ptr || deleted.file) ? sh.num_deleted : 0;
+    h->id_offset = sh.id_offset;
+    const size_t row_bytes = (size_t)h->dim * vs;
+    h->row_stride = round_up(row_bytes, 16);  // TMA bulk copies need 16-byte aligned rows and sizes
+
+    auto destroy_on_fail = [&](int rc) {
+        sptag_b200_destroy(h);
+        return rc;
+    };
+    if (cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess ||
+        cudaEventCreate(&h->ev_aux) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreate(&h->staging[0].stream) != cudaSuccess || cudaStreamCreate(&h->staging[1].stream) != cudaSuccess)
+        return destroy_on_fail(fail(SPTAG_B200_FAIL, "cudaEventCreate / cudaStreamCreate failed"));
+    cudaStream_t up = h->staging[0].stream;
+    // one spare row so a 16-byte padded read of the last row stays in bounds
+    if (int rc = h->d_vectors.ensure(((size_t)h->n + 1) * h->row_stride)) return destroy_on_fail(rc);
+    if (h->row_stride != row_bytes) cudaMemsetAsync(h->d_vectors.ptr, 0, ((size_t)h->n + 1) * h->row_stride, up);
+    if (int rc = upload_rows(vectors, h->d_vectors.ptr, (size_t)h->n, row_bytes, h->row_stride, up)) return destroy_on_fail(rc);
+    const size_t graph_row = (size_t)h->degree * 4;
+    if (int rc = h->d_graph.ensure((size_t)h->n * graph_row)) return destroy_on_fail(rc);
+    if (int rc = upload_rows(graph, h->d_graph.ptr, (size_t)h->n, graph_row, graph_row, up)) return destroy_on_fail(rc);
+    const size_t node_sz = (h->algo == SPTAG_B200_ALGO_BKT) ? 12 : 16;
+    const size_t node_bytes = (size_t)h->node_count * node_sz;
+    // BKT: one extra sentinel node (the reference's LoadTrees appends (-1,-1,-1), BKTree.h:662)
+    if (int rc = h->d_nodes.ensure(node_bytes + 16)) return destroy_on_fail(rc);
+    cudaMemsetAsync(h->d_nodes.ptr, 0xff, node_bytes + 16, up);
+    if (int rc = upload_rows(nodes, h->d_nodes.ptr, (size_t)h->node_count, node_sz, node_sz, up)) return destroy_on_fail(rc);
+    if (int rc = h->d_tree_starts.ensure((size_t)h->tree_num * 4)) return destroy_on_fail(rc);
+    cudaMemcpy(h->d_tree_starts.ptr, tree_starts, (size_t)h->tree_num * 4, cudaMemcpyHostToDevice);
+    if (h->num_deleted > 0) {
+        if (int rc = h->d_deleted.ensure((size_t)h->n)) return destroy_on_fail(rc);
+        if (int rc = upload_rows(deleted, h->d_deleted.ptr, 1, (size_t)h->n, (size_t)h->n, up)) return destroy_on_fail(rc);
+    }
+    // ids the kernels index with must be in range: a corrupt file fails here, not as a stray device read later
+    {
+        if (int rc = h->d_counter.ensure(256)) return destroy_on_fail(rc);
+        int* bad = (int*)h->d_counter.ptr + 8;
+        cudaMemsetAsync(bad, 0, 8, up);
+        const long long entries = (long long)h->n * h->degree;
+        validate_graph_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, up>>>((const int*)h->d_graph.ptr, entries, h->degree,
+                                                                                 h->n, h->node_count, bad);
+        if (h->algo == SPTAG_B200_ALGO_BKT)
+            validate_bkt_kernel<<<(h->node_count + 255) / 256, 256, 0, up>>>((const int*)h->d_nodes.ptr, h->node_count, h->n, bad + 1);
+        else
+            validate_kdt_kernel<<<(h->node_count + 255) / 256, 256, 0, up>>>((const int4*)h->d_nodes.ptr, h->node_count, h->n, bad + 1);
+        g_launches += 2;
+        int hb[2] = {0, 0};
+        if (cudaMemcpyAsync(hb, bad, 8, cudaMemcpyDeviceToHost, up) != cudaSuccess || cudaStreamSynchronize(up) != cudaSuccess)
+            return destroy_on_fail(fail(SPTAG_B200_FAIL, "index upload failed: %s", cudaGetErrorString(cudaGetLastError())));
+        if (hb[0] || hb[1])
+            return destroy_on_fail(fail(SPTAG_B200_FAIL, "index is corrupt: %d graph entries and %d tree nodes out of range", hb[0], hb[1]));
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess)
+        return destroy_on_fail(fail(SPTAG_B200_FAIL, "index upload failed"));
+    *out = h;
+    return SPTAG_B200_SUCCESS;
+}
+
 }  // namespace
 
 extern "C" {
@@ -474,87 +693,36 @@ int sptag_b200_create(const sptag_b200_index_desc* desc, sptag_b200_handle* out)
                     sizeof(sptag_b200_index_desc));
     if (desc->num_vectors <= 0 || !desc->vectors || !desc->graph || !desc->tree_nodes || !desc->tree_starts)
         return fail(SPTAG_B200_EMPTY_INDEX, "empty index");
-    if (desc->dim <= 0 || desc->graph_degree <= 0 || desc->tree_num <= 0 || desc->node_count <= 0)
-        return fail(SPTAG_B200_LACK_OF_INPUTS, "bad index shape");
-    const size_t vs = value_size(desc->value_type);
-    if (vs == 0) return fail(SPTAG_B200_LACK_OF_INPUTS, "bad value type %d", desc->value_type);
-
-    int device = desc->device;
-    if (device < 0) CUDA_OK(cudaGetDevice(&device));
-    DeviceGuard guard(device);
-    CUDA_OK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUDA_OK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10)
-        return fail(SPTAG_B200_FAIL, "device %d is sm_%d%d; this library is built for sm_100a only", device,
-                    prop.major, prop.minor);
-
-    auto* h = new sptag_b200_index();
-    h->device = device;
-    h->num_sms = prop.multiProcessorCount;
-    h->smem_optin = prop.sharedMemPerBlockOptin;
-    h->algo = desc->algo;
-    h->value_type = desc->value_type;
-    h->metric = desc->metric;
-    h->n = desc->num_vectors;
-    h->dim = desc->dim;
-    h->degree = desc->graph_degree;
-    h->tree_num = desc->tree_num;
-    h->node_count = desc->node_count;
-    h->num_deleted = desc->deleted ? desc->num_deleted : 0;
-    h->id_offset = desc->id_offset;
-    const size_t row_bytes = (size_t)h->dim * vs;
-    h->row_stride = round_up(row_bytes, 16);  // TMA bulk copies need 16-byte aligned rows and sizes
-
-    auto destroy_on_fail = [&](int rc) {
-        sptag_b200_destroy(h);
-        return rc;
-    };
-    // one spare row so a 16-byte padded read of the last row stays in bounds
-    if (int rc = h->d_vectors.ensure(((size_t)h->n + 1) * h->row_stride)) return destroy_on_fail(rc);
-    if (h->row_stride == row_bytes) {
-        if (cudaMemcpy(h->d_vectors.ptr, desc->vectors, (size_t)h->n * row_bytes, cudaMemcpyHostToDevice) !=
-            cudaSuccess)
-            return destroy_on_fail(fail(SPTAG_B200_FAIL, "vector upload failed"));
-    } else {
-        cudaMemset(h->d_vectors.ptr, 0, ((size_t)h->n + 1) * h->row_stride);
-        if (cudaMemcpy2D(h->d_vectors.ptr, h->row_stride, desc->vectors, row_bytes, row_bytes, (size_t)h->n,
-                         cudaMemcpyHostToDevice) != cudaSuccess)
-            return destroy_on_fail(fail(SPTAG_B200_FAIL, "vector upload failed"));
-    }
-    const size_t graph_bytes = (size_t)h->n * h->degree * 4;
-    if (int rc = h->d_graph.ensure(graph_bytes)) return destroy_on_fail(rc);
-    cudaMemcpy(h->d_graph.ptr, desc->graph, graph_bytes, cudaMemcpyHostToDevice);
-    const size_t node_bytes = (size_t)h->node_count * (h->algo == SPTAG_B200_ALGO_BKT ? 12 : 16);
-    // BKT: one extra sentinel node (the reference's LoadTrees appends (-1,-1,-1), BKTree.h:662)
-    if (int rc = h->d_nodes.ensure(node_bytes + 16)) return destroy_on_fail(rc);
-    cudaMemset(h->d_nodes.ptr, 0xff, node_bytes + 16);
-    cudaMemcpy(h->d_nodes.ptr, desc->tree_nodes, node_bytes, cudaMemcpyHostToDevice);
-    if (int rc = h->d_tree_starts.ensure((size_t)h->tree_num * 4)) return destroy_on_fail(rc);
-    cudaMemcpy(h->d_tree_starts.ptr, desc->tree_starts, (size_t)h->tree_num * 4, cudaMemcpyHostToDevice);
-    if (h->num_deleted > 0) {
-        if (int rc = h->d_deleted.ensure((size_t)h->n)) return destroy_on_fail(rc);
-        cudaMemcpy(h->d_deleted.ptr, desc->deleted, (size_t)h->n, cudaMemcpyHostToDevice);
-    }
-    if (cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess ||
-        cudaEventCreate(&h->ev_aux) != cudaSuccess)
-        return destroy_on_fail(fail(SPTAG_B200_FAIL, "cudaEventCreate failed"));
-    if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess)
-        return destroy_on_fail(fail(SPTAG_B200_FAIL, "index upload failed"));
-    *out = h;
-    return SPTAG_B200_SUCCESS;
+    IndexShape sh;
+    sh.device = desc->device;
+    sh.algo = desc->algo;
+    sh.value_type = desc->value_type;
+    sh.metric = desc->metric;
+    sh.n = desc->num_vectors;
+    sh.dim = desc->dim;
+    sh.degree = desc->graph_degree;
+    sh.tree_num = desc->tree_num;
+    sh.node_count = desc->node_count;
+    sh.num_deleted = desc->deleted ? desc->num_deleted : 0;
+    sh.id_offset = desc->id_offset;
+    ArraySource v, g, t, d;
+    v.ptr = desc->vectors;
+    g.ptr = desc->graph;
+    t.ptr = desc->tree_nodes;
+    d.ptr = sh.num_deleted > 0 ? desc->deleted : nullptr;
+    return build_handle(sh, v, g, desc->tree_starts, t, d, out);
 }
 
 void sptag_b200_destroy(sptag_b200_handle h) {
     if (!h) return;
     DeviceGuard guard(h->device);
     cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
     h->d_vectors.release();
     h->d_graph.release();
     h->d_nodes.release();
     h->d_tree_starts.release();
     h->d_deleted.release();
-    h->d_filter.release();
     h->d_graph_new.release();
     h->d_codebooks.release();
     h->d_rotation_t.release();
@@ -568,15 +736,42 @@ void sptag_b200_destroy(sptag_b200_handle h) {
     h->d_ng_spill.release();
     h->d_spt_spill.release();
     h->d_counter.release();
-    h->d_queries.release();
     h->d_ids.release();
     h->d_dists.release();
-    h->d_stats.release();
+    for (auto& st : h->staging) {
+        st.d_queries.release();
+        st.d_ids.release();
+        st.d_dists.release();
+        st.d_stats.release();
+        st.d_filter.release();
+        if (st.stream) cudaStreamDestroy(st.stream);
+    }
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     if (h->ev_stop) cudaEventDestroy(h->ev_stop);
     if (h->ev_aux) cudaEventDestroy(h->ev_aux);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
     delete h;
 }
+
+namespace {
+struct FileCloser {
+    std::vector<FILE*> files;
+    FILE* open(const std::string& path) {
+        FILE* f = std::fopen(path.c_str(), "rb");
+        if (f) files.push_back(f);
+        return f;
+    }
+    ~FileCloser() {
+        for (FILE* f : files) std::fclose(f);
+    }
+};
+long long file_size(FILE* f) {
+    if (fseeko(f, 0, SEEK_END) != 0) return -1;
+    const long long sz = (long long)ftello(f);
+    fseeko(f, 0, SEEK_SET);
+    return sz;
+}
+}  // namespace
 
 int sptag_b200_load(const char* folder, int32_t device, int32_t id_offset, sptag_b200_handle* out) {
     if (!folder || !out) return fail(SPTAG_B200_LACK_OF_INPUTS, "null argument");
@@ -598,73 +793,91 @@ int sptag_b200_load(const char* folder, int32_t device, int32_t id_offset, sptag
         auto it = kv.find(name);
         return it == kv.end() ? std::string(def) : it->second;
     };
-    sptag_b200_index_desc d;
-    memset(&d, 0, sizeof(d));
-    d.struct_size = sizeof(d);
-    d.device = device;
-    d.id_offset = id_offset;
+    IndexShape sh;
+    sh.device = device;
+    sh.id_offset = id_offset;
     const std::string algo = get("IndexAlgoType", "BKT");
     if (algo == "BKT")
-        d.algo = SPTAG_B200_ALGO_BKT;
+        sh.algo = SPTAG_B200_ALGO_BKT;
     else if (algo == "KDT")
-        d.algo = SPTAG_B200_ALGO_KDT;
+        sh.algo = SPTAG_B200_ALGO_KDT;
     else
         return fail(SPTAG_B200_LACK_OF_INPUTS, "unsupported IndexAlgoType %s", algo.c_str());
     const std::string vt = get("ValueType", "Float");
     if (vt == "Float")
-        d.value_type = SPTAG_B200_VT_FLOAT;
+        sh.value_type = SPTAG_B200_VT_FLOAT;
     else if (vt == "Int8")
-        d.value_type = SPTAG_B200_VT_INT8;
+        sh.value_type = SPTAG_B200_VT_INT8;
     else if (vt == "UInt8")
-        d.value_type = SPTAG_B200_VT_UINT8;
+        sh.value_type = SPTAG_B200_VT_UINT8;
     else if (vt == "Int16")
-        d.value_type = SPTAG_B200_VT_INT16;
+        sh.value_type = SPTAG_B200_VT_INT16;
     else
         return fail(SPTAG_B200_LACK_OF_INPUTS, "unsupported ValueType %s", vt.c_str());
     const std::string dm = get("DistCalcMethod", "Cosine");  // reference default is Cosine
-    d.metric = (dm == "L2") ? SPTAG_B200_METRIC_L2
-                            : (dm == "InnerProduct" ? SPTAG_B200_METRIC_INNERPRODUCT : SPTAG_B200_METRIC_COSINE);
+    sh.metric = (dm == "L2") ? SPTAG_B200_METRIC_L2
+                             : (dm == "InnerProduct" ? SPTAG_B200_METRIC_INNERPRODUCT : SPTAG_B200_METRIC_COSINE);
+    // the kernels implement the default seeding only (BKTree.h:696-769 with m_bfs == 0); a BFS-seeded index would
+    // return different neighbours than the reference, so refuse it
+    if (std::atoi(get("EnableBfs", "0").c_str()) != 0)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "EnableBfs != 0 (BFS tree seeding, BKTree.h:703-758) is not built");
 
-    std::vector<char> vec, graph, tree, del;
-    if (!read_file(dir + "/" + get("VectorFilePath", "vectors.bin"), vec) || vec.size() < 8)
-        return fail(SPTAG_B200_FAILED_OPEN_FILE, "cannot read vectors file in %s", folder);
-    if (!read_file(dir + "/" + get("GraphFilePath", "graph.bin"), graph) || graph.size() < 8)
-        return fail(SPTAG_B200_FAILED_OPEN_FILE, "cannot read graph file in %s", folder);
-    if (!read_file(dir + "/" + get("TreeFilePath", "tree.bin"), tree) || tree.size() < 8)
-        return fail(SPTAG_B200_FAILED_OPEN_FILE, "cannot read tree file in %s", folder);
-    const bool have_del = read_file(dir + "/" + get("DeleteVectorFilePath", "deletes.bin"), del) && del.size() >= 12;
+    FileCloser fc;
+    FILE* fv = fc.open(dir + "/" + get("VectorFilePath", "vectors.bin"));
+    FILE* fg = fc.open(dir + "/" + get("GraphFilePath", "graph.bin"));
+    FILE* ft = fc.open(dir + "/" + get("TreeFilePath", "tree.bin"));
+    if (!fv) return fail(SPTAG_B200_FAILED_OPEN_FILE, "cannot read vectors file in %s", folder);
+    if (!fg) return fail(SPTAG_B200_FAILED_OPEN_FILE, "cannot read graph file in %s", folder);
+    if (!ft) return fail(SPTAG_B200_FAILED_OPEN_FILE, "cannot read tree file in %s", folder);
+    FILE* fd = fc.open(dir + "/" + get("DeleteVectorFilePath", "deletes.bin"));
 
     // vectors.bin: int32 rows, int32 cols, rows*cols*T (Dataset.h:146-180)
-    const int32_t* vh = (const int32_t*)vec.data();
-    d.num_vectors = vh[0];
-    d.dim = vh[1];
-    if (vec.size() < 8 + (size_t)d.num_vectors * d.dim * value_size(d.value_type))
+    int32_t hdr[2];
+    if (std::fread(hdr, 4, 2, fv) != 2) return fail(SPTAG_B200_FAILED_OPEN_FILE, "cannot read vectors file in %s", folder);
+    sh.n = hdr[0];
+    sh.dim = hdr[1];
+    if (sh.n <= 0 || sh.dim <= 0) return fail(SPTAG_B200_EMPTY_INDEX, "empty index");
+    if (file_size(fv) < 8 + (long long)sh.n * sh.dim * (long long)value_size(sh.value_type))
         return fail(SPTAG_B200_FAIL, "vectors file truncated");
-    d.vectors = vec.data() + 8;
     // graph.bin: int32 N, int32 degree, N*degree int32 (NeighborhoodGraph.h:606-615)
-    const int32_t* gh = (const int32_t*)graph.data();
-    if (gh[0] != d.num_vectors) return fail(SPTAG_B200_FAIL, "graph rows %d != vectors %d", gh[0], d.num_vectors);
-    d.graph_degree = gh[1];
-    if (graph.size() < 8 + (size_t)gh[0] * gh[1] * 4) return fail(SPTAG_B200_FAIL, "graph file truncated");
-    d.graph = gh + 2;
+    if (std::fread(hdr, 4, 2, fg) != 2) return fail(SPTAG_B200_FAILED_OPEN_FILE, "cannot read graph file in %s", folder);
+    if (hdr[0] != sh.n) return fail(SPTAG_B200_FAIL, "graph rows %d != vectors %d", hdr[0], sh.n);
+    sh.degree = hdr[1];
+    if (sh.degree <= 0 || file_size(fg) < 8 + (long long)sh.n * sh.degree * 4) return fail(SPTAG_B200_FAIL, "graph file truncated");
     // tree.bin: int32 treeNumber, starts[], int32 nodeCount, nodes[] (BKTree.h:635-645, KDTree.h:123-133)
-    const int32_t* th = (const int32_t*)tree.data();
-    d.tree_num = th[0];
-    d.tree_starts = th + 1;
-    d.node_count = th[1 + d.tree_num];
-    d.tree_nodes = th + 2 + d.tree_num;
-    const size_t node_sz = d.algo == SPTAG_B200_ALGO_BKT ? 12 : 16;
-    if (tree.size() < (size_t)(2 + d.tree_num) * 4 + (size_t)d.node_count * node_sz)
+    const long long tsz = file_size(ft);
+    if (std::fread(hdr, 4, 1, ft) != 1) return fail(SPTAG_B200_FAILED_OPEN_FILE, "cannot read tree file in %s", folder);
+    sh.tree_num = hdr[0];
+    if (sh.tree_num <= 0 || (long long)sh.tree_num > (tsz - 8) / 4)
+        return fail(SPTAG_B200_FAIL, "tree file: bad tree count %d", sh.tree_num);
+    std::vector<int32_t> starts((size_t)sh.tree_num);
+    if (std::fread(starts.data(), 4, starts.size(), ft) != starts.size() || std::fread(hdr, 4, 1, ft) != 1)
         return fail(SPTAG_B200_FAIL, "tree file truncated");
+    sh.node_count = hdr[0];
+    const long long node_sz = sh.algo == SPTAG_B200_ALGO_BKT ? 12 : 16;
+    const long long nodes_off = (long long)(2 + sh.tree_num) * 4;
+    if (sh.node_count <= 0 || tsz < nodes_off + (long long)sh.node_count * node_sz) return fail(SPTAG_B200_FAIL, "tree file truncated");
     // deletes.bin: int32 count, then Dataset<int8> (int32 rows, int32 cols, bytes) (Labelset.h:78-83)
-    if (have_del) {
-        const int32_t* dh = (const int32_t*)del.data();
-        d.num_deleted = dh[0];
-        if (d.num_deleted > 0 && del.size() >= 12 + (size_t)d.num_vectors) d.deleted = (const int8_t*)(del.data() + 12);
-        else d.num_deleted = 0;
+    ArraySource v, g, t, d;
+    if (fd) {
+        int32_t dh[3];
+        if (std::fread(dh, 4, 3, fd) != 3) return fail(SPTAG_B200_FAIL, "deletes file truncated");
+        sh.num_deleted = dh[0];
+        if (sh.num_deleted > 0) {
+            // a short payload would silently resurrect every deleted vector: refuse it
+            if (file_size(fd) < 12 + (long long)sh.n) return fail(SPTAG_B200_FAIL, "deletes file truncated (%d tombstones declared)", sh.num_deleted);
+            d.file = fd;
+            d.offset = 12;
+        }
     }
+    v.file = fv;
+    v.offset = 8;
+    g.file = fg;
+    g.offset = 8;
+    t.file = ft;
+    t.offset = nodes_off;
     sptag_b200_handle h = nullptr;
-    if (int rc = sptag_b200_create(&d, &h)) return rc;
+    if (int rc = build_handle(sh, v, g, starts.data(), t, d, &h)) return rc;
     {
         auto it = kv.find("QuantizerFilePath");  // [Quantizer] section (VectorIndex.cpp:188-192)
         if (it != kv.end() && !it->second.empty()) {
@@ -821,33 +1034,98 @@ int sptag_b200_search_device(sptag_b200_handle h, const void* d_queries, int32_t
                               (cudaStream_t)cuda_stream);
 }
 
-int sptag_b200_search(sptag_b200_handle h, const void* queries, int32_t num_queries, int32_t k, int32_t* out_ids,
-                      float* out_dists, int32_t* out_stats) {
-    if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
-    if (num_queries < 0 || (num_queries > 0 && (!queries || !out_ids || !out_dists)))
-        return fail(SPTAG_B200_LACK_OF_INPUTS, "null buffer");
+namespace {
+// Host-buffer search: staging set, H2D, launch (under h->mu), D2H.  refine = the RefineSearchIndex flavour.
+int search_host_impl(sptag_b200_handle h, const void* queries, int32_t num_queries, int32_t k, CallOpts opts,
+                     const uint8_t* allowed, bool refine, int32_t* out_ids, float* out_dists, int32_t* out_stats) {
     if (num_queries == 0) return SPTAG_B200_SUCCESS;
-    std::lock_guard<std::mutex> lock(h->mu);
+    // a staging set of our own for the whole call: the one that is free, else wait for the next in turn
+    sptag_b200_index::Staging* st = nullptr;
+    std::unique_lock<std::mutex> slock;
+    for (auto& cand : h->staging) {
+        std::unique_lock<std::mutex> l(cand.mu, std::try_to_lock);
+        if (l.owns_lock()) {
+            st = &cand;
+            slock = std::move(l);
+            break;
+        }
+    }
+    if (!st) {
+        st = &h->staging[h->staging_rr.fetch_add(1) & 1u];
+        slock = std::unique_lock<std::mutex>(st->mu);
+    }
     DeviceGuard guard(h->device);
     const size_t qbytes = (size_t)num_queries * query_bytes(h);
     const size_t rn = (size_t)num_queries * k;
-    if (int rc = h->d_queries.ensure(qbytes)) return rc;
-    if (int rc = h->d_ids.ensure(rn * 4)) return rc;
-    if (int rc = h->d_dists.ensure(rn * 4)) return rc;
+    if (int rc = st->d_queries.ensure(qbytes)) return rc;
+    if (int rc = st->d_ids.ensure(rn * 4)) return rc;
+    if (int rc = st->d_dists.ensure(rn * 4)) return rc;
     if (out_stats)
-        if (int rc = h->d_stats.ensure((size_t)num_queries * kStatsPerQuery * 4)) return rc;
-    cudaStream_t stream = nullptr;
-    CUDA_OK(cudaMemcpyAsync(h->d_queries.ptr, queries, qbytes, cudaMemcpyHostToDevice, stream));
-    if (int rc = search_device_impl(h, h->d_queries.ptr, num_queries, k, (int*)h->d_ids.ptr, (float*)h->d_dists.ptr,
-                                    out_stats ? (int*)h->d_stats.ptr : nullptr, stream))
-        return rc;
-    CUDA_OK(cudaMemcpyAsync(out_ids, h->d_ids.ptr, rn * 4, cudaMemcpyDeviceToHost, stream));
-    CUDA_OK(cudaMemcpyAsync(out_dists, h->d_dists.ptr, rn * 4, cudaMemcpyDeviceToHost, stream));
+        if (int rc = st->d_stats.ensure((size_t)num_queries * kStatsPerQuery * 4)) return rc;
+    cudaStream_t stream = st->stream;
+    CUDA_OK(cudaMemcpyAsync(st->d_queries.ptr, queries, qbytes, cudaMemcpyHostToDevice, stream));
+    if (allowed) {
+        // SearchIndexWithFilter: the caller evaluated filterFunc once per vector; the map is this call's own copy
+        if (int rc = st->d_filter.ensure((size_t)h->n)) return rc;
+        CUDA_OK(cudaMemcpyAsync(st->d_filter.ptr, allowed, (size_t)h->n, cudaMemcpyHostToDevice, stream));
+        opts.d_filter = (const unsigned char*)st->d_filter.ptr;
+    }
+    {
+        std::lock_guard<std::mutex> lock(h->mu);  // configure + enqueue only; the copies above / below overlap other callers' kernels
+        if (int rc = search_device_impl(h, st->d_queries.ptr, num_queries, k, (int*)st->d_ids.ptr, (float*)st->d_dists.ptr,
+                                        out_stats ? (int*)st->d_stats.ptr : nullptr, stream, refine, opts)) {
+            cudaStreamSynchronize(stream);
+            return rc;
+        }
+    }
+    CUDA_OK(cudaMemcpyAsync(out_ids, st->d_ids.ptr, rn * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemcpyAsync(out_dists, st->d_dists.ptr, rn * 4, cudaMemcpyDeviceToHost, stream));
     if (out_stats)
-        CUDA_OK(cudaMemcpyAsync(out_stats, h->d_stats.ptr, (size_t)num_queries * kStatsPerQuery * 4,
+        CUDA_OK(cudaMemcpyAsync(out_stats, st->d_stats.ptr, (size_t)num_queries * kStatsPerQuery * 4,
                                 cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
     return SPTAG_B200_SUCCESS;
+}
+}  // namespace
+
+int sptag_b200_search_ex(sptag_b200_handle h, const void* queries, int32_t num_queries, int32_t k,
+                         const sptag_b200_search_options* options, int32_t* out_ids, float* out_dists,
+                         int32_t* out_stats) {
+    if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
+    if (num_queries < 0 || (num_queries > 0 && (!queries || !out_ids || !out_dists)))
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "null buffer");
+    CallOpts opts;
+    const uint8_t* allowed = nullptr;
+    if (options) {
+        if (options->struct_size != (int32_t)sizeof(sptag_b200_search_options))
+            return fail(SPTAG_B200_FAIL, "options size mismatch: %d vs %zu", options->struct_size, sizeof(sptag_b200_search_options));
+        opts.search_deleted = options->search_deleted ? 1 : 0;
+        opts.max_check = options->max_check > 0 ? options->max_check : 0;
+        allowed = options->allowed;
+        if (allowed && h->algo != SPTAG_B200_ALGO_BKT) return fail(SPTAG_B200_FAIL, "Not Support Filter on KDT Index!");
+    }
+    return search_host_impl(h, queries, num_queries, k, opts, allowed, false, out_ids, out_dists, out_stats);
+}
+
+int sptag_b200_refine_search(sptag_b200_handle h, const void* queries, int32_t num_queries, int32_t k,
+                             int32_t search_deleted, int32_t* out_ids, float* out_dists) {
+    if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
+    if (num_queries < 0 || (num_queries > 0 && (!queries || !out_ids || !out_dists)))
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "null buffer");
+    if (h->q_type != 0)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "refine on a quantized index (reconstruct + re-quantize) is not built");
+    CallOpts opts;
+    {
+        std::lock_guard<std::mutex> lock(h->mu);
+        opts.max_check = h->max_check_refine;  // workSpace->Reset(m_pGraph.m_iMaxCheckForRefineGraph, K)
+    }
+    opts.search_deleted = search_deleted ? 1 : 0;
+    return search_host_impl(h, queries, num_queries, k, opts, nullptr, true, out_ids, out_dists, nullptr);
+}
+
+int sptag_b200_search(sptag_b200_handle h, const void* queries, int32_t num_queries, int32_t k, int32_t* out_ids,
+                      float* out_dists, int32_t* out_stats) {
+    return sptag_b200_search_ex(h, queries, num_queries, k, nullptr, out_ids, out_dists, out_stats);
 }
 
 int sptag_b200_search_filtered(sptag_b200_handle h, const void* queries, int32_t num_queries, int32_t k,
@@ -855,24 +1133,16 @@ int sptag_b200_search_filtered(sptag_b200_handle h, const void* queries, int32_t
                                int32_t* out_stats) {
     if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
     if (!allowed) return fail(SPTAG_B200_LACK_OF_INPUTS, "null filter map");
-    if (h->algo != SPTAG_B200_ALGO_BKT) return fail(SPTAG_B200_FAIL, "Not Support Filter on KDT Index!");
-    int saved_check;
+    sptag_b200_search_options o;
+    memset(&o, 0, sizeof(o));
+    o.struct_size = (int32_t)sizeof(o);
     {
         std::lock_guard<std::mutex> lock(h->mu);
-        DeviceGuard guard(h->device);
-        if (int rc = h->d_filter.ensure((size_t)h->n)) return rc;
-        CUDA_OK(cudaMemcpy(h->d_filter.ptr, allowed, (size_t)h->n, cudaMemcpyHostToDevice));
-        saved_check = h->max_check;
-        if (max_check > 0) h->max_check = max_check;  // workSpace->Reset(maxCheck == 0 ? m_iMaxCheck : maxCheck, K)
-        h->use_filter = true;
+        o.search_deleted = h->search_deleted;  // the handle-wide default, as sptag_b200_search reads it
     }
-    const int rc = sptag_b200_search(h, queries, num_queries, k, out_ids, out_dists, out_stats);
-    {
-        std::lock_guard<std::mutex> lock(h->mu);
-        h->use_filter = false;
-        h->max_check = saved_check;
-    }
-    return rc;
+    o.max_check = max_check;  // workSpace->Reset(maxCheck == 0 ? m_iMaxCheck : maxCheck, K)
+    o.allowed = allowed;
+    return sptag_b200_search_ex(h, queries, num_queries, k, &o, out_ids, out_dists, out_stats);
 }
 
 int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num_nodes, int32_t cef,
@@ -897,9 +1167,10 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
     if (int rc = h->d_dists.ensure((size_t)batch * k * 4)) return rc;
     if (int rc = h->d_graph_new.ensure((size_t)num_nodes * neighborhood_size * 4)) return rc;
     cudaStream_t stream = nullptr;
-    const int saved_check = h->max_check, saved_sd = h->search_deleted;
-    h->max_check = h->max_check_refine;  // workSpace->Reset(m_pGraph.m_iMaxCheckForRefineGraph, CEF + 1)
-    h->search_deleted = 0;               // RefineNode(index, node, false, searchDeleted = false, CEF)
+    CallOpts ropts;
+    ropts.max_check = h->max_check_refine;  // workSpace->Reset(m_pGraph.m_iMaxCheckForRefineGraph, CEF + 1)
+    ropts.search_deleted = 0;               // RefineNode(index, node, false, searchDeleted = false, CEF)
+    ropts.refine_query_stride = h->row_stride;  // the queries are the index's own (padded) rows
     int rc = SPTAG_B200_SUCCESS;
     h->refine_search_ms = h->refine_rebuild_ms = 0.0;
     const unsigned char* dv = (const unsigned char*)h->d_vectors.ptr;
@@ -908,7 +1179,7 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
         const int nb = std::min(batch, num_nodes - done);
         const int first = first_node + done;
         rc = search_device_impl(h, dv + (size_t)first * h->row_stride, nb, k, (int*)h->d_ids.ptr, (float*)h->d_dists.ptr,
-                                nullptr, stream, /*refine=*/true);
+                                nullptr, stream, /*refine=*/true, ropts);
         if (rc) break;
         const int warps_per_block = 4;
         const unsigned blocks = (unsigned)((nb + warps_per_block - 1) / warps_per_block);
@@ -945,8 +1216,6 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
         }
         if (e != cudaSuccess) rc = fail(SPTAG_B200_FAIL, "refine pass failed: %s", cudaGetErrorString(e));
     }
-    h->max_check = saved_check;
-    h->search_deleted = saved_sd;
     if (rc) return rc;
     if (out_graph)
         CUDA_OK(cudaMemcpy(out_graph, h->d_graph_new.ptr, (size_t)num_nodes * neighborhood_size * 4, cudaMemcpyDeviceToHost));
@@ -976,6 +1245,11 @@ int sptag_b200_get_graph(sptag_b200_handle h, int32_t* out_graph) {
 int32_t sptag_b200_graph_degree(sptag_b200_handle h) { return h ? h->degree : 0; }
 
 int sptag_b200_iterator_open(sptag_b200_handle h, const void* queries, int32_t num_queries, sptag_b200_iter* out) {
+    return sptag_b200_iterator_open_ex(h, queries, num_queries, -1, out);
+}
+
+int sptag_b200_iterator_open_ex(sptag_b200_handle h, const void* queries, int32_t num_queries, int32_t search_deleted,
+                                sptag_b200_iter* out) {
     if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
     if (!out || !queries || num_queries <= 0) return fail(SPTAG_B200_LACK_OF_INPUTS, "null buffer");
     *out = nullptr;
@@ -992,13 +1266,16 @@ int sptag_b200_iterator_open(sptag_b200_handle h, const void* queries, int32_t n
     it->h = h;
     it->nq = num_queries;
     it->max_check = h->max_check;
-    it->search_deleted = h->search_deleted;
+    it->search_deleted = search_deleted < 0 ? h->search_deleted : (search_deleted ? 1 : 0);
     it->ng_length = p.ng_length;
     it->ng_lastlevel = p.ng_lastlevel;
     it->spt_length = p.spt_length;
     it->spt_lastlevel = p.spt_lastlevel;
     it->visited_words = p.visited_words;
-    it->ng_entries = p.ng_spill_entries;
+    // NGQueue arena: a plain scan inserts every node at most once (n + 2 bounds it), but after
+    // SearchIndexIterativeFromNeareast's nodeCheckStatus.clear() the leftovers of the finished search stay queued while
+    // every node may enter once more, so 2 (n + 2) is the bound; Heap::insert itself stops at `length`
+    it->ng_entries = (size_t)std::min<long long>((long long)p.ng_length, 2 * ((long long)h->n + 2)) + 2;
     it->spt_entries = p.spt_spill_entries;
     const size_t qbytes = (size_t)num_queries * query_bytes(h);
     int rc = 0;
@@ -1040,13 +1317,10 @@ int sptag_b200_iterator_next(sptag_b200_iter it, int32_t batch, int32_t* out_ids
     int grid = 0;
     size_t smem = 0;
     SearchKernelFn skern = nullptr;
-    const int saved_check = h->max_check, saved_sd = h->search_deleted;
-    h->max_check = it->max_check;  // the rented WorkSpace keeps the budget it was reset with
-    h->search_deleted = it->search_deleted;
-    const int rc0 = configure(h, batch, p, grid, smem, it->nq, skern);
-    h->max_check = saved_check;
-    h->search_deleted = saved_sd;
-    if (rc0) return rc0;
+    CallOpts iopts;
+    iopts.max_check = it->max_check;  // the rented WorkSpace keeps the budget it was reset with
+    iopts.search_deleted = it->search_deleted;
+    if (int rc0 = configure(h, batch, p, grid, smem, it->nq, skern, iopts)) return rc0;
     IterateKernelFn kern = pick_iterate_kernel(h, p.mres_cap);
     if (!kern) return fail(SPTAG_B200_LACK_OF_INPUTS, "max(MaxCheck/16, batch) = %d exceeds the supported 1024", p.mres_cap);
     if (it->topk_pad == 0) {  // the first Next creates the QueryResult: its size bounds every later batch
@@ -1054,6 +1328,11 @@ int sptag_b200_iterator_next(sptag_b200_iter it, int32_t batch, int32_t* out_ids
         while (pad < batch) pad <<= 1;
         it->topk_pad = pad;
         if (int rc = it->d_topk.ensure((size_t)it->nq * pad * 8)) return rc;
+    } else if (batch > it->topk_pad) {
+        // e.g. Next(batch) after SearchIndexIterativeFromNeareast(k) reset the slot cap: the per-query result arena
+        // was sized by the first call
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "batch = %d exceeds the iterator's result arena (%d, sized by its first call)",
+                    batch, it->topk_pad);
     }
     const size_t rn = (size_t)it->nq * batch;
     if (int rc = it->d_ids.ensure(rn * 4)) return rc;
@@ -1086,6 +1365,7 @@ int sptag_b200_iterator_next(sptag_b200_iter it, int32_t batch, int32_t* out_ids
     if (smem > h->smem_optin) return fail(SPTAG_B200_MEMORY_OVERFLOW, "shared memory per query slot %zu exceeds %zu", smem, h->smem_optin);
     CUDA_OK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaStream_t stream = nullptr;
+    if (int rc = scratch_acquire(h, stream)) return rc;
     CUDA_OK(cudaMemsetAsync(p.work_counter, 0, 4, stream));
     CUDA_OK(cudaEventRecord(h->ev_start, stream));
     kern<<<grid, 32, smem, stream>>>(p, (int*)it->d_state.ptr, (int*)it->d_counts.ptr, (unsigned char*)it->d_relaxed.ptr);
@@ -1093,6 +1373,7 @@ int sptag_b200_iterator_next(sptag_b200_iter it, int32_t batch, int32_t* out_ids
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(h->ev_stop, stream));
     h->timed = true;
+    if (int rc = scratch_release(h, stream)) return rc;
     CUDA_OK(cudaMemcpyAsync(out_ids, it->d_ids.ptr, rn * 4, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaMemcpyAsync(out_dists, it->d_dists.ptr, rn * 4, cudaMemcpyDeviceToHost, stream));
     if (out_counts) CUDA_OK(cudaMemcpyAsync(out_counts, it->d_counts.ptr, (size_t)it->nq * 4, cudaMemcpyDeviceToHost, stream));
@@ -1120,13 +1401,10 @@ int sptag_b200_iterator_next_from_nearest(sptag_b200_iter it, int32_t k, int32_t
     int grid = 0;
     size_t smem = 0;
     SearchKernelFn skern = nullptr;
-    const int saved_check = h->max_check, saved_sd = h->search_deleted;
-    h->max_check = it->max_check;
-    h->search_deleted = it->search_deleted;
-    const int rc0 = configure(h, k, p, grid, smem, it->nq, skern);
-    h->max_check = saved_check;
-    h->search_deleted = saved_sd;
-    if (rc0) return rc0;
+    CallOpts iopts;
+    iopts.max_check = it->max_check;
+    iopts.search_deleted = it->search_deleted;
+    if (int rc0 = configure(h, k, p, grid, smem, it->nq, skern, iopts)) return rc0;
     NearestFirstKernelFn kfirst = pick_nearest_first_kernel(h, p.mres_cap);
     IterateKernelFn knext = pick_iterate_kernel(h, p.mres_cap);
     if (!kfirst || !knext)
@@ -1136,6 +1414,9 @@ int sptag_b200_iterator_next_from_nearest(sptag_b200_iter it, int32_t k, int32_t
         while (pad < k) pad <<= 1;
         it->topk_pad = pad;
         if (int rc = it->d_topk.ensure((size_t)it->nq * pad * 8)) return rc;
+    } else if (k > it->topk_pad) {
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "k = %d exceeds the iterator's result arena (%d, sized by its first call)", k,
+                    it->topk_pad);
     }
     const size_t rn = (size_t)it->nq * k;
     if (int rc = it->d_ids.ensure(rn * 4)) return rc;
@@ -1166,6 +1447,7 @@ int sptag_b200_iterator_next_from_nearest(sptag_b200_iter it, int32_t k, int32_t
     p.filter = nullptr;
     if (smem > h->smem_optin) return fail(SPTAG_B200_MEMORY_OVERFLOW, "shared memory per query slot %zu exceeds %zu", smem, h->smem_optin);
     cudaStream_t stream = nullptr;
+    if (int rc = scratch_acquire(h, stream)) return rc;
     CUDA_OK(cudaMemsetAsync(p.work_counter, 0, 4, stream));
     CUDA_OK(cudaEventRecord(h->ev_start, stream));
     if (first) {
@@ -1181,6 +1463,7 @@ int sptag_b200_iterator_next_from_nearest(sptag_b200_iter it, int32_t k, int32_t
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(h->ev_stop, stream));
     h->timed = true;
+    if (int rc = scratch_release(h, stream)) return rc;
     CUDA_OK(cudaMemcpyAsync(out_ids, it->d_ids.ptr, rn * 4, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaMemcpyAsync(out_dists, it->d_dists.ptr, rn * 4, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));

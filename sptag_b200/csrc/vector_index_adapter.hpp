@@ -9,8 +9,9 @@
 //   SPTAG::ErrorCode      AnnService/inc/Core/DefinitionList.h:54-68 (same numeric values)
 // with the same names, argument meaning and error behaviour, so existing call sites
 // (Wrappers/src/CoreInterface.cpp:206-238, IndexSearcher/main.cpp:194-217) compile against it by
-// switching the namespace.  INTEGRATION.md shows the three-line patch that makes the reference's own
-// VectorIndex subclass forward to this adapter instead.
+// switching the namespace -- for hosts that do NOT link the reference at all.  Hosts that do use the real subclass,
+// sptag_vector_index.hpp (`class SPTAG::B200::Index : public SPTAG::VectorIndex`, compiled against the reference's
+// headers), which is the drop-in proper.
 #pragma once
 
 #include <cfloat>
@@ -79,8 +80,8 @@ private:
 // ResultIterator.h / ResultIterator.cpp: a resumable search for one target, over sptag_b200_iterator_*.
 class ResultIterator {
 public:
-    ResultIterator(sptag_b200_handle p_index, const void* p_target) : m_target(p_target) {
-        if (sptag_b200_iterator_open(p_index, p_target, 1, &m_it) != 0) m_it = nullptr;
+    ResultIterator(sptag_b200_handle p_index, const void* p_target, bool p_searchDeleted = false) : m_target(p_target) {
+        if (sptag_b200_iterator_open_ex(p_index, p_target, 1, p_searchDeleted ? 1 : 0, &m_it) != 0) m_it = nullptr;
     }
     ~ResultIterator() { Close(); }
     ResultIterator(const ResultIterator&) = delete;
@@ -158,26 +159,15 @@ public:
     // VectorIndex::SearchIndex(QueryResult&, bool) (VectorIndex.h:41; BKTIndex.cpp:595-620).
     // One query is one tiny batch on the device; prefer the batched overload.
     ErrorCode SearchIndex(QueryResult& p_query, bool p_searchDeleted = false) const {
-        SearchDeletedScope scope(m_handle, p_searchDeleted);
-        return SearchIndex(p_query.GetTarget(), 1, p_query.GetResultNum(), false, p_query.GetResults());
+        return SearchWith(p_query.GetTarget(), 1, p_query.GetResultNum(), p_searchDeleted, 0, nullptr, p_query.GetResults());
     }
 
     // VectorIndex::SearchIndex(const void*, int, int, bool, BasicResult*) (VectorIndex.h:103,
     // VectorIndex.cpp:454-463).  p_results is caller-owned [p_vectorCount x p_neighborCount].
+    // (metadata: this mirror has no MetadataSet; the real subclass, sptag_vector_index.hpp, fills Meta)
     ErrorCode SearchIndex(const void* p_vector, int p_vectorCount, int p_neighborCount, bool /*p_withMeta*/,
                           BasicResult* p_results) const {
-        if (!m_handle) return ErrorCode::EmptyIndex;
-        const size_t n = static_cast<size_t>(p_vectorCount) * p_neighborCount;
-        std::vector<std::int32_t> ids(n);
-        std::vector<float> dists(n);
-        int rc = sptag_b200_search(m_handle, p_vector, p_vectorCount, p_neighborCount, ids.data(), dists.data(),
-                                   nullptr);
-        if (rc != 0) return static_cast<ErrorCode>(rc);
-        for (size_t i = 0; i < n; ++i) {  // scatter the POD SoA into the caller's AoS
-            p_results[i].VID = ids[i];
-            p_results[i].Dist = dists[i];
-        }
-        return ErrorCode::Success;
+        return SearchWith(p_vector, p_vectorCount, p_neighborCount, false, 0, nullptr, p_results);
     }
 
     // VectorIndex::SearchIndexWithFilter (VectorIndex.h:57, BKTIndex.cpp:622-647).  The reference's callback sees the
@@ -185,22 +175,12 @@ public:
     // evaluated once per vector on the host before the batch runs on the device.
     template <typename Pred>
     ErrorCode SearchIndexWithFilter(QueryResult& p_query, Pred p_allowed, int maxCheck = 0, bool p_searchDeleted = false) const {
-        SearchDeletedScope scope(m_handle, p_searchDeleted);
         if (!m_handle) return ErrorCode::EmptyIndex;
         const SizeType n = GetNumSamples();
         std::vector<std::uint8_t> allowed((size_t)n);
         for (SizeType i = 0; i < n; ++i) allowed[(size_t)i] = p_allowed(i) ? 1 : 0;
-        const int k = p_query.GetResultNum();
-        std::vector<std::int32_t> ids((size_t)k);
-        std::vector<float> dists((size_t)k);
-        int rc = sptag_b200_search_filtered(m_handle, p_query.GetTarget(), 1, k, allowed.data(), maxCheck, ids.data(),
-                                            dists.data(), nullptr);
-        if (rc != 0) return static_cast<ErrorCode>(rc);
-        for (int i = 0; i < k; ++i) {
-            p_query.GetResult(i)->VID = ids[(size_t)i];
-            p_query.GetResult(i)->Dist = dists[(size_t)i];
-        }
-        return ErrorCode::Success;
+        return SearchWith(p_query.GetTarget(), 1, p_query.GetResultNum(), p_searchDeleted, maxCheck, allowed.data(),
+                          p_query.GetResults());
     }
 
     // VectorIndex::RefineSearchIndex (VectorIndex.h:53, BKTIndex.cpp:698-711) for a base vector of the index: the
@@ -252,8 +232,7 @@ public:
     // (index not ready, KDT)
     std::shared_ptr<ResultIterator> GetIterator(const void* p_target, bool p_searchDeleted = false) const {
         if (!m_handle) return nullptr;
-        SearchDeletedScope scope(m_handle, p_searchDeleted);  // the iterator samples the flag when it opens
-        auto it = std::make_shared<ResultIterator>(m_handle, p_target);
+        auto it = std::make_shared<ResultIterator>(m_handle, p_target, p_searchDeleted);
         if (!it->IsOpen()) return nullptr;
         return it;
     }
@@ -273,18 +252,28 @@ public:
     sptag_b200_handle Handle() const { return m_handle; }
 
 private:
-    // p_searchDeleted travels as the handle parameter "SearchDeleted" for the duration of one call; callers that mix
-    // both settings concurrently on one handle must serialise those calls themselves (the flag is per handle)
-    struct SearchDeletedScope {
-        sptag_b200_handle h;
-        bool on;
-        SearchDeletedScope(sptag_b200_handle p_h, bool p_on) : h(p_h), on(p_on) {
-            if (on) sptag_b200_set_param(h, "SearchDeleted", "1");
+    // p_searchDeleted, maxCheck and the filter map are per-call arguments of the C ABI (sptag_b200_search_options):
+    // nothing is written into the handle, so threads mixing different values do not interact
+    ErrorCode SearchWith(const void* p_vector, int p_vectorCount, int p_neighborCount, bool p_searchDeleted, int p_maxCheck,
+                         const std::uint8_t* p_allowed, BasicResult* p_results) const {
+        if (!m_handle) return ErrorCode::EmptyIndex;
+        const size_t n = static_cast<size_t>(p_vectorCount) * p_neighborCount;
+        std::vector<std::int32_t> ids(n);
+        std::vector<float> dists(n);
+        sptag_b200_search_options o;
+        std::memset(&o, 0, sizeof(o));
+        o.struct_size = (std::int32_t)sizeof(o);
+        o.search_deleted = p_searchDeleted ? 1 : 0;
+        o.max_check = p_maxCheck;
+        o.allowed = p_allowed;
+        int rc = sptag_b200_search_ex(m_handle, p_vector, p_vectorCount, p_neighborCount, &o, ids.data(), dists.data(), nullptr);
+        if (rc != 0) return static_cast<ErrorCode>(rc);
+        for (size_t i = 0; i < n; ++i) {  // scatter the POD SoA into the caller's AoS
+            p_results[i].VID = ids[i];
+            p_results[i].Dist = dists[i];
         }
-        ~SearchDeletedScope() {
-            if (on) sptag_b200_set_param(h, "SearchDeleted", "0");
-        }
-    };
+        return ErrorCode::Success;
+    }
     explicit VectorIndex(sptag_b200_handle h) : m_handle(h) {}
     sptag_b200_handle m_handle;
 };
