@@ -18,11 +18,15 @@ on a bounded sample of the same batch on the same index files.
 VectorIndex::LoadIndex + SearchIndex(batch)) on the same index folder.  The reference/oracle is only
 ever executed in that leg and in the cpu_baseline leg -- never on the product path.
 
-Multi-GPU (`--gpus N` under torchrun, one rank per GPU):
-  --mode replica (default): every rank holds the index and searches its OWN 10k-query batch; no
-        data-path collective (queries are the independent units); weak scaling.
-  --mode shard: vector-partition sharding: rank r holds shard r (ids offset), every rank
-        searches the SAME batch, results are exchanged with one NCCL all-gather and merged on the GPU.
+Multi-GPU (`--gpus N` under torchrun, one rank per GPU).  Default `--mode auto` runs BOTH forms and says which is which:
+  replica leg -> `value`: every rank holds the C2 index and searches its OWN 10k-query batch; no data-path collective
+        (queries are the independent units); weak scaling; this is the aggregate-QPS figure of the north star.
+  shard leg -> key `shard`: BASELINE config 5's form: rank r holds an independent index over vector
+        partition r (2.5M x 768 per GPU, ids offset), every rank searches the SAME batch, the per-shard top-k lists are
+        exchanged with ONE NCCL all-gather and merged on the GPU (sptag_b200/sharded.py ShardedSearch).  Its parity is
+        checked against the REFERENCE searched shard by shard (each rank runs oracle/_ref on its own shard, the lists
+        are host-merged by (Dist, VID), QueryResultSet.h:17-26) -- ids and distance bits.
+  `--mode replica` / `--mode shard` run one form only (shard: `value` is the shard-mode QPS over the N-shard corpus).
 """
 import argparse
 import json
@@ -49,7 +53,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="replica", choices=["replica", "shard"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "replica", "shard"])
+    ap.add_argument("--shard-n", type=int, default=2500000, help="vectors per GPU in the shard leg of --mode auto (config C5: 20M / 8)")
+    ap.add_argument("--shard-parity-sample", type=int, default=256, help="queries the reference searches shard by shard")
+    ap.add_argument("--builder", default="gpu", choices=["gpu", "reference"],
+                    help="reference: the index is built by the unmodified reference (oracle/_ref BuildIndex) on the host cores")
     # (--num-vectors: under `python -m torch.distributed.run` a bare --n is swallowed by torchrun's own
     #  abbreviation matching (--nnodes / --nproc-per-node), so multi-GPU launches must use the long name)
     ap.add_argument("--n", "--num-vectors", dest="n", type=int, default=1000000)
@@ -122,6 +130,8 @@ def index_folder(args, shard):
         key += "_%s%d_%s" % (args.quantizer, args.pq_m, args.raw_type)
     elif args.raw_type != "float":
         key += "_" + args.raw_type
+    if getattr(args, "builder", "gpu") == "reference":
+        key += "_refbuilt"
     return os.path.join(args.cache, key)
 
 
@@ -135,6 +145,21 @@ def ensure_index(args, shard, device):
     if os.path.exists(done):
         return folder
     t0 = time.time()
+    if getattr(args, "builder", "gpu") == "reference":
+        # the index SPTAG itself produces: the unmodified reference's BuildIndex (k-means BKT / KD-tree, TP-tree initial
+        # graph, RefineGraph passes) on the host cores, then its own SaveIndex
+        if args.quantizer != "none" or args.raw_type != "float":
+            raise SystemExit("--builder reference: float un-quantized indexes only")
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import reflib
+        x = gen_data(args, args.n, args.seed + 1000 * (shard + 1), device).cpu().numpy()
+        ridx = reflib.RefIndex.build(args.algo.upper(), x, args.metric, threads=os.cpu_count() or 1)
+        ridx.save(folder)
+        del ridx
+        with open(done, "w") as f:
+            f.write("ok\n")
+        log("index built by the reference in %.1fs -> %s" % (time.time() - t0, folder))
+        return folder
     torch.backends.cuda.matmul.allow_tf32 = True
     x = gen_data(args, args.n, args.seed + 1000 * (shard + 1), device)
     nodes, starts, graph = B.build_index(x, args.metric, seed=args.seed + shard, log=log, algo=args.algo.upper(),
@@ -394,6 +419,53 @@ def main():
         return 0
 
     # ------------------------------ B200 arm ------------------------------
+    return b200_arm(args, rank, local_rank, world, quantized, config)
+
+
+
+def host_info():
+    """What the reference arm's number depends on (1 745 QPS at 64 threads on one box, 5 319 at 128 on another)."""
+    info = {"cpu_count": os.cpu_count()}
+    try:
+        info["affinity_cpus"] = len(os.sched_getaffinity(0))
+    except Exception:
+        info["affinity_cpus"] = None
+    try:
+        info["numa_nodes"] = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
+    except Exception:
+        info["numa_nodes"] = None
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                info["cpu_model"] = ln.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return info
+
+
+def kept_traffic(workload_key, alg_bytes):
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from a kept
+    `ncu --set full` capture of the same workload (profiles/r02_ncu_traffic.json, written from the .ncu-rep by
+    tools/ncu_traffic.py); None when no capture of this workload is kept."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    try:
+        rec = json.load(open(path)).get(workload_key)
+    except Exception:
+        return None, None
+    if not rec:
+        return None, None
+    # the capture may have been taken with a different batch size: DRAM bytes per launch scale with the algorithmic
+    # bytes of the launch (same index, same budget), so report the measured ratio applied to this launch
+    ratio = rec["dram_bytes"] / float(rec["algorithmic_bytes"])
+    return ratio * alg_bytes, {"source": rec.get("source"), "dram_bytes_captured": rec["dram_bytes"],
+                               "algorithmic_bytes_captured": rec["algorithmic_bytes"], "queries_captured": rec.get("nq"),
+                               "traffic_over_algorithmic": ratio}
+
+
+def b200_arm(args, rank, local_rank, world, quantized, config):
     import numpy as np
     import torch
     import __graft_entry__
@@ -409,34 +481,63 @@ def main():
     if world > 1:
         import torch.distributed as dist
         import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=600))
 
-    # ---- set-up (untimed): index folder(s), device-resident index, queries, ground truth ----
-    shard = rank if args.mode == "shard" else 0
-    if world > 1 and args.mode == "replica":
+    mode = args.mode if world > 1 else "single"
+    do_main = mode in ("single", "auto", "replica")
+    do_shard = mode in ("auto", "shard")
+    line = None
+    if do_main:
+        line = main_leg(args, rank, local_rank, world, dev, dist, quantized, config, "replica" if world > 1 else "single")
+    shard = None
+    if do_shard:
+        torch.cuda.empty_cache()
+        shard = shard_leg(args, rank, local_rank, world, dev, dist, config)
+    if rank == 0:
+        if line is None:  # --mode shard: the shard figure is the line's value
+            line = {"metric": "queries_per_second", "value": shard["value"], "unit": "queries/s", "n_gpus": args.gpus,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": shard["ms_per_step"], "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": dict(config, parallelism="shard x%d" % world, n=shard["vectors_per_gpu"],
+                                   workload=shard["workload"]),
+                    "recall_at_10": None, "clocks": shard.pop("clocks", None), "e2e": shard["e2e"],
+                    "gpu_launches": shard["gpu_launches"], "roofline": shard["roofline"], "cpu_baseline": None,
+                    "parity_vs_reference": shard["parity_vs_reference"]}
+        line["shard"] = shard
+        if shard is not None and do_main:
+            line["config"]["parallelism"] = ("replica x%d -> `value` (aggregate QPS, no collective); shard x%d -> key `shard` "
+                                             "(config C5's form: NCCL all-gather + merge_topk_kernel)" % (world, world))
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main_leg(args, rank, local_rank, world, dev, dist, quantized, config, mode):
+    """The C2-style leg: every rank holds the whole index and searches its own batch (world == 1: the single-GPU bench)."""
+    import numpy as np
+    import torch
+    from sptag_b200 import B200Index, capi
+
+    # ---- set-up (untimed): index folder, device-resident index, queries, ground truth ----
+    if world > 1:
         if rank == 0:
             ensure_index(args, 0, dev)
         dist.barrier()
-    if world > 1 and args.mode == "shard" and not quantized and args.raw_type == "float":
-        folder = None
-        files = build_in_memory(args, shard, dev)   # no reference leg in this mode: nothing needs the folder
-    else:
-        folder = ensure_index(args, shard, dev)
-        files = load_folder_arrays(folder)
-    id_offset = shard * args.n if args.mode == "shard" else 0
+    folder = ensure_index(args, 0, dev)
     t0 = time.time()
-    idx = B200Index.create(algo=capi.ALGO_KDT if args.algo == "kdt" else capi.ALGO_BKT, value_type=files.value_type, metric=files.metric, vectors=files.vectors,
-                           graph=files.graph, tree_starts=files.tree_starts, tree_nodes=files.nodes,
-                           device=local_rank, id_offset=id_offset)
-    if quantized:
-        idx.set_quantizer(files.quantizer.blob())
+    # the native loader streams the reference's files into HBM (sptag_b200_load); the numpy view of the folder is only
+    # used by the untimed bookkeeping below (row size, ground truth)
+    files = load_folder_arrays(folder)
+    idx = B200Index.load(folder, device=local_rank)
     idx.set_param("MaxCheck", args.maxcheck)
     for kv in args.param:
         nm, v = kv.split("=", 1)
         idx.set_param(nm, v)
-    log("index uploaded to HBM in %.1fs" % (time.time() - t0))
+    log("index loaded into HBM in %.1fs (sptag_b200_load)" % (time.time() - t0))
 
-    qseed = args.seed + 7 + (rank if args.mode == "replica" else 0)
+    qseed = args.seed + 7 + rank
     d_q_f32 = gen_data(args, args.nq, qseed, dev)
     qdtype = torch.int8 if args.raw_type == "int8" else torch.float32
     d_q = d_q_f32.to(qdtype).contiguous()
@@ -449,21 +550,9 @@ def main():
     h_dists = torch.empty((args.nq, args.k), dtype=torch.float32, pin_memory=True)
     stream = torch.cuda.current_stream().cuda_stream
 
-    gathered_ids = gathered_d = m_ids = m_d = None
-    if args.mode == "shard" and world > 1:
-        gathered_ids = torch.empty((world * args.nq, args.k), dtype=torch.int32, device=dev)
-        gathered_d = torch.empty((world * args.nq, args.k), dtype=torch.float32, device=dev)
-        m_ids = torch.empty_like(d_ids)
-        m_d = torch.empty_like(d_dists)
-
-    def step_device(with_stats=False, local_only=False):
+    def step_device(with_stats=False):
         idx.search_device(d_q.data_ptr(), args.nq, args.k, d_ids.data_ptr(), d_dists.data_ptr(),
                           d_stats.data_ptr() if with_stats else 0, stream)
-        if gathered_ids is not None and not local_only:
-            dist.all_gather_into_tensor(gathered_ids, d_ids)
-            dist.all_gather_into_tensor(gathered_d, d_dists)
-            capi.merge_topk(local_rank, gathered_ids.data_ptr(), gathered_d.data_ptr(), world, args.nq, args.k,
-                            m_ids.data_ptr(), m_d.data_ptr(), stream)
 
     def step_e2e():
         # the call a user makes: host query buffer in, host results out (H2D + kernel + D2H, blocking)
@@ -482,32 +571,21 @@ def main():
     row_bytes = files.vectors.shape[1] * files.vectors.itemsize  # dim*4, or M code bytes when quantized
     alg_bytes = int((st[:, capi.ST_NDIST] * row_bytes + st[:, capi.ST_NEXPAND] * files.degree * 4
                      + st[:, capi.ST_NTREE] * (16 if args.algo == "kdt" else 12)).sum())
-    res_ids = (m_ids if m_ids is not None else d_ids).cpu().numpy()
-    shard_merge_check = None
-    if gathered_ids is not None:
-        from sptag_b200 import sharded
-        nchk = min(args.nq, 512)
-        gi = gathered_ids.view(world, args.nq, args.k)[:, :nchk].cpu().numpy()
-        gd = gathered_d.view(world, args.nq, args.k)[:, :nchk].cpu().numpy()
-        e_ids, e_d = sharded.merge_topk_host(gi, gd, args.k)
-        shard_merge_check = {"queries": nchk, "identical": bool((e_ids == res_ids[:nchk]).all()
-                                                                and (e_d == m_d[:nchk].cpu().numpy()).all()),
-                             "ids_from_other_shards": int((res_ids[:nchk] // args.n != rank).sum())}
+    res_ids = d_ids.cpu().numpy()
+    res_d = d_dists.cpu().numpy()
 
     # recall@10 against exact search (untimed)
-    recall = None
-    if args.mode == "replica" or world == 1:
-        from tools import gpu_index_builder as B
-        if quantized:  # ground truth on the raw vectors (regenerated: the folder only holds codes)
-            x_dev = gen_data(args, args.n, args.seed + 1000 * (shard + 1), dev)
-        else:
-            x_dev = torch.from_numpy(files.vectors).to(dev).float()   # int8 rows: exact truth on their float values
-        truth = B.exact_topk(x_dev, d_q_f32, args.k, args.metric)
-        del x_dev
-        torch.cuda.empty_cache()
-        recall = recall_at_k(res_ids, truth, args.k)
-        log("recall@%d = %.4f, mean D_q = %.0f, E_q = %.0f, Tn_q = %.0f" % (
-            args.k, recall, st[:, capi.ST_NDIST].mean(), st[:, capi.ST_NEXPAND].mean(), st[:, capi.ST_NTREE].mean()))
+    from tools import gpu_index_builder as B
+    if quantized:  # ground truth on the raw vectors (regenerated: the folder only holds codes)
+        x_dev = gen_data(args, args.n, args.seed + 1000, dev)
+    else:
+        x_dev = torch.from_numpy(np.ascontiguousarray(files.vectors)).to(dev).float()   # int8 rows: exact truth on their float values
+    truth = B.exact_topk(x_dev, d_q_f32, args.k, args.metric)
+    del x_dev
+    torch.cuda.empty_cache()
+    recall = recall_at_k(res_ids, truth, args.k)
+    log("recall@%d = %.4f, mean D_q = %.0f, E_q = %.0f, Tn_q = %.0f" % (
+        args.k, recall, st[:, capi.ST_NDIST].mean(), st[:, capi.ST_NEXPAND].mean(), st[:, capi.ST_NTREE].mean()))
 
     # ---- timed region 1: inputs resident in HBM (value, roofline) ----
     sampler = ClockSampler(local_rank)
@@ -533,32 +611,39 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    queries_per_step = args.nq * (world if args.mode == "replica" else 1)
+    queries_per_step = args.nq * world
     value = queries_per_step / (ms_step / 1000.0)
 
-    # ---- timed region 2: end to end through the C-ABI with host buffers ----
-    for _ in range(args.warmup):
-        step_e2e()
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = queries_per_step * args.steps / e2e_s
+    # ---- timed region 2: end to end through the C-ABI with host buffers (pinned, then pageable) ----
+    def time_e2e(fn):
+        for _ in range(args.warmup):
+            fn()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([sec], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        return queries_per_step * args.steps / sec
+
+    e2e_value = time_e2e(step_e2e)
+    # the same call from ordinary (pageable) numpy buffers -- what a caller that never pins memory sees
+    p_q = np.array(h_q.numpy(), copy=True)
+    p_ids = np.empty((args.nq, args.k), np.int32)
+    p_d = np.empty((args.nq, args.k), np.float32)
+    e2e_pageable = time_e2e(lambda: idx.search(p_q, args.k, out_ids=p_ids, out_dists=p_d))
     clocks = None
     if rank == 0:
         sampler.stop()
         clocks = sampler.summary(tm0, tm1)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+        idx.close()
+        return None
 
     # ---- roofline of the dominant (only) kernel of a step ----
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -571,44 +656,273 @@ def main():
     # with the library's own CUDA events (recorded on the launching stream around the launch)
     kms = []
     for _ in range(5):
-        step_device(local_only=True)  # rank 0 only from here on: no collectives
+        step_device()  # rank 0 only from here on: no collectives
         kms.append(idx.last_kernel_ms())
     kernel_ms = float(np.mean(kms))
     achieved = alg_bytes / (kernel_ms / 1000.0) / 1e9
+    kname = ("search_kernel<PQ,L2,BKT>" if quantized else "search_kernel<int8,L2,%s>" % args.algo.upper()
+             if args.raw_type == "int8" else
+             "search_kernel<%d,%s,%s>" % (args.dim if args.dim in (128, 768) else 0, args.metric, args.algo.upper()))
+    wkey = "%s_%s_%dx%d_mc%d%s" % (args.algo, args.metric, args.n, args.dim, args.maxcheck,
+                                    ("_%s%d" % (args.quantizer, args.pq_m)) if quantized else "")
+    traffic, traffic_note = kept_traffic(wkey, alg_bytes)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": ("search_kernel<PQ,L2,BKT>" if quantized else "search_kernel<int8,L2,%s>" % args.algo.upper()
-                           if args.raw_type == "int8" else
-                           "search_kernel<%d,%s,%s>" % (args.dim if args.dim in (128, 768) else 0, args.metric, args.algo.upper())), "kernel_ms": kernel_ms,
+                "traffic": traffic, "traffic_note": traffic_note, "kernel": kname, "kernel_ms": kernel_ms,
                 "kernel_ms_samples": [round(v, 3) for v in kms],
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "share_of_step": kernel_ms / ms_step}
 
-    # ---- cpu baseline on a bounded sample (rank 0, N=1 only) ----
+    # ---- cpu baseline on a bounded sample (rank 0, N=1 only) + parity against the reference itself ----
     cpu_baseline = None
     parity = None
     if args.gpus == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import reflib
         qn = h_q.numpy()
         threads = best_cpu_threads(folder, qn, args.k, args.maxcheck, each=quantized)
         probe, _, _ = cpu_search_leg(folder, qn, args.k, args.maxcheck, threads, min(args.nq, 512), each=quantized)
         sample = args.cpu_sample or int(max(512, min(args.nq, probe["value"] * 5.0)))
         cpu_baseline, cpu_ids, cpu_d = cpu_search_leg(folder, qn, args.k, args.maxcheck, threads, sample, repeats=3,
                                                       each=quantized)
-        same = int((cpu_ids == res_ids[:sample]).all(axis=1).sum())
-        parity = {"queries_compared": sample, "identical_id_lists": same}
         cpu_baseline.pop("seconds", None)
+        cpu_baseline["host"] = host_info()
+        cpu_baseline["threads_probed"] = sorted({os.cpu_count() or 1, max(1, (os.cpu_count() or 1) // 2)})
+        same_ids = (cpu_ids == res_ids[:sample]).all(axis=1)
+        same_bits = (cpu_d.view(np.int32) == res_d[:sample].view(np.int32)).all(axis=1)
+        parity = {"queries_compared": sample, "identical_id_lists": int(same_ids.sum()),
+                  "identical_distance_bits": int((same_ids & same_bits).sum())}
+        # the reference's own WorkSpace counters (m_iNumberOfCheckedLeaves, NGQueue / SPTQueue sizes at exit), read
+        # per query through the reference's work-space factory, against the kernel's counters
+        if reflib.have_ref() and not quantized:
+            nst = min(sample, 64)
+            ridx = reflib.RefIndex.load(folder)
+            ridx.set_param("MaxCheck", args.maxcheck)
+            ridx.enable_stats()
+            ok = 0
+            for i in range(nst):
+                _, _, rs = ridx.search_one_stats(qn[i], args.k)
+                dev_row = st[i]
+                ok += int(rs[0] == dev_row[capi.ST_CHECKED] and rs[2] == dev_row[capi.ST_NG_LEFT]
+                          and rs[3] == dev_row[capi.ST_SPT_LEFT])
+            parity["counter_queries"] = nst
+            parity["identical_counters"] = ok
+            parity["counters"] = "m_iNumberOfCheckedLeaves, NGQueue.size(), SPTQueue.size() at exit (WorkSpace.h:303-308)"
 
+    line_config = dict(config)
+    line_config["index_builder"] = ("reference (oracle/_ref VectorIndex::BuildIndex on the host cores)" if args.builder == "reference"
+                                    else "tools/gpu_index_builder.py (set-up utility; same files go to both arms)")
     line = {"metric": "queries_per_second", "value": value, "unit": "queries/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if not quantized else "u8 codes, f32 SDC sums", "data": "synthetic", "config": config,
-            "recall_at_10": recall, "clocks": clocks,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if not quantized else "u8 codes, f32 SDC sums", "data": "synthetic",
+            "config": line_config, "recall_at_10": recall, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": args.nq * args.dim * h_q.element_size(),
-                    "d2h_bytes_per_step": args.nq * args.k * 8},
+                    "d2h_bytes_per_step": args.nq * args.k * 8, "host_buffers": "pinned",
+                    "pageable_value": e2e_pageable},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "parity_vs_reference": parity, "shard_merge_check": shard_merge_check}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+            "parity_vs_reference": parity}
+    idx.close()
+    return line
+
+
+def shard_leg(args, rank, local_rank, world, dev, dist, config):
+    """BASELINE config 5's form: vector-partition shards, one NCCL all-gather, merge on the GPU; parity against the
+    reference searched shard by shard."""
+    import copy
+    import numpy as np
+    import torch
+    from sptag_b200 import B200Index, capi, sharded
+    from tools import gpu_index_builder as B
+
+    sargs = copy.copy(args)
+    sargs.n = args.shard_n if args.mode == "auto" else args.n
+    sargs.algo, sargs.quantizer, sargs.raw_type = "bkt", "none", "float"
+    files = build_in_memory(sargs, rank, dev)   # rank r builds and keeps shard r (no disk: 8 x 8 GB)
+    id_offset = rank * sargs.n
+    t0 = time.time()
+    idx = B200Index.create(algo=capi.ALGO_BKT, value_type=files.value_type, metric=files.metric, vectors=files.vectors,
+                           graph=files.graph, tree_starts=files.tree_starts, tree_nodes=files.nodes, device=local_rank,
+                           id_offset=id_offset)
+    idx.set_param("MaxCheck", args.maxcheck)
+    for kv in args.param:
+        nm, v = kv.split("=", 1)
+        idx.set_param(nm, v)
+    log("shard %d: %d x %d uploaded in %.1fs" % (rank, sargs.n, sargs.dim, time.time() - t0))
+
+    d_q = gen_data(sargs, args.nq, args.seed + 7, dev).contiguous()   # the SAME batch on every rank
+    h_q = torch.empty((args.nq, args.dim), dtype=torch.float32, pin_memory=True)
+    h_q.copy_(d_q)
+    d_ids = torch.empty((args.nq, args.k), dtype=torch.int32, device=dev)
+    d_dists = torch.empty((args.nq, args.k), dtype=torch.float32, device=dev)
+    d_stats = torch.zeros((args.nq, capi.STATS_PER_QUERY), dtype=torch.int32, device=dev)
+    m_ids = torch.empty_like(d_ids)
+    m_d = torch.empty_like(d_dists)
+    stream = torch.cuda.current_stream().cuda_stream
+    stats_on = [False]
+    marks = []
+
+    def local_search(q, k):
+        idx.search_device(q.data_ptr(), args.nq, k, d_ids.data_ptr(), d_dists.data_ptr(),
+                          d_stats.data_ptr() if stats_on[0] else 0, stream)
+        return d_ids, d_dists
+
+    def merge(g_ids, g_d, k):
+        capi.merge_topk(local_rank, g_ids.data_ptr(), g_d.data_ptr(), world, args.nq, k, m_ids.data_ptr(), m_d.data_ptr(), stream)
+        return m_ids, m_d
+
+    def mark():
+        if marks is not None and len(marks) < 4096:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append(e)
+
+    ss = sharded.ShardedSearch(dist, local_search, merge, world, on_exchange_start=mark, on_exchange_end=mark)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    stats_on[0] = True
+    ss.search(d_q, args.k)
+    stats_on[0] = False
+    torch.cuda.synchronize()
+    st = d_stats.cpu().numpy().astype(np.int64)
+    alg_bytes = int((st[:, capi.ST_NDIST] * sargs.dim * 4 + st[:, capi.ST_NEXPAND] * files.degree * 4 + st[:, capi.ST_NTREE] * 12).sum())
+    res_ids = m_ids.cpu().numpy()
+    res_d = m_d.cpu().numpy()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not args.no_clocks:
+        sampler.start()
+        time.sleep(0.3)
+    for _ in range(args.warmup):
+        ss.search(d_q, args.k)
+    sync_all()
+    del marks[:]
+    launches0 = capi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tm0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        ss.search(d_q, args.k)
+    ev1.record()
+    sync_all()
+    tm1 = time.time()
+    launches = capi.launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    exch_ms = sum(marks[2 * i].elapsed_time(marks[2 * i + 1]) for i in range(len(marks) // 2)) / max(1, len(marks) // 2)
+    t = torch.tensor([ms_total, exch_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t[0].item()) / args.steps
+    exch_ms = float(t[1].item())
+    value = args.nq / (ms_step / 1000.0)
+
+    # end to end: host queries in, merged host results out, every step
+    h_ids = torch.empty((args.nq, args.k), dtype=torch.int32, pin_memory=True)
+    h_d = torch.empty((args.nq, args.k), dtype=torch.float32, pin_memory=True)
+
+    def step_e2e():
+        d_q.copy_(h_q, non_blocking=True)
+        ss.search(d_q, args.k)
+        h_ids.copy_(m_ids, non_blocking=True)
+        h_d.copy_(m_d, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_e2e()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    sec = time.perf_counter() - t0
+    t = torch.tensor([sec], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = args.nq * args.steps / float(t.item())
+    clocks = None
+    if rank == 0:
+        sampler.stop()
+        clocks = sampler.summary(tm0, tm1)
+
+    kms = []
+    for _ in range(3):
+        local_search(d_q, args.k)
+        kms.append(idx.last_kernel_ms())
+    kernel_ms = float(np.mean(kms))
+
+    # ---- parity against the REFERENCE searched shard by shard (AggregatorService.cpp:215-412 analogue) ----
+    parity = {"error": None}
+    S = max(1, min(args.nq, args.shard_parity_sample))
+    ref_ids = torch.full((S, args.k), -1, dtype=torch.int32, device=dev)
+    ref_d = torch.zeros((S, args.k), dtype=torch.float32, device=dev)
+    ref_sec = 0.0
+    ref_ok = 1
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import reflib
+        if not reflib.have_ref():
+            raise RuntimeError("oracle/_ref is not built")
+        ini = B.ini_text(sargs.metric, files.degree)
+        ridx = reflib.RefIndex.load_memory(ini, files.vectors, files.graph, files.nodes, files.tree_starts)
+        ridx.set_param("MaxCheck", args.maxcheck)
+        threads = max(1, (os.cpu_count() or 1) // world)
+        r_ids, r_d, ref_sec = ridx.search(h_q.numpy()[:S], args.k, threads=threads)
+        r_ids = np.where(r_ids >= 0, r_ids + id_offset, r_ids).astype(np.int32)
+        ref_ids.copy_(torch.from_numpy(r_ids))
+        ref_d.copy_(torch.from_numpy(r_d))
+        del ridx
+    except Exception as e:  # parity must never take the timed numbers down with it
+        ref_ok = 0
+        parity["error"] = "rank %d: %s" % (rank, str(e)[:200])
+    okt = torch.tensor([ref_ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    g_ref_ids = torch.empty((world * S, args.k), dtype=torch.int32, device=dev)
+    g_ref_d = torch.empty((world * S, args.k), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(g_ref_ids, ref_ids)
+    dist.all_gather_into_tensor(g_ref_d, ref_d)
+    # the device-side per-shard lists of the same queries (before the merge), for a per-shard comparison as well
+    ss.search(d_q, args.k)
+    torch.cuda.synchronize()
+    g_dev_ids, g_dev_d = ss.gathered()
+    out = None
+    if rank == 0:
+        if int(okt.item()) == 1:
+            gi = g_ref_ids.view(world, S, args.k).cpu().numpy()
+            gd = g_ref_d.view(world, S, args.k).cpu().numpy()
+            e_ids, e_d = sharded.merge_topk_host(gi, gd, args.k)     # host merge by (Dist, VID), QueryResultSet.h:17-26
+            same_ids = (e_ids == res_ids[:S]).all(axis=1)
+            same_bits = (e_d.view(np.int32) == res_d[:S].view(np.int32)).all(axis=1)
+            di = g_dev_ids[:, :S].cpu().numpy()
+            dd = g_dev_d[:, :S].cpu().numpy()
+            per_shard = ((di == gi).all(axis=2) & (dd.view(np.int32) == gd.view(np.int32)).all(axis=2)).sum(axis=1)
+            parity = {"queries_compared": S, "identical_id_lists": int(same_ids.sum()),
+                      "identical_distance_bits": int((same_ids & same_bits).sum()),
+                      "per_shard_identical_lists": [int(v) for v in per_shard],
+                      "ids_from_other_shards": int((res_ids[:S] // sargs.n != 0).sum()),
+                      "method": "each rank ran the unmodified reference (oracle/_ref, VectorIndex::LoadIndex from memory blobs + "
+                                "SearchIndex(batch)) on ITS shard; the %d lists per query were merged on the host by (Dist, VID) "
+                                "and compared with the device all-gather + merge_topk_kernel result" % world,
+                      "reference_seconds_rank0": ref_sec}
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+        achieved = alg_bytes / (kernel_ms / 1000.0) / 1e9
+        out = {"parallelism": "shard x%d" % world, "vectors_per_gpu": sargs.n, "corpus_vectors": sargs.n * world,
+               "workload": "SPTAG-BKT, %d x %dx%d float32 %s shards, batch %d queries, k=%d, MaxCheck=%d" % (
+                   world, sargs.n, sargs.dim, sargs.metric.lower(), args.nq, args.k, args.maxcheck),
+               "value": value, "unit": "queries/s over the whole %d-vector corpus" % (sargs.n * world),
+               "ms_per_step": ms_step, "search_kernel_ms": kernel_ms, "exchange_merge_ms": exch_ms,
+               "exchange_bytes_per_rank": args.nq * args.k * 8,
+               "limiter": "the per-shard search (%.1f ms); the exchange is 2 all-gathers of %d KB per rank + one merge kernel "
+                          "(%.2f ms): launch/collective latency, not NVLink bandwidth" % (kernel_ms, args.nq * args.k * 4 // 1024, exch_ms),
+               "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": args.nq * args.dim * 4,
+                       "d2h_bytes_per_step": args.nq * args.k * 8},
+               "gpu_launches": int(launches), "collective": "NCCL all_gather_into_tensor x2 per step",
+               "comm_nranks_seen": world,
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": None, "kernel": "search_kernel<%d,%s,BKT>" % (sargs.dim if sargs.dim in (128, 768) else 0, sargs.metric),
+                            "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes, "scope": "rank 0's shard"},
+               "parity_vs_reference": parity, "clocks": clocks}
+    idx.close()
+    return out
 
 
 if __name__ == "__main__":

@@ -160,6 +160,23 @@ void* ref_load(const char* folder) {
     return h;
 }
 
+// VectorIndex::LoadIndex(config, blobs, index) (VectorIndex.cpp:745-792): the reference loads an index from memory
+// blobs that hold exactly the bytes of vectors.bin / tree.bin / graph.bin; `config` is the indexloader.ini text.
+// The index keeps pointing INTO the blobs (Dataset::Load(char*), Dataset.h:191-204): they must outlive it.  Used where an index exists only in memory
+// (bench.py's shard legs: eight 8-GB folders would not fit a scratch disk).
+void* ref_load_memory(const char* config, const void* vectors, unsigned long long vectors_len, const void* tree,
+                      unsigned long long tree_len, const void* graph, unsigned long long graph_len) {
+    std::vector<ByteArray> blobs;
+    blobs.push_back(ByteArray((std::uint8_t*)vectors, vectors_len, false));
+    blobs.push_back(ByteArray((std::uint8_t*)tree, tree_len, false));
+    blobs.push_back(ByteArray((std::uint8_t*)graph, graph_len, false));
+    std::shared_ptr<VectorIndex> idx;
+    if (VectorIndex::LoadIndex(std::string(config), blobs, idx) != ErrorCode::Success || !idx) return nullptr;
+    auto* h = new RefHandle();
+    h->index = idx;
+    return h;
+}
+
 void ref_free(void* h) { delete (RefHandle*)h; }
 
 int ref_set_param(void* h, const char* name, const char* value) {

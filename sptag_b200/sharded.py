@@ -45,26 +45,45 @@ def merge_topk_host(ids, dists, k):
 
 
 class ShardedSearch:
-    """search -> all-gather -> merge over a process group.
+    """search -> all-gather -> merge over a process group (the path bench.py's shard legs time).
 
     local_search(queries, k) -> (ids, dists) tensors on the group's device, ids already global
     merge(gathered_ids, gathered_dists, k) -> (ids, dists)
+    on_exchange_start / on_exchange_end: optional callables invoked right before the all-gather and right after the
+    merge (bench.py records CUDA events there to split search time from exchange + merge time).
     """
 
-    def __init__(self, dist, local_search, merge, world_size):
+    def __init__(self, dist, local_search, merge, world_size, on_exchange_start=None, on_exchange_end=None):
         self.dist = dist
         self.local_search = local_search
         self.merge = merge
         self.world_size = world_size
+        self.on_exchange_start = on_exchange_start
+        self.on_exchange_end = on_exchange_end
+        self._g_ids = self._g_d = None
 
     def search(self, queries, k):
         import torch
         ids, dists = self.local_search(queries, k)
         nq = ids.shape[0]
-        # concatenation along dim 0 == the [num_lists][nq][k] layout the merge kernel expects
-        g_ids = torch.empty((self.world_size * nq,) + tuple(ids.shape[1:]), dtype=ids.dtype, device=ids.device)
-        g_d = torch.empty((self.world_size * nq,) + tuple(dists.shape[1:]), dtype=dists.dtype, device=dists.device)
-        self.dist.all_gather_into_tensor(g_ids, ids.contiguous())
-        self.dist.all_gather_into_tensor(g_d, dists.contiguous())
+        if self.on_exchange_start:
+            self.on_exchange_start()
+        # concatenation along dim 0 == the [num_lists][nq][k] layout the merge kernel expects; the gather buffers are
+        # kept between calls (800 KB per rank at nq = 10k, k = 10)
+        shape_i = (self.world_size * nq,) + tuple(ids.shape[1:])
+        if self._g_ids is None or tuple(self._g_ids.shape) != shape_i or self._g_ids.device != ids.device:
+            self._g_ids = torch.empty(shape_i, dtype=ids.dtype, device=ids.device)
+            self._g_d = torch.empty(shape_i, dtype=dists.dtype, device=dists.device)
+        self.dist.all_gather_into_tensor(self._g_ids, ids.contiguous())
+        self.dist.all_gather_into_tensor(self._g_d, dists.contiguous())
         shape = (self.world_size, nq) + tuple(ids.shape[1:])
-        return self.merge(g_ids.view(shape), g_d.view(shape), k)
+        out = self.merge(self._g_ids.view(shape), self._g_d.view(shape), k)
+        if self.on_exchange_end:
+            self.on_exchange_end()
+        return out
+
+    def gathered(self):
+        """The per-shard lists of the last search: ([world, nq, k] ids, dists)."""
+        nq = self._g_ids.shape[0] // self.world_size
+        shape = (self.world_size, nq) + tuple(self._g_ids.shape[1:])
+        return self._g_ids.view(shape), self._g_d.view(shape)

@@ -123,6 +123,32 @@ class RefIndex:
     def load(cls, folder):
         return cls(ref().ref_load(folder.encode()))
 
+    @classmethod
+    def load_memory(cls, ini_text, vectors, graph, nodes, tree_starts):
+        """VectorIndex::LoadIndex(config, blobs): the blobs are the bytes of vectors.bin / tree.bin / graph.bin."""
+        def blob(header, *arrays):
+            total = 4 * len(header) + sum(a.nbytes for a in arrays)
+            b = np.empty(total, np.uint8)
+            b[:4 * len(header)] = np.array(header, np.int32).view(np.uint8)
+            at = 4 * len(header)
+            for a in arrays:
+                b[at:at + a.nbytes] = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
+                at += a.nbytes
+            return b
+        vb = blob([vectors.shape[0], vectors.shape[1]], vectors)
+        gb = blob([graph.shape[0], graph.shape[1]], np.ascontiguousarray(graph, np.int32))
+        ts = np.ascontiguousarray(tree_starts, np.int32)
+        tb = np.concatenate([np.array([ts.shape[0]], np.int32), ts, np.array([nodes.shape[0]], np.int32),
+                             np.ascontiguousarray(nodes, np.int32).reshape(-1)]).view(np.uint8)
+        L = ref()
+        L.ref_load_memory.restype = C.c_void_p
+        L.ref_load_memory.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        h = L.ref_load_memory(ini_text.encode(), vb.ctypes.data, vb.nbytes, tb.ctypes.data, tb.nbytes, gb.ctypes.data,
+                              gb.nbytes)
+        idx = cls(h)
+        idx._blobs = (vb, tb, gb)  # Dataset::Load(char*) keeps pointing into the blobs (Dataset.h:191-204)
+        return idx
+
     def save(self, folder):
         os.makedirs(folder, exist_ok=True)
         rc = ref().ref_save(self.h, folder.encode())

@@ -737,17 +737,21 @@ def save_index_folder(folder, vectors, graph, nodes, tree_starts, metric, kmeans
         np.array([0, N, 1], np.int32).tofile(f)  # Labelset: deleted count, then Dataset<int8>(N x 1)
         np.zeros(N, np.int8).tofile(f)
     with open(os.path.join(folder, "indexloader.ini"), "w") as f:
-        text = INI_TEMPLATE
-        if algo == "KDT":
-            # same [Index] body with the KD-tree parameters in place of the BKT ones (KDT/ParameterDefinitionList.h)
-            body = INI_TEMPLATE.split("TPTNumber=32", 1)[1]
-            text = KDT_INI_HEAD + "TPTNumber=32" + body.replace("NumTopDimensionTpTreeSplit", "NumTopDimensionTPTSplit")
-        if quantized:
-            text = "[Quantizer]\nQuantizerFilePath=quantizer.bin\n\n" + text.replace("ValueType=Float", "ValueType=UInt8")
-        elif value_type != "Float":
-            text = text.replace("ValueType=Float", "ValueType=" + value_type)
-        f.write(text.format(kmeans_k=kmeans_k, leaf_size=leaf_size, degree=graph.shape[1],
-                                    threads=os.cpu_count() or 1, metric=metric))
+        f.write(ini_text(metric, graph.shape[1], kmeans_k, leaf_size, quantized, algo, value_type))
+
+
+def ini_text(metric, degree, kmeans_k=32, leaf_size=8, quantized=False, algo="BKT", value_type="Float"):
+    """The indexloader.ini the reference's LoadIndex reads (VectorIndex.cpp:197-222, :617-681 / :745-792)."""
+    text = INI_TEMPLATE
+    if algo == "KDT":
+        # same [Index] body with the KD-tree parameters in place of the BKT ones (KDT/ParameterDefinitionList.h)
+        body = INI_TEMPLATE.split("TPTNumber=32", 1)[1]
+        text = KDT_INI_HEAD + "TPTNumber=32" + body.replace("NumTopDimensionTpTreeSplit", "NumTopDimensionTPTSplit")
+    if quantized:
+        text = "[Quantizer]\nQuantizerFilePath=quantizer.bin\n\n" + text.replace("ValueType=Float", "ValueType=UInt8")
+    elif value_type != "Float":
+        text = text.replace("ValueType=Float", "ValueType=" + value_type)
+    return text.format(kmeans_k=kmeans_k, leaf_size=leaf_size, degree=degree, threads=os.cpu_count() or 1, metric=metric)
 
 
 def exact_topk(x, q, k, metric, chunk=2048):
