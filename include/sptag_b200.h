@@ -192,12 +192,24 @@ int sptag_b200_distance_batch(sptag_b200_handle h, const void* queries, int32_t 
  * OpenMP, so its pass depends on thread timing; this is the deterministic double-buffered form).
  * out_graph (host, nullable): [num_nodes x neighborhood_size] new rows, -1 padded, local ids.
  * out_res_ids / out_res_dists (host, nullable): [num_nodes x (cef+1)] the refine-search result lists.
- * install != 0 (needs a full pass with neighborhood_size == the index's degree): the new rows replace the index's
- * graph on the device; duplicate-group back-pointers in the last slot are carried over (NeighborhoodGraph.h:395-401).
+ * install != 0 (needs a full pass): the new rows replace the index's graph on the device -- the index's degree becomes
+ * neighborhood_size, which may differ from the current one (RefineGraph's passes run on rows NeighborhoodScale times
+ * wider); duplicate-group back-pointers in the last slot are carried over (NeighborhoodGraph.h:395-401).
  * cef <= 2047.  Not available for quantized indexes. */
 int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num_nodes, int32_t cef,
                             int32_t neighborhood_size, float rng_factor, int32_t* out_graph, int32_t* out_res_ids,
                             float* out_res_dists, int32_t install);
+
+/* Replaces: NeighborhoodGraph::RefineGraph(index) (NeighborhoodGraph.h:460-492), the schedule BuildGraph runs after
+ * the initial graph: RefineIterations - 1 full passes with CEF x CEFScale candidates on rows of
+ * NeighborhoodSize x NeighborhoodScale entries, then one pass with CEF on rows of NeighborhoodSize entries; every pass
+ * is sptag_b200_refine_graph(install = 1) (deterministic double-buffered form, see there).  The index's graph ends with
+ * (int)((int)(neighborhood_size * neighborhood_scale) / neighborhood_scale) columns.  The reference's defaults
+ * (BKT/ParameterDefinitionList.h): RefineIterations 2, CEF 1000, GraphCEFScale 2, NeighborhoodSize 32,
+ * GraphNeighborhoodScale 2, RNGFactor 1.  RebuildGraph's in-degree repair (EnableRebuild, default off; its result
+ * depends on OpenMP thread timing in the reference) is not part of it. */
+int sptag_b200_refine_schedule(sptag_b200_handle h, int32_t refine_iterations, int32_t cef, float cef_scale,
+                               int32_t neighborhood_size, float neighborhood_scale, float rng_factor);
 
 /* Replaces: VectorIndex::RefineSearchIndex(QueryResult&, bool p_searchDeleted) (VectorIndex.h:53, BKTIndex.cpp:698-711,
  * KDTIndex.cpp:367-390) for a batch of arbitrary query vectors in HOST memory (element type of the index): the search
@@ -249,6 +261,20 @@ void sptag_b200_iterator_close(sptag_b200_iter it);
 int sptag_b200_merge_topk(int32_t device, const int32_t* d_ids, const float* d_dists, int32_t num_lists,
                           int32_t num_queries, int32_t k, int32_t* d_out_ids, float* d_out_dists,
                           void* cuda_stream);
+
+/* Vector-partition shards inside ONE process (the reference's Aggregator deployment, AggregatorService.cpp:215-412,
+ * fans each query out to its index servers and merges their lists): every shard is an ordinary handle, normally on
+ * its own GPU (sptag_b200_index_desc.device / sptag_b200_load's device) and with its own id_offset.  A group search
+ * copies the HOST query batch to every shard's GPU, runs all shard searches concurrently and merges on the first
+ * shard's GPU with the comparator of QueryResultSet.h:17-26 -- the merge kernel reads the other GPUs' result lists
+ * directly over NVLink peer access, so gather + merge is one kernel and there is no collective library call.
+ * (One process per GPU: exchange the lists with NCCL and call sptag_b200_merge_topk -- bench.py's shard leg.)
+ * The group borrows the handles; destroy it before them.  num_shards <= 16. */
+typedef struct sptag_b200_shard_group* sptag_b200_group;
+int sptag_b200_group_create(const sptag_b200_handle* shards, int32_t num_shards, sptag_b200_group* out);
+int sptag_b200_group_search(sptag_b200_group g, const void* queries, int32_t num_queries, int32_t k, int32_t* out_ids,
+                            float* out_dists);
+void sptag_b200_group_destroy(sptag_b200_group g);
 
 /* Device time in milliseconds of the search kernel(s) of the most recent sptag_b200_search*
  * call on this handle, measured with CUDA events on the launching stream (synchronises). */

@@ -28,7 +28,8 @@ EXPORTS = [
     "sptag_b200_algo", "sptag_b200_last_error", "sptag_b200_refine_graph", "sptag_b200_get_graph",
     "sptag_b200_graph_degree", "sptag_b200_iterator_open", "sptag_b200_iterator_next", "sptag_b200_iterator_close",
     "sptag_b200_iterator_next_from_nearest", "sptag_b200_search_ex", "sptag_b200_iterator_open_ex",
-    "sptag_b200_refine_search",
+    "sptag_b200_refine_search", "sptag_b200_refine_schedule", "sptag_b200_group_create", "sptag_b200_group_search",
+    "sptag_b200_group_destroy",
 ]
 
 
@@ -76,6 +77,11 @@ def lib():
                                            C.c_void_p, C.c_void_p]
         L.sptag_b200_iterator_open_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
         L.sptag_b200_refine_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.sptag_b200_refine_schedule.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_float]
+        L.sptag_b200_group_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]
+        L.sptag_b200_group_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.sptag_b200_group_destroy.argtypes = [C.c_void_p]
+        L.sptag_b200_group_destroy.restype = None
         L.sptag_b200_search_filtered.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                                  C.c_void_p, C.c_void_p, C.c_void_p]
         L.sptag_b200_search_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
@@ -258,6 +264,12 @@ class B200Index:
                                              dists.ctypes.data if want_results else None, 1 if install else 0))
         return (rows, ids, dists) if want_results else rows
 
+    def refine_schedule(self, refine_iterations=2, cef=1000, cef_scale=2.0, neighborhood=32, neighborhood_scale=2.0,
+                        rng_factor=1.0):
+        """NeighborhoodGraph::RefineGraph (NeighborhoodGraph.h:460-492) on the device; the graph is replaced in place."""
+        _check(lib().sptag_b200_refine_schedule(self._h, refine_iterations, cef, cef_scale, neighborhood,
+                                                neighborhood_scale, rng_factor))
+
     @property
     def graph_degree(self):
         return lib().sptag_b200_graph_degree(self._h)
@@ -332,6 +344,36 @@ class B200Iterators:
         if self._it:
             lib().sptag_b200_iterator_close(self._it)
             self._it = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class B200ShardGroup:
+    """Vector-partition shards of one process (sptag_b200_group_*): `shards` are B200Index objects, one per partition."""
+
+    def __init__(self, shards):
+        self.shards = list(shards)   # keep the handles alive
+        arr = (C.c_void_p * len(self.shards))(*[s._h for s in self.shards])
+        g = C.c_void_p()
+        _check(lib().sptag_b200_group_create(arr, len(self.shards), C.byref(g)))
+        self._g = g
+
+    def search(self, queries, k):
+        queries = np.ascontiguousarray(queries)
+        nq = queries.shape[0]
+        ids = np.empty((nq, k), np.int32)
+        dists = np.empty((nq, k), np.float32)
+        _check(lib().sptag_b200_group_search(self._g, queries.ctypes.data, nq, k, ids.ctypes.data, dists.ctypes.data))
+        return ids, dists
+
+    def close(self):
+        if self._g:
+            lib().sptag_b200_group_destroy(self._g)
+            self._g = C.c_void_p()
 
     def __del__(self):
         try:

@@ -97,11 +97,13 @@ __global__ void __launch_bounds__(128) rebuild_neighbors_kernel(const unsigned c
 }
 
 // Installing a refined graph: rows whose last slot named a duplicate group keep naming it (NeighborhoodGraph.h:395-401)
-__global__ void carry_backpointers_kernel(const int* __restrict__ old_graph, int* __restrict__ new_graph, int n, int degree) {
+// (the row width may change with the install: RefineGraph's passes run on rows NeighborhoodScale times wider)
+__global__ void carry_backpointers_kernel(const int* __restrict__ old_graph, int* __restrict__ new_graph, int n, int old_degree,
+                                          int new_degree) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int last = old_graph[(size_t)i * degree + degree - 1];
-    if (last < -1) new_graph[(size_t)i * degree + degree - 1] = last;
+    const int last = old_graph[(size_t)i * old_degree + old_degree - 1];
+    if (last < -1) new_graph[(size_t)i * new_degree + new_degree - 1] = last;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -200,6 +202,48 @@ __global__ void merge_topk_kernel(const int* __restrict__ ids, const float* __re
             const size_t at = ((size_t)l * nq + q) * k + cur[l];
             const int id = ids[at];
             const float d = dists[at];
+            if (id < 0) {  // unfilled tail of this list
+                cur[l] = k;
+                continue;
+            }
+            if (bl < 0 || d < bd || (d == bd && id < bid)) {
+                bl = l;
+                bd = d;
+                bid = id;
+            }
+        }
+        if (bl < 0) {
+            out_ids[(size_t)q * k + o] = -1;
+            out_dists[(size_t)q * k + o] = SPTAG_B200_MAXDIST;
+        } else {
+            out_ids[(size_t)q * k + o] = bid;
+            out_dists[(size_t)q * k + o] = bd;
+            cur[bl]++;
+        }
+    }
+}
+
+// Same merge reading every shard's list where the shard's search kernel left it: `lists.ids[l]` / `lists.dists[l]` are
+// [nq x k] arrays that may live in ANOTHER GPU's HBM (peer access over NVLink): the gather and the merge are one kernel,
+// there is no staging copy and no collective call (sptag_b200_group_search).
+struct ShardLists {
+    const int* ids[16];
+    const float* dists[16];
+};
+__global__ void merge_topk_peer_kernel(const ShardLists lists, int num_lists, int nq, int k, int* __restrict__ out_ids,
+                                       float* __restrict__ out_dists) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    int cur[16];
+    for (int l = 0; l < num_lists; ++l) cur[l] = 0;
+    for (int o = 0; o < k; ++o) {
+        int bl = -1, bid = -1;
+        float bd = 0.0f;
+        for (int l = 0; l < num_lists; ++l) {
+            if (cur[l] >= k) continue;
+            const size_t at = (size_t)q * k + cur[l];
+            const int id = lists.ids[l][at];
+            const float d = lists.dists[l][at];
             if (id < 0) {  // unfilled tail of this list
                 cur[l] = k;
                 continue;

@@ -1156,8 +1156,8 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
     if (cef < 1 || cef + 1 > 2048) return fail(SPTAG_B200_LACK_OF_INPUTS, "CEF = %d outside [1, 2047]", cef);
     if (neighborhood_size < 1 || neighborhood_size > 1024)
         return fail(SPTAG_B200_LACK_OF_INPUTS, "neighbourhood size %d outside [1, 1024]", neighborhood_size);
-    if (install && (first_node != 0 || num_nodes != h->n || neighborhood_size != h->degree))
-        return fail(SPTAG_B200_LACK_OF_INPUTS, "install needs a full pass with the index's own neighbourhood size");
+    if (install && (first_node != 0 || num_nodes != h->n))
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "install needs a full pass over the index");
     if (num_nodes == 0) return SPTAG_B200_SUCCESS;
     std::lock_guard<std::mutex> lock(h->mu);
     DeviceGuard guard(h->device);
@@ -1220,16 +1220,38 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
     if (out_graph)
         CUDA_OK(cudaMemcpy(out_graph, h->d_graph_new.ptr, (size_t)num_nodes * neighborhood_size * 4, cudaMemcpyDeviceToHost));
     if (install) {
-        // BuildGraph re-attaches the duplicate-group back-pointers after its refine passes (NeighborhoodGraph.h:395-401)
+        // BuildGraph re-attaches the duplicate-group back-pointers after its refine passes (NeighborhoodGraph.h:395-401).
+        // The installed rows may be wider or narrower than the current ones (RefineGraph's schedule, :460-492).
         const long long n = h->n;
         carry_backpointers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const int*)h->d_graph.ptr,
-                                                                                   (int*)h->d_graph_new.ptr, h->n, h->degree);
+                                                                                   (int*)h->d_graph_new.ptr, h->n, h->degree,
+                                                                                   neighborhood_size);
         g_launches++;
         CUDA_OK(cudaGetLastError());
         CUDA_OK(cudaStreamSynchronize(stream));
         std::swap(h->d_graph.ptr, h->d_graph_new.ptr);
         std::swap(h->d_graph.bytes, h->d_graph_new.bytes);
+        h->degree = neighborhood_size;
     }
+    return SPTAG_B200_SUCCESS;
+}
+
+int sptag_b200_refine_schedule(sptag_b200_handle h, int32_t refine_iterations, int32_t cef, float cef_scale,
+                                 int32_t neighborhood_size, float neighborhood_scale, float rng_factor) {
+    if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
+    if (refine_iterations < 0 || cef < 1 || neighborhood_size < 1 || !(cef_scale > 0.f) || !(neighborhood_scale > 0.f))
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "bad refine schedule");
+    // NeighborhoodGraph::BuildGraph runs its passes on rows of NeighborhoodSize x NeighborhoodScale entries
+    // (m_iNeighborhoodSize is that product while the graph is built); RefineGraph (NeighborhoodGraph.h:460-492):
+    //   passes 0 .. RefineIterations-2: RefineNode(..., (int)(CEF * CEFScale)) on the wide rows,
+    //   then m_iNeighborhoodSize = (int)(m_iNeighborhoodSize / NeighborhoodScale) and one pass with CEF.
+    const int wide = (int)(neighborhood_size * neighborhood_scale);
+    const int big_cef = (int)(cef * cef_scale);
+    const int narrow = (int)(wide / neighborhood_scale);
+    for (int iter = 0; iter < refine_iterations - 1; ++iter)
+        if (int rc = sptag_b200_refine_graph(h, 0, h->n, big_cef, wide, rng_factor, nullptr, nullptr, nullptr, 1)) return rc;
+    if (refine_iterations > 0)
+        if (int rc = sptag_b200_refine_graph(h, 0, h->n, cef, narrow, rng_factor, nullptr, nullptr, nullptr, 1)) return rc;
     return SPTAG_B200_SUCCESS;
 }
 
@@ -1548,6 +1570,142 @@ int sptag_b200_merge_topk(int32_t device, const int32_t* d_ids, const float* d_d
         d_ids, d_dists, num_lists, num_queries, k, d_out_ids, d_out_dists);
     g_launches++;
     CUDA_OK(cudaGetLastError());
+    return SPTAG_B200_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Vector-partition shards of ONE process (the reference's Aggregator deployment,
+// AggregatorService.cpp:215-412, fans a query out to its index servers and merges the lists): every shard is an
+// ordinary handle on its own GPU with its id_offset; a group search runs all shards at once and merges on the first
+// shard's GPU by reading the other GPUs' result lists through NVLink peer access inside the merge kernel.
+// ---------------------------------------------------------------------------------------------------------------
+struct sptag_b200_shard_group {
+    std::vector<sptag_b200_index*> shards;
+    struct PerShard {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        DeviceBuffer d_queries, d_ids, d_dists;
+    };
+    std::vector<PerShard> per;
+    DeviceBuffer d_out_ids, d_out_dists;  // on shards[0]'s device
+    cudaEvent_t ev_q = nullptr;
+    std::mutex mu;
+};
+
+int sptag_b200_group_create(const sptag_b200_handle* shards, int32_t num_shards, sptag_b200_group* out) {
+    if (!shards || !out) return fail(SPTAG_B200_LACK_OF_INPUTS, "null argument");
+    *out = nullptr;
+    if (num_shards < 1 || num_shards > 16) return fail(SPTAG_B200_LACK_OF_INPUTS, "num_shards %d outside [1, 16]", num_shards);
+    for (int i = 0; i < num_shards; ++i) {
+        if (!shards[i]) return fail(SPTAG_B200_EMPTY_INDEX, "shard %d is null", i);
+        if (shards[i]->dim != shards[0]->dim || shards[i]->value_type != shards[0]->value_type ||
+            shards[i]->metric != shards[0]->metric || shards[i]->q_type != shards[0]->q_type)
+            return fail(SPTAG_B200_DIMENSION_MISMATCH, "shard %d differs from shard 0 in dimension, value type, metric or quantizer", i);
+    }
+    auto* g = new sptag_b200_shard_group();
+    g->shards.assign(shards, shards + num_shards);
+    g->per.resize((size_t)num_shards);
+    const int home = shards[0]->device;
+    for (int i = 0; i < num_shards; ++i) {
+        DeviceGuard guard(shards[i]->device);
+        if (cudaStreamCreate(&g->per[(size_t)i].stream) != cudaSuccess ||
+            cudaEventCreateWithFlags(&g->per[(size_t)i].done, cudaEventDisableTiming) != cudaSuccess) {
+            sptag_b200_group_destroy(g);
+            return fail(SPTAG_B200_FAIL, "stream / event creation failed on device %d", shards[i]->device);
+        }
+        if (shards[i]->device != home) {  // the merge kernel on `home` dereferences this shard's result lists
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, home, shards[i]->device);
+            if (!can) {
+                sptag_b200_group_destroy(g);
+                return fail(SPTAG_B200_FAIL, "device %d cannot access device %d (no NVLink / P2P path)", home, shards[i]->device);
+            }
+            DeviceGuard hg(home);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(shards[i]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                sptag_b200_group_destroy(g);
+                return fail(SPTAG_B200_FAIL, "cudaDeviceEnablePeerAccess(%d -> %d): %s", home, shards[i]->device, cudaGetErrorString(e));
+            }
+            cudaGetLastError();
+        }
+    }
+    {
+        DeviceGuard guard(home);
+        if (cudaEventCreateWithFlags(&g->ev_q, cudaEventDisableTiming) != cudaSuccess) {
+            sptag_b200_group_destroy(g);
+            return fail(SPTAG_B200_FAIL, "event creation failed");
+        }
+    }
+    *out = g;
+    return SPTAG_B200_SUCCESS;
+}
+
+void sptag_b200_group_destroy(sptag_b200_group g) {
+    if (!g) return;
+    for (size_t i = 0; i < g->per.size(); ++i) {
+        DeviceGuard guard(g->shards[i]->device);
+        cudaDeviceSynchronize();
+        g->per[i].d_queries.release();
+        g->per[i].d_ids.release();
+        g->per[i].d_dists.release();
+        if (g->per[i].stream) cudaStreamDestroy(g->per[i].stream);
+        if (g->per[i].done) cudaEventDestroy(g->per[i].done);
+    }
+    if (!g->shards.empty()) {
+        DeviceGuard guard(g->shards[0]->device);
+        g->d_out_ids.release();
+        g->d_out_dists.release();
+        if (g->ev_q) cudaEventDestroy(g->ev_q);
+    }
+    delete g;
+}
+
+int sptag_b200_group_search(sptag_b200_group g, const void* queries, int32_t num_queries, int32_t k, int32_t* out_ids,
+                            float* out_dists) {
+    if (!g) return fail(SPTAG_B200_EMPTY_INDEX, "null group");
+    if (num_queries < 0 || (num_queries > 0 && (!queries || !out_ids || !out_dists)))
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "null buffer");
+    if (num_queries == 0) return SPTAG_B200_SUCCESS;
+    std::lock_guard<std::mutex> glock(g->mu);
+    const int ns = (int)g->shards.size();
+    const size_t qbytes = (size_t)num_queries * query_bytes(g->shards[0]);
+    const size_t rn = (size_t)num_queries * k;
+    ShardLists lists;
+    memset(&lists, 0, sizeof(lists));
+    // fan out: every GPU gets the batch and starts its own search; nothing here waits for a device
+    for (int i = 0; i < ns; ++i) {
+        sptag_b200_index* h = g->shards[(size_t)i];
+        auto& ps = g->per[(size_t)i];
+        DeviceGuard guard(h->device);
+        if (int rc = ps.d_queries.ensure(qbytes)) return rc;
+        if (int rc = ps.d_ids.ensure(rn * 4)) return rc;
+        if (int rc = ps.d_dists.ensure(rn * 4)) return rc;
+        CUDA_OK(cudaMemcpyAsync(ps.d_queries.ptr, queries, qbytes, cudaMemcpyHostToDevice, ps.stream));
+        {
+            std::lock_guard<std::mutex> lock(h->mu);
+            if (int rc = search_device_impl(h, ps.d_queries.ptr, num_queries, k, (int*)ps.d_ids.ptr, (float*)ps.d_dists.ptr, nullptr,
+                                            ps.stream))
+                return rc;
+        }
+        CUDA_OK(cudaEventRecord(ps.done, ps.stream));
+        lists.ids[i] = (const int*)ps.d_ids.ptr;
+        lists.dists[i] = (const float*)ps.d_dists.ptr;
+    }
+    // gather + merge in one kernel on shard 0's GPU: it reads the other GPUs' lists over NVLink
+    sptag_b200_index* h0 = g->shards[0];
+    DeviceGuard guard(h0->device);
+    if (int rc = g->d_out_ids.ensure(rn * 4)) return rc;
+    if (int rc = g->d_out_dists.ensure(rn * 4)) return rc;
+    cudaStream_t s0 = g->per[0].stream;
+    for (int i = 1; i < ns; ++i) CUDA_OK(cudaStreamWaitEvent(s0, g->per[(size_t)i].done, 0));
+    const int threads = 128;
+    merge_topk_peer_kernel<<<(num_queries + threads - 1) / threads, threads, 0, s0>>>(lists, ns, num_queries, k, (int*)g->d_out_ids.ptr,
+                                                                                       (float*)g->d_out_dists.ptr);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(out_ids, g->d_out_ids.ptr, rn * 4, cudaMemcpyDeviceToHost, s0));
+    CUDA_OK(cudaMemcpyAsync(out_dists, g->d_out_dists.ptr, rn * 4, cudaMemcpyDeviceToHost, s0));
+    CUDA_OK(cudaStreamSynchronize(s0));
     return SPTAG_B200_SUCCESS;
 }
 

@@ -108,6 +108,50 @@ def test_refine_install_then_search(name):
         idx.close()
 
 
+@pytest.mark.parametrize("name,iters,cef,cef_scale,nscale,mcr", [
+    ("bkt_l2_5k_100", 2, 1000, 2.0, 2.0, 2048),   # the reference's defaults: first pass CEF x CEFScale = 2000 on 64-wide rows
+    ("bkt_l2_dups", 3, 24, 2.0, 2.0, 256),        # duplicate back-pointers carried across the width changes
+    ("kdt_l2_10k_64", 2, 40, 1.5, 2.0, 512),
+])
+def test_refine_schedule_matches_pass_by_pass_oracle(name, iters, cef, cef_scale, nscale, mcr):
+    """NeighborhoodGraph::RefineGraph (NeighborhoodGraph.h:460-492): RefineIterations - 1 passes with CEF x CEFScale on
+    rows NeighborhoodScale times wider, then one pass with CEF on NeighborhoodSize rows.  Each device pass reads the
+    previous pass's graph; the oracle restates the same frozen-graph passes one after the other."""
+    from sptag_b200 import B200Index
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:60]
+    idx = B200Index.load(folder)
+    old_graph, old_degree = files.graph, files.degree
+    try:
+        idx.set_param("MaxCheckForRefineGraph", mcr)
+        idx.refine_schedule(iters, cef, cef_scale, old_degree, nscale, 1.0)
+        wide = int(old_degree * nscale)
+        narrow = int(wide / nscale)
+        back = old_graph[:, -1] < -1
+        for it in range(iters):
+            last = it == iters - 1
+            width = narrow if last else wide
+            o = reflib.OracleIndex(files)
+            o.max_check_refine = mcr
+            rows, _, _ = o.refine_nodes(0, files.n, cef if last else int(cef * cef_scale), width, 1.0)
+            rows[back, -1] = old_graph[back, -1]
+            files.graph = np.ascontiguousarray(rows)
+            files.degree = width
+        assert idx.graph_degree == narrow
+        assert np.array_equal(idx.get_graph(), files.graph)
+        o2 = reflib.OracleIndex(files)
+        o2.max_check = 1024
+        idx.set_param("MaxCheck", 1024)
+        ids, dists = idx.search(q, 10)
+        ids_o, d_o, _ = o2.search(q, 10)
+        assert np.array_equal(ids, ids_o)
+        assert np.array_equal(dists.view(np.int32), d_o.view(np.int32))
+    finally:
+        files.graph, files.degree = old_graph, old_degree
+        idx.close()
+
+
 def test_refine_argument_errors():
     from sptag_b200 import B200Index, capi
     idx = B200Index.load(data_folder("bkt_l2_3k_30"))
