@@ -19,10 +19,9 @@ static SearchKernelFn pick_rpl(int mres_cap, bool kdt) {
 }
 
 template <bool COSINE>
-static SearchKernelFn pick_dim(int dim, int mres_cap, bool kdt, bool direct) {
+static SearchKernelFn pick_dim(int dim, int mres_cap, bool kdt) {
     switch (dim) {
     case 128:
-        if (direct && !kdt && mres_cap <= 32 * 16) return search_kernel<128, COSINE, 16, false, false, 0, 16, true>;
         if (!kdt && mres_cap <= 32 * 16) return search_kernel<128, COSINE, 16, false, false, 0, 16>;  // 128 regs, 16/SM
         return pick_rpl<128, COSINE>(mres_cap, kdt);
     case 768:

@@ -20,11 +20,11 @@
 // reduced from there; the two priority queues keep their first entries in shared memory and spill
 // the tail of the array to a per-slot arena in HBM so the emulation stays exact at any size.
 //
-// search_kernel<DIM, COSINE, RPL, KDT, PQ, ELEM, MINB, DIRECT>:
+// search_kernel<DIM, COSINE, RPL, KDT, PQ, ELEM, MINB>:
 //   DIM    768 / 128: query slice in registers, fully unrolled; 0: any dimension (query in shared memory)
 //   RPL    registers per lane of the m_Results multiset (16: cap <= 512, 32: cap <= 1024)
 //   KDT    KD-tree flavour of the search loop;  PQ: rows are PQ codes;  ELEM 0 float, 1 int8, 2 uint8, 3 int16
-//   MINB   __launch_bounds__ minimum resident CTAs per SM (register cap);  DIRECT: experimental no-TMA row loads
+//   MINB   __launch_bounds__ minimum resident CTAs per SM (register cap)
 #pragma once
 
 #include <cuda_runtime.h>
@@ -88,8 +88,6 @@ struct SearchParams {
     int pq_adc, pq_dsub;
     const float* codebooks;
     float* adc_tables;                     // per slot, pq_m * pq_ks floats
-    // 1: small float rows are loaded straight from HBM into registers (no TMA ring) in the static-DIM kernels
-    int direct_load;
     // K > 32: the result set is the reference's own max-heap (QueryResultSet.h:77-120) in a per-slot HBM arena
     int2* topk;                            // per slot, topk_pad entries (id, distance bits); nullptr when k <= 32
     int topk_pad;                          // k rounded up to a power of two (the final sort is bitonic)
@@ -469,37 +467,61 @@ __device__ __forceinline__ void heap_insert(WarpHeap& h, int node, float d, int 
     __syncwarp();
 }
 
-// Heap::pop (Heap.h:73-82) + heapify (Heap.h:92-105).  Executed redundantly by every lane
-// (uniform loads broadcast); lane 0 stores.  Returns the old root.
+// Heap::pop (Heap.h:73-82) + heapify (Heap.h:92-105).  Executed redundantly by every lane (uniform loads broadcast);
+// lane 0 stores.  Returns the old root.
+// The two children of a node sit next to each other (indices 2p, 2p + 1 = 16 aligned bytes), so one 128-bit load
+// fetches both; the host keeps H odd, which puts a pair either wholly in shared memory (2p < H) or wholly in the HBM
+// arena.  The walk runs the shared-memory levels first and the arena levels second, each as a tight loop without the
+// per-access "which memory" branch.
 __device__ __forceinline__ int2 heap_pop(WarpHeap& h, int lane) {
     if (h.count == 0) return make_pair(-1, SPTAG_B200_MAXDIST);
-    const int2 top = heap_ld(h, 1);
+    const int2 top = h.s[1];
     const int2 cur = heap_ld(h, h.count);
-    h.count--;
+    const int n = --h.count;
     const float cd = pair_dist(cur);
     int parent = 1, next = 2;
-    while (next < h.count) {
-        int2 a = heap_ld(h, next);
-        const int2 b = heap_ld(h, next + 1);
-        if (pair_dist(a) > pair_dist(b)) {
-            next++;
-            a = b;
-        }
-        if (pair_dist(a) < cd) {
-            if (lane == 0) heap_st(h, parent, a);
-            parent = next;
-            next <<= 1;
-        } else
-            break;
-    }
-    if (next == h.count) {
-        const int2 a = heap_ld(h, next);
-        if (pair_dist(a) < cd) {
-            if (lane == 0) heap_st(h, parent, a);
-            parent = next;
+    bool placed = false;
+    {   // levels whose child pair lives in shared memory
+        const int lim = min(n, h.H);
+        while (next < lim) {
+            const int4 pr = *reinterpret_cast<const int4*>(h.s + next);
+            const bool right = __int_as_float(pr.y) > __int_as_float(pr.w);  // strict: the left child wins ties (Heap.h:96)
+            const int cn = right ? pr.z : pr.x, cb = right ? pr.w : pr.y;
+            next += right ? 1 : 0;
+            if (__int_as_float(cb) < cd) {
+                if (lane == 0) heap_st(h, parent, make_int2(cn, cb));
+                parent = next;
+                next <<= 1;
+            } else {
+                placed = true;
+                break;
+            }
         }
     }
-    if (lane == 0 && h.count > 0) heap_st(h, parent, cur);
+    if (!placed) {  // levels in the HBM arena (next >= H, or the walk is already at its end)
+        while (next < n) {
+            const int4 pr = *reinterpret_cast<const int4*>(h.g + next);
+            const bool right = __int_as_float(pr.y) > __int_as_float(pr.w);
+            const int cn = right ? pr.z : pr.x, cb = right ? pr.w : pr.y;
+            next += right ? 1 : 0;
+            if (__int_as_float(cb) < cd) {
+                if (lane == 0) heap_st(h, parent, make_int2(cn, cb));
+                parent = next;
+                next <<= 1;
+            } else {
+                placed = true;
+                break;
+            }
+        }
+        if (!placed && next == n) {  // a last level with a single child (Heap.h:104)
+            const int2 a = heap_ld(h, next);
+            if (pair_dist(a) < cd) {
+                if (lane == 0) heap_st(h, parent, a);
+                parent = next;
+            }
+        }
+    }
+    if (lane == 0 && n > 0) heap_st(h, parent, cur);
     __syncwarp();
     return top;
 }
@@ -580,7 +602,7 @@ struct BktNodeDev {
     int centerid, childStart, childEnd;
 };
 
-template <int DIM, bool COSINE, int RPL, bool PQ, int ELEM, bool DIRECT>
+template <int DIM, bool COSINE, int RPL, bool PQ, int ELEM>
 struct WarpSearch {
     const SearchParams& p;
     const int lane, half, j;
@@ -804,45 +826,117 @@ struct WarpSearch {
         ndist += cnt;
     }
 
-    // Small rows (<= 1 KB): the per-row TMA descriptor/mbarrier round trip costs more than it hides, so each
-    // half-warp lane loads "its" element of every 16-chunk (element 16c + j, the accumulator it owns in the
-    // reference's summation tree) of NR rows straight from HBM into registers, then runs the NR chains.
-    template <int NR>
-    __device__ __forceinline__ void compute_dists_direct(int cnt) {
-        constexpr int NCH = (DIM > 0) ? DIM / 16 : 1;
+    // ------------------------------------------------------------------------------------------------------------
+    // 512-byte float rows (DIM == 128): the fast path.  ncu on the generic path (profiles/r02_ncu_128_summary.md) showed
+    // the kernel bound by instruction issue and per-step latency, not by HBM: 21 % of the warp instructions managed the
+    // run-time-shaped TMA ring, 24 % were the half-warp distance with its shuffle tree, and the longest stall was the
+    // wait for the visited-bitmap atomics BEFORE the row fetch could even be issued.  Here
+    //   * the ring shape is a compile-time constant: 2 stages x 8 rows, row slots 576 B apart (64 mod 128);
+    //   * a quarter-warp (4 lanes) owns a row: lane q keeps accumulators 4q..4q+3 of the reference's 16, reads one
+    //     conflict-free LDS.128 per 16-element chunk, and the 16 -> 8 -> 4 folds are two xor-shuffle rounds
+    //     (acc256[j] = acc512[j] + acc512[j+8] pairs lanes q and q^2, acc128[j] = acc256[j] + acc256[j+4] pairs q and
+    //     q^1; fp32 addition is commutative, so every lane holds the reference's bits) -- 8 rows per pass;
+    //   * graph steps issue the row fetches for ALL valid neighbours before the bitmap atomics return and drop the
+    //     already-visited ones afterwards (about 10 % of the rows): one HBM latency less on every step's critical path.
+    // ------------------------------------------------------------------------------------------------------------
+    static constexpr bool kFast = (DIM == 128) && (ELEM == 0) && !PQ;
+    static constexpr int kFastRows = 8;
+    static constexpr int kFastStride = 128 * 4 + 64;
+    static constexpr int kFastRowBytes = 128 * 4;
+
+    __device__ __forceinline__ unsigned char* fast_slot(int st, int r) const {
+        return ring + (st * kFastRows + r) * kFastStride;
+    }
+    // rows [8t, 8t + rows) of the step: lane r of the first `rows` lanes fetches the row of vector `id`
+    __device__ __forceinline__ void fast_issue(int st, int rows, int id) {
+        if (lane == 0) mbar_arrive_expect_tx(&bars[st], (uint32_t)rows * (uint32_t)kFastRowBytes);
         __syncwarp();
-        for (int base = 0; base < cnt; base += 2 * NR) {
-            float v[NR][NCH];
+        if (lane < rows)
+            tma_load_1d(fast_slot(st, lane), p.vectors + (size_t)id * p.row_stride_bytes, (uint32_t)kFastRowBytes, &bars[st]);
+    }
+    // distance of the query to the 8 rows of stage `st`; lane 4r + q returns row r's value (all four lanes of a row)
+    template <bool COS = COSINE>
+    __device__ __forceinline__ float fast_dist8(int st) const {
+        const int r = lane >> 2, q = lane & 3;
+        const float4* row = reinterpret_cast<const float4*>(fast_slot(st, r)) + q;
+        const float4* qv = reinterpret_cast<const float4*>(qs) + q;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                const int ri = min(base + 2 * r + half, cnt - 1);
-                const float* row = reinterpret_cast<const float*>(p.vectors + (size_t)cand_id[ri] * p.row_stride_bytes);
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) v[r][c] = __ldcs(row + 16 * c + j);
-            }
-            float acc[NR];
-#pragma unroll
-            for (int r = 0; r < NR; ++r) acc[r] = 0.0f;
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                const float q = qr.q[c];
-#pragma unroll
-                for (int r = 0; r < NR; ++r) acc[r] = __fadd_rn(acc[r], dist_term<COSINE>(q, v[r][c]));
-            }
-#pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                const float a8 = __fadd_rn(acc[r], __shfl_down_sync(kFull, acc[r], 8, 16));
-                const float a4 = __fadd_rn(a8, __shfl_down_sync(kFull, a8, 4, 16));
-                const float a1 = __shfl_sync(kFull, a4, 1, 16);
-                const float a2 = __shfl_sync(kFull, a4, 2, 16);
-                const float a3 = __shfl_sync(kFull, a4, 3, 16);
-                const float sum = __fadd_rn(__fadd_rn(__fadd_rn(a4, a1), a2), a3);
-                const int ri = base + 2 * r + half;
-                if (j == 0 && ri < cnt) cand_dist[ri] = COSINE ? __fsub_rn(1.0f, sum) : sum;
+        for (int c = 0; c < 8; ++c) {
+            const float4 x = qv[4 * c];
+            const float4 y = row[4 * c];
+            a0 = __fadd_rn(a0, dist_term<COS>(x.x, y.x));
+            a1 = __fadd_rn(a1, dist_term<COS>(x.y, y.y));
+            a2 = __fadd_rn(a2, dist_term<COS>(x.z, y.z));
+            a3 = __fadd_rn(a3, dist_term<COS>(x.w, y.w));
+        }
+        // diff256 = lo(diff512) + hi(diff512): accumulators j and j + 8 live in lanes q and q ^ 2
+        a0 = __fadd_rn(a0, __shfl_xor_sync(kFull, a0, 2));
+        a1 = __fadd_rn(a1, __shfl_xor_sync(kFull, a1, 2));
+        a2 = __fadd_rn(a2, __shfl_xor_sync(kFull, a2, 2));
+        a3 = __fadd_rn(a3, __shfl_xor_sync(kFull, a3, 2));
+        // diff128 = lo(diff256) + hi(diff256): j and j + 4 live in lanes q and q ^ 1
+        a0 = __fadd_rn(a0, __shfl_xor_sync(kFull, a0, 1));
+        a1 = __fadd_rn(a1, __shfl_xor_sync(kFull, a1, 1));
+        a2 = __fadd_rn(a2, __shfl_xor_sync(kFull, a2, 1));
+        a3 = __fadd_rn(a3, __shfl_xor_sync(kFull, a3, 1));
+        const float sum = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+        return COS ? __fsub_rn(1.0f, sum) : sum;
+    }
+    // cand_id[0..cnt) -> cand_dist[0..cnt)
+    __device__ __forceinline__ void fast_compute_dists(int cnt) {
+        __syncwarp();
+        fence_proxy_async();
+        const int nst = (cnt + kFastRows - 1) >> 3;
+        const int myid = (lane < 16 && lane < cnt) ? cand_id[lane] : 0;
+        fast_issue(0, min(kFastRows, cnt), __shfl_sync(kFull, myid, lane & 7));
+        if (nst > 1) fast_issue(1, min(kFastRows, cnt - kFastRows), __shfl_sync(kFull, myid, 8 + (lane & 7)));
+        for (int t = 0; t < nst; ++t) {
+            const int st = t & 1;
+            mbar_wait(&bars[st], (phase_bits >> st) & 1u);
+            phase_bits ^= (1u << st);
+            const float d = fast_dist8(st);
+            const int ri = kFastRows * t + (lane >> 2);
+            if ((lane & 3) == 0 && ri < cnt) cand_dist[ri] = d;
+            __syncwarp();
+            if (t + 2 < nst) {
+                fence_proxy_async();
+                const int base = kFastRows * (t + 2);
+                fast_issue(st, min(kFastRows, cnt - base), (base + (lane & 7) < cnt) ? cand_id[base + (lane & 7)] : 0);
             }
         }
         __syncwarp();
         ndist += cnt;
+    }
+    // Graph step: `nn` = this lane's neighbour id, valid for lanes < nvalid (nvalid <= 32).  Row fetches start at once
+    // (call fast_step_begin before the bitmap atomics), fast_step_finish leaves every valid lane's distance in
+    // cand_dist[lane] (by neighbour position, not compacted).
+    __device__ __forceinline__ void fast_step_begin(int nn, int nvalid) {
+        __syncwarp();
+        fence_proxy_async();
+        if (nvalid > 0) fast_issue(0, min(kFastRows, nvalid), __shfl_sync(kFull, nn, lane & 7));
+        if (nvalid > kFastRows) fast_issue(1, min(kFastRows, nvalid - kFastRows), __shfl_sync(kFull, nn, 8 + (lane & 7)));
+    }
+    __device__ __forceinline__ void fast_step_finish(int nn, int nvalid, unsigned freshmask) {
+        const int nst = (nvalid + kFastRows - 1) >> 3;
+        for (int t = 0; t < nst; ++t) {
+            const int st = t & 1;
+            mbar_wait(&bars[st], (phase_bits >> st) & 1u);
+            phase_bits ^= (1u << st);
+            if ((freshmask >> (kFastRows * t)) & 0xffu) {  // nothing new among these 8: skip the arithmetic
+                const float d = fast_dist8(st);
+                const int ri = kFastRows * t + (lane >> 2);
+                if ((lane & 3) == 0) cand_dist[ri] = d;
+            }
+            __syncwarp();
+            if (t + 2 < nst) {
+                fence_proxy_async();
+                const int base = kFastRows * (t + 2);
+                fast_issue(st, min(kFastRows, nvalid - base), __shfl_sync(kFull, nn, base + (lane & 7)));
+            }
+        }
+        __syncwarp();
+        ndist += __popc(freshmask);
     }
 
     __device__ __forceinline__ void compute_dists(int cnt) {
@@ -851,8 +945,8 @@ struct WarpSearch {
             compute_dists_pq(cnt);
             return;
         }
-        if (DIRECT) {  // compile-time: the TMA path below is not even instantiated for these kernels
-            compute_dists_direct<2>(cnt);
+        if (kFast) {  // compile-time
+            fast_compute_dists(cnt);
             return;
         }
         __syncwarp();
@@ -954,6 +1048,10 @@ struct WarpSearch {
         init_search_trees();
         search_trees(p.initial_pivots);
         const int checkPos = p.degree - 1;
+        // The graph row of the node that is on top of NGQueue AFTER a pop is fetched while the popped node's step runs
+        // (the CPU does the same with _mm_prefetch, BKTIndex.cpp:283-288); when that node is the next one popped -- the
+        // common case -- its row is already in a register.
+        int pre_id = -1, pre_nn = -1;
         while (ng.count != 0) {
             const int2 gnode = heap_pop(ng, lane);
             int tmpNode = gnode.x;
@@ -961,7 +1059,13 @@ struct WarpSearch {
             const int* node = p.graph + (size_t)tmpNode * p.degree;
             nexpand++;
             // lane i reads neighbour i of the first 32-wide chunk while the accept logic runs
-            int nn = (lane <= checkPos) ? node[lane] : -1;
+            int nn;
+            if (tmpNode == pre_id)
+                nn = pre_nn;
+            else
+                nn = (lane <= checkPos) ? node[lane] : -1;
+            pre_id = (ng.count != 0) ? ng.s[1].x : -1;
+            pre_nn = (pre_id >= 0 && lane <= checkPos) ? p.graph[(size_t)pre_id * p.degree + lane] : -1;
 
             if (gdist <= worst_d) {
                 const int checkNode = node[checkPos];
@@ -995,6 +1099,7 @@ struct WarpSearch {
                 const unsigned negmask = __ballot_sync(kFull, in_row && nn < 0) | ~__ballot_sync(kFull, in_row);
                 const int first_neg = negmask ? (__ffs(negmask) - 1) : 32;
                 const bool active = lane < first_neg;
+                if (kFast) fast_step_begin(nn, first_neg);  // row fetches overlap the bitmap round trip below
                 // a repeated id inside the row is "visited" by the time its second copy is reached
                 const unsigned same = __match_any_sync(kFull, active ? nn : (-1 - lane));
                 const bool leader = active && ((__ffs(same) - 1) == lane);
@@ -1006,20 +1111,38 @@ struct WarpSearch {
                 }
                 const unsigned freshmask = __ballot_sync(kFull, fresh);
                 const int cnt = __popc(freshmask);
-                __syncwarp();
-                if (fresh) {
-                    const int rank = __popc(freshmask & ((1u << lane) - 1u));
-                    cand_id[rank] = nn;
-                    if (vlog != nullptr && vlog_count + rank < (int)p.vlog_entries) vlog[vlog_count + rank] = (unsigned)(nn >> 5);
+                float myd;
+                int myid;
+                unsigned maybe;
+                if (kFast) {
+                    if (fresh && vlog != nullptr) {
+                        const int rank = __popc(freshmask & ((1u << lane) - 1u));
+                        if (vlog_count + rank < (int)p.vlog_entries) vlog[vlog_count + rank] = (unsigned)(nn >> 5);
+                    }
+                    vlog_count += cnt;
+                    fast_step_finish(nn, first_neg, freshmask);
+                    // distances sit at the neighbours' own positions; the replay below walks the fresh ones in
+                    // neighbour order, which is the order the compacted list had
+                    myd = fresh ? cand_dist[lane] : SPTAG_B200_MAXDIST;
+                    myid = nn;
+                    checked += cnt;
+                    maybe = __ballot_sync(kFull, fresh && !(myd > mres.worst));
+                } else {
+                    __syncwarp();
+                    if (fresh) {
+                        const int rank = __popc(freshmask & ((1u << lane) - 1u));
+                        cand_id[rank] = nn;
+                        if (vlog != nullptr && vlog_count + rank < (int)p.vlog_entries) vlog[vlog_count + rank] = (unsigned)(nn >> 5);
+                    }
+                    vlog_count += cnt;
+                    compute_dists(cnt);
+                    // m_Results.worst() never increases, so a candidate above the current worst is rejected
+                    // whenever its turn comes; only the others are replayed in neighbour order (BKTIndex.cpp:338-344)
+                    myd = (lane < cnt) ? cand_dist[lane] : SPTAG_B200_MAXDIST;
+                    myid = (lane < cnt) ? cand_id[lane] : -1;
+                    checked += cnt;
+                    maybe = __ballot_sync(kFull, lane < cnt && !(myd > mres.worst));
                 }
-                vlog_count += cnt;
-                compute_dists(cnt);
-                // m_Results.worst() never increases, so a candidate above the current worst is rejected
-                // whenever its turn comes; only the others are replayed in neighbour order (BKTIndex.cpp:338-344)
-                const float myd = (lane < cnt) ? cand_dist[lane] : SPTAG_B200_MAXDIST;
-                const int myid = (lane < cnt) ? cand_id[lane] : -1;
-                checked += cnt;
-                unsigned maybe = __ballot_sync(kFull, lane < cnt && !(myd > mres.worst));
                 while (maybe) {
                     const int r = __ffs(maybe) - 1;
                     maybe &= maybe - 1;
@@ -1200,12 +1323,19 @@ struct WarpSearch {
     __device__ __forceinline__ void kdt_search() {
         for (int t = 0; t < p.tree_num; ++t) kdt_search_node(p.tree_starts[t], 0.0f);
         kdt_search_trees(p.initial_pivots);
+        int pre_id = -1, pre_nn = -1;  // graph row of NGQueue's new top, fetched one step ahead (see bkt_search)
         while (ng.count != 0) {
             const int2 gnode = heap_pop(ng, lane);
             const float gdist = pair_dist(gnode);
             const int* node = p.graph + (size_t)gnode.x * p.degree;
             nexpand++;
-            int nn = (lane < p.degree) ? node[lane] : -1;
+            int nn;
+            if (gnode.x == pre_id)
+                nn = pre_nn;
+            else
+                nn = (lane < p.degree) ? node[lane] : -1;
+            pre_id = (ng.count != 0) ? ng.s[1].x : -1;
+            pre_nn = (pre_id >= 0 && lane < p.degree) ? p.graph[(size_t)pre_id * p.degree + lane] : -1;
             if (not_deleted(gnode.x)) {
                 if (!add_point(gnode.x, gdist) && checked > p.max_check) return;
             }
@@ -1217,6 +1347,7 @@ struct WarpSearch {
                 const unsigned negmask = __ballot_sync(kFull, in_row && nn < 0) | ~__ballot_sync(kFull, in_row);
                 const int first_neg = negmask ? (__ffs(negmask) - 1) : 32;
                 const bool active = lane < first_neg;
+                if (kFast) fast_step_begin(nn, first_neg);
                 const unsigned same = __match_any_sync(kFull, active ? nn : (-1 - lane));
                 const bool leader = active && ((__ffs(same) - 1) == lane);
                 bool fresh = false;
@@ -1227,19 +1358,37 @@ struct WarpSearch {
                 }
                 const unsigned freshmask = __ballot_sync(kFull, fresh);
                 const int cnt = __popc(freshmask);
-                __syncwarp();
-                if (fresh) {
-                    const int rank = __popc(freshmask & ((1u << lane) - 1u));
-                    cand_id[rank] = nn;
-                    if (vlog != nullptr && vlog_count + rank < (int)p.vlog_entries) vlog[vlog_count + rank] = (unsigned)(nn >> 5);
-                }
-                vlog_count += cnt;
-                compute_dists(cnt);
-                for (int r = 0; r < cnt; ++r) {
-                    const float d = cand_dist[r];
-                    if (d <= upperBound) bLocalOpt = false;
-                    checked++;
-                    heap_insert(ng, cand_id[r], d, lane);
+                if (kFast) {
+                    if (fresh && vlog != nullptr) {
+                        const int rank = __popc(freshmask & ((1u << lane) - 1u));
+                        if (vlog_count + rank < (int)p.vlog_entries) vlog[vlog_count + rank] = (unsigned)(nn >> 5);
+                    }
+                    vlog_count += cnt;
+                    fast_step_finish(nn, first_neg, freshmask);
+                    const float myd = fresh ? cand_dist[lane] : SPTAG_B200_MAXDIST;
+                    if (__any_sync(kFull, fresh && myd <= upperBound)) bLocalOpt = false;
+                    checked += cnt;
+                    unsigned m = freshmask;  // every new neighbour enters NGQueue, in neighbour order (KDTIndex.cpp:212-223)
+                    while (m) {
+                        const int r = __ffs(m) - 1;
+                        m &= m - 1;
+                        heap_insert(ng, __shfl_sync(kFull, nn, r), __shfl_sync(kFull, myd, r), lane);
+                    }
+                } else {
+                    __syncwarp();
+                    if (fresh) {
+                        const int rank = __popc(freshmask & ((1u << lane) - 1u));
+                        cand_id[rank] = nn;
+                        if (vlog != nullptr && vlog_count + rank < (int)p.vlog_entries) vlog[vlog_count + rank] = (unsigned)(nn >> 5);
+                    }
+                    vlog_count += cnt;
+                    compute_dists(cnt);
+                    for (int r = 0; r < cnt; ++r) {
+                        const float d = cand_dist[r];
+                        if (d <= upperBound) bLocalOpt = false;
+                        checked++;
+                        heap_insert(ng, cand_id[r], d, lane);
+                    }
                 }
                 if (first_neg < 32) break;
             }
@@ -1263,12 +1412,11 @@ struct WarpSearch {
 // ------------------------------------------------------------------------------------------
 // MINB = minimum resident single-warp CTAs per SM the compiler must allow (caps registers): the PQ variant is
 // bound by per-step latency, so more resident queries win (80 registers, 24 per SM: +32 % QPS, profiles/r01_sweep_c2.txt)
-template <int DIM, bool COSINE, int RPL, bool KDT, bool PQ = false, int ELEM = 0, int MINB = 1, bool DIRECT = false>
+template <int DIM, bool COSINE, int RPL, bool KDT, bool PQ = false, int ELEM = 0, int MINB = 1>
 __global__ void __launch_bounds__(32, MINB) search_kernel(const SearchParams p) {
-    static_assert(!DIRECT || (DIM > 0 && DIM <= 256 && DIM % 16 == 0 && ELEM == 0 && !PQ), "direct loads: small static float rows");
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x;
-    WarpSearch<DIM, COSINE, RPL, PQ, ELEM, DIRECT> w(p, lane);
+    WarpSearch<DIM, COSINE, RPL, PQ, ELEM> w(p, lane);
     w.ring = smem;
     w.cand_id = reinterpret_cast<int*>(smem + p.off_cand);
     w.cand_dist = reinterpret_cast<float*>(smem + p.off_cand + 128);
@@ -1349,12 +1497,14 @@ __global__ void __launch_bounds__(32, MINB) search_kernel(const SearchParams p) 
             const float* qg = reinterpret_cast<const float*>(p.queries + (size_t)q * p.query_stride_bytes);
             // static dims that are multiples of 16 never read the shared copy in the BKT flavour (no tails, no
             // KD split test), so those instantiations keep the query in registers only and give the 3 KB back
-            constexpr bool kRegsOnly = (DIM > 0) && (DIM % 16 == 0) && !KDT;
+            // (128-d rows: the fast path reads the query from shared memory with broadcast LDS.128 and holds no slice)
+            constexpr bool kRegsOnly = (DIM == 768) && !KDT;
+            constexpr bool kFastRows128 = (DIM == 128) && (ELEM == 0) && !PQ;
             if (!kRegsOnly) {
                 for (int i = lane; i < p.dim; i += 32) w.qs[i] = qg[i];
                 __syncwarp();
             }
-            if (DIM > 0) {
+            if (DIM > 0 && !kFastRows128) {
 #pragma unroll
                 for (int c = 0; c < DIM / 16; ++c) w.qr.q[c] = __ldg(qg + 16 * c + (lane & 15));
             }
@@ -1422,7 +1572,7 @@ __global__ void __launch_bounds__(32, 12) iterate_kernel(const SearchParams p, i
                                                          unsigned char* __restrict__ out_relaxed) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x;
-    WarpSearch<0, COSINE, RPL, false, ELEM, false> w(p, lane);
+    WarpSearch<0, COSINE, RPL, false, ELEM> w(p, lane);
     w.ring = smem;
     w.cand_id = reinterpret_cast<int*>(smem + p.off_cand);
     w.cand_dist = reinterpret_cast<float*>(smem + p.off_cand + 128);
@@ -1516,7 +1666,7 @@ template <bool COSINE, int RPL, int ELEM>
 __global__ void __launch_bounds__(32, 12) nearest_first_kernel(const SearchParams p, int* __restrict__ state) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x;
-    WarpSearch<0, COSINE, RPL, false, ELEM, false> w(p, lane);
+    WarpSearch<0, COSINE, RPL, false, ELEM> w(p, lane);
     w.ring = smem;
     w.cand_id = reinterpret_cast<int*>(smem + p.off_cand);
     w.cand_dist = reinterpret_cast<float*>(smem + p.off_cand + 128);

@@ -102,7 +102,6 @@ struct sptag_b200_index {
     // SM matter more than on-chip queue capacity (sweep in profiles/r01_sweep_c2.txt).  0 = auto.
     int h_ng = 0, h_spt = 0;
     int simd_width = 16;
-    int direct_load = 0;          // 1: <=1 KB float rows bypass the TMA ring (static-DIM kernels only)
     int slot_scheme = 0;          // 0 auto, 1 = 128-multiple stride + staggered odd slots, 2 = stride 64 mod 128
     int visited_log = -1;         // -1 auto (bitmap > 256 KB per slot), 0 clear per query, 1 log + selective clear
     int visited_log_entries = 0;  // 0 = auto
@@ -175,8 +174,7 @@ SearchKernelFn pick_kernel(const sptag_b200_index* h, int mres_cap) {
     if (h->value_type == SPTAG_B200_VT_INT8) return pick_int8_kernel(false, !l2, mres_cap, kdt);
     if (h->value_type == SPTAG_B200_VT_UINT8) return pick_int8_kernel(true, !l2, mres_cap, kdt);
     if (h->value_type == SPTAG_B200_VT_INT16) return pick_int16_kernel(!l2, mres_cap, kdt);
-    const bool direct = (h->direct_load != 0);
-    return l2 ? pick_float_kernel_l2(h->dim, mres_cap, kdt, direct) : pick_float_kernel_cosine(h->dim, mres_cap, kdt, direct);
+    return l2 ? pick_float_kernel_l2(h->dim, mres_cap, kdt) : pick_float_kernel_cosine(h->dim, mres_cap, kdt);
 }
 
 // What one call may override (the reference passes these per call: p_searchDeleted of SearchIndex / GetIterator,
@@ -246,9 +244,6 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     p.spt_length = alloc_check * 10;
     p.spt_lastlevel = heap_lastlevel(p.spt_length);
     p.mres_cap = std::max(eff_max_check / 16, k);
-    // must mirror pick_dim: the direct-load instantiation exists for 128-d float BKT with the 16-register m_Results file
-    p.direct_load = (h->direct_load != 0 && !pq && h->value_type == SPTAG_B200_VT_FLOAT && h->dim == 128 &&
-                     h->algo == SPTAG_B200_ALGO_BKT && p.mres_cap <= 512) ? 1 : 0;
     p.sdc = (const float*)h->d_sdc.ptr;
     p.pq_m = h->q_m;
     p.pq_ks = h->q_ks;
@@ -276,9 +271,14 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
         if (h->slot_scheme == 2) p.slot_stagger = 0;
         p.slot_stride = (int)(p.slot_stagger ? a : b);
     }
-    if (p.direct_load) {  // the ring is not used: keep the minimum
-        stage_rows = 2;
-        stages = 1;
+    // 512-byte float rows run the fixed-shape fast path (search_kernels.cuh kFast): 2 stages x 8 rows, slots 576 B apart;
+    // must mirror WarpSearch::kFast
+    const bool fast128 = !pq && h->value_type == SPTAG_B200_VT_FLOAT && h->dim == 128;
+    if (fast128) {
+        stage_rows = 8;
+        stages = 2;
+        p.slot_stride = 128 * 4 + 64;
+        p.slot_stagger = 0;
     }
     if (pq) {  // every candidate row of a step in one TMA batch; rows are M bytes
         stage_rows = 32;
@@ -293,8 +293,10 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     bool relayout_done = false;
     int fit = 0;
 relayout:
-    p.h_ng = (h->h_ng > 0 ? h->h_ng : (big_rows ? 64 : 128)) + extra_ng;
-    p.h_spt = (h->h_spt > 0 ? h->h_spt : (big_rows ? 32 : 64)) + extra_spt;
+    // odd: a node's two children (indices 2p, 2p + 1) are fetched with one 128-bit load, so a pair must not straddle the
+    // shared-memory head and the HBM arena (heap_pop)
+    p.h_ng = ((h->h_ng > 0 ? h->h_ng : (big_rows ? 64 : 128)) + extra_ng) | 1;
+    p.h_spt = ((h->h_spt > 0 ? h->h_spt : (big_rows ? 32 : 64)) + extra_spt) | 1;
     size_t off = (size_t)stage_rows * stages * p.slot_stride;
     p.off_ng = (int)off;
     off += round_up((size_t)(p.h_ng + 1) * 8, 16);
@@ -306,7 +308,7 @@ relayout:
     off += round_up((size_t)stages * 8, 16);
     p.off_query = (int)off;
     const bool query_in_regs_only = !pq && h->value_type == SPTAG_B200_VT_FLOAT && h->algo == SPTAG_B200_ALGO_BKT &&
-                                    (h->dim == 128 || h->dim == 768);  // must mirror kRegsOnly in search_kernel
+                                    h->dim == 768;  // must mirror kRegsOnly in search_kernel
     off += query_in_regs_only ? 16 : round_up((size_t)h->dim * 4 + 16, 16);  // float query, or M row offsets for PQ
     smem = round_up(off, 128);
     if (smem > h->smem_optin)
@@ -342,8 +344,9 @@ relayout:
 
     // ---- per-slot scratch ----
     p.visited_words = round_up(((size_t)h->n + 1 + 31) / 32, 4);
-    p.ng_spill_entries = (size_t)std::min<long long>((long long)p.ng_length, (long long)h->n + 2) + 2;
-    p.spt_spill_entries = (size_t)std::min<long long>((long long)p.spt_length, (long long)h->node_count + 2) + 2;
+    // (even entry counts keep every slot's arena 16-byte aligned for the paired child loads)
+    p.ng_spill_entries = round_up((size_t)std::min<long long>((long long)p.ng_length, (long long)h->n + 2) + 2, 2);
+    p.spt_spill_entries = round_up((size_t)std::min<long long>((long long)p.spt_length, (long long)h->node_count + 2) + 2, 2);
     const size_t alloc_slots = (size_t)h->num_sms * per_sm;
     {
         const size_t before = h->d_visited.bytes;
@@ -988,7 +991,6 @@ int sptag_b200_set_param(sptag_b200_handle h, const char* name, const char* valu
     else if (n == "B200.VisitedLog") h->visited_log = (int)v;
     else if (n == "B200.VisitedLogEntries") h->visited_log_entries = (int)v;
     else if (n == "B200.SlotScheme") h->slot_scheme = (int)v;
-    else if (n == "B200.DirectLoad") h->direct_load = (int)v;
     else if (n == "EnableADC") h->q_adc = (v != 0);  // VectorIndex::SetQuantizerADC (VectorIndex.h:136-138)
     else return fail(SPTAG_B200_PARAM_NOT_FOUND, "unknown parameter %s", name);
     return SPTAG_B200_SUCCESS;
@@ -1014,7 +1016,6 @@ int sptag_b200_get_param(sptag_b200_handle h, const char* name, char* value_out,
     else if (n == "B200.VisitedLog") v = h->visited_log;
     else if (n == "B200.VisitedLogEntries") v = h->visited_log_entries;
     else if (n == "B200.SlotScheme") v = h->slot_scheme;
-    else if (n == "B200.DirectLoad") v = h->direct_load;
     else if (n == "EnableADC") v = h->q_adc;
     else if (n == "B200.LastRefineSearchUs") v = (long)(h->refine_search_ms * 1000.0);    // read-only: device time
     else if (n == "B200.LastRefineRebuildUs") v = (long)(h->refine_rebuild_ms * 1000.0);  // of the last refine pass
@@ -1297,7 +1298,7 @@ int sptag_b200_iterator_open_ex(sptag_b200_handle h, const void* queries, int32_
     // NGQueue arena: a plain scan inserts every node at most once (n + 2 bounds it), but after
     // SearchIndexIterativeFromNeareast's nodeCheckStatus.clear() the leftovers of the finished search stay queued while
     // every node may enter once more, so 2 (n + 2) is the bound; Heap::insert itself stops at `length`
-    it->ng_entries = (size_t)std::min<long long>((long long)p.ng_length, 2 * ((long long)h->n + 2)) + 2;
+    it->ng_entries = round_up((size_t)std::min<long long>((long long)p.ng_length, 2 * ((long long)h->n + 2)) + 2, 2);
     it->spt_entries = p.spt_spill_entries;
     const size_t qbytes = (size_t)num_queries * query_bytes(h);
     int rc = 0;
