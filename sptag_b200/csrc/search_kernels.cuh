@@ -498,22 +498,58 @@ __device__ __forceinline__ int2 heap_pop(WarpHeap& h, int lane) {
             }
         }
     }
-    if (!placed) {  // levels in the HBM arena (next >= H, or the walk is already at its end)
-        while (next < n) {
-            const int4 pr = *reinterpret_cast<const int4*>(h.g + next);
-            const bool right = __int_as_float(pr.y) > __int_as_float(pr.w);
-            const int cn = right ? pr.z : pr.x, cb = right ? pr.w : pr.y;
-            next += right ? 1 : 0;
-            if (__int_as_float(cb) < cd) {
-                if (lane == 0) heap_st(h, parent, make_int2(cn, cb));
-                parent = next;
-                next <<= 1;
-            } else {
-                placed = true;
-                break;
+    if (!placed) {
+        if (next > h.H) {
+            // Levels in the HBM arena.  Walking them one dependent load at a time costs a memory round trip per level (the
+            // profile's second-largest stall); instead the whole 5-level subtree below the current node is fetched in
+            // ONE gather -- lane l loads the child pair number l of the 31 pairs in breadth-first order, pair (t, o) =
+            // indices (next << t) + 2 o, +1 -- every lane picks its pair's smaller child by the reference's rule, and the
+            // walk is then replayed from registers with shuffles.  One round trip per 5 levels.
+            while (!placed && next <= n) {
+                const int t = 31 - __clz(lane + 1);
+                const int o = lane + 1 - (1 << t);
+                const int idx = (next << t) + 2 * o;
+                const bool two = (lane < 31) && (idx < n);   // both children exist
+                const bool one = (lane < 31) && (idx == n);  // a last level with a single child (Heap.h:104)
+                int4 pr = make_int4(0, 0, 0, 0);
+                if (two) {
+                    pr = *reinterpret_cast<const int4*>(h.g + idx);
+                } else if (one) {
+                    const int2 a = h.g[idx];
+                    pr.x = a.x;
+                    pr.y = a.y;
+                }
+                const bool right = two && (__int_as_float(pr.y) > __int_as_float(pr.w));
+                const int cn = right ? pr.z : pr.x, cb = right ? pr.w : pr.y;
+                const unsigned m_two = __ballot_sync(kFull, two), m_one = __ballot_sync(kFull, one);
+                const unsigned m_right = __ballot_sync(kFull, right);
+                int oo = 0;
+#pragma unroll
+                for (int tt = 0; tt < 5; ++tt) {
+                    if (placed) break;
+                    const int L = (1 << tt) - 1 + oo;
+                    const int pidx = (next << tt) + 2 * oo;
+                    const int scn = __shfl_sync(kFull, cn, L), scb = __shfl_sync(kFull, cb, L);
+                    if ((m_two >> L) & 1u) {
+                        const int r = (int)((m_right >> L) & 1u);
+                        if (__int_as_float(scb) < cd) {
+                            if (lane == 0) heap_st(h, parent, make_int2(scn, scb));
+                            parent = pidx + r;
+                            oo = 2 * oo + r;
+                        } else {
+                            placed = true;
+                        }
+                    } else {
+                        if (((m_one >> L) & 1u) && __int_as_float(scb) < cd) {
+                            if (lane == 0) heap_st(h, parent, make_int2(scn, scb));
+                            parent = pidx;
+                        }
+                        placed = true;  // no (further) children
+                    }
+                }
+                next = parent << 1;  // (only used when all five levels moved up)
             }
-        }
-        if (!placed && next == n) {  // a last level with a single child (Heap.h:104)
+        } else if (next == n) {  // a last level with a single child, in shared memory
             const int2 a = heap_ld(h, next);
             if (pair_dist(a) < cd) {
                 if (lane == 0) heap_st(h, parent, a);
@@ -836,8 +872,8 @@ struct WarpSearch {
     //     conflict-free LDS.128 per 16-element chunk, and the 16 -> 8 -> 4 folds are two xor-shuffle rounds
     //     (acc256[j] = acc512[j] + acc512[j+8] pairs lanes q and q^2, acc128[j] = acc256[j] + acc256[j+4] pairs q and
     //     q^1; fp32 addition is commutative, so every lane holds the reference's bits) -- 8 rows per pass;
-    //   * graph steps issue the row fetches for ALL valid neighbours before the bitmap atomics return and drop the
-    //     already-visited ones afterwards (about 10 % of the rows): one HBM latency less on every step's critical path.
+    // (Fetching ALL valid neighbours' rows before the bitmap atomics return was tried and measured 12 % slower: only
+    //  56 % of a row's neighbours are new on average at 1M x 128, so the extra row traffic outweighs the hidden latency.)
     // ------------------------------------------------------------------------------------------------------------
     static constexpr bool kFast = (DIM == 128) && (ELEM == 0) && !PQ;
     static constexpr int kFastRows = 8;
@@ -908,37 +944,6 @@ struct WarpSearch {
         __syncwarp();
         ndist += cnt;
     }
-    // Graph step: `nn` = this lane's neighbour id, valid for lanes < nvalid (nvalid <= 32).  Row fetches start at once
-    // (call fast_step_begin before the bitmap atomics), fast_step_finish leaves every valid lane's distance in
-    // cand_dist[lane] (by neighbour position, not compacted).
-    __device__ __forceinline__ void fast_step_begin(int nn, int nvalid) {
-        __syncwarp();
-        fence_proxy_async();
-        if (nvalid > 0) fast_issue(0, min(kFastRows, nvalid), __shfl_sync(kFull, nn, lane & 7));
-        if (nvalid > kFastRows) fast_issue(1, min(kFastRows, nvalid - kFastRows), __shfl_sync(kFull, nn, 8 + (lane & 7)));
-    }
-    __device__ __forceinline__ void fast_step_finish(int nn, int nvalid, unsigned freshmask) {
-        const int nst = (nvalid + kFastRows - 1) >> 3;
-        for (int t = 0; t < nst; ++t) {
-            const int st = t & 1;
-            mbar_wait(&bars[st], (phase_bits >> st) & 1u);
-            phase_bits ^= (1u << st);
-            if ((freshmask >> (kFastRows * t)) & 0xffu) {  // nothing new among these 8: skip the arithmetic
-                const float d = fast_dist8(st);
-                const int ri = kFastRows * t + (lane >> 2);
-                if ((lane & 3) == 0) cand_dist[ri] = d;
-            }
-            __syncwarp();
-            if (t + 2 < nst) {
-                fence_proxy_async();
-                const int base = kFastRows * (t + 2);
-                fast_issue(st, min(kFastRows, nvalid - base), __shfl_sync(kFull, nn, base + (lane & 7)));
-            }
-        }
-        __syncwarp();
-        ndist += __popc(freshmask);
-    }
-
     __device__ __forceinline__ void compute_dists(int cnt) {
         if (cnt <= 0) return;
         if (PQ) {
@@ -1043,32 +1048,60 @@ struct WarpSearch {
         }
     }
 
-    // BKT::Index<T>::Search<notDeleted, CheckDup, AlwaysTrue> (BKTIndex.cpp:268-352)
+    // The visited-set update of one 32-wide chunk of a graph row (OptHashPosVector::CheckAndSet per neighbour, in
+    // neighbour order): the scan stops at the first negative entry (BKTIndex.cpp:333-336); a repeated id inside the row is
+    // "visited" by the time its second copy is reached, so only the first occurrence (the leader) touches the bitmap.
+    // issue_mark starts the atomics and returns without reading their result; the caller overlaps other work with the
+    // round trip and asks for the verdict later.
+    struct RowMark {
+        int first_neg;
+        bool leader;
+        unsigned bit, old;
+    };
+    __device__ __forceinline__ RowMark issue_mark(int nn, bool in_row) {
+        RowMark m;
+        const unsigned negmask = __ballot_sync(kFull, in_row && nn < 0) | ~__ballot_sync(kFull, in_row);
+        m.first_neg = negmask ? (__ffs(negmask) - 1) : 32;
+        const bool active = lane < m.first_neg;
+        const unsigned same = __match_any_sync(kFull, active ? nn : (-1 - lane));
+        m.leader = active && ((__ffs(same) - 1) == lane);
+        m.bit = 1u << (nn & 31);
+        m.old = 0xffffffffu;
+        if (m.leader) m.old = atomicOr(&visited[nn >> 5], m.bit);
+        return m;
+    }
+    // L2 prefetch of the bitmap words the next step will update (no data returns to the SM)
+    __device__ __forceinline__ void prefetch_marks(int nn) {
+        if (nn >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(visited + (nn >> 5)));
+    }
+
+    // BKT::Index<T>::Search<notDeleted, CheckDup, AlwaysTrue> (BKTIndex.cpp:268-352).
+    // One step's memory round trips are data-dependent (queue root -> graph row -> visited set -> vectors), so the order
+    // inside a step is chosen to overlap them: the root of NGQueue is the popped node before the sift-down runs, so the
+    // accept / stop logic (which never looks at the queue) and the visited-set atomics are issued first and Heap::pop's
+    // sift-down runs while they are in flight; the graph row of the node that is on top AFTER the pop is fetched a step
+    // ahead (the CPU does the same with _mm_prefetch, BKTIndex.cpp:283-288), and when it is still on top at the end of
+    // the step the bitmap words of its neighbours are prefetched into L2.
     __device__ __forceinline__ void bkt_search() {
         init_search_trees();
         search_trees(p.initial_pivots);
         const int checkPos = p.degree - 1;
-        // The graph row of the node that is on top of NGQueue AFTER a pop is fetched while the popped node's step runs
-        // (the CPU does the same with _mm_prefetch, BKTIndex.cpp:283-288); when that node is the next one popped -- the
-        // common case -- its row is already in a register.
         int pre_id = -1, pre_nn = -1;
         while (ng.count != 0) {
-            const int2 gnode = heap_pop(ng, lane);
+            const int2 gnode = ng.s[1];  // what Heap::pop will return
             int tmpNode = gnode.x;
             const float gdist = pair_dist(gnode);
             const int* node = p.graph + (size_t)tmpNode * p.degree;
             nexpand++;
-            // lane i reads neighbour i of the first 32-wide chunk while the accept logic runs
+            // lane i holds neighbour i of the first 32-wide chunk
             int nn;
             if (tmpNode == pre_id)
                 nn = pre_nn;
             else
                 nn = (lane <= checkPos) ? node[lane] : -1;
-            pre_id = (ng.count != 0) ? ng.s[1].x : -1;
-            pre_nn = (pre_id >= 0 && lane <= checkPos) ? p.graph[(size_t)pre_id * p.degree + lane] : -1;
 
             if (gdist <= worst_d) {
-                const int checkNode = node[checkPos];
+                const int checkNode = (checkPos < 32) ? __shfl_sync(kFull, nn, checkPos) : node[checkPos];
                 if (checkNode < -1) {
                     // duplicate group: the back-pointer names the BKT node listing exact duplicates
                     const int tn = -2 - checkNode;
@@ -1088,61 +1121,40 @@ struct WarpSearch {
                 }
             } else {
                 if (not_deleted(tmpNode)) {
-                    if (gdist > mres.worst || checked > p.max_check) return;
+                    if (gdist > mres.worst || checked > p.max_check) {
+                        heap_pop(ng, lane);  // the reference popped before it looked (NGQueue survives in the iterator flavour)
+                        return;
+                    }
                 }
             }
 
+            RowMark mark = issue_mark(nn, lane <= checkPos);
+            heap_pop(ng, lane);  // sift-down, while the atomics are in flight
+            pre_id = (ng.count != 0) ? ng.s[1].x : -1;
+            pre_nn = (pre_id >= 0 && lane <= checkPos) ? p.graph[(size_t)pre_id * p.degree + lane] : -1;
+
             for (int cbase = 0; cbase <= checkPos; cbase += 32) {
-                if (cbase > 0) nn = (cbase + lane <= checkPos) ? node[cbase + lane] : -1;
-                const bool in_row = (cbase + lane <= checkPos);
-                // the scan stops at the first negative entry (BKTIndex.cpp:333-336)
-                const unsigned negmask = __ballot_sync(kFull, in_row && nn < 0) | ~__ballot_sync(kFull, in_row);
-                const int first_neg = negmask ? (__ffs(negmask) - 1) : 32;
-                const bool active = lane < first_neg;
-                if (kFast) fast_step_begin(nn, first_neg);  // row fetches overlap the bitmap round trip below
-                // a repeated id inside the row is "visited" by the time its second copy is reached
-                const unsigned same = __match_any_sync(kFull, active ? nn : (-1 - lane));
-                const bool leader = active && ((__ffs(same) - 1) == lane);
-                bool fresh = false;
-                if (leader) {
-                    const unsigned bit = 1u << (nn & 31);
-                    const unsigned old = atomicOr(&visited[nn >> 5], bit);
-                    fresh = (old & bit) == 0;
+                if (cbase > 0) {
+                    nn = (cbase + lane <= checkPos) ? node[cbase + lane] : -1;
+                    mark = issue_mark(nn, cbase + lane <= checkPos);
                 }
+                const bool fresh = mark.leader && (mark.old & mark.bit) == 0;
                 const unsigned freshmask = __ballot_sync(kFull, fresh);
                 const int cnt = __popc(freshmask);
-                float myd;
-                int myid;
-                unsigned maybe;
-                if (kFast) {
-                    if (fresh && vlog != nullptr) {
-                        const int rank = __popc(freshmask & ((1u << lane) - 1u));
-                        if (vlog_count + rank < (int)p.vlog_entries) vlog[vlog_count + rank] = (unsigned)(nn >> 5);
-                    }
-                    vlog_count += cnt;
-                    fast_step_finish(nn, first_neg, freshmask);
-                    // distances sit at the neighbours' own positions; the replay below walks the fresh ones in
-                    // neighbour order, which is the order the compacted list had
-                    myd = fresh ? cand_dist[lane] : SPTAG_B200_MAXDIST;
-                    myid = nn;
-                    checked += cnt;
-                    maybe = __ballot_sync(kFull, fresh && !(myd > mres.worst));
-                } else {
-                    __syncwarp();
-                    if (fresh) {
-                        const int rank = __popc(freshmask & ((1u << lane) - 1u));
-                        cand_id[rank] = nn;
-                        if (vlog != nullptr && vlog_count + rank < (int)p.vlog_entries) vlog[vlog_count + rank] = (unsigned)(nn >> 5);
-                    }
-                    vlog_count += cnt;
-                    compute_dists(cnt);
-                    // m_Results.worst() never increases, so a candidate above the current worst is rejected
-                    // whenever its turn comes; only the others are replayed in neighbour order (BKTIndex.cpp:338-344)
-                    myd = (lane < cnt) ? cand_dist[lane] : SPTAG_B200_MAXDIST;
-                    myid = (lane < cnt) ? cand_id[lane] : -1;
-                    checked += cnt;
-                    maybe = __ballot_sync(kFull, lane < cnt && !(myd > mres.worst));
+                __syncwarp();
+                if (fresh) {
+                    const int rank = __popc(freshmask & ((1u << lane) - 1u));
+                    cand_id[rank] = nn;
+                    if (vlog != nullptr && vlog_count + rank < (int)p.vlog_entries) vlog[vlog_count + rank] = (unsigned)(nn >> 5);
                 }
+                vlog_count += cnt;
+                compute_dists(cnt);
+                // m_Results.worst() never increases, so a candidate above the current worst is rejected
+                // whenever its turn comes; only the others are replayed in neighbour order (BKTIndex.cpp:338-344)
+                const float myd = (lane < cnt) ? cand_dist[lane] : SPTAG_B200_MAXDIST;
+                const int myid = (lane < cnt) ? cand_id[lane] : -1;
+                checked += cnt;
+                unsigned maybe = __ballot_sync(kFull, lane < cnt && !(myd > mres.worst));
                 while (maybe) {
                     const int r = __ffs(maybe) - 1;
                     maybe &= maybe - 1;
@@ -1150,9 +1162,10 @@ struct WarpSearch {
                     const int id = __shfl_sync(kFull, myid, r);
                     if (mres.insert(d, lane)) heap_insert(ng, id, d, lane);
                 }
-                if (first_neg < 32) break;
+                if (mark.first_neg < 32) break;
             }
             if (heap_top_dist(ng) > heap_top_dist(spt)) search_trees(p.other_pivots + checked);
+            if (pre_id >= 0 && ng.count != 0 && ng.s[1].x == pre_id) prefetch_marks(pre_nn);
         }
     }
 
@@ -1325,7 +1338,7 @@ struct WarpSearch {
         kdt_search_trees(p.initial_pivots);
         int pre_id = -1, pre_nn = -1;  // graph row of NGQueue's new top, fetched one step ahead (see bkt_search)
         while (ng.count != 0) {
-            const int2 gnode = heap_pop(ng, lane);
+            const int2 gnode = ng.s[1];  // what Heap::pop will return
             const float gdist = pair_dist(gnode);
             const int* node = p.graph + (size_t)gnode.x * p.degree;
             nexpand++;
@@ -1334,63 +1347,41 @@ struct WarpSearch {
                 nn = pre_nn;
             else
                 nn = (lane < p.degree) ? node[lane] : -1;
-            pre_id = (ng.count != 0) ? ng.s[1].x : -1;
-            pre_nn = (pre_id >= 0 && lane < p.degree) ? p.graph[(size_t)pre_id * p.degree + lane] : -1;
             if (not_deleted(gnode.x)) {
-                if (!add_point(gnode.x, gdist) && checked > p.max_check) return;
+                if (!add_point(gnode.x, gdist) && checked > p.max_check) {
+                    heap_pop(ng, lane);
+                    return;
+                }
             }
             const float upperBound = fmaxf(worst_d, gdist);
             bool bLocalOpt = true;
+            RowMark mark = issue_mark(nn, lane < p.degree);
+            heap_pop(ng, lane);  // sift-down, while the atomics are in flight
+            pre_id = (ng.count != 0) ? ng.s[1].x : -1;
+            pre_nn = (pre_id >= 0 && lane < p.degree) ? p.graph[(size_t)pre_id * p.degree + lane] : -1;
             for (int cbase = 0; cbase < p.degree; cbase += 32) {
-                if (cbase > 0) nn = (cbase + lane < p.degree) ? node[cbase + lane] : -1;
-                const bool in_row = (cbase + lane < p.degree);
-                const unsigned negmask = __ballot_sync(kFull, in_row && nn < 0) | ~__ballot_sync(kFull, in_row);
-                const int first_neg = negmask ? (__ffs(negmask) - 1) : 32;
-                const bool active = lane < first_neg;
-                if (kFast) fast_step_begin(nn, first_neg);
-                const unsigned same = __match_any_sync(kFull, active ? nn : (-1 - lane));
-                const bool leader = active && ((__ffs(same) - 1) == lane);
-                bool fresh = false;
-                if (leader) {
-                    const unsigned bit = 1u << (nn & 31);
-                    const unsigned old = atomicOr(&visited[nn >> 5], bit);
-                    fresh = (old & bit) == 0;
+                if (cbase > 0) {
+                    nn = (cbase + lane < p.degree) ? node[cbase + lane] : -1;
+                    mark = issue_mark(nn, cbase + lane < p.degree);
                 }
+                const bool fresh = mark.leader && (mark.old & mark.bit) == 0;
                 const unsigned freshmask = __ballot_sync(kFull, fresh);
                 const int cnt = __popc(freshmask);
-                if (kFast) {
-                    if (fresh && vlog != nullptr) {
-                        const int rank = __popc(freshmask & ((1u << lane) - 1u));
-                        if (vlog_count + rank < (int)p.vlog_entries) vlog[vlog_count + rank] = (unsigned)(nn >> 5);
-                    }
-                    vlog_count += cnt;
-                    fast_step_finish(nn, first_neg, freshmask);
-                    const float myd = fresh ? cand_dist[lane] : SPTAG_B200_MAXDIST;
-                    if (__any_sync(kFull, fresh && myd <= upperBound)) bLocalOpt = false;
-                    checked += cnt;
-                    unsigned m = freshmask;  // every new neighbour enters NGQueue, in neighbour order (KDTIndex.cpp:212-223)
-                    while (m) {
-                        const int r = __ffs(m) - 1;
-                        m &= m - 1;
-                        heap_insert(ng, __shfl_sync(kFull, nn, r), __shfl_sync(kFull, myd, r), lane);
-                    }
-                } else {
-                    __syncwarp();
-                    if (fresh) {
-                        const int rank = __popc(freshmask & ((1u << lane) - 1u));
-                        cand_id[rank] = nn;
-                        if (vlog != nullptr && vlog_count + rank < (int)p.vlog_entries) vlog[vlog_count + rank] = (unsigned)(nn >> 5);
-                    }
-                    vlog_count += cnt;
-                    compute_dists(cnt);
-                    for (int r = 0; r < cnt; ++r) {
-                        const float d = cand_dist[r];
-                        if (d <= upperBound) bLocalOpt = false;
-                        checked++;
-                        heap_insert(ng, cand_id[r], d, lane);
-                    }
+                __syncwarp();
+                if (fresh) {
+                    const int rank = __popc(freshmask & ((1u << lane) - 1u));
+                    cand_id[rank] = nn;
+                    if (vlog != nullptr && vlog_count + rank < (int)p.vlog_entries) vlog[vlog_count + rank] = (unsigned)(nn >> 5);
                 }
-                if (first_neg < 32) break;
+                vlog_count += cnt;
+                compute_dists(cnt);
+                // every new neighbour enters NGQueue, in neighbour order (KDTIndex.cpp:212-223)
+                const float myd = (lane < cnt) ? cand_dist[lane] : SPTAG_B200_MAXDIST;
+                const int myid = (lane < cnt) ? cand_id[lane] : -1;
+                if (__any_sync(kFull, lane < cnt && myd <= upperBound)) bLocalOpt = false;
+                checked += cnt;
+                for (int r = 0; r < cnt; ++r) heap_insert(ng, __shfl_sync(kFull, myid, r), __shfl_sync(kFull, myd, r), lane);
+                if (mark.first_neg < 32) break;
             }
             if (bLocalOpt)
                 no_better++;
@@ -1403,6 +1394,7 @@ struct WarpSearch {
                     break;
                 }
             }
+            if (pre_id >= 0 && ng.count != 0 && ng.s[1].x == pre_id) prefetch_marks(pre_nn);
         }
     }
 };
