@@ -135,6 +135,10 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// L2 prefetch of a contiguous block by the TMA unit (no data returns to the SM)
+__device__ __forceinline__ void tma_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -404,15 +408,19 @@ struct WarpHeap {
     int H;
     int count;
     int length, lastlevel;
+    // register copy of the LAST element (index tail_idx; valid while tail_idx == count): Heap::pop starts by moving the
+    // last element to the root, and deep in the HBM arena that read is a full memory round trip at the head of every
+    // pop's dependency chain.  Inserts know what they leave at the last position; a pop fetches the new last element
+    // ahead of time.
+    int2 tail;
+    int tail_idx;
 };
 
-__device__ __forceinline__ int2 heap_ld(const WarpHeap& h, int i) { return i <= h.H ? h.s[i] : h.g[i]; }
-__device__ __forceinline__ void heap_st(const WarpHeap& h, int i, int2 v) {
-    if (i <= h.H)
-        h.s[i] = v;
-    else
-        h.g[i] = v;
-}
+// one access path for both halves of the array: the select yields a generic pointer, so there is no branch (and no
+// divergence when the lanes of an insert straddle the shared-memory head and the arena)
+__device__ __forceinline__ int2* heap_at(const WarpHeap& h, int i) { return (i <= h.H) ? (h.s + i) : (h.g + i); }
+__device__ __forceinline__ int2 heap_ld(const WarpHeap& h, int i) { return *heap_at(h, i); }
+__device__ __forceinline__ void heap_st(const WarpHeap& h, int i, int2 v) { *heap_at(h, i) = v; }
 __device__ __forceinline__ float pair_dist(int2 v) { return __int_as_float(v.y); }
 __device__ __forceinline__ int2 make_pair(int node, float d) { return make_int2(node, __float_as_int(d)); }
 
@@ -452,6 +460,7 @@ __device__ __forceinline__ void heap_insert(WarpHeap& h, int node, float d, int 
         }
         if (d > best) return;
         loc = besti;
+        h.tail_idx = -1;
     } else {
         loc = ++h.count;
     }
@@ -464,6 +473,15 @@ __device__ __forceinline__ void heap_insert(WarpHeap& h, int node, float d, int 
         heap_st(h, loc >> lane, av);
     else if (lane == s)
         heap_st(h, loc >> s, make_pair(node, d));
+    if (loc == h.count) {  // what now sits at the last position: the new element, or its parent moved down
+        if (s == 0) {
+            h.tail = make_pair(node, d);
+        } else {
+            h.tail.x = __shfl_sync(kFull, av.x, 0);
+            h.tail.y = __shfl_sync(kFull, av.y, 0);
+        }
+        h.tail_idx = loc;
+    }
     __syncwarp();
 }
 
@@ -476,7 +494,7 @@ __device__ __forceinline__ void heap_insert(WarpHeap& h, int node, float d, int 
 __device__ __forceinline__ int2 heap_pop(WarpHeap& h, int lane) {
     if (h.count == 0) return make_pair(-1, SPTAG_B200_MAXDIST);
     const int2 top = h.s[1];
-    const int2 cur = heap_ld(h, h.count);
+    const int2 cur = (h.tail_idx == h.count) ? h.tail : heap_ld(h, h.count);
     const int n = --h.count;
     const float cd = pair_dist(cur);
     int parent = 1, next = 2;
@@ -559,6 +577,11 @@ __device__ __forceinline__ int2 heap_pop(WarpHeap& h, int lane) {
     }
     if (lane == 0 && n > 0) heap_st(h, parent, cur);
     __syncwarp();
+    h.tail_idx = -1;
+    if (n > h.H) {  // the next pop's first read, issued now; an insert in between simply overwrites the copy
+        h.tail = h.g[n];
+        h.tail_idx = n;
+    }
     return top;
 }
 
@@ -927,6 +950,10 @@ struct WarpSearch {
         const int myid = (lane < 16 && lane < cnt) ? cand_id[lane] : 0;
         fast_issue(0, min(kFastRows, cnt), __shfl_sync(kFull, myid, lane & 7));
         if (nst > 1) fast_issue(1, min(kFastRows, cnt - kFastRows), __shfl_sync(kFull, myid, 8 + (lane & 7)));
+        // the ring holds 16 rows; the rows of the later stages start their trip from HBM to L2 now, so that their TMA
+        // copy -- issued when a ring stage frees up -- finds them there
+        if (lane >= 2 * kFastRows && lane < cnt)
+            tma_prefetch_l2(p.vectors + (size_t)cand_id[lane] * p.row_stride_bytes, (uint32_t)kFastRowBytes);
         for (int t = 0; t < nst; ++t) {
             const int st = t & 1;
             mbar_wait(&bars[st], (phase_bits >> st) & 1u);
@@ -1452,6 +1479,7 @@ __global__ void __launch_bounds__(32, MINB) search_kernel(const SearchParams p) 
         w.vlog_count = 0;
         w.ng.count = 0;
         w.spt.count = 0;
+        w.ng.tail_idx = w.spt.tail_idx = -1;
         w.mres.reset(p.mres_cap, lane);
         w.tk_d = SPTAG_B200_MAXDIST;
         w.tk_id = -1;
@@ -1600,6 +1628,7 @@ __global__ void __launch_bounds__(32, 12) iterate_kernel(const SearchParams p, i
         w.tk = p.topk + (size_t)q * p.topk_pad;
         w.ng.count = st[0];
         w.spt.count = st[1];
+        w.ng.tail_idx = w.spt.tail_idx = -1;
         const bool is_first = st[2] != 0;
         int relaxed = st[3];
         const int slots = st[4];
@@ -1696,6 +1725,7 @@ __global__ void __launch_bounds__(32, 12) nearest_first_kernel(const SearchParam
         w.vlog_count = 0;
         w.ng.count = 0;
         w.spt.count = 0;
+        w.ng.tail_idx = w.spt.tail_idx = -1;
         w.mres.reset(max(p.max_check / 16, p.k), lane);
         w.tk_d = SPTAG_B200_MAXDIST;
         w.tk_id = -1;

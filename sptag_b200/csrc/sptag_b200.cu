@@ -324,6 +324,9 @@ relayout:
     int per_sm = h->queries_per_sm;
     if (per_sm <= 0) per_sm = fit;  // the kernel is latency-bound per warp: fill the SM
     if (h->queries_per_sm <= 0 && big_rows) per_sm = std::min(per_sm, 14);  // 3 KB rows: 14 beats 15 (HBM-bound, sweep)
+    // 512 B rows: 14 slots leave 2 KB more shared memory per queue head than 16 and shorten the tail of a 10k-query batch
+    // (profiles/r02_sweep_128.txt: 521k vs 504k QPS; at batches >= 20k queries 16 wins by 2-3 %)
+    if (h->queries_per_sm <= 0 && fast128 && nq <= 16384) per_sm = std::min(per_sm, 14);
     per_sm = std::max(1, std::min(per_sm, fit));
     if (h->h_ng <= 0 && h->h_spt <= 0 && !relayout_done) {
         // Spare shared memory of a slot (at this residency) goes to the queue heads: 3/4 NGQueue, 1/4 SPTQueue
