@@ -421,6 +421,14 @@ struct WarpHeap {
 __device__ __forceinline__ int2* heap_at(const WarpHeap& h, int i) { return (i <= h.H) ? (h.s + i) : (h.g + i); }
 __device__ __forceinline__ int2 heap_ld(const WarpHeap& h, int i) { return *heap_at(h, i); }
 __device__ __forceinline__ void heap_st(const WarpHeap& h, int i, int2 v) { *heap_at(h, i) = v; }
+// branchy round-1 accessors (see heap_pop_seq)
+__device__ __forceinline__ int2 heap_ld_br(const WarpHeap& h, int i) { return i <= h.H ? h.s[i] : h.g[i]; }
+__device__ __forceinline__ void heap_st_br(const WarpHeap& h, int i, int2 v) {
+    if (i <= h.H)
+        h.s[i] = v;
+    else
+        h.g[i] = v;
+}
 __device__ __forceinline__ float pair_dist(int2 v) { return __int_as_float(v.y); }
 __device__ __forceinline__ int2 make_pair(int node, float d) { return make_int2(node, __float_as_int(d)); }
 
@@ -432,7 +440,11 @@ __device__ __forceinline__ float heap_top_dist(const WarpHeap& h) {
 // Heap::insert (Heap.h:39-62).  The sift-up path (the ancestors loc>>1, loc>>2, ...) is loaded by
 // one lane per level, the stop level is found with a ballot, and the shifted parents plus the new
 // value are stored in one step -- the resulting array is identical to the sequential loop's.
+template <bool TAIL = true>
 __device__ __forceinline__ void heap_insert(WarpHeap& h, int node, float d, int lane) {
+    // TAIL (fast path): branch-free generic-pointer accesses + the register copy of the last element
+#define SPTAG_B200_HLD(i) (TAIL ? heap_ld(h, (i)) : heap_ld_br(h, (i)))
+#define SPTAG_B200_HST(i, v) do { if (TAIL) heap_st(h, (i), (v)); else heap_st_br(h, (i), (v)); } while (0)
     int loc;
     if (h.count == h.length) {
         // full heap: replace the first maximum of the last level [lastlevel, length] (Heap.h:43-49)
@@ -440,7 +452,7 @@ __device__ __forceinline__ void heap_insert(WarpHeap& h, int node, float d, int 
         int besti = 0x7fffffff;
         bool have = false;
         for (int i = h.lastlevel + lane; i <= h.length; i += 32) {
-            float v = pair_dist(heap_ld(h, i));
+            float v = pair_dist(SPTAG_B200_HLD(i));
             if (!have || v > best) {  // strict '<' in the reference keeps the earliest maximum
                 best = v;
                 besti = i;
@@ -460,20 +472,20 @@ __device__ __forceinline__ void heap_insert(WarpHeap& h, int node, float d, int 
         }
         if (d > best) return;
         loc = besti;
-        h.tail_idx = -1;
+        if (TAIL) h.tail_idx = -1;
     } else {
         loc = ++h.count;
     }
     const int anc = loc >> (lane + 1);
     int2 av = make_int2(0, 0);
-    if (anc > 0) av = heap_ld(h, anc);
+    if (anc > 0) av = SPTAG_B200_HLD(anc);
     const bool stop = (anc <= 0) || !(d < pair_dist(av));
     const int s = __ffs(__ballot_sync(kFull, stop)) - 1;  // levels 0..s-1 move down
     if (lane < s)
-        heap_st(h, loc >> lane, av);
+        SPTAG_B200_HST(loc >> lane, av);
     else if (lane == s)
-        heap_st(h, loc >> s, make_pair(node, d));
-    if (loc == h.count) {  // what now sits at the last position: the new element, or its parent moved down
+        SPTAG_B200_HST(loc >> s, make_pair(node, d));
+    if (TAIL && loc == h.count) {  // what now sits at the last position: the new element, or its parent moved down
         if (s == 0) {
             h.tail = make_pair(node, d);
         } else {
@@ -484,6 +496,47 @@ __device__ __forceinline__ void heap_insert(WarpHeap& h, int node, float d, int 
     }
     __syncwarp();
 }
+#undef SPTAG_B200_HLD
+#undef SPTAG_B200_HST
+
+// Round-1 forms, kept for every kernel except the 512-byte-row fast path: one dependent load per level and a branch per
+// access.  They hold fewer values live than the paired / gathered pop below, which matters where the register cap is
+// what sets the residency (768-d rows: 15 slots at 127 registers; PQ: 24 slots at 80) -- measured on a B200, the newer
+// forms cost those kernels 7-17 % (spills, lower occupancy) while the latency they remove is hidden there anyway.
+// Heap::pop (Heap.h:73-82) + heapify (Heap.h:92-105), level by level.
+__device__ __forceinline__ int2 heap_pop_seq(WarpHeap& h, int lane) {
+    if (h.count == 0) return make_pair(-1, SPTAG_B200_MAXDIST);
+    const int2 top = heap_ld_br(h, 1);
+    const int2 cur = heap_ld_br(h, h.count);
+    h.count--;
+    const float cd = pair_dist(cur);
+    int parent = 1, next = 2;
+    while (next < h.count) {
+        int2 a = heap_ld_br(h, next);
+        const int2 b = heap_ld_br(h, next + 1);
+        if (pair_dist(a) > pair_dist(b)) {
+            next++;
+            a = b;
+        }
+        if (pair_dist(a) < cd) {
+            if (lane == 0) heap_st_br(h, parent, a);
+            parent = next;
+            next <<= 1;
+        } else
+            break;
+    }
+    if (next == h.count) {
+        const int2 a = heap_ld_br(h, next);
+        if (pair_dist(a) < cd) {
+            if (lane == 0) heap_st_br(h, parent, a);
+            parent = next;
+        }
+    }
+    if (lane == 0 && h.count > 0) heap_st_br(h, parent, cur);
+    __syncwarp();
+    return top;
+}
+
 
 // Heap::pop (Heap.h:73-82) + heapify (Heap.h:92-105).  Executed redundantly by every lane (uniform loads broadcast);
 // lane 0 stores.  Returns the old root.
@@ -491,10 +544,11 @@ __device__ __forceinline__ void heap_insert(WarpHeap& h, int node, float d, int 
 // fetches both; the host keeps H odd, which puts a pair either wholly in shared memory (2p < H) or wholly in the HBM
 // arena.  The walk runs the shared-memory levels first and the arena levels second, each as a tight loop without the
 // per-access "which memory" branch.
+template <bool TAIL = true>
 __device__ __forceinline__ int2 heap_pop(WarpHeap& h, int lane) {
     if (h.count == 0) return make_pair(-1, SPTAG_B200_MAXDIST);
     const int2 top = h.s[1];
-    const int2 cur = (h.tail_idx == h.count) ? h.tail : heap_ld(h, h.count);
+    const int2 cur = (TAIL && h.tail_idx == h.count) ? h.tail : heap_ld(h, h.count);
     const int n = --h.count;
     const float cd = pair_dist(cur);
     int parent = 1, next = 2;
@@ -577,10 +631,12 @@ __device__ __forceinline__ int2 heap_pop(WarpHeap& h, int lane) {
     }
     if (lane == 0 && n > 0) heap_st(h, parent, cur);
     __syncwarp();
-    h.tail_idx = -1;
-    if (n > h.H) {  // the next pop's first read, issued now; an insert in between simply overwrites the copy
-        h.tail = h.g[n];
-        h.tail_idx = n;
+    if (TAIL) {
+        h.tail_idx = -1;
+        if (n > h.H) {  // the next pop's first read, issued now; an insert in between simply overwrites the copy
+            h.tail = h.g[n];
+            h.tail_idx = n;
+        }
     }
     return top;
 }
@@ -694,6 +750,16 @@ struct WarpSearch {
 
     __device__ __forceinline__ WarpSearch(const SearchParams& p_, int lane_)
         : p(p_), lane(lane_), half(lane_ >> 4), j(lane_ & 15) {}
+
+    // Everything but the 512-byte-row fast path keeps the round-1 step order and queue code (see heap_pop_seq): those
+    // kernels' residency is set by a register cap (768-d: 15 slots at 127 registers, PQ: 24 at 80) or by the uncapped
+    // register count (integer rows), and the extra live values of the newer code cost them 7-17 % on a B200.
+    static constexpr bool kLean = !((DIM == 128) && (ELEM == 0) && !PQ);
+    __device__ __forceinline__ void hins(WarpHeap& h, int node, float d) { heap_insert<!kLean>(h, node, d, lane); }
+    __device__ __forceinline__ int2 hpop(WarpHeap& h) {
+        if (kLean) return heap_pop_seq(h, lane);
+        return heap_pop<true>(h, lane);
+    }
 
     __device__ __forceinline__ unsigned char* slot_ptr(int s) const {
         return ring + (size_t)s * p.slot_stride + (p.slot_stagger ? ((s & 1) << 6) : 0);
@@ -1036,7 +1102,7 @@ struct WarpSearch {
             if (lane < cnt) cand_id[lane] = p.nodes[3 * (base + lane)];
             ntree += cnt;
             compute_dists(cnt);
-            for (int r = 0; r < cnt; ++r) heap_insert(spt, base + r, cand_dist[r], lane);
+            for (int r = 0; r < cnt; ++r) hins(spt, base + r, cand_dist[r]);
         }
     }
 
@@ -1049,7 +1115,7 @@ struct WarpSearch {
                 __syncwarp();
                 if (lane == 0) cand_id[0] = centerid;
                 compute_dists(1);
-                heap_insert(spt, start, cand_dist[0], lane);
+                hins(spt, start, cand_dist[0]);
             } else {
                 push_children(cs, ce);
             }
@@ -1059,17 +1125,17 @@ struct WarpSearch {
     // BKTree::SearchTrees (BKTree.h:771-799)
     __device__ __forceinline__ void search_trees(int limit) {
         while (spt.count != 0) {
-            const int2 bcell = heap_pop(spt, lane);
+            const int2 bcell = hpop(spt);
             const int centerid = p.nodes[3 * bcell.x], cs = p.nodes[3 * bcell.x + 1], ce = p.nodes[3 * bcell.x + 2];
             ntree++;
             if (cs < 0) {
                 if (!check_and_set_uniform(centerid)) {
                     checked++;
-                    heap_insert(ng, centerid, pair_dist(bcell), lane);
+                    hins(ng, centerid, pair_dist(bcell));
                 }
                 if (checked >= limit) break;
             } else {
-                if (!check_and_set_uniform(centerid)) heap_insert(ng, centerid, pair_dist(bcell), lane);
+                if (!check_and_set_uniform(centerid)) hins(ng, centerid, pair_dist(bcell));
                 push_children(cs, ce);
             }
         }
@@ -1109,7 +1175,7 @@ struct WarpSearch {
     // sift-down runs while they are in flight; the graph row of the node that is on top AFTER the pop is fetched a step
     // ahead (the CPU does the same with _mm_prefetch, BKTIndex.cpp:283-288), and when it is still on top at the end of
     // the step the bitmap words of its neighbours are prefetched into L2.
-    __device__ __forceinline__ void bkt_search() {
+    __device__ __forceinline__ void bkt_search_fast() {
         init_search_trees();
         search_trees(p.initial_pivots);
         const int checkPos = p.degree - 1;
@@ -1149,16 +1215,18 @@ struct WarpSearch {
             } else {
                 if (not_deleted(tmpNode)) {
                     if (gdist > mres.worst || checked > p.max_check) {
-                        heap_pop(ng, lane);  // the reference popped before it looked (NGQueue survives in the iterator flavour)
+                        hpop(ng);  // the reference popped before it looked (NGQueue survives in the iterator flavour)
                         return;
                     }
                 }
             }
 
             RowMark mark = issue_mark(nn, lane <= checkPos);
-            heap_pop(ng, lane);  // sift-down, while the atomics are in flight
-            pre_id = (ng.count != 0) ? ng.s[1].x : -1;
-            pre_nn = (pre_id >= 0 && lane <= checkPos) ? p.graph[(size_t)pre_id * p.degree + lane] : -1;
+            hpop(ng);  // sift-down, while the atomics are in flight
+            if (!kLean) {
+                pre_id = (ng.count != 0) ? ng.s[1].x : -1;
+                pre_nn = (pre_id >= 0 && lane <= checkPos) ? p.graph[(size_t)pre_id * p.degree + lane] : -1;
+            }
 
             for (int cbase = 0; cbase <= checkPos; cbase += 32) {
                 if (cbase > 0) {
@@ -1187,13 +1255,110 @@ struct WarpSearch {
                     maybe &= maybe - 1;
                     const float d = __shfl_sync(kFull, myd, r);
                     const int id = __shfl_sync(kFull, myid, r);
-                    if (mres.insert(d, lane)) heap_insert(ng, id, d, lane);
+                    if (mres.insert(d, lane)) hins(ng, id, d);
                 }
                 if (mark.first_neg < 32) break;
             }
             if (heap_top_dist(ng) > heap_top_dist(spt)) search_trees(p.other_pivots + checked);
-            if (pre_id >= 0 && ng.count != 0 && ng.s[1].x == pre_id) prefetch_marks(pre_nn);
+            if (!kLean && pre_id >= 0 && ng.count != 0 && ng.s[1].x == pre_id) prefetch_marks(pre_nn);
         }
+    }
+
+    // BKT::Index<T>::Search<notDeleted, CheckDup, AlwaysTrue> (BKTIndex.cpp:268-352), round-1 step order (pop, row, visited, rows)
+    __device__ __forceinline__ void bkt_search_legacy() {
+        init_search_trees();
+        search_trees(p.initial_pivots);
+        const int checkPos = p.degree - 1;
+        while (ng.count != 0) {
+            const int2 gnode = hpop(ng);
+            int tmpNode = gnode.x;
+            const float gdist = pair_dist(gnode);
+            const int* node = p.graph + (size_t)tmpNode * p.degree;
+            nexpand++;
+            // lane i reads neighbour i of the first 32-wide chunk while the accept logic runs
+            int nn = (lane <= checkPos) ? node[lane] : -1;
+
+            if (gdist <= worst_d) {
+                const int checkNode = node[checkPos];
+                if (checkNode < -1) {
+                    // duplicate group: the back-pointer names the BKT node listing exact duplicates
+                    const int tn = -2 - checkNode;
+                    const int tcs = p.nodes[3 * tn + 1], tce = p.nodes[3 * tn + 2];
+                    int i = -tcs;
+                    do {
+                        if (not_deleted(tmpNode)) {
+                            if (check_filter(tmpNode)) {
+                                if (!add_point(tmpNode, gdist) || p.never_dup) break;
+                            }
+                        }
+                        if (i <= 0) break;
+                        tmpNode = p.nodes[3 * i];
+                    } while (i++ < tce);
+                } else {
+                    if (not_deleted(tmpNode) && check_filter(tmpNode)) add_point(tmpNode, gdist);
+                }
+            } else {
+                if (not_deleted(tmpNode)) {
+                    if (gdist > mres.worst || checked > p.max_check) return;
+                }
+            }
+
+            for (int cbase = 0; cbase <= checkPos; cbase += 32) {
+                if (cbase > 0) nn = (cbase + lane <= checkPos) ? node[cbase + lane] : -1;
+                const bool in_row = (cbase + lane <= checkPos);
+                // the scan stops at the first negative entry (BKTIndex.cpp:333-336)
+                const unsigned negmask = __ballot_sync(kFull, in_row && nn < 0) | ~__ballot_sync(kFull, in_row);
+                const int first_neg = negmask ? (__ffs(negmask) - 1) : 32;
+                const bool active = lane < first_neg;
+                // a repeated id inside the row is "visited" by the time its second copy is reached
+                const unsigned same = __match_any_sync(kFull, active ? nn : (-1 - lane));
+                const bool leader = active && ((__ffs(same) - 1) == lane);
+                bool fresh = false;
+                if (leader) {
+                    const unsigned bit = 1u << (nn & 31);
+                    const unsigned old = atomicOr(&visited[nn >> 5], bit);
+                    fresh = (old & bit) == 0;
+                }
+                const unsigned freshmask = __ballot_sync(kFull, fresh);
+                const int cnt = __popc(freshmask);
+                __syncwarp();
+                if (fresh) {
+                    const int rank = __popc(freshmask & ((1u << lane) - 1u));
+                    cand_id[rank] = nn;
+                    if (vlog != nullptr && vlog_count + rank < (int)p.vlog_entries) vlog[vlog_count + rank] = (unsigned)(nn >> 5);
+                }
+                vlog_count += cnt;
+                compute_dists(cnt);
+                // m_Results.worst() never increases, so a candidate above the current worst is rejected
+                // whenever its turn comes; only the others are replayed in neighbour order (BKTIndex.cpp:338-344)
+                const float myd = (lane < cnt) ? cand_dist[lane] : SPTAG_B200_MAXDIST;
+                const int myid = (lane < cnt) ? cand_id[lane] : -1;
+                checked += cnt;
+                unsigned maybe = __ballot_sync(kFull, lane < cnt && !(myd > mres.worst));
+                while (maybe) {
+                    const int r = __ffs(maybe) - 1;
+                    maybe &= maybe - 1;
+                    const float d = __shfl_sync(kFull, myd, r);
+                    const int id = __shfl_sync(kFull, myid, r);
+                    if (mres.insert(d, lane)) hins(ng, id, d);
+                }
+                if (first_neg < 32) break;
+            }
+            if (heap_top_dist(ng) > heap_top_dist(spt)) search_trees(p.other_pivots + checked);
+        }
+    }
+
+    __device__ __forceinline__ void bkt_search() {
+        if (kLean)
+            bkt_search_legacy();
+        else
+            bkt_search_fast();
+    }
+    __device__ __forceinline__ void kdt_search() {
+        if (kLean)
+            kdt_search_legacy();
+        else
+            kdt_search_fast();
     }
 
     // ------------------------------------------------------------------------------------
@@ -1211,7 +1376,7 @@ struct WarpSearch {
         int count = 0;
         const int checkPos = p.degree - 1;
         while (ng.count != 0) {
-            const int2 gnode = heap_pop(ng, lane);
+            const int2 gnode = hpop(ng);
             const int popped = gnode.x;
             const float gdist = pair_dist(gnode);
             const int* node = p.graph + (size_t)popped * p.degree;
@@ -1239,7 +1404,7 @@ struct WarpSearch {
                     for (int r = 0; r < cnt; ++r) {  // the distance is taken first, CheckAndSet second (:394-401)
                         const int mid = cand_id[r];
                         const float md = cand_dist[r];
-                        if (!check_and_set_uniform(mid)) heap_insert(ng, mid, md, lane);
+                        if (!check_and_set_uniform(mid)) hins(ng, mid, md);
                     }
                     __syncwarp();
                 }
@@ -1267,7 +1432,7 @@ struct WarpSearch {
                 for (int r = 0; r < cnt; ++r) {
                     const int id = cand_id[r];
                     const float d = cand_dist[r];
-                    heap_insert(ng, id, d, lane);
+                    hins(ng, id, d);
                     mres.insert(d, lane);
                 }
                 __syncwarp();
@@ -1305,7 +1470,7 @@ struct WarpSearch {
             __syncwarp();
             if (fresh) cand_id[__popc(freshmask & ((1u << lane) - 1u))] = nn;
             compute_dists(cnt);
-            for (int r = 0; r < cnt; ++r) heap_insert(ng, cand_id[r], cand_dist[r], lane);
+            for (int r = 0; r < cnt; ++r) hins(ng, cand_id[r], cand_dist[r]);
             __syncwarp();
             if (first_neg < 32) break;
         }
@@ -1326,7 +1491,7 @@ struct WarpSearch {
                 __syncwarp();
                 if (lane == 0) cand_id[0] = index;
                 compute_dists(1);
-                heap_insert(ng, index, cand_dist[0], lane);
+                hins(ng, index, cand_dist[0]);
                 return;
             }
             const int4 tn = __ldg(reinterpret_cast<const int4*>(p.nodes) + node);  // {left, right, split_dim, split_value}
@@ -1348,19 +1513,19 @@ struct WarpSearch {
                 otherChild = tn.x;
                 bestChild = tn.y;
             }
-            heap_insert(spt, otherChild, distanceBound, lane);
+            hins(spt, otherChild, distanceBound);
             node = bestChild;
         }
     }
 
     __device__ __forceinline__ void kdt_search_trees(int limit) {
         while (spt.count != 0 && checked < limit) {
-            const int2 tcell = heap_pop(spt, lane);
+            const int2 tcell = hpop(spt);
             kdt_search_node(tcell.x, pair_dist(tcell));
         }
     }
 
-    __device__ __forceinline__ void kdt_search() {
+    __device__ __forceinline__ void kdt_search_fast() {
         for (int t = 0; t < p.tree_num; ++t) kdt_search_node(p.tree_starts[t], 0.0f);
         kdt_search_trees(p.initial_pivots);
         int pre_id = -1, pre_nn = -1;  // graph row of NGQueue's new top, fetched one step ahead (see bkt_search)
@@ -1376,14 +1541,14 @@ struct WarpSearch {
                 nn = (lane < p.degree) ? node[lane] : -1;
             if (not_deleted(gnode.x)) {
                 if (!add_point(gnode.x, gdist) && checked > p.max_check) {
-                    heap_pop(ng, lane);
+                    hpop(ng);
                     return;
                 }
             }
             const float upperBound = fmaxf(worst_d, gdist);
             bool bLocalOpt = true;
             RowMark mark = issue_mark(nn, lane < p.degree);
-            heap_pop(ng, lane);  // sift-down, while the atomics are in flight
+            hpop(ng);  // sift-down, while the atomics are in flight
             pre_id = (ng.count != 0) ? ng.s[1].x : -1;
             pre_nn = (pre_id >= 0 && lane < p.degree) ? p.graph[(size_t)pre_id * p.degree + lane] : -1;
             for (int cbase = 0; cbase < p.degree; cbase += 32) {
@@ -1407,7 +1572,7 @@ struct WarpSearch {
                 const int myid = (lane < cnt) ? cand_id[lane] : -1;
                 if (__any_sync(kFull, lane < cnt && myd <= upperBound)) bLocalOpt = false;
                 checked += cnt;
-                for (int r = 0; r < cnt; ++r) heap_insert(ng, __shfl_sync(kFull, myid, r), __shfl_sync(kFull, myd, r), lane);
+                for (int r = 0; r < cnt; ++r) hins(ng, __shfl_sync(kFull, myid, r), __shfl_sync(kFull, myd, r));
                 if (mark.first_neg < 32) break;
             }
             if (bLocalOpt)
@@ -1422,6 +1587,66 @@ struct WarpSearch {
                 }
             }
             if (pre_id >= 0 && ng.count != 0 && ng.s[1].x == pre_id) prefetch_marks(pre_nn);
+        }
+    }
+
+    __device__ __forceinline__ void kdt_search_legacy() {
+        for (int t = 0; t < p.tree_num; ++t) kdt_search_node(p.tree_starts[t], 0.0f);
+        kdt_search_trees(p.initial_pivots);
+        while (ng.count != 0) {
+            const int2 gnode = hpop(ng);
+            const float gdist = pair_dist(gnode);
+            const int* node = p.graph + (size_t)gnode.x * p.degree;
+            nexpand++;
+            int nn = (lane < p.degree) ? node[lane] : -1;
+            if (not_deleted(gnode.x)) {
+                if (!add_point(gnode.x, gdist) && checked > p.max_check) return;
+            }
+            const float upperBound = fmaxf(worst_d, gdist);
+            bool bLocalOpt = true;
+            for (int cbase = 0; cbase < p.degree; cbase += 32) {
+                if (cbase > 0) nn = (cbase + lane < p.degree) ? node[cbase + lane] : -1;
+                const bool in_row = (cbase + lane < p.degree);
+                const unsigned negmask = __ballot_sync(kFull, in_row && nn < 0) | ~__ballot_sync(kFull, in_row);
+                const int first_neg = negmask ? (__ffs(negmask) - 1) : 32;
+                const bool active = lane < first_neg;
+                const unsigned same = __match_any_sync(kFull, active ? nn : (-1 - lane));
+                const bool leader = active && ((__ffs(same) - 1) == lane);
+                bool fresh = false;
+                if (leader) {
+                    const unsigned bit = 1u << (nn & 31);
+                    const unsigned old = atomicOr(&visited[nn >> 5], bit);
+                    fresh = (old & bit) == 0;
+                }
+                const unsigned freshmask = __ballot_sync(kFull, fresh);
+                const int cnt = __popc(freshmask);
+                __syncwarp();
+                if (fresh) {
+                    const int rank = __popc(freshmask & ((1u << lane) - 1u));
+                    cand_id[rank] = nn;
+                    if (vlog != nullptr && vlog_count + rank < (int)p.vlog_entries) vlog[vlog_count + rank] = (unsigned)(nn >> 5);
+                }
+                vlog_count += cnt;
+                compute_dists(cnt);
+                for (int r = 0; r < cnt; ++r) {
+                    const float d = cand_dist[r];
+                    if (d <= upperBound) bLocalOpt = false;
+                    checked++;
+                    hins(ng, cand_id[r], d);
+                }
+                if (first_neg < 32) break;
+            }
+            if (bLocalOpt)
+                no_better++;
+            else
+                no_better = 0;
+            if (no_better > p.no_better_threshold) {
+                if (tree_checked <= checked / 10) {
+                    kdt_search_trees(p.other_pivots + checked);
+                } else if (gdist > worst_d) {
+                    break;
+                }
+            }
         }
     }
 };

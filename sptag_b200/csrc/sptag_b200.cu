@@ -326,7 +326,7 @@ relayout:
     if (h->queries_per_sm <= 0 && big_rows) per_sm = std::min(per_sm, 14);  // 3 KB rows: 14 beats 15 (HBM-bound, sweep)
     // 512 B rows: 14 slots leave 2 KB more shared memory per queue head than 16 and shorten the tail of a 10k-query batch
     // (profiles/r02_sweep_128.txt: 521k vs 504k QPS; at batches >= 20k queries 16 wins by 2-3 %)
-    if (h->queries_per_sm <= 0 && fast128 && nq <= 16384) per_sm = std::min(per_sm, 14);
+    if (h->queries_per_sm <= 0 && fast128 && h->algo == SPTAG_B200_ALGO_BKT && nq <= 16384) per_sm = std::min(per_sm, 14);
     per_sm = std::max(1, std::min(per_sm, fit));
     if (h->h_ng <= 0 && h->h_spt <= 0 && !relayout_done) {
         // Spare shared memory of a slot (at this residency) goes to the queue heads: 3/4 NGQueue, 1/4 SPTQueue
