@@ -416,14 +416,9 @@ struct WarpHeap {
     int tail_idx;
 };
 
-// one access path for both halves of the array: the select yields a generic pointer, so there is no branch (and no
-// divergence when the lanes of an insert straddle the shared-memory head and the arena)
-__device__ __forceinline__ int2* heap_at(const WarpHeap& h, int i) { return (i <= h.H) ? (h.s + i) : (h.g + i); }
-__device__ __forceinline__ int2 heap_ld(const WarpHeap& h, int i) { return *heap_at(h, i); }
-__device__ __forceinline__ void heap_st(const WarpHeap& h, int i, int2 v) { *heap_at(h, i) = v; }
-// branchy round-1 accessors (see heap_pop_seq)
-__device__ __forceinline__ int2 heap_ld_br(const WarpHeap& h, int i) { return i <= h.H ? h.s[i] : h.g[i]; }
-__device__ __forceinline__ void heap_st_br(const WarpHeap& h, int i, int2 v) {
+// (a branch-free variant -- select a generic pointer, one LD/ST -- was measured 3.8 % slower on BKT 1M x 128)
+__device__ __forceinline__ int2 heap_ld(const WarpHeap& h, int i) { return i <= h.H ? h.s[i] : h.g[i]; }
+__device__ __forceinline__ void heap_st(const WarpHeap& h, int i, int2 v) {
     if (i <= h.H)
         h.s[i] = v;
     else
@@ -442,9 +437,9 @@ __device__ __forceinline__ float heap_top_dist(const WarpHeap& h) {
 // value are stored in one step -- the resulting array is identical to the sequential loop's.
 template <bool TAIL = true>
 __device__ __forceinline__ void heap_insert(WarpHeap& h, int node, float d, int lane) {
-    // TAIL (fast path): branch-free generic-pointer accesses + the register copy of the last element
-#define SPTAG_B200_HLD(i) (TAIL ? heap_ld(h, (i)) : heap_ld_br(h, (i)))
-#define SPTAG_B200_HST(i, v) do { if (TAIL) heap_st(h, (i), (v)); else heap_st_br(h, (i), (v)); } while (0)
+    // TAIL (fast BKT path): keep the register copy of the last element up to date
+#define SPTAG_B200_HLD(i) heap_ld(h, (i))
+#define SPTAG_B200_HST(i, v) heap_st(h, (i), (v))
     int loc;
     if (h.count == h.length) {
         // full heap: replace the first maximum of the last level [lastlevel, length] (Heap.h:43-49)
@@ -506,33 +501,33 @@ __device__ __forceinline__ void heap_insert(WarpHeap& h, int node, float d, int 
 // Heap::pop (Heap.h:73-82) + heapify (Heap.h:92-105), level by level.
 __device__ __forceinline__ int2 heap_pop_seq(WarpHeap& h, int lane) {
     if (h.count == 0) return make_pair(-1, SPTAG_B200_MAXDIST);
-    const int2 top = heap_ld_br(h, 1);
-    const int2 cur = heap_ld_br(h, h.count);
+    const int2 top = heap_ld(h, 1);
+    const int2 cur = heap_ld(h, h.count);
     h.count--;
     const float cd = pair_dist(cur);
     int parent = 1, next = 2;
     while (next < h.count) {
-        int2 a = heap_ld_br(h, next);
-        const int2 b = heap_ld_br(h, next + 1);
+        int2 a = heap_ld(h, next);
+        const int2 b = heap_ld(h, next + 1);
         if (pair_dist(a) > pair_dist(b)) {
             next++;
             a = b;
         }
         if (pair_dist(a) < cd) {
-            if (lane == 0) heap_st_br(h, parent, a);
+            if (lane == 0) heap_st(h, parent, a);
             parent = next;
             next <<= 1;
         } else
             break;
     }
     if (next == h.count) {
-        const int2 a = heap_ld_br(h, next);
+        const int2 a = heap_ld(h, next);
         if (pair_dist(a) < cd) {
-            if (lane == 0) heap_st_br(h, parent, a);
+            if (lane == 0) heap_st(h, parent, a);
             parent = next;
         }
     }
-    if (lane == 0 && h.count > 0) heap_st_br(h, parent, cur);
+    if (lane == 0 && h.count > 0) heap_st(h, parent, cur);
     __syncwarp();
     return top;
 }
@@ -760,6 +755,13 @@ struct WarpSearch {
         if (kLean) return heap_pop_seq(h, lane);
         return heap_pop<true>(h, lane);
     }
+    // KDT flavour: every new neighbour is inserted (8 inserts per pop), so keeping the tail copy current costs more than
+    // the read it saves (measured: 815k vs 765k QPS at KDT 1M x 128)
+    __device__ __forceinline__ void hins_k(WarpHeap& h, int node, float d) { heap_insert<false>(h, node, d, lane); }
+    __device__ __forceinline__ int2 hpop_k(WarpHeap& h) {
+        if (kLean) return heap_pop_seq(h, lane);
+        return heap_pop<false>(h, lane);
+    }
 
     __device__ __forceinline__ unsigned char* slot_ptr(int s) const {
         return ring + (size_t)s * p.slot_stride + (p.slot_stagger ? ((s & 1) << 6) : 0);
@@ -901,6 +903,7 @@ struct WarpSearch {
     const float* pq_table;
     // the SDC table is read-only for the whole kernel (non-coherent path is fine); an ADC table was written by
     // this warp a moment ago, so it is read with ordinary loads
+    // (an L2 evict_last policy on these look-ups was measured 11 % slower at 2M x 100)
     __device__ __forceinline__ float pq_ld(const float* a) const { return p.pq_adc ? *a : __ldg(a); }
 
     // PQ rows: all (<= 32) code rows of the step are staged by one TMA batch, then lane r sums the M
@@ -1177,10 +1180,16 @@ struct WarpSearch {
     // the step the bitmap words of its neighbours are prefetched into L2.
     __device__ __forceinline__ void bkt_search_fast() {
         init_search_trees();
-        search_trees(p.initial_pivots);
         const int checkPos = p.degree - 1;
         int pre_id = -1, pre_nn = -1;
-        while (ng.count != 0) {
+        // (search_trees appears once in the code: the kernels are far larger than the instruction cache.  First trip:
+        //  SearchTrees(NumberOfInitialDynamicPivots) before the loop; later trips: the re-seeding test at the end of a step)
+        bool reseed = true;
+        int tree_limit = p.initial_pivots;
+        for (;;) {
+            if (reseed) search_trees(tree_limit);
+            if (pre_id >= 0 && ng.count != 0 && ng.s[1].x == pre_id) prefetch_marks(pre_nn);
+            if (ng.count == 0) break;
             const int2 gnode = ng.s[1];  // what Heap::pop will return
             int tmpNode = gnode.x;
             const float gdist = pair_dist(gnode);
@@ -1193,6 +1202,7 @@ struct WarpSearch {
             else
                 nn = (lane <= checkPos) ? node[lane] : -1;
 
+            bool stop = false;
             if (gdist <= worst_d) {
                 const int checkNode = (checkPos < 32) ? __shfl_sync(kFull, nn, checkPos) : node[checkPos];
                 if (checkNode < -1) {
@@ -1213,16 +1223,16 @@ struct WarpSearch {
                     if (not_deleted(tmpNode) && check_filter(tmpNode)) add_point(tmpNode, gdist);
                 }
             } else {
-                if (not_deleted(tmpNode)) {
-                    if (gdist > mres.worst || checked > p.max_check) {
-                        hpop(ng);  // the reference popped before it looked (NGQueue survives in the iterator flavour)
-                        return;
-                    }
-                }
+                if (not_deleted(tmpNode)) stop = (gdist > mres.worst || checked > p.max_check);
             }
 
-            RowMark mark = issue_mark(nn, lane <= checkPos);
-            hpop(ng);  // sift-down, while the atomics are in flight
+            RowMark mark;
+            mark.first_neg = 0;
+            mark.leader = false;
+            mark.bit = mark.old = 0u;
+            if (!stop) mark = issue_mark(nn, lane <= checkPos);
+            hpop(ng);  // sift-down, while the atomics are in flight (the reference pops before it looks at the node)
+            if (stop) return;
             if (!kLean) {
                 pre_id = (ng.count != 0) ? ng.s[1].x : -1;
                 pre_nn = (pre_id >= 0 && lane <= checkPos) ? p.graph[(size_t)pre_id * p.degree + lane] : -1;
@@ -1491,7 +1501,7 @@ struct WarpSearch {
                 __syncwarp();
                 if (lane == 0) cand_id[0] = index;
                 compute_dists(1);
-                hins(ng, index, cand_dist[0]);
+                hins_k(ng, index, cand_dist[0]);
                 return;
             }
             const int4 tn = __ldg(reinterpret_cast<const int4*>(p.nodes) + node);  // {left, right, split_dim, split_value}
@@ -1513,14 +1523,14 @@ struct WarpSearch {
                 otherChild = tn.x;
                 bestChild = tn.y;
             }
-            hins(spt, otherChild, distanceBound);
+            hins_k(spt, otherChild, distanceBound);
             node = bestChild;
         }
     }
 
     __device__ __forceinline__ void kdt_search_trees(int limit) {
         while (spt.count != 0 && checked < limit) {
-            const int2 tcell = hpop(spt);
+            const int2 tcell = hpop_k(spt);
             kdt_search_node(tcell.x, pair_dist(tcell));
         }
     }
@@ -1541,14 +1551,14 @@ struct WarpSearch {
                 nn = (lane < p.degree) ? node[lane] : -1;
             if (not_deleted(gnode.x)) {
                 if (!add_point(gnode.x, gdist) && checked > p.max_check) {
-                    hpop(ng);
+                    hpop_k(ng);
                     return;
                 }
             }
             const float upperBound = fmaxf(worst_d, gdist);
             bool bLocalOpt = true;
             RowMark mark = issue_mark(nn, lane < p.degree);
-            hpop(ng);  // sift-down, while the atomics are in flight
+            hpop_k(ng);  // sift-down, while the atomics are in flight
             pre_id = (ng.count != 0) ? ng.s[1].x : -1;
             pre_nn = (pre_id >= 0 && lane < p.degree) ? p.graph[(size_t)pre_id * p.degree + lane] : -1;
             for (int cbase = 0; cbase < p.degree; cbase += 32) {
@@ -1572,7 +1582,7 @@ struct WarpSearch {
                 const int myid = (lane < cnt) ? cand_id[lane] : -1;
                 if (__any_sync(kFull, lane < cnt && myd <= upperBound)) bLocalOpt = false;
                 checked += cnt;
-                for (int r = 0; r < cnt; ++r) hins(ng, __shfl_sync(kFull, myid, r), __shfl_sync(kFull, myd, r));
+                for (int r = 0; r < cnt; ++r) hins_k(ng, __shfl_sync(kFull, myid, r), __shfl_sync(kFull, myd, r));
                 if (mark.first_neg < 32) break;
             }
             if (bLocalOpt)
