@@ -672,6 +672,29 @@ def main_leg(args, rank, local_rank, world, dev, dist, quantized, config, mode):
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "share_of_step": kernel_ms / ms_step}
 
+    if quantized:
+        # The quantized kernel's HBM bytes are only the M code bytes per distance; what it really moves is the SDC table:
+        # one 4-byte look-up per sub-vector, each a 32-byte L2 sector request unless lanes of the same instruction share a
+        # sector.  Upper bound on the L2 -> SM traffic of one launch = look-ups x 32 B; the kept ncu capture gives the
+        # sectors actually requested (l1tex__t_sectors_pipe_lsu_mem_global_op_ld).  Roof: the L2 slice throughput cap of
+        # the microarchitecture notes (~6300 B/clk full chip, measured on B300; x the SM clock of this run).
+        lookups = int(st[:, capi.ST_NDIST].sum()) * args.pq_m
+        clk_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        l2_peak = 6300.0 * clk_mhz * 1e6 / 1e9
+        rec = None
+        try:
+            rec = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json"))).get(wkey)
+        except Exception:
+            rec = None
+        sect_ratio = (rec or {}).get("l1_global_ld_sectors_per_lookup")
+        upper = lookups * 32.0
+        roofline["l2_gather"] = {"bound": "l2 sector gather (SDC table)", "lookups_per_launch": lookups,
+                                 "upper_bound_bytes": upper,
+                                 "measured_sectors_per_lookup": sect_ratio,
+                                 "achieved": (upper * (sect_ratio or 1.0)) / (kernel_ms / 1000.0) / 1e9, "unit": "GB/s",
+                                 "peak": l2_peak, "peak_source": "B300_MICROARCH.md LTS cap 6300 B/clk x %.0f MHz (not measured on this box)" % clk_mhz,
+                                 "frac": (upper * (sect_ratio or 1.0)) / (kernel_ms / 1000.0) / 1e9 / l2_peak}
+
     # ---- cpu baseline on a bounded sample (rank 0, N=1 only) + parity against the reference itself ----
     cpu_baseline = None
     parity = None

@@ -1269,8 +1269,8 @@ struct WarpSearch {
                 }
                 if (mark.first_neg < 32) break;
             }
-            if (heap_top_dist(ng) > heap_top_dist(spt)) search_trees(p.other_pivots + checked);
-            if (!kLean && pre_id >= 0 && ng.count != 0 && ng.s[1].x == pre_id) prefetch_marks(pre_nn);
+            reseed = heap_top_dist(ng) > heap_top_dist(spt);
+            tree_limit = p.other_pivots + checked;
         }
     }
 

@@ -51,6 +51,7 @@ def main():
     ap.add_argument("--key")
     ap.add_argument("--alg-bytes", type=float)
     ap.add_argument("--nq", type=int)
+    ap.add_argument("--lookups", type=float, help="quantized runs: table look-ups of the launch (sum D_q x M)")
     a = ap.parse_args()
     launches = [l for l in read_raw(a.report) if a.kernel in l.get("Kernel Name", ("", ""))[0]]
     if not launches:
@@ -79,6 +80,9 @@ def main():
         rec[a.key] = {"dram_bytes": dram, "algorithmic_bytes": a.alg_bytes, "nq": a.nq,
                       "source": "ncu --set full --clock-control none, one launch; report %s" % os.path.basename(a.report),
                       "dram_read_bytes": scaled("dram__bytes_read.sum"), "dram_write_bytes": scaled("dram__bytes_write.sum")}
+        if a.lookups and "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum" in vals:
+            rec[a.key]["l1_global_ld_sectors"] = vals["l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"][0]
+            rec[a.key]["l1_global_ld_sectors_per_lookup"] = vals["l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"][0] / a.lookups
         with open(path, "w") as f:
             json.dump(rec, f, indent=1, sort_keys=True)
         print("  recorded under %s in %s" % (a.key, path))
