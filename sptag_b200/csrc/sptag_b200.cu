@@ -105,13 +105,26 @@ struct sptag_b200_index {
     int slot_scheme = 0;          // 0 auto, 1 = 128-multiple stride + staggered odd slots, 2 = stride 64 mod 128
     int visited_log = -1;         // -1 auto (bitmap > 256 KB per slot), 0 clear per query, 1 log + selective clear
     int visited_log_entries = 0;  // 0 = auto
-    bool visited_clean = false;   // the whole d_visited buffer is known to be zero
     // PQ / OPQ quantizer (null when q_type == 0)
     int q_type = 0, q_rtype = SPTAG_B200_VT_FLOAT, q_m = 0, q_ks = 0, q_dsub = 0;
     int q_adc = 0;  // IQuantizer::SetEnableADC (not serialized by the reference either)
-    DeviceBuffer d_codebooks, d_rotation_t, d_sdc, d_codes, d_raw, d_adc;
+    DeviceBuffer d_codebooks, d_rotation_t, d_sdc, d_raw;
     // scratch
-    DeviceBuffer d_visited, d_ng_spill, d_spt_spill, d_counter, d_vlog, d_topk;
+    // Everything a search launch writes besides its outputs.  Two sets: a launch normally takes set 0; when set 0 is
+    // still busy with a launch from ANOTHER stream the new launch takes set 1 (allocated on first use), so two batches
+    // can be in flight -- the second kernel's CTAs take over SM by SM as the first kernel's persistent warps run out of
+    // queries, which hides the tail of a batch (~14 % of a 10k-query batch at 512-byte rows, profiles/r02_sweep_128.txt).
+    struct Scratch {
+        DeviceBuffer d_visited, d_ng_spill, d_spt_spill, d_counter, d_vlog, d_topk, d_codes, d_adc;
+        bool visited_clean = false;   // the whole d_visited buffer is known to be zero
+        cudaEvent_t ev_done = nullptr;  // recorded after every kernel that uses this set; the next launch on it waits
+        cudaStream_t last_stream = nullptr;
+        bool used = false;
+        void release() {
+            d_visited.release(); d_ng_spill.release(); d_spt_spill.release(); d_counter.release(); d_vlog.release();
+            d_topk.release(); d_codes.release(); d_adc.release();
+        }
+    } scratch[2];
     DeviceBuffer d_ids, d_dists;                      // refine pass: per-batch result lists
     // Host-buffer entry points: two staging sets, each with its own stream, so that one caller's H2D / D2H overlaps
     // another caller's kernel (the kernels themselves share the per-slot scratch and are ordered by ev_done)
@@ -121,7 +134,6 @@ struct sptag_b200_index {
         DeviceBuffer d_queries, d_ids, d_dists, d_stats, d_filter;
     } staging[2];
     std::atomic<unsigned> staging_rr{0};
-    cudaEvent_t ev_done = nullptr;  // recorded after every kernel that uses the handle's scratch; the next launch waits on it
     DeviceBuffer d_graph_new;                         // sptag_b200_refine_graph: the pass's output rows
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_aux = nullptr;
     double refine_search_ms = 0.0, refine_rebuild_ms = 0.0;  // device time of the last sptag_b200_refine_graph call
@@ -189,7 +201,8 @@ struct CallOpts {
 
 // Fill SearchParams + launch geometry for this handle.  Allocates per-slot scratch.  Caller holds h->mu.
 int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& smem, int nq, SearchKernelFn& kern,
-              const CallOpts& opts = CallOpts()) {
+              const CallOpts& opts = CallOpts(), int set = 0) {
+    sptag_b200_index::Scratch& sc = h->scratch[set];
     const int eff_max_check = opts.max_check > 0 ? opts.max_check : h->max_check;
     const int eff_search_deleted = opts.search_deleted >= 0 ? opts.search_deleted : h->search_deleted;
     if (h->algo != SPTAG_B200_ALGO_BKT && h->algo != SPTAG_B200_ALGO_KDT)
@@ -352,9 +365,9 @@ relayout:
     p.spt_spill_entries = round_up((size_t)std::min<long long>((long long)p.spt_length, (long long)h->node_count + 2) + 2, 2);
     const size_t alloc_slots = (size_t)h->num_sms * per_sm;
     {
-        const size_t before = h->d_visited.bytes;
-        if (int rc = h->d_visited.ensure(alloc_slots * p.visited_words * 4)) return rc;
-        if (h->d_visited.bytes != before) h->visited_clean = false;
+        const size_t before = sc.d_visited.bytes;
+        if (int rc = sc.d_visited.ensure(alloc_slots * p.visited_words * 4)) return rc;
+        if (sc.d_visited.bytes != before) sc.visited_clean = false;
     }
     const bool use_log = h->visited_log < 0 ? (p.visited_words * 4 > 256 * 1024) : (h->visited_log != 0);
     if (use_log) {
@@ -362,37 +375,37 @@ relayout:
                                                     : (size_t)std::max(65536, 8 * alloc_check);
         entries = std::min(entries, (size_t)h->n + 2);
         p.vlog_entries = entries;
-        if (int rc = h->d_vlog.ensure(alloc_slots * entries * 4)) return rc;
-        p.vlog = (unsigned int*)h->d_vlog.ptr;
-        if (!h->visited_clean) {  // log mode relies on every query leaving its bitmap zeroed
-            CUDA_OK(cudaMemset(h->d_visited.ptr, 0, h->d_visited.bytes));
-            h->visited_clean = true;
+        if (int rc = sc.d_vlog.ensure(alloc_slots * entries * 4)) return rc;
+        p.vlog = (unsigned int*)sc.d_vlog.ptr;
+        if (!sc.visited_clean) {  // log mode relies on every query leaving its bitmap zeroed
+            CUDA_OK(cudaMemset(sc.d_visited.ptr, 0, sc.d_visited.bytes));
+            sc.visited_clean = true;
         }
     } else {
         p.vlog = nullptr;
         p.vlog_entries = 0;
-        h->visited_clean = false;  // clear-per-query mode leaves the last query's bits behind
+        sc.visited_clean = false;  // clear-per-query mode leaves the last query's bits behind
     }
-    if (int rc = h->d_ng_spill.ensure(alloc_slots * p.ng_spill_entries * 8)) return rc;
-    if (int rc = h->d_spt_spill.ensure(alloc_slots * p.spt_spill_entries * 8)) return rc;
-    if (int rc = h->d_counter.ensure(256)) return rc;
+    if (int rc = sc.d_ng_spill.ensure(alloc_slots * p.ng_spill_entries * 8)) return rc;
+    if (int rc = sc.d_spt_spill.ensure(alloc_slots * p.spt_spill_entries * 8)) return rc;
+    if (int rc = sc.d_counter.ensure(256)) return rc;
     p.adc_tables = nullptr;
     if (p.pq_adc) {  // one M x Ks fp32 table per resident query
-        if (int rc = h->d_adc.ensure(alloc_slots * (size_t)h->q_m * h->q_ks * 4)) return rc;
-        p.adc_tables = (float*)h->d_adc.ptr;
+        if (int rc = sc.d_adc.ensure(alloc_slots * (size_t)h->q_m * h->q_ks * 4)) return rc;
+        p.adc_tables = (float*)sc.d_adc.ptr;
     }
     p.topk = nullptr;
     if (k > 32) {  // result heap of the reference in HBM, one arena per slot
         int pad = 64;
         while (pad < k) pad <<= 1;
         p.topk_pad = pad;
-        if (int rc = h->d_topk.ensure(alloc_slots * (size_t)pad * 8)) return rc;
-        p.topk = (int2*)h->d_topk.ptr;
+        if (int rc = sc.d_topk.ensure(alloc_slots * (size_t)pad * 8)) return rc;
+        p.topk = (int2*)sc.d_topk.ptr;
     }
-    p.visited = (unsigned int*)h->d_visited.ptr;
-    p.ng_spill = (int2*)h->d_ng_spill.ptr;
-    p.spt_spill = (int2*)h->d_spt_spill.ptr;
-    p.work_counter = (unsigned int*)h->d_counter.ptr;
+    p.visited = (unsigned int*)sc.d_visited.ptr;
+    p.ng_spill = (int2*)sc.d_ng_spill.ptr;
+    p.spt_spill = (int2*)sc.d_spt_spill.ptr;
+    p.work_counter = (unsigned int*)sc.d_counter.ptr;
     return 0;
 }
 
@@ -419,13 +432,24 @@ int quantize_device(sptag_b200_index* h, const void* d_raw, int n, unsigned char
 // Every kernel that touches the handle's shared scratch (visited bitmaps, queue arenas, work counter, quantized-query
 // buffer) is ordered after the previous one, whatever stream it was launched on: the caller's stream waits on ev_done
 // before the launch sequence and records it afterwards.  Caller holds h->mu.
-int scratch_acquire(sptag_b200_index* h, cudaStream_t stream) {
-    CUDA_OK(cudaStreamWaitEvent(stream, h->ev_done, 0));
+int scratch_acquire(sptag_b200_index* h, cudaStream_t stream, int set = 0) {
+    if (h->scratch[set].used) CUDA_OK(cudaStreamWaitEvent(stream, h->scratch[set].ev_done, 0));
     return 0;
 }
-int scratch_release(sptag_b200_index* h, cudaStream_t stream) {
-    CUDA_OK(cudaEventRecord(h->ev_done, stream));
+int scratch_release(sptag_b200_index* h, cudaStream_t stream, int set = 0) {
+    CUDA_OK(cudaEventRecord(h->scratch[set].ev_done, stream));
+    h->scratch[set].used = true;
+    h->scratch[set].last_stream = stream;
     return 0;
+}
+// Set 0 unless it is still busy with a launch from another stream (then set 1, if that one is free or also busy on
+// this very stream).  Single-stream callers therefore never allocate the second set.
+int pick_scratch(sptag_b200_index* h, cudaStream_t stream) {
+    sptag_b200_index::Scratch& a = h->scratch[0];
+    if (!a.used || a.last_stream == stream || cudaEventQuery(a.ev_done) == cudaSuccess) return 0;
+    sptag_b200_index::Scratch& b = h->scratch[1];
+    if (!b.used || b.last_stream == stream || cudaEventQuery(b.ev_done) == cudaSuccess) return 1;
+    return 0;  // both busy elsewhere: queue behind set 0
 }
 
 // refine = true: the RefineSearchIndex flavour (BKTIndex.cpp:698-711) -- queries are base rows of the index itself
@@ -438,22 +462,31 @@ int search_device_impl(sptag_b200_index* h, const void* d_queries, int nq, int k
     int grid = 0;
     size_t smem = 0;
     SearchKernelFn kern = nullptr;
-    if (int rc = configure(h, k, p, grid, smem, nq, kern, opts)) return rc;
-    if (int rc = scratch_acquire(h, stream)) return rc;
+    int set = refine ? 0 : pick_scratch(h, stream);
+    if (int rc = configure(h, k, p, grid, smem, nq, kern, opts, set)) {
+        if (set == 0) return rc;
+        // the second scratch set did not fit in HBM: run behind the first one instead
+        h->scratch[1].release();
+        cudaGetLastError();
+        set = 0;
+        if (int rc0 = configure(h, k, p, grid, smem, nq, kern, opts, set)) return rc0;
+    }
+    sptag_b200_index::Scratch& sc = h->scratch[set];
+    if (int rc = scratch_acquire(h, stream, set)) return rc;
     p.queries = (const unsigned char*)d_queries;
     p.query_stride_bytes = (size_t)h->dim * value_size(h->value_type);
     if (h->q_type != 0) {
         // QueryResultSet::SetTarget -> IQuantizer::QuantizeVector (QueryResultSet.h:46-60): raw -> M code bytes
         if (h->q_adc) {  // ADC: the kernel needs the rotated float vector, not codes
             const size_t dimq = (size_t)h->q_m * h->q_dsub;
-            if (int rc = h->d_codes.ensure((size_t)nq * dimq * 4)) return rc;
-            if (int rc = quantize_device(h, d_queries, nq, nullptr, stream, (float*)h->d_codes.ptr)) return rc;
-            p.queries = (const unsigned char*)h->d_codes.ptr;
+            if (int rc = sc.d_codes.ensure((size_t)nq * dimq * 4)) return rc;
+            if (int rc = quantize_device(h, d_queries, nq, nullptr, stream, (float*)sc.d_codes.ptr)) return rc;
+            p.queries = (const unsigned char*)sc.d_codes.ptr;
             p.query_stride_bytes = dimq * 4;
         } else {
-            if (int rc = h->d_codes.ensure((size_t)nq * h->q_m)) return rc;
-            if (int rc = quantize_device(h, d_queries, nq, (unsigned char*)h->d_codes.ptr, stream)) return rc;
-            p.queries = (const unsigned char*)h->d_codes.ptr;
+            if (int rc = sc.d_codes.ensure((size_t)nq * h->q_m)) return rc;
+            if (int rc = quantize_device(h, d_queries, nq, (unsigned char*)sc.d_codes.ptr, stream)) return rc;
+            p.queries = (const unsigned char*)sc.d_codes.ptr;
             p.query_stride_bytes = (size_t)h->q_m;
         }
     }
@@ -473,7 +506,7 @@ int search_device_impl(sptag_b200_index* h, const void* d_queries, int nq, int k
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(h->ev_stop, stream));
     h->timed = true;
-    return scratch_release(h, stream);
+    return scratch_release(h, stream, set);
 }
 
 struct DeviceGuard {
@@ -635,7 +668,8 @@ int build_handle(const IndexShape& sh, const ArraySource& vectors, const ArraySo
     };
     if (cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess ||
         cudaEventCreate(&h->ev_aux) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->scratch[0].ev_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->scratch[1].ev_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreate(&h->staging[0].stream) != cudaSuccess || cudaStreamCreate(&h->staging[1].stream) != cudaSuccess)
         return destroy_on_fail(fail(SPTAG_B200_FAIL, "cudaEventCreate / cudaStreamCreate failed"));
     cudaStream_t up = h->staging[0].stream;
@@ -660,8 +694,8 @@ int build_handle(const IndexShape& sh, const ArraySource& vectors, const ArraySo
     }
     // ids the kernels index with must be in range: a corrupt file fails here, not as a stray device read later
     {
-        if (int rc = h->d_counter.ensure(256)) return destroy_on_fail(rc);
-        int* bad = (int*)h->d_counter.ptr + 8;
+        if (int rc = h->scratch[0].d_counter.ensure(256)) return destroy_on_fail(rc);
+        int* bad = (int*)h->scratch[0].d_counter.ptr + 8;
         cudaMemsetAsync(bad, 0, 8, up);
         const long long entries = (long long)h->n * h->degree;
         validate_graph_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, up>>>((const int*)h->d_graph.ptr, entries, h->degree,
@@ -733,15 +767,11 @@ void sptag_b200_destroy(sptag_b200_handle h) {
     h->d_codebooks.release();
     h->d_rotation_t.release();
     h->d_sdc.release();
-    h->d_codes.release();
     h->d_raw.release();
-    h->d_adc.release();
-    h->d_visited.release();
-    h->d_vlog.release();
-    h->d_topk.release();
-    h->d_ng_spill.release();
-    h->d_spt_spill.release();
-    h->d_counter.release();
+    for (auto& sc : h->scratch) {
+        sc.release();
+        if (sc.ev_done) cudaEventDestroy(sc.ev_done);
+    }
     h->d_ids.release();
     h->d_dists.release();
     for (auto& st : h->staging) {
@@ -755,7 +785,6 @@ void sptag_b200_destroy(sptag_b200_handle h) {
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     if (h->ev_stop) cudaEventDestroy(h->ev_stop);
     if (h->ev_aux) cudaEventDestroy(h->ev_aux);
-    if (h->ev_done) cudaEventDestroy(h->ev_done);
     delete h;
 }
 
@@ -965,10 +994,13 @@ int sptag_b200_quantize(sptag_b200_handle h, const void* raw_vectors, int32_t nu
     DeviceGuard guard(h->device);
     const size_t rbytes = (size_t)num * query_bytes(h);
     if (int rc = h->d_raw.ensure(rbytes)) return rc;
-    if (int rc = h->d_codes.ensure((size_t)num * h->q_m)) return rc;
+    DeviceBuffer& d_codes = h->scratch[0].d_codes;
+    if (int rc = d_codes.ensure((size_t)num * h->q_m)) return rc;
     CUDA_OK(cudaMemcpy(h->d_raw.ptr, raw_vectors, rbytes, cudaMemcpyHostToDevice));
-    if (int rc = quantize_device(h, h->d_raw.ptr, num, (unsigned char*)h->d_codes.ptr, nullptr)) return rc;
-    CUDA_OK(cudaMemcpy(codes_out, h->d_codes.ptr, (size_t)num * h->q_m, cudaMemcpyDeviceToHost));
+    if (int rc = scratch_acquire(h, nullptr, 0)) return rc;
+    if (int rc = quantize_device(h, h->d_raw.ptr, num, (unsigned char*)d_codes.ptr, nullptr)) return rc;
+    if (int rc = scratch_release(h, nullptr, 0)) return rc;
+    CUDA_OK(cudaMemcpy(codes_out, d_codes.ptr, (size_t)num * h->q_m, cudaMemcpyDeviceToHost));
     return SPTAG_B200_SUCCESS;
 }
 
