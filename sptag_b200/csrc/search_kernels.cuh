@@ -432,6 +432,35 @@ __device__ __forceinline__ float heap_top_dist(const WarpHeap& h) {
     return h.count == 0 ? SPTAG_B200_MAXDIST : pair_dist(h.s[1]);
 }
 
+// Heap::insert on a FULL heap (Heap.h:43-49): the slot of the first maximum of the last level [lastlevel, length], or
+// -1 when the new value is larger than that maximum and is dropped.
+static __device__ __noinline__ int heap_full_slot(const int2* hs, const int2* hg, int H, int lastlevel, int length, float d, int lane) {
+    float best = -1.0f;
+    int besti = 0x7fffffff;
+    bool have = false;
+    for (int i = lastlevel + lane; i <= length; i += 32) {
+        const int2 e = (i <= H) ? hs[i] : hg[i];
+        const float v = __int_as_float(e.y);
+        if (!have || v > best) {  // strict '<' in the reference keeps the earliest maximum
+            best = v;
+            besti = i;
+            have = true;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(kFull, best, o);
+        const int oi = __shfl_xor_sync(kFull, besti, o);
+        const bool oh = __shfl_xor_sync(kFull, (int)have, o) != 0;
+        if (oh && (!have || ob > best || (ob == best && oi < besti))) {
+            best = ob;
+            besti = oi;
+            have = true;
+        }
+    }
+    return (d > best) ? -1 : besti;
+}
+
 // Heap::insert (Heap.h:39-62).  The sift-up path (the ancestors loc>>1, loc>>2, ...) is loaded by
 // one lane per level, the stop level is found with a ballot, and the shifted parents plus the new
 // value are stored in one step -- the resulting array is identical to the sequential loop's.
@@ -442,31 +471,10 @@ __device__ __forceinline__ void heap_insert(WarpHeap& h, int node, float d, int 
 #define SPTAG_B200_HST(i, v) heap_st(h, (i), (v))
     int loc;
     if (h.count == h.length) {
-        // full heap: replace the first maximum of the last level [lastlevel, length] (Heap.h:43-49)
-        float best = -1.0f;
-        int besti = 0x7fffffff;
-        bool have = false;
-        for (int i = h.lastlevel + lane; i <= h.length; i += 32) {
-            float v = pair_dist(SPTAG_B200_HLD(i));
-            if (!have || v > best) {  // strict '<' in the reference keeps the earliest maximum
-                best = v;
-                besti = i;
-                have = true;
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            float ob = __shfl_xor_sync(kFull, best, o);
-            int oi = __shfl_xor_sync(kFull, besti, o);
-            bool oh = __shfl_xor_sync(kFull, (int)have, o) != 0;
-            if (oh && (!have || ob > best || (ob == best && oi < besti))) {
-                best = ob;
-                besti = oi;
-                have = true;
-            }
-        }
-        if (d > best) return;
-        loc = besti;
+        // full heap (Heap.h:43-49): rare, and ~80 instructions per inlined copy of insert -- kept out of line because the
+        // kernels are several times larger than the instruction cache
+        loc = heap_full_slot(h.s, h.g, h.H, h.lastlevel, h.length, d, lane);
+        if (loc < 0) return;
         if (TAIL) h.tail_idx = -1;
     } else {
         loc = ++h.count;
@@ -1131,14 +1139,15 @@ struct WarpSearch {
             const int2 bcell = hpop(spt);
             const int centerid = p.nodes[3 * bcell.x], cs = p.nodes[3 * bcell.x + 1], ce = p.nodes[3 * bcell.x + 2];
             ntree++;
+            // leaf or internal node alike: a centre that was not visited yet enters NGQueue (BKTree.h:780-795); only new
+            // LEAVES count as checked
+            if (!check_and_set_uniform(centerid)) {
+                if (cs < 0) checked++;
+                hins(ng, centerid, pair_dist(bcell));
+            }
             if (cs < 0) {
-                if (!check_and_set_uniform(centerid)) {
-                    checked++;
-                    hins(ng, centerid, pair_dist(bcell));
-                }
                 if (checked >= limit) break;
             } else {
-                if (!check_and_set_uniform(centerid)) hins(ng, centerid, pair_dist(bcell));
                 push_children(cs, ce);
             }
         }
@@ -1277,9 +1286,14 @@ struct WarpSearch {
     // BKT::Index<T>::Search<notDeleted, CheckDup, AlwaysTrue> (BKTIndex.cpp:268-352), round-1 step order (pop, row, visited, rows)
     __device__ __forceinline__ void bkt_search_legacy() {
         init_search_trees();
-        search_trees(p.initial_pivots);
         const int checkPos = p.degree - 1;
-        while (ng.count != 0) {
+        // (one copy of search_trees in the code: first trip = SearchTrees(NumberOfInitialDynamicPivots), later trips = the
+        //  re-seeding test at the end of a step)
+        bool reseed = true;
+        int tree_limit = p.initial_pivots;
+        for (;;) {
+            if (reseed) search_trees(tree_limit);
+            if (ng.count == 0) break;
             const int2 gnode = hpop(ng);
             int tmpNode = gnode.x;
             const float gdist = pair_dist(gnode);
@@ -1354,7 +1368,8 @@ struct WarpSearch {
                 }
                 if (first_neg < 32) break;
             }
-            if (heap_top_dist(ng) > heap_top_dist(spt)) search_trees(p.other_pivots + checked);
+            reseed = heap_top_dist(ng) > heap_top_dist(spt);
+            tree_limit = p.other_pivots + checked;
         }
     }
 
