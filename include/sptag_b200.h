@@ -118,8 +118,9 @@ void sptag_b200_destroy(sptag_b200_handle h);
  * sptag_b200_iterator_open_ex); the refine pass always runs with 0 like NeighborhoodGraph::RefineNode.  Additional B200 tuning knobs (not in the
  * reference) are prefixed "B200.": B200.QueriesPerSM, B200.StageRows, B200.Stages,
  * B200.NGCacheEntries, B200.SPTCacheEntries, B200.SimdWidth (which DistanceUtils summation tree to
- * reproduce bit-exactly: 16 = AVX-512, the only one built -- 8 / 4 make the search calls return
- * LackOfInputs rather than a differently rounded distance), B200.VisitedLog (-1 auto, 0 clear the
+ * reproduce bit-exactly -- the reference picks by cpuid, DistanceUtils.h:118-163: 16 = AVX-512 (default; all specialised
+ * kernels), 8 = AVX / AVX2, 4 = SSE; 8 and 4 are built for float, int8 and uint8 rows and run the generic-dimension
+ * kernels; int16 rows and quantized indexes exist in the AVX-512 form only and return LackOfInputs otherwise), B200.VisitedLog (-1 auto, 0 clear the
  * visited bitmap per query, 1 log the touched words and clear only those: for indexes of tens of millions
  * of vectors), B200.VisitedLogEntries. */
 int sptag_b200_set_param(sptag_b200_handle h, const char* name, const char* value);

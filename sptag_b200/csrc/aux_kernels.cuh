@@ -12,7 +12,7 @@ namespace sptag_b200 {
 template <bool COSINE, int ELEM>
 __global__ void distance_batch_kernel(const unsigned char* vectors, unsigned long long row_stride_bytes, int n,
                                       int dim, const void* queries_v, int nq, const int* ids, int ids_per_query,
-                                      float* out) {
+                                      float* out, int simd_width) {
     const int lane = threadIdx.x & 31;
     const int j = lane & 15;
     const long long hw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
@@ -31,12 +31,15 @@ __global__ void distance_batch_kernel(const unsigned char* vectors, unsigned lon
         const float* row = reinterpret_cast<const float*>(vectors + (size_t)(ok ? id : 0) * row_stride_bytes);
         const float* qv = reinterpret_cast<const float*>(queries_v) + (size_t)q * dim;
         QueryRegs<0> qr;
-        d = half_warp_distance<0, COSINE>(row, qr, qv, dim, j);
+        if (simd_width != 16)
+            d = half_warp_distance_w<COSINE>(row, qv, dim, j, simd_width);
+        else
+            d = half_warp_distance<0, COSINE>(row, qr, qv, dim, j);
     } else {
         // the host pads the query stride to a multiple of 4 bytes (2-/4-byte loads in the lane terms)
         const unsigned char* qv = reinterpret_cast<const unsigned char*>(queries_v) +
                                   (size_t)q * (((size_t)dim * (ELEM == 3 ? 2 : 1) + 3) & ~(size_t)3);
-        d = half_warp_distance_elem<COSINE, ELEM>(vectors + (size_t)(ok ? id : 0) * row_stride_bytes, qv, dim, j);
+        d = half_warp_distance_elem_w<COSINE, ELEM>(vectors + (size_t)(ok ? id : 0) * row_stride_bytes, qv, dim, j, simd_width);
     }
     if (valid && j == 0) out[item] = ok ? d : SPTAG_B200_MAXDIST;
 }
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(128) rebuild_neighbors_kernel(const unsigned c
                                                                 const int* __restrict__ res_ids,
                                                                 const float* __restrict__ res_dists, int num_results,
                                                                 int neighborhood, float rng_factor,
-                                                                int* __restrict__ out_graph) {
+                                                                int* __restrict__ out_graph, int simd_width) {
     extern __shared__ int kept_sm[];  // neighborhood ints per warp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, j = lane & 15, half = lane >> 4;
     const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -78,10 +81,14 @@ __global__ void __launch_bounds__(128) rebuild_neighbors_kernel(const unsigned c
             float d;
             if (ELEM == 0) {
                 QueryRegs<0> qr;
-                d = half_warp_distance<0, COSINE>(reinterpret_cast<const float*>(row), qr,
-                                                  reinterpret_cast<const float*>(cand), dim, j);
+                if (simd_width != 16)
+                    d = half_warp_distance_w<COSINE>(reinterpret_cast<const float*>(row), reinterpret_cast<const float*>(cand), dim,
+                                                     j, simd_width);
+                else
+                    d = half_warp_distance<0, COSINE>(reinterpret_cast<const float*>(row), qr,
+                                                      reinterpret_cast<const float*>(cand), dim, j);
             } else {
-                d = half_warp_distance_elem<COSINE, ELEM>(row, cand, dim, j);
+                d = half_warp_distance_elem_w<COSINE, ELEM>(row, cand, dim, j, simd_width);
             }
             const bool reject = (j == 0) && (__fmul_rn(rng_factor, d) < dist);
             if (__any_sync(kFull, reject)) good = false;

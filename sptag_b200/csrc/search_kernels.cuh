@@ -88,6 +88,9 @@ struct SearchParams {
     int pq_adc, pq_dsub;
     const float* codebooks;
     float* adc_tables;                     // per slot, pq_m * pq_ks floats
+    // which DistanceUtils summation tree to reproduce: 16 = AVX-512 (all specialised paths), 8 = AVX / AVX2, 4 = SSE
+    // (DistanceUtils.h:118-163 picks one by cpuid; a reference host without AVX-512 rounds differently)
+    int simd_width;
     // K > 32: the result set is the reference's own max-heap (QueryResultSet.h:77-120) in a per-slot HBM arena
     int2* topk;                            // per slot, topk_pad entries (id, distance bits); nullptr when k <= 32
     int topk_pad;                          // k rounded up to a power of two (the final sort is bitonic)
@@ -252,6 +255,34 @@ __device__ __forceinline__ void half_warp_distance_n(const float* const (&row)[N
     }
 }
 
+// The AVX (8 accumulators, DistanceUtils.cpp ComputeL2Distance_AVX / ComputeCosineDistance_AVX: 16 elements per trip as
+// two 8-wide adds, then the 8 -> 4 fold, 4-wide tail steps, scalar tail) and SSE (4 accumulators) float trees, for a
+// reference host whose cpuid dispatch lands below AVX-512.  Lanes j < width of the half-warp own the accumulators;
+// result valid in lane j == 0.  Must be called by all 32 lanes.
+template <bool COSINE>
+__device__ __forceinline__ float half_warp_distance_w(const float* __restrict__ row, const float* __restrict__ qs, int dim,
+                                                      int j, int width) {
+    float acc = 0.0f;
+    int i = 0;
+    if (width == 8) {
+        for (; i + 16 <= dim; i += 16) {
+            if (j < 8) {
+                acc = __fadd_rn(acc, dist_term<COSINE>(qs[i + j], row[i + j]));
+                acc = __fadd_rn(acc, dist_term<COSINE>(qs[i + 8 + j], row[i + 8 + j]));
+            }
+        }
+        acc = __fadd_rn(acc, __shfl_down_sync(kFull, acc, 4, 16));  // a4[j] = a8[j] + a8[j + 4]
+    }
+    for (; i + 4 <= dim; i += 4)
+        if (j < 4) acc = __fadd_rn(acc, dist_term<COSINE>(qs[i + j], row[i + j]));
+    const float a1 = __shfl_sync(kFull, acc, 1, 16);
+    const float a2 = __shfl_sync(kFull, acc, 2, 16);
+    const float a3 = __shfl_sync(kFull, acc, 3, 16);
+    float sum = __fadd_rn(__fadd_rn(__fadd_rn(acc, a1), a2), a3);
+    for (; i < dim; ++i) sum = dist_tail<COSINE>(qs[i], row[i], sum);
+    return COSINE ? __fsub_rn(1.0f, sum) : sum;
+}
+
 template <int DIM, bool COSINE>
 __device__ __forceinline__ float half_warp_distance(const float* __restrict__ row, const QueryRegs<DIM>& qr,
                                                     const float* __restrict__ qs, int dim, int j) {
@@ -314,6 +345,33 @@ __device__ __forceinline__ float half_warp_distance_int(const unsigned char* __r
     const float a2 = __shfl_sync(kFull, a4, 2, 16);
     const float a3 = __shfl_sync(kFull, a4, 3, 16);
     float s = __fadd_rn(__fadd_rn(__fadd_rn(a4, a1), a2), a3);
+    for (; i + 4 <= dim; i += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            s = __fadd_rn(s, dist_term<COSINE>((float)byte_val<UNSIGNED>(x[i + k]), (float)byte_val<UNSIGNED>(row[i + k])));
+    }
+    for (; i < dim; ++i) s = dist_tail<COSINE>((float)byte_val<UNSIGNED>(x[i]), (float)byte_val<UNSIGNED>(row[i]), s);
+    return COSINE ? __fsub_rn(UNSIGNED ? 65025.0f : 16129.0f, s) : s;
+}
+
+// AVX2 (32-byte steps, 8 lanes) and SSE (16-byte steps, 4 lanes) variants of the same int8 / uint8 kernels
+template <bool COSINE, bool UNSIGNED>
+__device__ __forceinline__ float half_warp_distance_int_w(const unsigned char* __restrict__ row,
+                                                          const unsigned char* __restrict__ x, int dim, int j, int width) {
+    float acc = 0.0f;
+    int i = 0;
+    const int lane_off = 16 * (j >> 2) + 2 * (j & 3);
+    if (width == 8) {
+        for (; i + 32 <= dim; i += 32)
+            if (j < 8) acc = __fadd_rn(acc, int_lane_term<COSINE, UNSIGNED>(x, row, i + lane_off));
+        acc = __fadd_rn(acc, __shfl_down_sync(kFull, acc, 4, 16));
+    }
+    for (; i + 16 <= dim; i += 16)
+        if (j < 4) acc = __fadd_rn(acc, int_lane_term<COSINE, UNSIGNED>(x, row, i + lane_off));
+    const float a1 = __shfl_sync(kFull, acc, 1, 16);
+    const float a2 = __shfl_sync(kFull, acc, 2, 16);
+    const float a3 = __shfl_sync(kFull, acc, 3, 16);
+    float s = __fadd_rn(__fadd_rn(__fadd_rn(acc, a1), a2), a3);
     for (; i + 4 <= dim; i += 4) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -389,6 +447,13 @@ __device__ __forceinline__ float half_warp_distance_elem(const unsigned char* __
     if (ELEM == 3)
         return half_warp_distance_i16<COSINE>(reinterpret_cast<const short*>(row), reinterpret_cast<const short*>(x), dim, j);
     return half_warp_distance_int<COSINE, ELEM == 2>(row, x, dim, j);
+}
+// the same with the summation tree chosen at run time (16 / 8 / 4); int16 rows exist in the AVX-512 form only
+template <bool COSINE, int ELEM>
+__device__ __forceinline__ float half_warp_distance_elem_w(const unsigned char* __restrict__ row,
+                                                           const unsigned char* __restrict__ x, int dim, int j, int width) {
+    if (ELEM == 3 || width == 16) return half_warp_distance_elem<COSINE, ELEM>(row, x, dim, j);
+    return half_warp_distance_int_w<COSINE, ELEM == 2>(row, x, dim, j, width);
 }
 // the query element the KD split test reads (KDTree.h:255)
 template <int ELEM>
@@ -1072,7 +1137,8 @@ struct WarpSearch {
             const int base = t * p.stage_rows;
             const int rows = min(p.stage_rows, cnt - base);
             int pr = 0;
-            for (; ELEM == 0 && 2 * pr + 2 < rows; pr += 2) {  // two row pairs per pass: 2 independent chains per lane
+            const bool narrow = p.simd_width != 16;  // AVX / SSE trees: generic one-pair loop below
+            for (; ELEM == 0 && !narrow && 2 * pr + 2 < rows; pr += 2) {  // two row pairs per pass: 2 independent chains per lane
                 const int r0 = 2 * pr + half, r1 = r0 + 2;
                 const float* const rws[2] = {reinterpret_cast<const float*>(slot_ptr(st * p.stage_rows + r0)),
                                              reinterpret_cast<const float*>(slot_ptr(st * p.stage_rows + r1))};
@@ -1088,10 +1154,13 @@ struct WarpSearch {
                 float d;
                 if (ELEM == 0) {
                     const float* row = reinterpret_cast<const float*>(slot_ptr(st * p.stage_rows + r));
-                    d = half_warp_distance<DIM, COSINE>(row, qr, qs, p.dim, j);
+                    if (narrow)
+                        d = half_warp_distance_w<COSINE>(row, qs, p.dim, j, p.simd_width);
+                    else
+                        d = half_warp_distance<DIM, COSINE>(row, qr, qs, p.dim, j);
                 } else {
-                    d = half_warp_distance_elem<COSINE, ELEM>(slot_ptr(st * p.stage_rows + r),
-                                                              reinterpret_cast<const unsigned char*>(qs), p.dim, j);
+                    d = half_warp_distance_elem_w<COSINE, ELEM>(slot_ptr(st * p.stage_rows + r),
+                                                                reinterpret_cast<const unsigned char*>(qs), p.dim, j, p.simd_width);
                 }
                 if (j == 0 && r < rows) cand_dist[base + r] = d;
             }

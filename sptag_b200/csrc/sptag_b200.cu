@@ -186,7 +186,8 @@ SearchKernelFn pick_kernel(const sptag_b200_index* h, int mres_cap) {
     if (h->value_type == SPTAG_B200_VT_INT8) return pick_int8_kernel(false, !l2, mres_cap, kdt);
     if (h->value_type == SPTAG_B200_VT_UINT8) return pick_int8_kernel(true, !l2, mres_cap, kdt);
     if (h->value_type == SPTAG_B200_VT_INT16) return pick_int16_kernel(!l2, mres_cap, kdt);
-    return l2 ? pick_float_kernel_l2(h->dim, mres_cap, kdt) : pick_float_kernel_cosine(h->dim, mres_cap, kdt);
+    const int kdim = (h->simd_width == 16) ? h->dim : 0;  // the 128- / 768-d specialisations are AVX-512 trees
+    return l2 ? pick_float_kernel_l2(kdim, mres_cap, kdt) : pick_float_kernel_cosine(kdim, mres_cap, kdt);
 }
 
 // What one call may override (the reference passes these per call: p_searchDeleted of SearchIndex / GetIterator,
@@ -224,8 +225,11 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
         if ((long long)h->dim * maxterm >= (1ll << 31))
             return fail(SPTAG_B200_LACK_OF_INPUTS, "dimension %d too large for the integer distance kernels", h->dim);
     }
-    if (h->simd_width != 16)
-        return fail(SPTAG_B200_LACK_OF_INPUTS, "B200.SimdWidth %d not built (16 only)", h->simd_width);
+    if (h->simd_width != 16 && h->simd_width != 8 && h->simd_width != 4)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "B200.SimdWidth %d: 16 (AVX-512), 8 (AVX / AVX2) or 4 (SSE)", h->simd_width);
+    if (h->simd_width != 16 && (pq || h->value_type == SPTAG_B200_VT_INT16))
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "B200.SimdWidth %d: the AVX / SSE summation trees are built for float, int8 and uint8 "
+                                              "rows (int16 and the quantizer tables exist in the AVX-512 form only)", h->simd_width);
     if (k < 1 || k > 2048) return fail(SPTAG_B200_LACK_OF_INPUTS, "k = %d outside the supported range [1, 2048]", k);
 
     memset(&p, 0, sizeof(p));
@@ -257,6 +261,7 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     p.spt_length = alloc_check * 10;
     p.spt_lastlevel = heap_lastlevel(p.spt_length);
     p.mres_cap = std::max(eff_max_check / 16, k);
+    p.simd_width = h->simd_width;
     p.sdc = (const float*)h->d_sdc.ptr;
     p.pq_m = h->q_m;
     p.pq_ks = h->q_ks;
@@ -286,7 +291,7 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     }
     // 512-byte float rows run the fixed-shape fast path (search_kernels.cuh kFast): 2 stages x 8 rows, slots 576 B apart;
     // must mirror WarpSearch::kFast
-    const bool fast128 = !pq && h->value_type == SPTAG_B200_VT_FLOAT && h->dim == 128;
+    const bool fast128 = !pq && h->value_type == SPTAG_B200_VT_FLOAT && h->dim == 128 && h->simd_width == 16;
     if (fast128) {
         stage_rows = 8;
         stages = 2;
@@ -321,7 +326,7 @@ relayout:
     off += round_up((size_t)stages * 8, 16);
     p.off_query = (int)off;
     const bool query_in_regs_only = !pq && h->value_type == SPTAG_B200_VT_FLOAT && h->algo == SPTAG_B200_ALGO_BKT &&
-                                    h->dim == 768;  // must mirror kRegsOnly in search_kernel
+                                    h->dim == 768 && h->simd_width == 16;  // must mirror kRegsOnly in search_kernel
     off += query_in_regs_only ? 16 : round_up((size_t)h->dim * 4 + 16, 16);  // float query, or M row offsets for PQ
     smem = round_up(off, 128);
     if (smem > h->smem_optin)
@@ -1224,7 +1229,7 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
 #define SPTAG_B200_RB(COS, EL)                                                                                          \
     rebuild_neighbors_kernel<COS, EL><<<blocks, warps_per_block * 32, smem, stream>>>(                                   \
         dv, h->row_stride, h->dim, first, nb, (const int*)h->d_ids.ptr, (const float*)h->d_dists.ptr, k,                 \
-        neighborhood_size, rng_factor, rows)
+        neighborhood_size, rng_factor, rows, h->simd_width)
         if (h->value_type == SPTAG_B200_VT_FLOAT) {
             if (l2) SPTAG_B200_RB(false, 0); else SPTAG_B200_RB(true, 0);
         } else if (h->value_type == SPTAG_B200_VT_INT8) {
@@ -1574,7 +1579,7 @@ int sptag_b200_distance_batch(sptag_b200_handle h, const void* queries, int32_t 
         const bool l2 = (h->metric == SPTAG_B200_METRIC_L2);
 #define SPTAG_B200_DB(COS, EL)                                                                                        \
     distance_batch_kernel<COS, EL><<<(unsigned)blocks, threads>>>(dv, h->row_stride, h->n, h->dim, dq.ptr, num_queries, \
-                                                                  (const int*)di.ptr, ids_per_query, (float*)dout.ptr)
+                                                                  (const int*)di.ptr, ids_per_query, (float*)dout.ptr, h->simd_width)
         if (h->value_type == SPTAG_B200_VT_FLOAT) {
             if (l2) SPTAG_B200_DB(false, 0); else SPTAG_B200_DB(true, 0);
         } else if (h->value_type == SPTAG_B200_VT_INT8) {

@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/r02_gpu_final2.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r02_gpu_final2.log
 for mc in 8192 512 1024 2048 4096 16384; do
 python bench.py --algo kdt --n 10000000 --dim 128 --metric L2 --rank-dim 16 --maxcheck $mc --in-flight 2 --steps 10 > gpurun_out/r02_bench_kdt_10m128_mc$mc.json 2> gpurun_out/r02_bench_kdt_10m128_mc$mc.err; echo "mc $mc rc=$?"
 python -c "
