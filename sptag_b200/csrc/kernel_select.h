@@ -13,8 +13,9 @@ typedef void (*IterateKernelFn)(const SearchParams, int*, int*, unsigned char*);
 typedef void (*NearestFirstKernelFn)(const SearchParams, int*);
 
 // float rows; dim 128 / 768 select the register-resident query variants
-SearchKernelFn pick_float_kernel_l2(int dim, int mres_cap, bool kdt);
-SearchKernelFn pick_float_kernel_cosine(int dim, int mres_cap, bool kdt);
+// slots: query slots per SM the host aims at (512-byte rows: register-capped variants above 16)
+SearchKernelFn pick_float_kernel_l2(int dim, int mres_cap, bool kdt, int slots);
+SearchKernelFn pick_float_kernel_cosine(int dim, int mres_cap, bool kdt, int slots);
 // value_type: SPTAG_B200_VT_INT8 / UINT8 / INT16
 SearchKernelFn pick_int8_kernel(bool is_unsigned, bool cosine, int mres_cap, bool kdt);
 SearchKernelFn pick_int16_kernel(bool cosine, int mres_cap, bool kdt);

@@ -629,7 +629,7 @@ __device__ __forceinline__ int2 heap_pop(WarpHeap& h, int lane) {
             const int cn = right ? pr.z : pr.x, cb = right ? pr.w : pr.y;
             next += right ? 1 : 0;
             if (__int_as_float(cb) < cd) {
-                if (lane == 0) heap_st(h, parent, make_int2(cn, cb));
+                if (lane == 0) h.s[parent] = make_int2(cn, cb);  // parent < next < lim <= H: always the shared-memory head
                 parent = next;
                 next <<= 1;
             } else {
@@ -974,10 +974,11 @@ struct WarpSearch {
 
     // distances of the query to cand_id[0..cnt) -> cand_dist[0..cnt).  cnt <= 32.
     const float* pq_table;
-    // the SDC table is read-only for the whole kernel (non-coherent path is fine); an ADC table was written by
-    // this warp a moment ago, so it is read with ordinary loads
+    // one table entry.  Ordinary loads for both tables: an ADC table was written by this warp a moment ago, and a
+    // per-look-up choice between ld.global and ld.global.nc made ptxas emit BOTH address computations and both loads,
+    // predicated, for every look-up (14 instructions per look-up instead of 5).
     // (an L2 evict_last policy on these look-ups was measured 11 % slower at 2M x 100)
-    __device__ __forceinline__ float pq_ld(const float* a) const { return p.pq_adc ? *a : __ldg(a); }
+    static __device__ __forceinline__ float pq_ld(const float* tb, unsigned idx) { return tb[idx]; }
 
     // PQ rows: all (<= 32) code rows of the step are staged by one TMA batch, then lane r sums the M
     // table entries of candidate r in subvector order -- the reference's single float accumulator
@@ -993,8 +994,10 @@ struct WarpSearch {
         mbar_wait(&bars[0], phase_bits & 1u);
         phase_bits ^= 1u;
         if (lane < cnt) {
-            const unsigned char* row = ring + (size_t)lane * p.slot_stride;
-            const int* qoff = reinterpret_cast<const int*>(qs);
+            const unsigned char* row = ring + (unsigned)lane * (unsigned)p.slot_stride;
+            // row offsets of the query's table rows (< M * Ks * Ks, fits 32 bits): unsigned indices keep every address
+            // one IMAD.WIDE.U32; the offsets are read four at a time; a code byte is one PRMT
+            const unsigned* qoff = reinterpret_cast<const unsigned*>(qs);
             const float* tb = pq_table;  // the shared SDC table, or this slot's ADC table of the current query
             float acc = 0.0f;
             // 16 look-ups in flight per lane (their addresses do not depend on the running sum), then the sum in
@@ -1006,21 +1009,26 @@ struct WarpSearch {
                 const unsigned ws[4] = {w.x, w.y, w.z, w.w};
                 float t[16];
 #pragma unroll
-                for (int b = 0; b < 16; ++b)
-                    t[b] = pq_ld(tb + qoff[i + b] + ((ws[b >> 2] >> (8 * (b & 3))) & 255u));
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 qo = *reinterpret_cast<const uint4*>(qoff + i + 4 * c);
+                    t[4 * c + 0] = pq_ld(tb, qo.x + __byte_perm(ws[c], 0u, 0x4440u));
+                    t[4 * c + 1] = pq_ld(tb, qo.y + __byte_perm(ws[c], 0u, 0x4441u));
+                    t[4 * c + 2] = pq_ld(tb, qo.z + __byte_perm(ws[c], 0u, 0x4442u));
+                    t[4 * c + 3] = pq_ld(tb, qo.w + __byte_perm(ws[c], 0u, 0x4443u));
+                }
 #pragma unroll
                 for (int b = 0; b < 16; ++b) acc = __fadd_rn(acc, t[b]);
             }
             const int m4 = p.pq_m & ~3;
             for (; i < m4; i += 4) {
                 const unsigned w = *reinterpret_cast<const unsigned*>(row + i);
-                const float t0 = pq_ld(tb + qoff[i] + (w & 255u));
-                const float t1 = pq_ld(tb + qoff[i + 1] + ((w >> 8) & 255u));
-                const float t2 = pq_ld(tb + qoff[i + 2] + ((w >> 16) & 255u));
-                const float t3 = pq_ld(tb + qoff[i + 3] + (w >> 24));
+                const float t0 = pq_ld(tb, qoff[i] + __byte_perm(w, 0u, 0x4440u));
+                const float t1 = pq_ld(tb, qoff[i + 1] + __byte_perm(w, 0u, 0x4441u));
+                const float t2 = pq_ld(tb, qoff[i + 2] + __byte_perm(w, 0u, 0x4442u));
+                const float t3 = pq_ld(tb, qoff[i + 3] + __byte_perm(w, 0u, 0x4443u));
                 acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, t0), t1), t2), t3);
             }
-            for (; i < p.pq_m; ++i) acc = __fadd_rn(acc, pq_ld(tb + qoff[i] + row[i]));
+            for (; i < p.pq_m; ++i) acc = __fadd_rn(acc, pq_ld(tb, qoff[i] + (unsigned)row[i]));
             cand_dist[lane] = acc;
         }
         __syncwarp();
@@ -1084,29 +1092,33 @@ struct WarpSearch {
         const float sum = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
         return COS ? __fsub_rn(1.0f, sum) : sum;
     }
-    // cand_id[0..cnt) -> cand_dist[0..cnt)
+    // cand_id[0..cnt) -> cand_dist[0..cnt).  p.stages = 2: the ring holds two 8-row stages (the copy of pass t + 1 overlaps
+    // the arithmetic of pass t); p.stages = 1: one stage -- half the shared memory per slot, which is what lets 20-24
+    // query slots fit on an SM (the other warps fill the gap instead of this warp's second stage)
     __device__ __forceinline__ void fast_compute_dists(int cnt) {
         __syncwarp();
         fence_proxy_async();
         const int nst = (cnt + kFastRows - 1) >> 3;
+        const bool two = p.stages == 2;
         const int myid = (lane < 16 && lane < cnt) ? cand_id[lane] : 0;
         fast_issue(0, min(kFastRows, cnt), __shfl_sync(kFull, myid, lane & 7));
-        if (nst > 1) fast_issue(1, min(kFastRows, cnt - kFastRows), __shfl_sync(kFull, myid, 8 + (lane & 7)));
-        // the ring holds 16 rows; the rows of the later stages start their trip from HBM to L2 now, so that their TMA
-        // copy -- issued when a ring stage frees up -- finds them there
-        if (lane >= 2 * kFastRows && lane < cnt)
+        if (two && nst > 1) fast_issue(1, min(kFastRows, cnt - kFastRows), __shfl_sync(kFull, myid, 8 + (lane & 7)));
+        // the rows that do not fit the ring start their trip from HBM to L2 now, so that their TMA copy -- issued when a
+        // ring stage frees up -- finds them there
+        if (lane >= (two ? 2 * kFastRows : kFastRows) && lane < cnt)
             tma_prefetch_l2(p.vectors + (size_t)cand_id[lane] * p.row_stride_bytes, (uint32_t)kFastRowBytes);
         for (int t = 0; t < nst; ++t) {
-            const int st = t & 1;
+            const int st = two ? (t & 1) : 0;
             mbar_wait(&bars[st], (phase_bits >> st) & 1u);
             phase_bits ^= (1u << st);
             const float d = fast_dist8(st);
             const int ri = kFastRows * t + (lane >> 2);
             if ((lane & 3) == 0 && ri < cnt) cand_dist[ri] = d;
             __syncwarp();
-            if (t + 2 < nst) {
+            const int nt = two ? t + 2 : t + 1;  // the pass that reuses this stage
+            if (nt < nst) {
                 fence_proxy_async();
-                const int base = kFastRows * (t + 2);
+                const int base = kFastRows * nt;
                 fast_issue(st, min(kFastRows, cnt - base), (base + (lane & 7) < cnt) ? cand_id[base + (lane & 7)] : 0);
             }
         }

@@ -98,6 +98,7 @@ struct sptag_b200_index {
     int queries_per_sm = 0;  // 0 = auto
     int stage_rows = 0;      // 0 = auto
     int stages = 2;
+    bool stages_set = false;  // B200.Stages was set explicitly
     // Small queue caches + a small ring: the kernel is latency-bound per warp, so resident queries per
     // SM matter more than on-chip queue capacity (sweep in profiles/r01_sweep_c2.txt).  0 = auto.
     int h_ng = 0, h_spt = 0;
@@ -179,7 +180,7 @@ IterateKernelFn pick_iterate_kernel(const sptag_b200_index* h, int mres_cap) {
 
 // The kernel instantiation for this index / parameter set (nullptr: unsupported m_Results capacity); the
 // instantiations live in kern_*.cu (kernel_select.h)
-SearchKernelFn pick_kernel(const sptag_b200_index* h, int mres_cap) {
+SearchKernelFn pick_kernel(const sptag_b200_index* h, int mres_cap, int slots = 0) {
     const bool kdt = (h->algo == SPTAG_B200_ALGO_KDT);
     if (h->q_type != 0) return pick_pq_kernel(mres_cap);  // quantized: BKT + L2 only (PQQuantizer.h:130-136)
     const bool l2 = (h->metric == SPTAG_B200_METRIC_L2);
@@ -187,7 +188,7 @@ SearchKernelFn pick_kernel(const sptag_b200_index* h, int mres_cap) {
     if (h->value_type == SPTAG_B200_VT_UINT8) return pick_int8_kernel(true, !l2, mres_cap, kdt);
     if (h->value_type == SPTAG_B200_VT_INT16) return pick_int16_kernel(!l2, mres_cap, kdt);
     const int kdim = (h->simd_width == 16) ? h->dim : 0;  // the 128- / 768-d specialisations are AVX-512 trees
-    return l2 ? pick_float_kernel_l2(kdim, mres_cap, kdt) : pick_float_kernel_cosine(kdim, mres_cap, kdt);
+    return l2 ? pick_float_kernel_l2(kdim, mres_cap, kdt, slots) : pick_float_kernel_cosine(kdim, mres_cap, kdt, slots);
 }
 
 // What one call may override (the reference passes these per call: p_searchDeleted of SearchIndex / GetIterator,
@@ -292,9 +293,32 @@ int configure(sptag_b200_index* h, int k, SearchParams& p, int& grid, size_t& sm
     // 512-byte float rows run the fixed-shape fast path (search_kernels.cuh kFast): 2 stages x 8 rows, slots 576 B apart;
     // must mirror WarpSearch::kFast
     const bool fast128 = !pq && h->value_type == SPTAG_B200_VT_FLOAT && h->dim == 128 && h->simd_width == 16;
+    // ... with register-capped kernel variants for more than 16 query slots per SM (B200.QueriesPerSM); those run a
+    // one-stage ring (B200.Stages = 1 selects it at any residency) so that the slot's shared memory still fits
+    // Default residency for 512-byte rows: all warps start together and a query costs about the same for every warp,
+    // so a batch runs in ceil(nq / slots) near-lockstep rounds and a mostly empty last round is lost time (measured at
+    // 10k queries: 18 slots 594k QPS, 20 slots 575k, 22 slots 502k).  Pick the slot count in [14, 20] whose last round
+    // is fullest, weighted by the measured per-slot-count throughput (saturates at 17+).
+    int want_slots = fast128 ? h->queries_per_sm : 0;
+    if (fast128 && want_slots <= 0) {
+        static const double weight[7] = {0.88, 0.92, 0.97, 1.0, 1.0, 1.0, 1.0};  // 14 .. 20 slots
+        double best = -1.0;
+        for (int s = 14; s <= 20; ++s) {
+            const long long slots = (long long)h->num_sms * s;
+            const long long rounds = ((long long)nq + slots - 1) / slots;
+            const double score = weight[s - 14] * (double)nq / (double)(rounds * slots);
+            if (score > best + 1e-9) {
+                best = score;
+                want_slots = s;
+            }
+        }
+        if ((long long)nq <= (long long)h->num_sms * 14) want_slots = 14;  // one round: fewer slots, larger queue heads
+    }
     if (fast128) {
         stage_rows = 8;
-        stages = 2;
+        // one 8-row stage unless B200.Stages = 2 is asked for at <= 16 slots: the second stage's 4.6 KB serve better as
+        // queue heads (16 slots: 565k QPS with one stage, 553k with two)
+        stages = (h->stages_set && h->stages == 2 && want_slots <= 16) ? 2 : 1;
         p.slot_stride = 128 * 4 + 64;
         p.slot_stagger = 0;
     }
@@ -332,7 +356,7 @@ relayout:
     if (smem > h->smem_optin)
         return fail(SPTAG_B200_MEMORY_OVERFLOW, "shared memory per query slot %zu exceeds %zu", smem, h->smem_optin);
 
-    kern = pick_kernel(h, p.mres_cap);
+    kern = pick_kernel(h, p.mres_cap, want_slots);
     if (!kern)
         return fail(SPTAG_B200_LACK_OF_INPUTS, "max(MaxCheck/16, K) = %d exceeds what this index type supports (2048; quantized: 1024)", p.mres_cap);
     CUDA_OK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -344,7 +368,7 @@ relayout:
     if (h->queries_per_sm <= 0 && big_rows) per_sm = std::min(per_sm, 14);  // 3 KB rows: 14 beats 15 (HBM-bound, sweep)
     // 512 B rows: 14 slots leave 2 KB more shared memory per queue head than 16 and shorten the tail of a 10k-query batch
     // (profiles/r02_sweep_128.txt: 521k vs 504k QPS; at batches >= 20k queries 16 wins by 2-3 %)
-    if (h->queries_per_sm <= 0 && fast128 && h->algo == SPTAG_B200_ALGO_BKT && nq <= 16384) per_sm = std::min(per_sm, 14);
+    if (h->queries_per_sm <= 0 && fast128) per_sm = std::min(per_sm, want_slots);
     per_sm = std::max(1, std::min(per_sm, fit));
     if (h->h_ng <= 0 && h->h_spt <= 0 && !relayout_done) {
         // Spare shared memory of a slot (at this residency) goes to the queue heads: 3/4 NGQueue, 1/4 SPTQueue
@@ -1024,7 +1048,7 @@ int sptag_b200_set_param(sptag_b200_handle h, const char* name, const char* valu
     else if (n == "ThresholdOfNumberOfContinuousNoBetterPropagation") h->no_better_threshold = (int)v;
     else if (n == "B200.QueriesPerSM") h->queries_per_sm = (int)v;
     else if (n == "B200.StageRows") h->stage_rows = (int)v;
-    else if (n == "B200.Stages") h->stages = (int)v;
+    else if (n == "B200.Stages") { h->stages = (int)v; h->stages_set = true; }
     else if (n == "B200.NGCacheEntries") h->h_ng = (int)v;
     else if (n == "B200.SPTCacheEntries") h->h_spt = (int)v;
     else if (n == "B200.SimdWidth") h->simd_width = (int)v;
