@@ -107,10 +107,13 @@ def gen_data(args, n, seed, device):
         x = torch.randn((n, args.dim), generator=g, device=device, dtype=torch.float32)
     else:
         # BASELINE.md "low-rank synthetic": x = z.A + 0.1*eps, A entries N(0,1)/sqrt(r)
-        ga = torch.Generator(device=device)
-        ga.manual_seed(args.seed)  # the mixing matrix is shared by base vectors, shards and queries
+        # the mixing matrix is shared by base vectors, shards and queries -- and by indexes prepared on another machine
+        # (build/bench_cache: the reference-built folder is built on the CPU container), so it always comes from the CPU
+        # generator, whatever device the rest is drawn on
+        ga = torch.Generator(device="cpu")
+        ga.manual_seed(args.seed)
         r = args.rank_dim
-        A = torch.randn((r, args.dim), generator=ga, device=device, dtype=torch.float32) / (r ** 0.5)
+        A = (torch.randn((r, args.dim), generator=ga, device="cpu", dtype=torch.float32) / (r ** 0.5)).to(device)
         z = torch.randn((n, r), generator=g, device=device, dtype=torch.float32)
         x = z @ A
         x += 0.1 * torch.randn((n, args.dim), generator=g, device=device, dtype=torch.float32)
