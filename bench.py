@@ -40,6 +40,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BUILDER_VERSION = 3
+L2_BYTES = 126 * 1000 * 1000  # B200 L2 (B200_PROFILING.md)
+
+
+def l2_policy_text(row_bytes_total):
+    gb = row_bytes_total / 1e9
+    if row_bytes_total > 4 * L2_BYTES:
+        return "index (%.2f GB of vector rows) and per-step traffic are larger than L2; no explicit flush" % gb
+    if row_bytes_total > L2_BYTES:
+        return ("index (%.2f GB of vector rows) is only %.1fx the L2: rows are partly L2-resident between steps, no explicit "
+                "flush -- this line is not an HBM-roofline measurement" % (gb, row_bytes_total / L2_BYTES))
+    return ("index (%.3f GB of vector rows) fits the L2: rows are L2-resident, no explicit flush -- this line is not an "
+            "HBM-roofline measurement" % gb)
 
 
 def log(*a):
@@ -370,8 +382,7 @@ def main():
     config = {"workload": workload, "index": "%s+RNG(degree 32)" % args.algo.upper(), "n": args.n, "dim": args.dim,
               "metric": args.metric, "batch": args.nq, "k": args.k, "max_check": args.maxcheck,
               "parallelism": ("%s x%d" % (args.mode, args.gpus)) if args.gpus > 1 else "single GPU",
-              "l2_policy": "index (%.2f GB of vector rows) and per-step traffic are larger than L2; no explicit flush"
-                           % (args.n * (args.pq_m if quantized else args.dim * 4) / 1e9)}
+              "l2_policy": l2_policy_text(args.n * (args.pq_m if quantized else args.dim * 4))}
 
     # ------------------------------ reference arm ------------------------------
     if args.impl == "reference":
@@ -706,12 +717,19 @@ def main_leg(args, rank, local_rank, world, dev, dist, quantized, config, mode):
     wkey = "%s_%s_%dx%d_mc%d%s" % (args.algo, args.metric, args.n, args.dim, args.maxcheck,
                                     ("_%s%d" % (args.quantizer, args.pq_m)) if quantized else "")
     traffic, traffic_note = kept_traffic(wkey, alg_bytes)
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    row_bytes_total = args.n * (args.pq_m if quantized else args.dim * (1 if args.raw_type == "int8" else 4))
+    roofline = {"bound": "hbm" if row_bytes_total > 4 * L2_BYTES else "hbm (index partly or wholly L2-resident: see l2_note)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_note": traffic_note, "kernel": kname, "kernel_ms": kernel_ms,
                 "kernel_ms_samples": [round(v, 3) for v in kms],
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "share_of_step": kernel_ms / ms_step}
 
+    if row_bytes_total <= 4 * L2_BYTES:
+        roofline["l2_note"] = ("the vector rows (%.0f MB) are not much larger than the 126 MB L2, so part of the algorithmic "
+                               "bytes are served by L2 hits and never reach HBM: `achieved` / `frac` count algorithmic bytes "
+                               "and can exceed the HBM peak here; the HBM roofline bounds the configurations whose rows are "
+                               "several times the L2 (C2: 3.07 GB)" % (row_bytes_total / 1e6))
     if quantized:
         # The quantized kernel's HBM bytes are only the M code bytes per distance; what it really moves is the SDC table:
         # one 4-byte look-up per sub-vector, each a 32-byte L2 sector request unless lanes of the same instruction share a

@@ -55,6 +55,8 @@ SPECS = {
     "bkt2_l2_6k_32": ("BKT", "L2", lambda: reflib.gen_iid(6000, 32, 71), lambda: reflib.gen_iid(200, 32, 72), "BKTNumber=2"),
     "kdt2_l2_6k_32": ("KDT", "L2", lambda: reflib.gen_iid(6000, 32, 73), lambda: reflib.gen_iid(200, 32, 74), "KDTNumber=2"),
     "kdt_l2_10k_64": ("KDT", "L2", lambda: reflib.gen_iid(10000, 64, 14), lambda: reflib.gen_iid(300, 64, 15), ""),
+    # 512-byte rows under a KD-tree: the fast-path KDT kernel (search_kernel<128, ..., KDT>)
+    "kdt_l2_8k_128": ("KDT", "L2", lambda: reflib.gen_lowrank(8000, 128, 16, 91), lambda: reflib.gen_lowrank(300, 128, 16, 92), ""),
 }
 
 

@@ -103,6 +103,32 @@ def test_tuning_knobs_do_not_change_results(knobs):
         idx.close()
 
 
+@pytest.mark.parametrize("knobs", [
+    {},                                                  # default: one-stage ring, slot count from the batch size
+    {"B200.QueriesPerSM": 17},                           # the register-capped (96 registers) 20-slot instantiation
+    {"B200.QueriesPerSM": 20},
+    {"B200.QueriesPerSM": 16, "B200.Stages": 2},         # two-stage ring
+    {"B200.QueriesPerSM": 6, "B200.Stages": 2, "B200.NGCacheEntries": 64, "B200.SPTCacheEntries": 32},
+    {"B200.QueriesPerSM": 20, "B200.NGCacheEntries": 32, "B200.SPTCacheEntries": 16},  # queues mostly in the HBM arenas
+])
+@pytest.mark.parametrize("name", ["bkt_l2_10k_128", "bkt_cos_10k_128", "kdt_l2_8k_128"])
+def test_512_byte_row_variants(name, knobs):
+    """128-d float rows run the fixed-shape fast path; its ring depth and its register-capped high-residency
+    instantiation are chosen per launch (sptag_b200.cu configure) -- every variant must return the reference's bits."""
+    from sptag_b200 import B200Index
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:300]
+    idx = B200Index.load(folder)
+    for pname, v in knobs.items():
+        idx.set_param(pname, v)
+    try:
+        for mc in [8192, 512]:
+            _compare(idx, files, q, 10, mc, "%s %s" % (name, knobs))
+    finally:
+        idx.close()
+
+
 @pytest.mark.parametrize("k", [1, 5, 32, 33, 100, 500])
 def test_result_counts(k):
     from sptag_b200 import B200Index
