@@ -196,7 +196,9 @@ int sptag_b200_distance_batch(sptag_b200_handle h, const void* queries, int32_t 
  * install != 0 (needs a full pass): the new rows replace the index's graph on the device -- the index's degree becomes
  * neighborhood_size, which may differ from the current one (RefineGraph's passes run on rows NeighborhoodScale times
  * wider); duplicate-group back-pointers in the last slot are carried over (NeighborhoodGraph.h:395-401).
- * cef <= 2047.  Not available for quantized indexes. */
+ * cef <= 2047.  Quantized indexes: as RefineNode does (NeighborhoodGraph.h:538-543), the node's code row is reconstructed,
+ * quantized again and searched with that; RebuildNeighbors uses the quantizer's SDC distance; K = cef + 1 <= 1024 there,
+ * and ADC must be off (with ADC on the reference's RebuildNeighbors reads a code row as a distance table). */
 int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num_nodes, int32_t cef,
                             int32_t neighborhood_size, float rng_factor, int32_t* out_graph, int32_t* out_res_ids,
                             float* out_res_dists, int32_t install);

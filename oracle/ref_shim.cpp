@@ -110,8 +110,15 @@ static int refine_nodes_t(VectorIndex* idx, int first, int num, int cef, int nei
     for (int i = 0; i < num; ++i) {
         const int node = first + i;
         COMMON::QueryResultSet<T> query((const T*)idx->GetSample(node), k);
+        void* rec_query = nullptr;
+        if (idx->m_pQuantizer) {  // RefineNode on a quantized index (NeighborhoodGraph.h:538-543), verbatim
+            rec_query = ALIGN_ALLOC(idx->m_pQuantizer->ReconstructSize());
+            idx->m_pQuantizer->ReconstructVector((const uint8_t*)query.GetTarget(), rec_query);
+            query.SetTarget((T*)rec_query, idx->m_pQuantizer);
+        }
         idx->RefineSearchIndex(query, false);
         rng.RebuildNeighbors(idx, node, out_graph + (size_t)i * neighborhood, query.GetResults(), k);
+        if (rec_query) ALIGN_FREE(rec_query);
         for (int j = 0; j < k; ++j) {
             if (res_ids) res_ids[(size_t)i * k + j] = query.GetResult(j)->VID;
             if (res_dists) res_dists[(size_t)i * k + j] = query.GetResult(j)->Dist;
@@ -248,6 +255,12 @@ void ref_quantizer_encode(void* q, const void* raw, int nvec, unsigned char* out
     const size_t rs = quant->ReconstructSize(), m = quant->GetNumSubvectors();
 #pragma omp parallel for
     for (int i = 0; i < nvec; ++i) quant->QuantizeVector((const std::uint8_t*)raw + i * rs, out + i * m, false);
+}
+// IQuantizer::ReconstructVector: M code bytes -> ReconstructSize() bytes of the reconstruct type
+void ref_quantizer_reconstruct(void* q, const unsigned char* codes, int nvec, void* out) {
+    auto& quant = *(std::shared_ptr<COMMON::IQuantizer>*)q;
+    const size_t rs = quant->ReconstructSize(), m = quant->GetNumSubvectors();
+    for (int i = 0; i < nvec; ++i) quant->ReconstructVector(codes + i * m, (std::uint8_t*)out + i * rs);
 }
 // IQuantizer::L2Distance on two code vectors (SDC table lookups when ADC is off, PQQuantizer.h:110-128)
 float ref_quantizer_l2(void* q, const unsigned char* a, const unsigned char* b) {

@@ -356,6 +356,39 @@ void ora_quantizer_encode(const ora_quantizer* q, const void* raw, int32_t n, ui
     }
 }
 
+/* IQuantizer::ReconstructVector for one code row.
+ * PQQuantizer<T>::ReconstructVector (PQQuantizer.h:196-205): the codewords, copied.
+ * OPQQuantizer<T>::ReconstructVector (OPQQuantizer.h:124-131): the float codewords, then
+ * m_VectorMatrixMultiply<T>(m_OPQMatrix, pre, out): out[i] = (T)(m_base - m_fdot(pre, row_i of m_OPQMatrix)), m_base = 1,
+ * m_fdot = float cosine distance (OPQQuantizer.h:198-206); the (T) cast is C's truncation toward zero. */
+static void reconstruct_one(const ora_quantizer* q, const uint8_t* code, void* out, float* tmp /* dim */)
+{
+    const int m = q->m, ks = q->ks, d = q->dsub, dim = m * d;
+    float* pre = (q->qtype == ORA_Q_OPQ) ? tmp : (float*)out; /* PQ is restated for float codebooks only */
+    for (int i = 0; i < m; i++)
+        memcpy(pre + (size_t)i * d, q->codebooks + ((size_t)i * ks + code[i]) * d, sizeof(float) * (size_t)d);
+    if (q->qtype != ORA_Q_OPQ) return;
+    for (int i = 0; i < dim; i++) {
+        const float v = 1 - dist_f32(1, q->simd_width, pre, q->rotation + (size_t)i * dim, dim);
+        switch (q->rtype) {
+        case ORA_INT8: ((int8_t*)out)[i] = (int8_t)(int32_t)v; break;
+        case ORA_UINT8: ((uint8_t*)out)[i] = (uint8_t)(int32_t)v; break;
+        case ORA_INT16: ((int16_t*)out)[i] = (int16_t)(int32_t)v; break;
+        default: ((float*)out)[i] = v; break;
+        }
+    }
+}
+
+void ora_quantizer_reconstruct(const ora_quantizer* q, const uint8_t* codes, int32_t n, void* out)
+{
+    static const size_t elem[4] = {1, 1, 2, 4};
+    const int dim = q->m * q->dsub;
+    const size_t rs = elem[q->rtype] * (size_t)dim;
+    float* tmp = (float*)malloc(sizeof(float) * (size_t)dim);
+    for (int32_t i = 0; i < n; i++) reconstruct_one(q, codes + (size_t)i * q->m, (char*)out + (size_t)i * rs, tmp);
+    free(tmp);
+}
+
 float ora_quantizer_l2(const ora_quantizer* q, const uint8_t* x, const uint8_t* y)
 {
     float out = 0;
@@ -918,7 +951,6 @@ int ora_search_batch(const ora_index* idx, const void* queries, int32_t nq, int3
         }
         free(res);
         free(qcode);
-        free(qtable);
         free(qtmp);
         ws_free(&ws);
     }
@@ -971,7 +1003,12 @@ int ora_refine_nodes(const ora_index* idx, int32_t first_node, int32_t num_nodes
 {
     static const size_t elem[4] = {1, 1, 2, 4};
     const size_t row_bytes = elem[idx->value_type] * (size_t)idx->dim;
-    if (idx->quantizer || idx->filter) return 1; /* quantized refine (reconstruct + re-quantize) is not restated */
+    const ora_quantizer* quant = idx->quantizer;
+    if (idx->filter) return 1;
+    if (quant && (idx->tree_kind != ORA_BKT || (quant->qtype == ORA_Q_PQ && quant->rtype != ORA_FLOAT))) return 1;
+    /* with ADC on, the reference's RebuildNeighbors passes two code rows to the ADC branch of L2Distance, which reads the
+     * first as a float table (out of bounds, PQQuantizer.h:114-119): not a defined operation, not restated */
+    if (quant && quant->enable_adc) return 1;
     if (first_node < 0 || num_nodes < 0 || first_node + num_nodes > idx->n || cef < 1 || neighborhood < 1) return 1;
     const int k = cef + 1;
     const int alloc_check = idx->max_check > idx->max_check_refine ? idx->max_check : idx->max_check_refine;
@@ -985,10 +1022,21 @@ int ora_refine_nodes(const ora_index* idx, int32_t first_node, int32_t num_nodes
         ws_t ws;
         ws_init(&ws, idx->n, alloc_check);
         res_t* res = (res_t*)malloc(sizeof(res_t) * (size_t)k);
+        /* quantized index (NeighborhoodGraph.h:538-543): the node's code row is reconstructed, and SetTarget quantizes
+         * the reconstruction again -- that, not the stored row, is what the search uses */
+        const int qdim = quant ? quant->m * quant->dsub : 0;
+        void* rec = quant ? malloc(4 * (size_t)qdim) : NULL;
+        uint8_t* qcode = quant ? (uint8_t*)malloc((size_t)quant->m) : NULL;
+        float* qtmp = quant ? (float*)malloc(sizeof(float) * 2 * (size_t)qdim) : NULL;
 #pragma omp for schedule(dynamic, 10)
         for (int32_t i = 0; i < num_nodes; i++) {
             const int32_t node = first_node + i;
             qctx_t c = {idx, (const char*)idx->vectors + (size_t)node * row_bytes, row_bytes, idx->metric != ORA_L2};
+            if (quant) {
+                reconstruct_one(quant, (const uint8_t*)c.query, rec, qtmp);
+                quantize_one(quant, rec, qcode, qtmp);
+                c.query = qcode;
+            }
             for (int j = 0; j < k; j++) {
                 res[j].vid = -1;
                 res[j].dist = kMaxDist();
@@ -1005,6 +1053,9 @@ int ora_refine_nodes(const ora_index* idx, int32_t first_node, int32_t num_nodes
                 for (int j = 0; j < k; j++) res_dists[(size_t)i * k + j] = res[j].dist;
         }
         free(res);
+        free(rec);
+        free(qcode);
+        free(qtmp);
         ws_free(&ws);
     }
     return 0;

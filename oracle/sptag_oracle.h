@@ -92,6 +92,8 @@ void ora_distance_f32_many(int32_t metric, int32_t simd_width, const float* a, c
 void ora_quantizer_init(ora_quantizer* q);
 /* IQuantizer::QuantizeVector(vec, out, ADC=false): n raw vectors -> n x m code bytes */
 void ora_quantizer_encode(const ora_quantizer* q, const void* raw, int32_t n, uint8_t* out);
+/* IQuantizer::ReconstructVector (PQQuantizer.h:196-205, OPQQuantizer.h:124-131): n code rows -> n raw vectors of rtype */
+void ora_quantizer_reconstruct(const ora_quantizer* q, const uint8_t* codes, int32_t n, void* out);
 /* PQQuantizer::L2Distance with ADC off (SDC table sum, PQQuantizer.h:110-128) */
 float ora_quantizer_l2(const ora_quantizer* q, const uint8_t* x, const uint8_t* y);
 

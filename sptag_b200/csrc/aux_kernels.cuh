@@ -191,6 +191,87 @@ __global__ void pq_quantize_kernel(const unsigned char* __restrict__ raw, int ra
     }
 }
 
+// IQuantizer::ReconstructVector for a batch of code rows: one CTA per row (NeighborhoodGraph::RefineNode on a quantized
+// index reconstructs the node's row and lets SetTarget quantize the reconstruction again, NeighborhoodGraph.h:538-543).
+//   PQQuantizer<float> (PQQuantizer.h:196-205): the codewords, copied.
+//   OPQQuantizer<T> (OPQQuantizer.h:124-131): out[i] = (T)(m_base - m_fdot(pre, row i of m_OPQMatrix)), m_base = 1,
+//   m_fdot = float cosine distance (:198-206); (T) = the C cast (truncation toward zero).
+// raw_type: 0 int8, 1 uint8, 2 int16, 3 float.  out rows are packed (dim elements of the reconstruct type).
+__global__ void pq_reconstruct_kernel(const unsigned char* __restrict__ codes, unsigned long long code_stride_bytes, int nvec,
+                                      const float* __restrict__ codebooks, const float* __restrict__ rotation, int m,
+                                      int ks, int dsub, int raw_type, unsigned char* __restrict__ out) {
+    extern __shared__ float qsm[];  // pre[dim]
+    const int dim = m * dsub;
+    const int v = blockIdx.x;
+    if (v >= nvec) return;
+    const unsigned char* code = codes + (size_t)v * code_stride_bytes;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+        const int sv = i / dsub, e = i - sv * dsub;
+        qsm[i] = codebooks[((size_t)sv * ks + code[sv]) * dsub + e];
+    }
+    __syncthreads();
+    const size_t esize = (raw_type == 3) ? 4 : (raw_type == 2 ? 2 : 1);
+    unsigned char* dst = out + (size_t)v * dim * esize;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+        float f = qsm[i];
+        if (rotation != nullptr) f = __fsub_rn(1.0f, exact_dist_thread<true>(qsm, rotation + (size_t)i * dim, dim));
+        switch (raw_type) {
+        case 0: reinterpret_cast<signed char*>(dst)[i] = (signed char)(__float2int_rz(f) & 0xff); break;
+        case 1: dst[i] = (unsigned char)(__float2int_rz(f) & 0xff); break;
+        case 2: reinterpret_cast<short*>(dst)[i] = (short)(__float2int_rz(f) & 0xffff); break;
+        default: reinterpret_cast<float*>(dst)[i] = f; break;
+        }
+    }
+}
+
+// RebuildNeighbors on a quantized index: ComputeDistance(kept row, candidate row) is the quantizer's L2Distance on two
+// code rows -- the SDC table sum in sub-vector order with one float accumulator (PQQuantizer.h:120-127).  One warp per
+// node; lane k tests the candidate against kept neighbour k (32 kept rows per pass), any rejection drops it -- the
+// reference's loop with its early exit is the same predicate.
+__global__ void __launch_bounds__(128) rebuild_neighbors_pq_kernel(const unsigned char* __restrict__ codes,
+                                                                   unsigned long long row_stride_bytes, int m, int ks,
+                                                                   const float* __restrict__ sdc, int first_node,
+                                                                   int num_nodes, const int* __restrict__ res_ids,
+                                                                   const float* __restrict__ res_dists, int num_results,
+                                                                   int neighborhood, float rng_factor,
+                                                                   int* __restrict__ out_graph) {
+    extern __shared__ int kept_sm[];  // neighborhood ints per warp
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (w >= num_nodes) return;
+    int* kept = kept_sm + warp * neighborhood;
+    const int node = first_node + (int)w;
+    const int* ids = res_ids + (size_t)w * num_results;
+    const float* ds = res_dists + (size_t)w * num_results;
+    int count = 0;
+    for (int r = 0; r < num_results && count < neighborhood; ++r) {
+        const int vid = ids[r];
+        if (vid < 0) break;
+        if (vid == node) continue;
+        const float dist = ds[r];
+        const unsigned char* cand = codes + (size_t)vid * row_stride_bytes;
+        bool good = true;
+        for (int k0 = 0; k0 < count && good; k0 += 32) {
+            bool reject = false;
+            if (k0 + lane < count) {
+                const unsigned char* row = codes + (size_t)kept[k0 + lane] * row_stride_bytes;
+                float acc = 0.0f;
+                for (int i = 0; i < m; ++i)
+                    acc = __fadd_rn(acc, __ldg(sdc + ((size_t)i * ks + row[i]) * ks + cand[i]));
+                reject = __fmul_rn(rng_factor, acc) < dist;
+            }
+            if (__any_sync(kFull, reject)) good = false;
+        }
+        if (good) {
+            if (lane == 0) kept[count] = vid;
+            ++count;
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    for (int t = lane; t < neighborhood; t += 32) out_graph[(size_t)w * neighborhood + t] = (t < count) ? kept[t] : -1;
+}
+
 // ------------------------------------------------------------------------------------------
 // k-way merge of per-shard top-k lists (QueryResultSet.h:17-26 comparator): one thread per query
 // ------------------------------------------------------------------------------------------

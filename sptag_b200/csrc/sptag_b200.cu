@@ -109,7 +109,8 @@ struct sptag_b200_index {
     // PQ / OPQ quantizer (null when q_type == 0)
     int q_type = 0, q_rtype = SPTAG_B200_VT_FLOAT, q_m = 0, q_ks = 0, q_dsub = 0;
     int q_adc = 0;  // IQuantizer::SetEnableADC (not serialized by the reference either)
-    DeviceBuffer d_codebooks, d_rotation_t, d_sdc, d_raw;
+    DeviceBuffer d_codebooks, d_rotation_t, d_rotation, d_sdc, d_raw;
+    DeviceBuffer d_rec;  // refine on a quantized index: the batch's reconstructed rows
     // scratch
     // Everything a search launch writes besides its outputs.  Two sets: a launch normally takes set 0; when set 0 is
     // still busy with a launch from ANOTHER stream the new launch takes set 1 (allocated on first use), so two batches
@@ -795,6 +796,8 @@ void sptag_b200_destroy(sptag_b200_handle h) {
     h->d_graph_new.release();
     h->d_codebooks.release();
     h->d_rotation_t.release();
+    h->d_rotation.release();
+    h->d_rec.release();
     h->d_sdc.release();
     h->d_raw.release();
     for (auto& sc : h->scratch) {
@@ -999,6 +1002,9 @@ int sptag_b200_set_quantizer(sptag_b200_handle h, const void* blob, int64_t blob
             }
         if (int rc = h->d_rotation_t.ensure(dim * dim * 4)) return rc;
         CUDA_OK(cudaMemcpy(h->d_rotation_t.ptr, rt.data(), dim * dim * 4, cudaMemcpyHostToDevice));
+        // m_OPQMatrix as stored: the rows ReconstructVector multiplies with (OPQQuantizer.h:124-131)
+        if (int rc = h->d_rotation.ensure(dim * dim * 4)) return rc;
+        CUDA_OK(cudaMemcpy(h->d_rotation.ptr, rot, dim * dim * 4, cudaMemcpyHostToDevice));
     }
     // InitializeDistanceTables (PQQuantizer.h:333-348) on the device, same summation tree as the reference
     const size_t entries = (size_t)m * ks * ks;
@@ -1214,8 +1220,10 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
                             int32_t neighborhood_size, float rng_factor, int32_t* out_graph, int32_t* out_res_ids,
                             float* out_res_dists, int32_t install) {
     if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
-    if (h->q_type != 0)
-        return fail(SPTAG_B200_LACK_OF_INPUTS, "refine on a quantized index (reconstruct + re-quantize) is not built");
+    const bool pq = (h->q_type != 0);
+    if (pq && h->q_adc)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "refine on a quantized index with ADC on: the reference's RebuildNeighbors reads a "
+                                              "code row as a distance table there (PQQuantizer.h:114-119); turn ADC off");
     if (first_node < 0 || num_nodes < 0 || (long long)first_node + num_nodes > h->n)
         return fail(SPTAG_B200_LACK_OF_INPUTS, "node range [%d, %d) outside the index", first_node, first_node + num_nodes);
     if (cef < 1 || cef + 1 > 2048) return fail(SPTAG_B200_LACK_OF_INPUTS, "CEF = %d outside [1, 2047]", cef);
@@ -1240,10 +1248,30 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
     h->refine_search_ms = h->refine_rebuild_ms = 0.0;
     const unsigned char* dv = (const unsigned char*)h->d_vectors.ptr;
     const bool l2 = (h->metric == SPTAG_B200_METRIC_L2);
+    if (pq) {
+        // RefineNode on a quantized index (NeighborhoodGraph.h:538-543): the query is NOT the stored code row but what
+        // SetTarget makes of its reconstruction, so each batch is reconstructed into packed raw vectors and goes through
+        // the ordinary raw-query path of search_device_impl (QuantizeVector on the device)
+        ropts.refine_query_stride = 0;
+        if (int rc2 = h->d_rec.ensure((size_t)batch * query_bytes(h))) return rc2;
+    }
     for (int done = 0; done < num_nodes && rc == SPTAG_B200_SUCCESS; done += batch) {
         const int nb = std::min(batch, num_nodes - done);
         const int first = first_node + done;
-        rc = search_device_impl(h, dv + (size_t)first * h->row_stride, nb, k, (int*)h->d_ids.ptr, (float*)h->d_dists.ptr,
+        const unsigned char* queries = dv + (size_t)first * h->row_stride;
+        if (pq) {
+            const size_t rsmem = (size_t)h->q_m * h->q_dsub * sizeof(float);
+            if (rsmem > 48 * 1024)
+                CUDA_OK(cudaFuncSetAttribute(pq_reconstruct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+            pq_reconstruct_kernel<<<nb, 128, rsmem, stream>>>(queries, h->row_stride, nb, (const float*)h->d_codebooks.ptr,
+                                                            h->q_type == 2 ? (const float*)h->d_rotation.ptr : nullptr,
+                                                            h->q_m, h->q_ks, h->q_dsub, h->q_rtype,
+                                                            (unsigned char*)h->d_rec.ptr);
+            g_launches++;
+            CUDA_OK(cudaGetLastError());
+            queries = (const unsigned char*)h->d_rec.ptr;
+        }
+        rc = search_device_impl(h, queries, nb, k, (int*)h->d_ids.ptr, (float*)h->d_dists.ptr,
                                 nullptr, stream, /*refine=*/true, ropts);
         if (rc) break;
         const int warps_per_block = 4;
@@ -1254,7 +1282,11 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
     rebuild_neighbors_kernel<COS, EL><<<blocks, warps_per_block * 32, smem, stream>>>(                                   \
         dv, h->row_stride, h->dim, first, nb, (const int*)h->d_ids.ptr, (const float*)h->d_dists.ptr, k,                 \
         neighborhood_size, rng_factor, rows, h->simd_width)
-        if (h->value_type == SPTAG_B200_VT_FLOAT) {
+        if (pq) {
+            rebuild_neighbors_pq_kernel<<<blocks, warps_per_block * 32, smem, stream>>>(
+                dv, h->row_stride, h->q_m, h->q_ks, (const float*)h->d_sdc.ptr, first, nb, (const int*)h->d_ids.ptr,
+                (const float*)h->d_dists.ptr, k, neighborhood_size, rng_factor, rows);
+        } else if (h->value_type == SPTAG_B200_VT_FLOAT) {
             if (l2) SPTAG_B200_RB(false, 0); else SPTAG_B200_RB(true, 0);
         } else if (h->value_type == SPTAG_B200_VT_INT8) {
             if (l2) SPTAG_B200_RB(false, 1); else SPTAG_B200_RB(true, 1);

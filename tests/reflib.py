@@ -72,6 +72,7 @@ def ref():
         L.ref_quantizer_m.argtypes = [C.c_void_p]
         L.ref_quantizer_reconstruct_dim.argtypes = [C.c_void_p]
         L.ref_quantizer_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_quantizer_reconstruct.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_quantizer_l2.restype = C.c_float
         L.ref_quantizer_l2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_set_adc.argtypes = [C.c_void_p, C.c_int]
@@ -461,6 +462,12 @@ class RefQuantizer:
         b = np.ascontiguousarray(b, np.uint8)
         return ref().ref_quantizer_l2(self.h, a.ctypes.data, b.ctypes.data)
 
+    def reconstruct(self, codes, dtype):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        out = np.empty((codes.shape[0], self.dim), dtype)
+        ref().ref_quantizer_reconstruct(self.h, codes.ctypes.data, codes.shape[0], out.ctypes.data)
+        return out
+
 
 # ------------------------------------------------------------------------------------------------
 # C restatement
@@ -499,6 +506,12 @@ class OracleQuantizer:
         b = np.ascontiguousarray(b, np.uint8)
         return ora().ora_quantizer_l2(C.byref(self.struct), a.ctypes.data, b.ctypes.data)
 
+    def reconstruct(self, codes, dtype):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        out = np.empty((codes.shape[0], self.q.dim), dtype)
+        ora().ora_quantizer_reconstruct(C.byref(self.struct), codes.ctypes.data, codes.shape[0], out.ctypes.data)
+        return out
+
 
 class _OraIndex(C.Structure):
     _fields_ = [("n", C.c_int32), ("dim", C.c_int32), ("value_type", C.c_int32), ("metric", C.c_int32),
@@ -536,6 +549,7 @@ def ora():
         L.ora_iter_next_from_nearest.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.ora_quantizer_init.argtypes = [C.POINTER(_OraQuantizer)]
         L.ora_quantizer_encode.argtypes = [C.POINTER(_OraQuantizer), C.c_void_p, C.c_int32, C.c_void_p]
+        L.ora_quantizer_reconstruct.argtypes = [C.POINTER(_OraQuantizer), C.c_void_p, C.c_int32, C.c_void_p]
         L.ora_quantizer_l2.restype = C.c_float
         L.ora_quantizer_l2.argtypes = [C.POINTER(_OraQuantizer), C.c_void_p, C.c_void_p]
         _ora = L

@@ -27,6 +27,12 @@ CASES = [
     ("bkt_i16_l2_4k_27", 40, 512, 400),
     ("bkt_i16_cos_5k_40", 40, 512, 400),
     ("kdt_i16_l2_5k_32", 40, 512, 400),
+    # quantized indexes (NeighborhoodGraph.h:538-543): reconstruct the node's code row, quantize the reconstruction again,
+    # search with that, RebuildNeighbors through the quantizer's SDC distance
+    ("bkt_pq_6k_32", 64, 1024, 400),
+    ("bkt_opq_6k_48", 100, 2048, 400),
+    ("bkt_opq_i8_8k_100", 40, 512, 400),
+    ("bkt_opq_i8_8k_100", 1000, 8192, 200),   # K = 1001: the result set in HBM
 ]
 
 
@@ -166,6 +172,7 @@ def test_refine_argument_errors():
         idx.close()
     q = B200Index.load(data_folder("bkt_pq_6k_32"))
     try:
+        q.set_param("EnableADC", 1)   # the reference's RebuildNeighbors is undefined with ADC on (reads a code row as a table)
         with pytest.raises(capi.SptagB200Error):
             q.refine_graph(10)
     finally:

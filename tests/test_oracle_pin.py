@@ -261,6 +261,9 @@ def test_quantizer_bit_exact_vs_reference(oracle_lib, tmp_path, opq, rtype):
     dr = np.array([rq.l2(cr[i], cr[i + 1]) for i in range(500)], np.float32)
     do = np.array([oq.l2(co[i], co[i + 1]) for i in range(500)], np.float32)
     assert np.array_equal(dr.view(np.int32), do.view(np.int32))   # SDC table sum
+    rr, ro = rq.reconstruct(cr, xs.dtype), oq.reconstruct(co, xs.dtype)
+    assert np.array_equal(rr.view(np.uint8), ro.view(np.uint8))   # ReconstructVector (incl. the OPQ back-rotation + cast)
+    assert np.array_equal(rq.encode(rr), oq.encode(ro))           # ... and what RefineNode makes of it (SetTarget)
 
 
 @needs_ref
@@ -390,6 +393,31 @@ def test_filtered_search_bit_exact_vs_reference(oracle_lib, name):
 def test_refine_bit_exact_vs_reference(oracle_lib, name, cef, mcr):
     """NeighborhoodGraph::RefineNode per node on the loaded index (RefineSearchIndex + RebuildNeighbors run by the
     reference itself) against the oracle's restatement."""
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    r = reflib.RefIndex.load(folder)
+    r.set_param("MaxCheckForRefineGraph", mcr)
+    o = reflib.OracleIndex(files)
+    o.max_check_refine = mcr
+    num = min(files.n, 300)
+    first = files.n // 3
+    for nbh, factor in [(files.degree, 1.0), (12, 1.3)]:
+        rows_r, ids_r, d_r = r.refine_nodes(first, num, cef, nbh, factor, threads=4)
+        rows_o, ids_o, d_o = o.refine_nodes(first, num, cef, nbh, factor, threads=4)
+        assert np.array_equal(ids_r, ids_o), name
+        assert np.array_equal(d_r.view(np.int32), d_o.view(np.int32)), name
+        assert np.array_equal(rows_r, rows_o), name
+
+
+@needs_ref
+@pytest.mark.parametrize("name,cef,mcr", [("bkt_pq_6k_32", 64, 1024), ("bkt_opq_6k_48", 100, 2048),
+                                          ("bkt_opq_i8_8k_100", 40, 512)])
+def test_quantized_refine_bit_exact_vs_reference(oracle_lib, name, cef, mcr):
+    """RefineNode on a quantized index (NeighborhoodGraph.h:538-543): the node's code row is reconstructed, SetTarget
+    quantizes the reconstruction again, RefineSearchIndex runs on that and RebuildNeighbors compares code rows through
+    the quantizer's distance -- the reference itself against the oracle's restatement.  (ADC off, as at build time:
+    with SetQuantizerADC(true) the reference's RebuildNeighbors hands two CODE rows to the ADC branch of L2Distance,
+    which reads the first one as a float table -- out of bounds; neither the oracle nor the device offers that.)"""
     folder = data_folder(name)
     files = reflib.IndexFiles(folder)
     r = reflib.RefIndex.load(folder)
