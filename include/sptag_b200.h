@@ -209,10 +209,22 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
  * is sptag_b200_refine_graph(install = 1) (deterministic double-buffered form, see there).  The index's graph ends with
  * (int)((int)(neighborhood_size * neighborhood_scale) / neighborhood_scale) columns.  The reference's defaults
  * (BKT/ParameterDefinitionList.h): RefineIterations 2, CEF 1000, GraphCEFScale 2, NeighborhoodSize 32,
- * GraphNeighborhoodScale 2, RNGFactor 1.  RebuildGraph's in-degree repair (EnableRebuild, default off; its result
- * depends on OpenMP thread timing in the reference) is not part of it. */
+ * GraphNeighborhoodScale 2, RNGFactor 1.  With EnableRebuild the reference runs the schedule on rows twice as wide
+ * (NeighborhoodGraph.h:369) and calls RebuildGraph afterwards: pass 2 x NeighborhoodSize here, then
+ * sptag_b200_rebuild_graph. */
 int sptag_b200_refine_schedule(sptag_b200_handle h, int32_t refine_iterations, int32_t cef, float cef_scale,
                                int32_t neighborhood_size, float neighborhood_scale, float rng_factor);
+
+/* Replaces: NeighborhoodGraph::RebuildGraph(index) (NeighborhoodGraph.h:404-456), the in-degree repair BuildGraph runs
+ * after its refine passes when EnableRebuild is set (:388-391).  The index's graph rows must hold 2 x N candidates
+ * (current degree even, N = degree / 2): the first N / 2 stay, the other slots are refilled from entries [N / 2, 2 N) --
+ * first those whose target has an in-degree below N / 2, then the earliest others -- in index order, the in-degree array
+ * following every change.  The reference's node loop updates that array from all OpenMP threads without synchronisation,
+ * so its result depends on thread timing; this call computes its single-thread order (node 0, 1, 2, ...), which is
+ * sequential by construction (one warp walks the nodes).
+ * out_graph (host, nullable): [n x N] new rows.  install != 0: the rows replace the index's graph (degree becomes N;
+ * duplicate-group back-pointers are re-attached to the last slot, NeighborhoodGraph.h:395-401). */
+int sptag_b200_rebuild_graph(sptag_b200_handle h, int32_t* out_graph, int32_t install);
 
 /* Replaces: VectorIndex::RefineSearchIndex(QueryResult&, bool p_searchDeleted) (VectorIndex.h:53, BKTIndex.cpp:698-711,
  * KDTIndex.cpp:367-390) for a batch of arbitrary query vectors in HOST memory (element type of the index): the search

@@ -329,6 +329,34 @@ int ref_search_filtered(void* h, const void* queries, int nq, long long stride_b
     return bad;
 }
 
+// NeighborhoodGraph::RebuildGraph (NeighborhoodGraph.h:404-456) run by the reference itself on a graph handed in as
+// [n x stride] rows (2 x neighborhood candidates each), single-threaded: the reference's loop updates its in-degree array
+// from every OpenMP thread without synchronisation, so only its one-thread order is a function of the input.
+// h: a loaded index with n samples (RebuildGraph ends with a GraphAccuracyEstimation log line that reads them).
+int ref_rebuild_graph(void* h, int* graph, int n, int stride, int neighborhood) {
+    auto& idx = ((RefHandle*)h)->index;
+    if (idx->GetNumSamples() != n) return 1;
+    std::vector<char> mem(sizeof(SizeType) + sizeof(DimensionType) + (size_t)n * stride * sizeof(SizeType));
+    *(SizeType*)mem.data() = n;
+    *(DimensionType*)(mem.data() + sizeof(SizeType)) = stride;
+    memcpy(mem.data() + sizeof(SizeType) + sizeof(DimensionType), graph, (size_t)n * stride * sizeof(SizeType));
+    COMMON::RelativeNeighborhoodGraph g;
+    if (g.LoadGraph(mem.data(), idx->m_iDataBlockSize, idx->m_iDataCapacity) != ErrorCode::Success) return 1;
+    g.m_iNeighborhoodSize = neighborhood;  // BuildGraph halves it before the call (NeighborhoodGraph.h:388-390)
+    const int before = omp_get_max_threads();
+    omp_set_num_threads(1);
+    switch (idx->GetVectorValueType()) {
+    case VectorValueType::Float: g.RebuildGraph<float>(idx.get()); break;
+    case VectorValueType::Int8: g.RebuildGraph<std::int8_t>(idx.get()); break;
+    case VectorValueType::UInt8: g.RebuildGraph<std::uint8_t>(idx.get()); break;
+    case VectorValueType::Int16: g.RebuildGraph<std::int16_t>(idx.get()); break;
+    default: omp_set_num_threads(before); return 1;
+    }
+    omp_set_num_threads(before);
+    for (int i = 0; i < n; ++i) memcpy(graph + (size_t)i * stride, g[i], (size_t)stride * sizeof(SizeType));
+    return 0;
+}
+
 int ref_refine_nodes(void* h, int first, int num, int cef, int neighborhood, float rng_factor, int threads,
                      int* out_graph, int* res_ids, float* res_dists) {
     auto& idx = ((RefHandle*)h)->index;

@@ -397,6 +397,54 @@ float ora_quantizer_l2(const ora_quantizer* q, const uint8_t* x, const uint8_t* 
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* NeighborhoodGraph::RebuildGraph (NeighborhoodGraph.h:404-456), the in-degree repair that BuildGraph runs after its
+ * refine passes when EnableRebuild is set: rows hold 2 x neighborhood candidates (row stride `stride` >= that); the first
+ * neighborhood/2 stay, the other neighborhood/2 slots are refilled from entries [neighborhood/2, 2 x neighborhood) --
+ * first the ones whose target has an in-degree below neighborhood/2, then the earliest others -- in index order, the
+ * in-degree array following every change.  The reference runs the node loop under OpenMP without synchronising the
+ * in-degree array (its result depends on thread timing); this is its single-thread order, node by node.            */
+/* ------------------------------------------------------------------------------------------ */
+int ora_rebuild_graph(int32_t* graph, int32_t n, int32_t stride, int32_t neighborhood)
+{
+    if (n < 0 || neighborhood < 2 || stride < 2 * neighborhood) return 1;
+    int32_t* indegree = (int32_t*)calloc((size_t)(n > 0 ? n : 1), sizeof(int32_t));
+    uint8_t* reserve = (uint8_t*)malloc((size_t)2 * neighborhood);
+    for (int32_t i = 0; i < n; i++) {
+        const int32_t* outnodes = graph + (size_t)i * stride;
+        for (int32_t j = 0; j < neighborhood; j++)
+            if (outnodes[j] >= 0) indegree[outnodes[j]]++;
+    }
+    const int rebuild_threshold = neighborhood / 2;
+    const int rebuildstart = neighborhood / 2;
+    for (int32_t i = 0; i < n; i++) {
+        int32_t* outnodes = graph + (size_t)i * stride;
+        memset(reserve, 0, (size_t)2 * neighborhood);
+        int total = 0;
+        for (int32_t j = rebuildstart; j < neighborhood * 2; j++)
+            if (outnodes[j] >= 0 && indegree[outnodes[j]] < rebuild_threshold) {
+                reserve[j] = 1;
+                total++;
+            }
+        for (int32_t j = rebuildstart; j < neighborhood * 2 && total < neighborhood - rebuildstart; j++) {
+            if (!reserve[j]) {
+                reserve[j] = 1;
+                total++;
+            }
+        }
+        for (int32_t j = rebuildstart, z = rebuildstart; j < neighborhood; j++) {
+            while (!reserve[z]) z++;
+            if (outnodes[j] >= 0) indegree[outnodes[j]] = indegree[outnodes[j]] - 1;
+            if (outnodes[z] >= 0) indegree[outnodes[z]] = indegree[outnodes[z]] + 1;
+            outnodes[j] = outnodes[z];
+            z++;
+        }
+    }
+    free(reserve);
+    free(indegree);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* Heap<NodeDistPair>  (Heap.h:13-106, SearchResult.h:11-27)                                   */
 /* ------------------------------------------------------------------------------------------ */
 

@@ -92,6 +92,10 @@ void ora_distance_f32_many(int32_t metric, int32_t simd_width, const float* a, c
 void ora_quantizer_init(ora_quantizer* q);
 /* IQuantizer::QuantizeVector(vec, out, ADC=false): n raw vectors -> n x m code bytes */
 void ora_quantizer_encode(const ora_quantizer* q, const void* raw, int32_t n, uint8_t* out);
+/* NeighborhoodGraph::RebuildGraph (NeighborhoodGraph.h:404-456) in its single-thread order, in place: graph is
+ * [n x stride] with 2*neighborhood candidates per row; afterwards the first `neighborhood` entries of a row are its
+ * neighbours.  Returns 0. */
+int ora_rebuild_graph(int32_t* graph, int32_t n, int32_t stride, int32_t neighborhood);
 /* IQuantizer::ReconstructVector (PQQuantizer.h:196-205, OPQQuantizer.h:124-131): n code rows -> n raw vectors of rtype */
 void ora_quantizer_reconstruct(const ora_quantizer* q, const uint8_t* codes, int32_t n, void* out);
 /* PQQuantizer::L2Distance with ADC off (SDC table sum, PQQuantizer.h:110-128) */

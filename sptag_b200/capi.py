@@ -28,7 +28,7 @@ EXPORTS = [
     "sptag_b200_algo", "sptag_b200_last_error", "sptag_b200_refine_graph", "sptag_b200_get_graph",
     "sptag_b200_graph_degree", "sptag_b200_iterator_open", "sptag_b200_iterator_next", "sptag_b200_iterator_close",
     "sptag_b200_iterator_next_from_nearest", "sptag_b200_search_ex", "sptag_b200_iterator_open_ex",
-    "sptag_b200_refine_search", "sptag_b200_refine_schedule", "sptag_b200_group_create", "sptag_b200_group_search",
+    "sptag_b200_refine_search", "sptag_b200_refine_schedule", "sptag_b200_rebuild_graph", "sptag_b200_group_create", "sptag_b200_group_search",
     "sptag_b200_group_destroy",
 ]
 
@@ -78,6 +78,7 @@ def lib():
         L.sptag_b200_iterator_open_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
         L.sptag_b200_refine_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.sptag_b200_refine_schedule.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_float]
+        L.sptag_b200_rebuild_graph.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.sptag_b200_group_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]
         L.sptag_b200_group_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.sptag_b200_group_destroy.argtypes = [C.c_void_p]
@@ -269,6 +270,13 @@ class B200Index:
         """NeighborhoodGraph::RefineGraph (NeighborhoodGraph.h:460-492) on the device; the graph is replaced in place."""
         _check(lib().sptag_b200_refine_schedule(self._h, refine_iterations, cef, cef_scale, neighborhood,
                                                 neighborhood_scale, rng_factor))
+
+    def rebuild_graph(self, install=False):
+        """NeighborhoodGraph::RebuildGraph (EnableRebuild's in-degree repair, NeighborhoodGraph.h:404-456) in its
+        single-thread order; the index's rows must hold 2 x N candidates.  -> new rows [n, N]."""
+        rows = np.empty((self.num_vectors, self.graph_degree // 2), np.int32)
+        _check(lib().sptag_b200_rebuild_graph(self._h, rows.ctypes.data, 1 if install else 0))
+        return rows
 
     @property
     def graph_degree(self):

@@ -114,6 +114,82 @@ __global__ void carry_backpointers_kernel(const int* __restrict__ old_graph, int
 }
 
 // ------------------------------------------------------------------------------------------
+// NeighborhoodGraph::RebuildGraph (NeighborhoodGraph.h:404-456): EnableRebuild's in-degree repair.  Rows hold 2 x ns
+// candidates; the first ns/2 stay; the other ns - ns/2 slots are refilled from entries [ns/2, 2 ns): the ones whose target's
+// in-degree is below ns/2 first, then the earliest others, in index order; the in-degree array follows every change.
+// The reference runs its node loop under OpenMP with an unsynchronised in-degree array, so only its one-thread order is a
+// function of the input; that order is inherently sequential over the nodes (node i's choice depends on what nodes < i
+// did), so ONE warp walks the nodes, lane-parallel inside a row.  Offline, default-off in the reference.
+// Duplicate-group back-pointers (< -1, last slot) are not neighbours: read as -1 here, re-attached by the caller.
+// ------------------------------------------------------------------------------------------
+__global__ void indegree_count_kernel(const int* __restrict__ graph, long long n, int stride, int ns, int* __restrict__ indegree) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * ns) return;
+    const int v = graph[(t / ns) * stride + (t % ns)];
+    if (v >= 0) atomicAdd(&indegree[v], 1);
+}
+
+constexpr int kRebuildMaxChunks = 48;  // (2 ns - ns/2) / 32 chunks: ns <= 1024
+
+__global__ void __launch_bounds__(32) rebuild_graph_kernel(const int* __restrict__ old_graph, int n, int stride, int ns,
+                                                           int* indegree, int* __restrict__ new_graph) {
+    __shared__ unsigned lowmask[kRebuildMaxChunks], validmask[kRebuildMaxChunks];
+    const int lane = threadIdx.x;
+    const unsigned lt = (1u << lane) - 1u;
+    const int start = ns / 2, thr = ns / 2, need = ns - start, span = 2 * ns - start;
+    const int chunks = (span + 31) / 32;
+    for (int i = 0; i < n; ++i) {
+        const int* row = old_graph + (size_t)i * stride;
+        int* out = new_graph + (size_t)i * ns;
+        for (int j = lane; j < start; j += 32) {
+            const int v = row[j];
+            out[j] = v < -1 ? -1 : v;
+        }
+        // which candidates point at a node with a low in-degree (as it is after nodes 0 .. i-1)
+        int c1 = 0;
+        for (int ch = 0; ch < chunks; ++ch) {
+            const int c = ch * 32 + lane;
+            const bool in = c < span;
+            int v = in ? row[start + c] : -1;
+            if (v < -1) v = -1;
+            const bool low = in && v >= 0 && __ldcg(&indegree[v]) < thr;
+            const unsigned lm = __ballot_sync(kFull, low), vm = __ballot_sync(kFull, in);
+            if (lane == 0) {
+                lowmask[ch] = lm;
+                validmask[ch] = vm;
+            }
+            c1 += __popc(lm);
+        }
+        __syncwarp();
+        // the reserved set in index order: the low ones (the first `need` of them), topped up with the earliest others
+        const bool enough = c1 >= need;
+        int remaining = enough ? need : need - c1;  // how many of the rationed class may still be taken
+        int placed = 0;
+        for (int ch = 0; ch < chunks; ++ch) {
+            const unsigned lm = lowmask[ch], vm = validmask[ch];
+            const unsigned rationed = enough ? lm : (vm & ~lm);
+            const int take = min(__popc(rationed), remaining);
+            const bool rat_sel = ((rationed >> lane) & 1u) && (__popc(rationed & lt) < take);
+            const bool sel = enough ? rat_sel : (((lm >> lane) & 1u) || rat_sel);
+            const unsigned sm = __ballot_sync(kFull, sel);
+            remaining -= take;
+            const int c = ch * 32 + lane;
+            int v = (c < span) ? row[start + c] : -1;
+            if (v < -1) v = -1;
+            if (sel) {
+                out[start + placed + __popc(sm & lt)] = v;
+                if (v >= 0) atomicAdd(&indegree[v], 1);
+            }
+            placed += __popc(sm);
+            // the entries this pass overwrites, [start, ns), give their in-degree back
+            if (c < ns - start && v >= 0) atomicSub(&indegree[v], 1);
+        }
+        __threadfence();  // node i + 1 reads the in-degrees this node wrote
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // PQ / OPQ quantizer kernels (query side + tables; PQQuantizer.h:138-180, :333-348, OPQQuantizer.h:96-121)
 // ------------------------------------------------------------------------------------------
 

@@ -1333,6 +1333,48 @@ int sptag_b200_refine_graph(sptag_b200_handle h, int32_t first_node, int32_t num
     return SPTAG_B200_SUCCESS;
 }
 
+int sptag_b200_rebuild_graph(sptag_b200_handle h, int32_t* out_graph, int32_t install) {
+    if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceGuard guard(h->device);
+    const int stride = h->degree, ns = h->degree / 2;
+    if ((h->degree & 1) || ns < 2 || ns > 1024)
+        return fail(SPTAG_B200_LACK_OF_INPUTS, "RebuildGraph needs rows of 2 x N candidates, N in [2, 1024] (degree is %d)", h->degree);
+    const long long n = h->n;
+    DeviceBuffer d_indegree;
+    if (int rc = d_indegree.ensure((size_t)std::max<long long>(n, 1) * 4)) return rc;
+    if (int rc = h->d_graph_new.ensure((size_t)n * ns * 4)) {
+        d_indegree.release();
+        return rc;
+    }
+    cudaStream_t stream = nullptr;
+    cudaError_t e = cudaMemsetAsync(d_indegree.ptr, 0, (size_t)n * 4, stream);
+    if (e == cudaSuccess) {
+        const long long total = n * ns;
+        indegree_count_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const int*)h->d_graph.ptr, n, stride, ns,
+                                                                                  (int*)d_indegree.ptr);
+        rebuild_graph_kernel<<<1, 32, 0, stream>>>((const int*)h->d_graph.ptr, (int)n, stride, ns, (int*)d_indegree.ptr,
+                                                  (int*)h->d_graph_new.ptr);
+        g_launches += 2;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    d_indegree.release();
+    if (e != cudaSuccess) return fail(SPTAG_B200_FAIL, "rebuild graph failed: %s", cudaGetErrorString(e));
+    if (out_graph) CUDA_OK(cudaMemcpy(out_graph, h->d_graph_new.ptr, (size_t)n * ns * 4, cudaMemcpyDeviceToHost));
+    if (install) {
+        carry_backpointers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const int*)h->d_graph.ptr,
+                                                                                   (int*)h->d_graph_new.ptr, h->n, h->degree, ns);
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaStreamSynchronize(stream));
+        std::swap(h->d_graph.ptr, h->d_graph_new.ptr);
+        std::swap(h->d_graph.bytes, h->d_graph_new.bytes);
+        h->degree = ns;
+    }
+    return SPTAG_B200_SUCCESS;
+}
+
 int sptag_b200_refine_schedule(sptag_b200_handle h, int32_t refine_iterations, int32_t cef, float cef_scale,
                                  int32_t neighborhood_size, float neighborhood_scale, float rng_factor) {
     if (!h) return fail(SPTAG_B200_EMPTY_INDEX, "null handle");

@@ -72,6 +72,7 @@ def ref():
         L.ref_quantizer_m.argtypes = [C.c_void_p]
         L.ref_quantizer_reconstruct_dim.argtypes = [C.c_void_p]
         L.ref_quantizer_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_rebuild_graph.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.ref_quantizer_reconstruct.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_quantizer_l2.restype = C.c_float
         L.ref_quantizer_l2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -216,6 +217,15 @@ class RefIndex:
         if rc != 0:
             raise RuntimeError("reference refine failed: %d" % rc)
         return rows, ids, dists
+
+    def rebuild_graph(self, graph, neighborhood):
+        """NeighborhoodGraph::RebuildGraph run by the reference (one thread) on `graph` [n, stride >= 2*neighborhood];
+        returns the rows afterwards (the first `neighborhood` entries of a row are its neighbours)."""
+        g = np.ascontiguousarray(graph, np.int32).copy()
+        rc = ref().ref_rebuild_graph(self.h, g.ctypes.data, g.shape[0], g.shape[1], neighborhood)
+        if rc != 0:
+            raise RuntimeError("ref_rebuild_graph failed")
+        return g
 
     def search_flag(self, queries, k, search_deleted, threads=0):
         """SearchIndex(QueryResult&, p_searchDeleted) per query."""
@@ -549,6 +559,7 @@ def ora():
         L.ora_iter_next_from_nearest.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.ora_quantizer_init.argtypes = [C.POINTER(_OraQuantizer)]
         L.ora_quantizer_encode.argtypes = [C.POINTER(_OraQuantizer), C.c_void_p, C.c_int32, C.c_void_p]
+        L.ora_rebuild_graph.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
         L.ora_quantizer_reconstruct.argtypes = [C.POINTER(_OraQuantizer), C.c_void_p, C.c_int32, C.c_void_p]
         L.ora_quantizer_l2.restype = C.c_float
         L.ora_quantizer_l2.argtypes = [C.POINTER(_OraQuantizer), C.c_void_p, C.c_void_p]
@@ -659,6 +670,14 @@ class _OraIterator:
 # synthetic data (BASELINE.md generators, numpy flavour -- parity is always checked on the SAME
 # saved index files, so the exact libstdc++ sequence is not needed)
 # ------------------------------------------------------------------------------------------------
+def oracle_rebuild_graph(graph, neighborhood):
+    """oracle/sptag_oracle.c ora_rebuild_graph on a copy of `graph` [n, stride]."""
+    g = np.ascontiguousarray(graph, np.int32).copy()
+    if ora().ora_rebuild_graph(g.ctypes.data, g.shape[0], g.shape[1], neighborhood) != 0:
+        raise RuntimeError("ora_rebuild_graph failed")
+    return g
+
+
 def gen_iid(n, dim, seed):
     return np.random.default_rng(seed).standard_normal((n, dim), dtype=np.float32)
 

@@ -158,6 +158,49 @@ def test_refine_schedule_matches_pass_by_pass_oracle(name, iters, cef, cef_scale
         idx.close()
 
 
+@pytest.mark.parametrize("name,widen_to", [("bkt_l2_20k_32", 0), ("bkt_l2_dups", 0), ("kdt_l2_10k_64", 0),
+                                           ("bkt_l2_5k_100", 48), ("bkt_u8_l2_6k_128", 20)])
+def test_rebuild_graph_matches_oracle(name, widen_to):
+    """EnableRebuild's in-degree repair (NeighborhoodGraph::RebuildGraph, NeighborhoodGraph.h:404-456) on the device against
+    the oracle's restatement of its single-thread order (pinned to the reference itself in tests/test_oracle_pin.py); on
+    the index's own 32-wide rows (N = 16) and on rows a refine pass installed with another width; then installed and
+    searched."""
+    from sptag_b200 import B200Index
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    q = np.load(os.path.join(folder, "queries.npy"))[:100]
+    idx = B200Index.load(folder)
+    old_graph, old_degree = files.graph, files.degree
+    try:
+        if widen_to:
+            idx.set_param("MaxCheckForRefineGraph", 512)
+            idx.refine_graph(60, neighborhood=widen_to, install=True)
+        wide = idx.get_graph()
+        n2 = wide.shape[1] // 2
+        g = wide.copy()
+        g[g < -1] = -1                      # back-pointers are not neighbours; BuildGraph attaches them afterwards
+        expect = reflib.oracle_rebuild_graph(g, n2)[:, :n2]
+        rows = idx.rebuild_graph(install=True)
+        assert np.array_equal(rows, expect), name
+        back = wide[:, -1] < -1
+        expect = expect.copy()
+        expect[back, -1] = wide[back, -1]
+        assert idx.graph_degree == n2
+        assert np.array_equal(idx.get_graph(), expect)
+        files.graph, files.degree = np.ascontiguousarray(expect), n2
+        o = reflib.OracleIndex(files)
+        for mc in (1024, 64):
+            o.max_check = mc
+            idx.set_param("MaxCheck", mc)
+            ids, dists = idx.search(q, 10)
+            ids_o, d_o, _ = o.search(q, 10)
+            assert np.array_equal(ids, ids_o)
+            assert np.array_equal(dists.view(np.int32), d_o.view(np.int32))
+    finally:
+        files.graph, files.degree = old_graph, old_degree
+        idx.close()
+
+
 def test_refine_argument_errors():
     from sptag_b200 import B200Index, capi
     idx = B200Index.load(data_folder("bkt_l2_3k_30"))

@@ -435,6 +435,30 @@ def test_quantized_refine_bit_exact_vs_reference(oracle_lib, name, cef, mcr):
 
 
 @needs_ref
+@pytest.mark.parametrize("name,nbh", [("bkt_l2_20k_32", 16), ("bkt_l2_10k_128", 16), ("bkt_l2_dups", 16), ("kdt_l2_10k_64", 8),
+                                      ("bkt_i8_cos_6k_64", 12)])
+def test_rebuild_graph_bit_exact_vs_reference(oracle_lib, name, nbh):
+    """NeighborhoodGraph::RebuildGraph (EnableRebuild's in-degree repair, NeighborhoodGraph.h:404-456) run by the
+    reference itself, single-threaded, on rows of 2 x nbh candidates -- the index's own graph rows (32 wide), a widened
+    copy with -1 padding, and a copy with a skewed in-degree -- against the oracle's restatement."""
+    folder = data_folder(name)
+    files = reflib.IndexFiles(folder)
+    r = reflib.RefIndex.load(folder)
+    g0 = files.graph[:, :2 * nbh].copy()
+    g0[g0 < 0] = -1                       # (duplicate back-pointers are re-attached after RebuildGraph, :395-401)
+    rng = np.random.default_rng(7)
+    g1 = np.concatenate([g0, -np.ones((files.n, 5), np.int32)], axis=1)        # stride > 2 x nbh
+    g2 = g0.copy()                                                            # many edges into few nodes + holes
+    g2[:, nbh // 2:nbh] = rng.integers(0, 50, size=(files.n, nbh - nbh // 2))
+    g2[rng.random(g2.shape) < 0.05] = -1
+    for g in (g0, g1, g2):
+        a = r.rebuild_graph(g, nbh)
+        b = reflib.oracle_rebuild_graph(g, nbh)
+        assert np.array_equal(a, b), name
+        assert not np.array_equal(a[:, :nbh], g[:, :nbh])   # it did something
+
+
+@needs_ref
 def test_iterator_known_answer_of_the_reference(oracle_lib):
     """Test/src/IterativeScanTest.cpp: line data, MaxCheck 5, query (0,...): two Next(5) calls return ids 0..9 in order
     with RelaxedMono set -- run on the reference itself and on the oracle."""
