@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_refine.py tests/test_capi_symbols.py -q -x --timeout 600 > gpurun_out/r02_gpu_rebuild.log 2>&1; echo "pytest rc=$?"; tail -30 gpurun_out/r02_gpu_rebuild.log
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/r02_gpu_final4.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r02_gpu_final4.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/r02_smoke.log
