@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/r02_gpu_final4.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r02_gpu_final4.log
-timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/r02_smoke.log
+timeout 900 python tools/rebuild_bench.py --num-vectors 1000000 --dim 128 > gpurun_out/r02_rebuild_1m128.json 2> gpurun_out/r02_rebuild_1m128.err; echo "rc=$?"; tail -1 gpurun_out/r02_rebuild_1m128.json; tail -3 gpurun_out/r02_rebuild_1m128.err
