@@ -116,8 +116,10 @@ void sptag_b200_destroy(sptag_b200_handle h);
  * (VectorIndex.h:136-138) for quantized indexes; "SearchDeleted" (0/1) = the handle-wide DEFAULT of the
  * p_searchDeleted argument (the per-call value is sptag_b200_search_options.search_deleted /
  * sptag_b200_iterator_open_ex); the refine pass always runs with 0 like NeighborhoodGraph::RefineNode.  Additional B200 tuning knobs (not in the
- * reference) are prefixed "B200.": B200.QueriesPerSM, B200.StageRows, B200.Stages,
- * B200.NGCacheEntries, B200.SPTCacheEntries, B200.SimdWidth (which DistanceUtils summation tree to
+ * reference) are prefixed "B200.": B200.QueriesPerSM (query slots per SM, 0 = auto: what registers and shared memory allow;
+ * for 512-byte float rows the slot count in [14, 20] that fills the batch's last round best), B200.StageRows, B200.Stages
+ * (depth of the row ring; 512-byte float rows run one stage unless 2 is set explicitly at <= 16 slots),
+ * B200.NGCacheEntries, B200.SPTCacheEntries (queue entries kept in shared memory, 0 = the slot's spare), B200.SimdWidth (which DistanceUtils summation tree to
  * reproduce bit-exactly -- the reference picks by cpuid, DistanceUtils.h:118-163: 16 = AVX-512 (default; all specialised
  * kernels), 8 = AVX / AVX2, 4 = SSE; 8 and 4 are built for float, int8 and uint8 rows and run the generic-dimension
  * kernels; int16 rows and quantized indexes exist in the AVX-512 form only and return LackOfInputs otherwise), B200.VisitedLog (-1 auto, 0 clear the
