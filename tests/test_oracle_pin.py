@@ -136,6 +136,23 @@ def test_oracle_refine_matches_golden_reference_outputs(oracle_lib, name):
     assert np.array_equal(rows, r["rows"]), name
 
 
+def rebuild_golden_cases():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "rebuild", "*.npz")))
+
+
+@pytest.mark.parametrize("name", rebuild_golden_cases())
+def test_oracle_rebuild_graph_matches_golden_reference_outputs(oracle_lib, name):
+    """the reference's own NeighborhoodGraph::RebuildGraph (one thread) on the committed indexes' rows and
+    on a skewed copy (tests/golden/make_golden_rebuild.py) against ora_rebuild_graph.  Needs no reference at test time."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    r = np.load(os.path.join(GOLDEN, "rebuild", name + ".npz"))
+    nbh = int(r["neighborhood"])
+    own = g["graph"].astype(np.int32).copy()
+    own[own < 0] = -1
+    assert np.array_equal(reflib.oracle_rebuild_graph(own, nbh)[:, :nbh], r["own_rows"]), name
+    assert np.array_equal(reflib.oracle_rebuild_graph(r["skewed_in"], nbh)[:, :nbh], r["skewed_rows"]), name
+
+
 def iterator_golden_cases():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "iterator", "*.npz")))
 
