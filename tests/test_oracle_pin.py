@@ -153,6 +153,42 @@ def test_oracle_rebuild_graph_matches_golden_reference_outputs(oracle_lib, name)
     assert np.array_equal(reflib.oracle_rebuild_graph(r["skewed_in"], nbh)[:, :nbh], r["skewed_rows"]), name
 
 
+def quantized_golden_cases():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "quantized", "*.npz")))
+
+
+@pytest.mark.parametrize("name", quantized_golden_cases())
+def test_oracle_matches_golden_quantized_reference_outputs(oracle_lib, tmp_path, name):
+    """SURVEY.md 8a row A10 + 8 f2 on committed fixtures (tests/golden/make_golden_quantized.py): an index the reference built
+    over PQ / OPQ codes, its SDC and ADC searches on raw queries, ReconstructVector, and RefineNode on the quantized index --
+    all produced by the reference, checked against the oracle without the reference present."""
+    g = np.load(os.path.join(GOLDEN, "quantized", name + ".npz"))
+    files = reflib.IndexFiles.__new__(reflib.IndexFiles)
+    _files_from_npz(files, g)
+    qpath = str(tmp_path / "quantizer.bin")
+    g["quantizer_blob"].tofile(qpath)
+    files.quantizer = reflib.Quantizer.read(qpath)
+    q, k = g["queries"], int(g["k"])
+    for adc, tag in ((False, "sdc"), (True, "adc")):
+        for i, mc in enumerate(g["max_checks"].tolist()):
+            o = reflib.OracleIndex(files)
+            o.max_check = int(mc)
+            o.enable_adc = adc
+            ids, dists, _ = o.search(q, k)
+            assert np.array_equal(ids, g["ref_ids_" + tag][i]), (name, tag, mc)
+            assert np.array_equal(dists.view(np.int32), g["ref_dists_" + tag][i].view(np.int32)), (name, tag, mc)
+    oq = reflib.OracleQuantizer(files.quantizer)
+    rec = oq.reconstruct(files.vectors[:64], g["reconstructed"].dtype)
+    assert np.array_equal(rec.view(np.uint8), g["reconstructed"].view(np.uint8)), name
+    o = reflib.OracleIndex(files)
+    o.max_check_refine = int(g["refine_max_check"])
+    num = g["refine_rows"].shape[0]
+    rows, ids, dists = o.refine_nodes(0, num, int(g["refine_cef"]), int(g["refine_neighborhood"]), float(g["refine_rng_factor"]))
+    assert np.array_equal(ids, g["refine_ids"]), name
+    assert np.array_equal(dists.view(np.int32), g["refine_dists"].view(np.int32)), name
+    assert np.array_equal(rows, g["refine_rows"]), name
+
+
 def iterator_golden_cases():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "iterator", "*.npz")))
 
